@@ -1,0 +1,68 @@
+"""Option sets and seeded inputs shared by the parity tests (oracle vs reference vs CUDA)."""
+import numpy as np
+
+from fastplong_b200 import Options, pack_reads, synth
+
+S, E = synth.ADAPTER_START, synth.ADAPTER_END
+
+FASTA5 = [  # a 5-entry adapter "FASTA" in std::map header order, incl. a 72-bp entry and one absent from reads
+    "CTGTCTCTTATACACATCTCCGAGCCCACGAGAC",
+    "AGATCGGAAGAGCACACGTCTGAACTCCAGTCACGGCTACATCTCGTATGCCGTCTTCTGCTTGAAAAAAGGGTTT",
+    "GGTTCA",
+    "TTTCTGTTGGTGCTGATATTGCT",
+    "ACTTGCCTGTCGCTCTATCTTC",
+]
+
+OPTION_SETS = {
+    "default_se": Options(start_adapter=S),
+    "cut_polyx_cplx": Options(start_adapter=S, end_adapter=E, cut_front=True, cut_tail=True, cut_window_size=10,
+                              trim_poly_x=True, low_complexity_filter=True),
+    "trims_limits": Options(start_adapter=S, trim_front=5, trim_tail=7, mean_qual=10, n_base_limit=2,
+                            length_limit=400, n_percent_limit=3, unqualified_percent_limit=30),
+    "loose_ed": Options(start_adapter=S, distance_threshold=0.3, trimming_extension=4, cut_tail=True,
+                        cut_tail_window_size=1, cut_tail_mean_quality=25),
+    "fasta5": Options(start_adapter=S, adapter_fasta=FASTA5, trim_poly_x=True, poly_x_min_len=8),
+    "literal_auto": Options(start_adapter="auto", end_adapter="auto", cut_front=True, cut_front_window_size=7,
+                            cut_front_mean_quality=15),
+    "no_adapter_no_filters": Options(disable_adapter_trimming=True, disable_quality_filtering=True,
+                                     disable_length_filtering=True),
+    "empty_adapters": Options(start_adapter="", end_adapter="", disable_quality_filtering=True),
+    "strict_ed0": Options(start_adapter=S, distance_threshold=0.0, trimming_extension=0, qualified_quality_phred=20,
+                          length_required=100),
+    "end_only_wide_window": Options(start_adapter="", end_adapter=E, cut_front=True, cut_tail=True,
+                                    cut_window_size=100, cut_mean_quality=12, trim_tail=3),
+}
+
+
+def planted_fasta_reads(seed, n=120):
+    """Reads with FASTA5 entries planted at either end (noisy), for the fasta5 option set."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        L = int(rng.integers(60, 900))
+        s = bytearray(synth.BASES[rng.integers(0, 4, size=L)].tobytes())
+        for side in (0, 1):
+            if rng.random() < 0.6:
+                a = FASTA5[int(rng.integers(len(FASTA5)))].encode()
+                if side == 1:
+                    a = a[: int(rng.integers(max(6, len(a) // 2), len(a) + 1))]
+                else:
+                    a = a[len(a) - int(rng.integers(max(6, len(a) // 2), len(a) + 1)):]
+                a = synth._noisy(rng, a, 0.06)
+                k = int(rng.integers(0, 12))
+                if len(a) + k < L:
+                    if side == 0:
+                        s[k:k + len(a)] = a
+                    else:
+                        s[L - k - len(a):L - k] = a
+        q = (np.rint(rng.normal(20, 8, size=L)).clip(1, 50).astype(np.uint8) + 33).tobytes()
+        out.append((bytes(s), q))
+    return out
+
+
+def adversarial_batch(seed):
+    return pack_reads(synth.adversarial_reads(seed) + planted_fasta_reads(seed + 1000))
+
+
+def ont_batch(seed, n=300, mean=2000, **kw):
+    return synth.ont_like(n, mean, seed, **kw)

@@ -1,0 +1,50 @@
+"""Differential test: the oracle restatement vs the UNMODIFIED reference operators (oracle/_ref/libfplref.so) on
+seeded batches beyond the committed fixtures.  Skipped where the prebuilt reference library is absent."""
+import numpy as np
+import pytest
+
+import cases
+from fastplong_b200 import Options, pack_reads, synth
+from oracle_lib import OracleEngine, RefEngine, compare_results, compare_stats, have_ref
+
+pytestmark = pytest.mark.skipif(not have_ref(), reason="oracle/_ref/libfplref.so not built")
+
+
+def check(opt, batch, what):
+    o, r = OracleEngine(opt), RefEngine(opt)
+    compare_results(o.process(batch), r.process(batch), what)
+    cyc = max(1, int(batch.lens.max()) if batch.n_reads else 1)
+    for w in (0, 1):
+        compare_stats(o.stats(w, cyc), r.stats(w, cyc), f"{what}/stats{w}")
+    compare_stats(o.counters(), r.counters(), what + "/counters")
+
+
+@pytest.mark.parametrize("name", sorted(cases.OPTION_SETS))
+@pytest.mark.parametrize("seed", [1, 2])
+def test_adversarial(name, seed):
+    check(cases.OPTION_SETS[name], cases.adversarial_batch(seed), f"{name}/adv{seed}")
+
+
+@pytest.mark.parametrize("name", sorted(cases.OPTION_SETS))
+def test_ont_like(name):
+    check(cases.OPTION_SETS[name], cases.ont_batch(77, n=150, mean=2500, p_chimera=0.05, p_polya=0.05), name + "/ont")
+
+
+def test_edit_distance_random_pairs():
+    rng = np.random.default_rng(5)
+    o, r = OracleEngine(Options()), RefEngine(Options())
+    for _ in range(3000):
+        la, lb = int(rng.integers(0, 150)), int(rng.integers(0, 150))
+        a = synth.BASES[rng.integers(0, 4, size=la)].tobytes()
+        b = synth.BASES[rng.integers(0, 4, size=lb)].tobytes()
+        if rng.random() < 0.5 and la:
+            b = a[: int(rng.integers(0, la + 1))] + b[: int(rng.integers(0, 6))]
+        assert o.edit_distance(a, b) == r.edit_distance(a, b)
+    for la, lb in ((700, 650), (641, 10), (64, 65), (128, 129), (640, 640)):
+        a = synth.BASES[rng.integers(0, 4, size=la)].tobytes()
+        b = synth.BASES[rng.integers(0, 4, size=lb)].tobytes()
+        assert o.edit_distance(a, b) == r.edit_distance(a, b)
+
+
+def test_empty_batch():
+    check(cases.OPTION_SETS["default_se"], pack_reads([]), "empty")
