@@ -1,0 +1,182 @@
+"""ctypes binding of libfplgpu.so (include/fplgpu.h) — the product path used by tests, bench.py and the multi-GPU
+driver.  There is no fallback: if the CUDA library is missing or no device is usable, construction raises."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+from .abi import FplAdapters, FplBatch, FplOptions, RESULT_DTYPE
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libfplgpu.so")
+
+_lib = None
+
+
+class FplError(RuntimeError):
+    pass
+
+
+def load_library():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FplError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(there is no CPU fallback for the hot path)")
+    lib = C.CDLL(LIB_PATH)
+    lib.fpl_last_error.restype = C.c_char_p
+    lib.fpl_abi_version.restype = C.c_int
+    lib.fpl_create.argtypes = [C.POINTER(FplOptions), C.POINTER(FplAdapters), C.POINTER(C.c_void_p)]
+    lib.fpl_destroy.argtypes = [C.c_void_p]
+    lib.fpl_destroy.restype = None
+    lib.fpl_process_host.argtypes = [C.c_void_p, C.POINTER(FplBatch), C.c_void_p]
+    lib.fpl_process_device.argtypes = [C.c_void_p, C.POINTER(FplBatch), C.c_void_p]
+    lib.fpl_sync.argtypes = [C.c_void_p]
+    lib.fpl_fetch_results.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    lib.fpl_stats_cycles.argtypes = [C.c_void_p]
+    lib.fpl_stats_cycles.restype = C.c_int64
+    lib.fpl_stats_reserve.argtypes = [C.c_void_p, C.c_int64]
+    lib.fpl_stats_download.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]
+    lib.fpl_stats_device_ptr.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+    lib.fpl_counter_words.argtypes = [C.c_void_p]
+    lib.fpl_counter_words.restype = C.c_int64
+    lib.fpl_counters_download.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    lib.fpl_counters_device_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+    lib.fpl_reset.argtypes = [C.c_void_p]
+    lib.fpl_last_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
+    lib.fpl_launch_count.argtypes = [C.c_void_p]
+    lib.fpl_launch_count.restype = C.c_int64
+    lib.fpl_set_timing.argtypes = [C.c_void_p, C.c_int]
+    if lib.fpl_abi_version() != abi.ABI_VERSION:
+        raise FplError("libfplgpu.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+EXPORTS = ["fpl_last_error", "fpl_abi_version", "fpl_create", "fpl_destroy", "fpl_process_host", "fpl_process_device",
+           "fpl_sync", "fpl_fetch_results", "fpl_stats_cycles", "fpl_stats_reserve", "fpl_stats_download",
+           "fpl_stats_device_ptr", "fpl_counter_words", "fpl_counters_download", "fpl_counters_device_ptr",
+           "fpl_reset", "fpl_last_kernel_times", "fpl_launch_count", "fpl_set_timing"]
+
+
+class _DeviceArray:
+    """Wraps a raw device pointer for torch.as_tensor via __cuda_array_interface__ (int64 vector)."""
+
+    def __init__(self, ptr, n_words, owner):
+        self.__cuda_array_interface__ = {"shape": (int(n_words),), "typestr": "<i8", "data": (int(ptr), False),
+                                         "version": 2}
+        self._owner = owner
+
+
+class Engine:
+    """One context = one worker's state (2 Stats + FilterResult accumulators) on one GPU."""
+
+    def __init__(self, options):
+        self.lib = load_library()
+        self.options = options
+        o, ad, keep = options.to_abi()
+        self._keep = (o, ad, keep)
+        self.n_adapters = 2 + len(options.adapter_fasta)
+        h = C.c_void_p()
+        if self.lib.fpl_create(C.byref(o), C.byref(ad), C.byref(h)) != 0:
+            raise FplError(self.lib.fpl_last_error().decode())
+        self.h = h
+
+    def _check(self, rc):
+        if rc != 0:
+            raise FplError(self.lib.fpl_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.fpl_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --- processSingleEnd over a packed batch ---
+    def process(self, batch, out=None):
+        """Host batch (numpy / pinned buffers) -> per-read records (numpy structured array)."""
+        res = out if out is not None else np.zeros(batch.n_reads, dtype=RESULT_DTYPE)
+        b = batch.to_abi()
+        self._check(self.lib.fpl_process_host(self.h, C.byref(b), res.ctypes.data))
+        return res
+
+    def process_device(self, seq_ptr, qual_ptr, offsets_ptr, lens_ptr, n_reads, n_bytes, results_ptr=None):
+        b = FplBatch(seq_ptr, qual_ptr, offsets_ptr, lens_ptr, n_reads, n_bytes)
+        self._check(self.lib.fpl_process_device(self.h, C.byref(b), results_ptr))
+
+    def sync(self):
+        self._check(self.lib.fpl_sync(self.h))
+
+    def fetch_results(self, n):
+        res = np.zeros(n, dtype=RESULT_DTYPE)
+        self._check(self.lib.fpl_fetch_results(self.h, res.ctypes.data, n))
+        return res
+
+    # --- accumulators ---
+    @property
+    def cycles(self):
+        return int(self.lib.fpl_stats_cycles(self.h))
+
+    def reserve_cycles(self, cycles):
+        self._check(self.lib.fpl_stats_reserve(self.h, int(cycles)))
+
+    def stats(self, which, cycles=None):
+        """The FPL_STATS_WORDS block, re-laid out to `cycles` columns if given (must cover every non-zero cycle)."""
+        cap = self.cycles
+        raw = np.zeros(abi.stats_words(cap), dtype=np.int64)
+        self._check(self.lib.fpl_stats_download(self.h, which, raw.ctypes.data, raw.shape[0]))
+        if cycles is None or cycles == cap:
+            return raw
+        return relayout_stats(raw, cap, int(cycles))
+
+    def counters(self):
+        n = int(self.lib.fpl_counter_words(self.h))
+        out = np.zeros(n, dtype=np.int64)
+        self._check(self.lib.fpl_counters_download(self.h, out.ctypes.data, n))
+        return out
+
+    def stats_device(self, which):
+        p, n = C.c_void_p(), C.c_int64()
+        self._check(self.lib.fpl_stats_device_ptr(self.h, which, C.byref(p), C.byref(n)))
+        return _DeviceArray(p.value, n.value, self)
+
+    def counters_device(self):
+        p, n = C.c_void_p(), C.c_int64()
+        self._check(self.lib.fpl_counters_device_ptr(self.h, C.byref(p), C.byref(n)))
+        return _DeviceArray(p.value, n.value, self)
+
+    def reset(self):
+        self._check(self.lib.fpl_reset(self.h))
+
+    # --- measurement ---
+    def set_timing(self, on=True):
+        self._check(self.lib.fpl_set_timing(self.h, int(on)))
+
+    def kernel_times(self):
+        names = (C.c_char_p * 16)()
+        ms = (C.c_float * 16)()
+        k = self.lib.fpl_last_kernel_times(self.h, names, ms, 16)
+        return {names[i].decode(): float(ms[i]) for i in range(k)}
+
+    @property
+    def launch_count(self):
+        return int(self.lib.fpl_launch_count(self.h))
+
+
+def relayout_stats(raw, cap, cycles):
+    """[16][cap] + tail  ->  [16][cycles] + tail; raises if a dropped column is non-zero."""
+    rows = raw[:16 * cap].reshape(16, cap)
+    out = np.zeros(abi.stats_words(cycles), dtype=np.int64)
+    n = min(cap, cycles)
+    out[:16 * cycles].reshape(16, cycles)[:, :n] = rows[:, :n]
+    if cap > cycles and rows[:, cycles:].any():
+        raise ValueError("stats block has non-zero cycles beyond the requested width")
+    out[16 * cycles:] = raw[16 * cap:]
+    return out

@@ -1,0 +1,443 @@
+// C-ABI implementation of include/fplgpu.h: context management, device tables, batch tiling and kernel sequencing.
+// No CPU fallback anywhere: every entry point fails loudly when CUDA is unusable.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "fpl_device.cuh"
+
+static_assert(sizeof(fpl_options) == 128, "fpl_options ABI size");
+static_assert(sizeof(fpl_read_result) == 64, "fpl_read_result ABI size");
+static_assert(sizeof(ReadState) == 64, "ReadState size");
+static_assert(sizeof(StatSeg) == 24, "StatSeg size");
+
+// kernel launchers (fpl_trim.cu, fpl_scan.cu, fpl_stats.cu)
+void launch_trim(const DevParams&, const DevBatch&, ReadState*, fpl_read_result*, unsigned long long*, cudaStream_t);
+void launch_scan(const DevParams&, const DevBatch&, ReadState*, cudaStream_t);
+void launch_final(const DevParams&, const DevBatch&, const ReadState*, fpl_read_result*, StatSeg*, cudaStream_t);
+void launch_count(const fpl_read_result*, int64_t, unsigned long long*, cudaStream_t);
+void launch_cycle_stats(const uint8_t*, const uint8_t*, const StatSeg*, int64_t, int64_t, unsigned long long*, int64_t,
+                        cudaStream_t);
+void launch_read_qual(const uint8_t*, const StatSeg*, int64_t, unsigned long long*, int64_t, fpl_read_result*,
+                      cudaStream_t);
+void launch_make_preseg(const DevBatch&, StatSeg*, cudaStream_t);
+
+static thread_local char g_err[512] = "";
+
+static int fail(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return -1;
+}
+
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+enum { K_PRESEG, K_CYCLE_PRE, K_QUAL_PRE, K_TRIM, K_SCAN, K_FINAL, K_COUNT, K_CYCLE_POST, K_QUAL_POST, K_NKERNELS };
+static const char* const kKernelNames[K_NKERNELS] = {"k_make_preseg", "k_cycle_stats(pre)", "k_read_qual(pre)",
+                                                     "k_trim", "k_scan", "k_final", "k_count",
+                                                     "k_cycle_stats(post)", "k_read_qual(post)"};
+
+struct fpl_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    DevParams P;
+    int n_adapters = 0;
+    uint8_t* d_adapters = nullptr;
+    int* d_alen = nullptr;
+    uint4* d_peq = nullptr;
+    uint32_t* d_peq16 = nullptr;
+    // accumulators
+    int64_t C = 0;
+    unsigned long long* d_stats[2] = {nullptr, nullptr};
+    unsigned long long* d_counters = nullptr;
+    int64_t counter_words = 0;
+    // per-read work buffers
+    int64_t cap_reads = 0;
+    ReadState* d_state = nullptr;
+    fpl_read_result* d_results = nullptr;
+    StatSeg* d_preseg = nullptr;
+    StatSeg* d_postseg = nullptr;
+    int64_t last_n = 0;
+    fpl_read_result* last_results = nullptr;  // where the last call's records live (device)
+    // staging for host batches
+    int64_t cap_bytes = 0;
+    uint8_t* d_seq = nullptr;
+    uint8_t* d_qual = nullptr;
+    int64_t cap_idx = 0;
+    int64_t* d_offsets = nullptr;
+    int32_t* d_lens = nullptr;
+    std::vector<int32_t> h_lens;
+    // tiling + measurement
+    int64_t tile_bases = 0;
+    bool timing = false;
+    float kernel_ms[K_NKERNELS];
+    int64_t launches = 0;
+    struct Ev { int k; cudaEvent_t a, b; };
+    std::vector<Ev> events;
+    std::vector<cudaEvent_t> pool;
+};
+
+static int ensure_reads(fpl_ctx* c, int64_t n) {
+    if (n <= c->cap_reads) return 0;
+    int64_t cap = c->cap_reads ? c->cap_reads : 1024;
+    while (cap < n) cap *= 2;
+    cudaFree(c->d_state); cudaFree(c->d_results); cudaFree(c->d_preseg); cudaFree(c->d_postseg);
+    c->d_state = nullptr; c->d_results = nullptr; c->d_preseg = nullptr; c->d_postseg = nullptr; c->cap_reads = 0;
+    CK(cudaMalloc(&c->d_state, sizeof(ReadState) * cap));
+    CK(cudaMalloc(&c->d_results, sizeof(fpl_read_result) * cap));
+    CK(cudaMalloc(&c->d_preseg, sizeof(StatSeg) * cap));
+    CK(cudaMalloc(&c->d_postseg, sizeof(StatSeg) * 2 * cap));
+    c->cap_reads = cap;
+    return 0;
+}
+
+static int reserve_cycles(fpl_ctx* c, int64_t need) {
+    if (need <= c->C) return 0;
+    int64_t nc = c->C ? c->C : 1024;
+    while (nc < need) nc *= 2;
+    for (int w = 0; w < 2; w++) {
+        unsigned long long* nb = nullptr;
+        CK(cudaMalloc(&nb, sizeof(unsigned long long) * FPL_STATS_WORDS(nc)));
+        CK(cudaMemsetAsync(nb, 0, sizeof(unsigned long long) * FPL_STATS_WORDS(nc), c->stream));
+        if (c->d_stats[w]) {
+            // rows b*C + c move to b*nc + c; the tail moves to 16*nc
+            CK(cudaMemcpy2DAsync(nb, sizeof(unsigned long long) * nc, c->d_stats[w], sizeof(unsigned long long) * c->C,
+                                 sizeof(unsigned long long) * c->C, 16, cudaMemcpyDeviceToDevice, c->stream));
+            CK(cudaMemcpyAsync(nb + 16 * nc, c->d_stats[w] + 16 * c->C, sizeof(unsigned long long) * FPL_STATS_TAIL,
+                               cudaMemcpyDeviceToDevice, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            cudaFree(c->d_stats[w]);
+        }
+        c->d_stats[w] = nb;
+    }
+    c->C = nc;
+    return 0;
+}
+
+static cudaEvent_t get_event(fpl_ctx* c) {
+    if (!c->pool.empty()) { cudaEvent_t e = c->pool.back(); c->pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct Timed {
+    fpl_ctx* c; int k; cudaEvent_t a = nullptr, b = nullptr;
+    Timed(fpl_ctx* c_, int k_) : c(c_), k(k_) {
+        if (c->timing) { a = get_event(c); b = get_event(c); cudaEventRecord(a, c->stream); }
+    }
+    ~Timed() {
+        c->launches++;
+        if (c->timing) { cudaEventRecord(b, c->stream); c->events.push_back({k, a, b}); }
+    }
+};
+
+static void collect_times(fpl_ctx* c) {
+    for (auto& e : c->events) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) c->kernel_ms[e.k] += ms;
+        c->pool.push_back(e.a); c->pool.push_back(e.b);
+    }
+    c->events.clear();
+}
+
+// Runs every kernel over reads [0, n) of a device-resident batch whose lens are known on the host.
+static int run_batch(fpl_ctx* c, const DevBatch& full, const int32_t* h_lens, fpl_read_result* d_res_out) {
+    const int64_t n = full.n_reads;
+    CK(cudaSetDevice(c->device));
+    for (int k = 0; k < K_NKERNELS; k++) c->kernel_ms[k] = 0;
+    collect_times(c);
+    for (int k = 0; k < K_NKERNELS; k++) c->kernel_ms[k] = 0;
+    c->last_n = n;
+    if (ensure_reads(c, n)) return -1;
+    fpl_read_result* d_res = d_res_out ? d_res_out : c->d_results;
+    c->last_results = d_res;
+    int64_t max_len = 0;
+    for (int64_t i = 0; i < n; i++) {
+        if (h_lens[i] < 0) return fail("read %lld has a negative length", (long long)i);
+        if (h_lens[i] > max_len) max_len = h_lens[i];
+    }
+    if (reserve_cycles(c, max_len > 0 ? max_len : 1)) return -1;
+    // tiles of reads whose payload stays L2-resident across the kernels that revisit it
+    int64_t r0 = 0;
+    while (r0 < n) {
+        int64_t r1 = r0, bases = 0, tmax = 0;
+        while (r1 < n && (r1 == r0 || bases + h_lens[r1] <= c->tile_bases)) {
+            bases += h_lens[r1];
+            if (h_lens[r1] > tmax) tmax = h_lens[r1];
+            r1++;
+        }
+        DevBatch b = full;
+        b.offsets = full.offsets + r0; b.lens = full.lens + r0; b.n_reads = r1 - r0;
+        ReadState* st = c->d_state + r0;
+        fpl_read_result* res = d_res + r0;
+        StatSeg* pre = c->d_preseg + r0;
+        StatSeg* post = c->d_postseg + 2 * r0;
+        cudaStream_t s = c->stream;
+        { Timed t(c, K_PRESEG); launch_make_preseg(b, pre, s); }
+        { Timed t(c, K_TRIM); launch_trim(c->P, b, st, res, c->d_counters, s); }
+        { Timed t(c, K_CYCLE_PRE); launch_cycle_stats(full.seq, full.qual, pre, b.n_reads, tmax, c->d_stats[0], c->C, s); }
+        { Timed t(c, K_QUAL_PRE); launch_read_qual(full.qual, pre, b.n_reads, c->d_stats[0], c->C, res, s); }
+        { Timed t(c, K_SCAN); launch_scan(c->P, b, st, s); }
+        { Timed t(c, K_FINAL); launch_final(c->P, b, st, res, post, s); }
+        { Timed t(c, K_COUNT); launch_count(res, b.n_reads, c->d_counters, s); }
+        { Timed t(c, K_CYCLE_POST); launch_cycle_stats(full.seq, full.qual, post, 2 * b.n_reads, tmax, c->d_stats[1], c->C, s); }
+        { Timed t(c, K_QUAL_POST); launch_read_qual(full.qual, post, 2 * b.n_reads, c->d_stats[1], c->C, res, s); }
+        r0 = r1;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" {
+
+const char* fpl_last_error(void) { return g_err; }
+int fpl_abi_version(void) { return FPL_ABI_VERSION; }
+
+int fpl_create(const fpl_options* opt, const fpl_adapters* ad, fpl_ctx** out) {
+    g_err[0] = 0;
+    if (!opt || !ad || !out) return fail("fpl_create: null argument");
+    if (opt->struct_size != (int32_t)sizeof(fpl_options))
+        return fail("fpl_create: fpl_options.struct_size %d != %d (ABI mismatch)", opt->struct_size, (int)sizeof(fpl_options));
+    if (opt->ed_max < 0 || opt->ed_max > 1.0) return fail("fpl_create: ed_max must be within 0..1");
+    if (opt->trim_front < 0 || opt->trim_tail < 0) return fail("fpl_create: trim_front/trim_tail must be >= 0");
+    if ((opt->cut_front_enabled && (opt->cut_front_window < 1 || opt->cut_front_window > FPL_MAX_WINDOW)) ||
+        (opt->cut_tail_enabled && (opt->cut_tail_window < 1 || opt->cut_tail_window > FPL_MAX_WINDOW)))
+        return fail("fpl_create: cut window size must be within 1..%d", FPL_MAX_WINDOW);
+    const int n = 2 + (ad->n_fasta > 0 ? ad->n_fasta : 0);
+    if (n > FPL_MAX_ADAPTERS) return fail("fpl_create: %d adapters exceed FPL_MAX_ADAPTERS=%d", n, FPL_MAX_ADAPTERS);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail("fpl_create: no usable CUDA device (%s); libfplgpu has no CPU fallback", cudaGetErrorString(e));
+    if (opt->device < 0 || opt->device >= ndev) return fail("fpl_create: device %d out of range (%d devices)", opt->device, ndev);
+    CK(cudaSetDevice(opt->device));
+    fpl_ctx* c = new fpl_ctx();
+    c->device = opt->device;
+    c->n_adapters = n;
+    // host tables
+    std::vector<uint8_t> h_ad((size_t)n * FPL_MAX_ADAPTER_LEN, 0);
+    std::vector<int> h_alen(n, 0);
+    std::vector<uint4> h_peq((size_t)n * 256, make_uint4(0, 0, 0, 0));
+    std::vector<uint32_t> h_peq16((size_t)n * 256, 0);
+    for (int k = 0; k < n; k++) {
+        const char* s = k == 0 ? ad->start : k == 1 ? ad->end : ad->fasta[k - 2];
+        if (!s) s = "";
+        size_t len = strlen(s);
+        if (len > FPL_MAX_ADAPTER_LEN) {
+            delete c;
+            return fail("fpl_create: adapter %d is %zu bp, longer than FPL_MAX_ADAPTER_LEN=%d", k, len, FPL_MAX_ADAPTER_LEN);
+        }
+        h_alen[k] = (int)len;
+        memcpy(&h_ad[(size_t)k * FPL_MAX_ADAPTER_LEN], s, len);
+        const int plen = (int)len < FPL_PATTERN_LEN ? (int)len : FPL_PATTERN_LEN;
+        for (size_t j = 0; j < len; j++) {
+            uint8_t ch = (uint8_t)s[j];
+            uint32_t* w = reinterpret_cast<uint32_t*>(&h_peq[(size_t)k * 256 + ch]);
+            w[j >> 5] |= 1u << (j & 31);
+            if ((int)j < plen) h_peq16[(size_t)k * 256 + ch] |= 1u << j;                            // first plen chars
+            if ((int)j >= (int)len - plen) h_peq16[(size_t)k * 256 + ch] |= 1u << (16 + j - (len - plen));  // last plen chars
+        }
+    }
+    memset(&c->P, 0, sizeof(c->P));
+    c->P.opt = *opt;
+    c->P.n_adapters = n;
+    for (int i = 0; i <= FPL_MAX_ADAPTER_LEN; i++) c->P.thr[i] = (short)(int)round(opt->ed_max * i);  // src/adaptertrimmer.cpp:73
+#define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail("%s failed: %s", #call, cudaGetErrorString(e_)); fpl_destroy(c); return -1; } } while (0)
+    CKC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CKC(cudaMalloc(&c->d_adapters, h_ad.size()));
+    CKC(cudaMalloc(&c->d_alen, sizeof(int) * n));
+    CKC(cudaMalloc(&c->d_peq, sizeof(uint4) * h_peq.size()));
+    CKC(cudaMalloc(&c->d_peq16, sizeof(uint32_t) * h_peq16.size()));
+    CKC(cudaMemcpy(c->d_adapters, h_ad.data(), h_ad.size(), cudaMemcpyHostToDevice));
+    CKC(cudaMemcpy(c->d_alen, h_alen.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+    CKC(cudaMemcpy(c->d_peq, h_peq.data(), sizeof(uint4) * h_peq.size(), cudaMemcpyHostToDevice));
+    CKC(cudaMemcpy(c->d_peq16, h_peq16.data(), sizeof(uint32_t) * h_peq16.size(), cudaMemcpyHostToDevice));
+    c->P.adapters = c->d_adapters; c->P.alen = c->d_alen; c->P.peq = c->d_peq; c->P.peq16 = c->d_peq16;
+    c->counter_words = FPL_COUNTER_WORDS(n);
+    CKC(cudaMalloc(&c->d_counters, sizeof(unsigned long long) * c->counter_words));
+    CKC(cudaMemset(c->d_counters, 0, sizeof(unsigned long long) * c->counter_words));
+    const char* tb = getenv("FPL_TILE_MBASES");
+    c->tile_bases = (tb && atoll(tb) > 0 ? atoll(tb) : 24) * 1000000ll;
+    for (int k = 0; k < K_NKERNELS; k++) c->kernel_ms[k] = 0;
+    if (reserve_cycles(c, 1024)) { fpl_destroy(c); return -1; }
+    CKC(cudaStreamSynchronize(c->stream));
+#undef CKC
+    *out = c;
+    return 0;
+}
+
+void fpl_destroy(fpl_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    collect_times(c);
+    for (auto e : c->pool) cudaEventDestroy(e);
+    cudaFree(c->d_adapters); cudaFree(c->d_alen); cudaFree(c->d_peq); cudaFree(c->d_peq16);
+    cudaFree(c->d_stats[0]); cudaFree(c->d_stats[1]); cudaFree(c->d_counters);
+    cudaFree(c->d_state); cudaFree(c->d_results); cudaFree(c->d_preseg); cudaFree(c->d_postseg);
+    cudaFree(c->d_seq); cudaFree(c->d_qual); cudaFree(c->d_offsets); cudaFree(c->d_lens);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int fpl_process_device(fpl_ctx* c, const fpl_batch* b, fpl_read_result* results_dev) {
+    g_err[0] = 0;
+    if (!c || !b) return fail("fpl_process_device: null argument");
+    CK(cudaSetDevice(c->device));
+    const int64_t n = b->n_reads;
+    if (n < 0) return fail("fpl_process_device: negative n_reads");
+    c->h_lens.resize((size_t)n);
+    if (n) {
+        CK(cudaMemcpyAsync(c->h_lens.data(), b->lens, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    DevBatch d = {b->seq, b->qual, b->offsets, b->lens, n};
+    return run_batch(c, d, c->h_lens.data(), results_dev);
+}
+
+int fpl_sync(fpl_ctx* c) {
+    if (!c) return fail("fpl_sync: null context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    collect_times(c);
+    return 0;
+}
+
+int fpl_process_host(fpl_ctx* c, const fpl_batch* b, fpl_read_result* results) {
+    g_err[0] = 0;
+    if (!c || !b) return fail("fpl_process_host: null argument");
+    CK(cudaSetDevice(c->device));
+    const int64_t n = b->n_reads;
+    if (n < 0 || b->n_bytes < 0) return fail("fpl_process_host: negative size");
+    if (n > 0 && !results) return fail("fpl_process_host: results is null");
+    // validate the slot layout on the host (cheap, O(reads))
+    for (int64_t i = 0; i < n; i++) {
+        const int64_t o = b->offsets[i];
+        if (o < 0 || (o & 15) || b->lens[i] < 0 || o + b->lens[i] > b->n_bytes)
+            return fail("fpl_process_host: read %lld has a bad slot (offset %lld, len %d, n_bytes %lld; offsets must be multiples of 16)",
+                        (long long)i, (long long)o, b->lens[i], (long long)b->n_bytes);
+    }
+    const int64_t need = b->n_bytes + 64;  // tail pad for whole-word over-reads
+    if (need > c->cap_bytes) {
+        cudaFree(c->d_seq); cudaFree(c->d_qual); c->d_seq = c->d_qual = nullptr; c->cap_bytes = 0;
+        CK(cudaMalloc(&c->d_seq, need));
+        CK(cudaMalloc(&c->d_qual, need));
+        c->cap_bytes = need;
+    }
+    if (n > c->cap_idx) {
+        cudaFree(c->d_offsets); cudaFree(c->d_lens); c->d_offsets = nullptr; c->d_lens = nullptr; c->cap_idx = 0;
+        CK(cudaMalloc(&c->d_offsets, sizeof(int64_t) * n));
+        CK(cudaMalloc(&c->d_lens, sizeof(int32_t) * n));
+        c->cap_idx = n;
+    }
+    if (b->n_bytes) {
+        CK(cudaMemcpyAsync(c->d_seq, b->seq, b->n_bytes, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->d_qual, b->qual, b->n_bytes, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemsetAsync(c->d_seq + b->n_bytes, 0, 64, c->stream));
+        CK(cudaMemsetAsync(c->d_qual + b->n_bytes, 0, 64, c->stream));
+    }
+    if (n) {
+        CK(cudaMemcpyAsync(c->d_offsets, b->offsets, sizeof(int64_t) * n, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->d_lens, b->lens, sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream));
+    }
+    DevBatch d = {c->d_seq, c->d_qual, c->d_offsets, c->d_lens, n};
+    if (run_batch(c, d, b->lens, nullptr)) return -1;
+    if (n) CK(cudaMemcpyAsync(results, c->d_results, sizeof(fpl_read_result) * n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    collect_times(c);
+    return 0;
+}
+
+int fpl_fetch_results(fpl_ctx* c, fpl_read_result* results, int64_t n) {
+    if (!c || !results) return fail("fpl_fetch_results: null argument");
+    if (n > c->last_n) return fail("fpl_fetch_results: only %lld records available", (long long)c->last_n);
+    CK(cudaSetDevice(c->device));
+    if (n) CK(cudaMemcpyAsync(results, c->last_results, sizeof(fpl_read_result) * n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    collect_times(c);
+    return 0;
+}
+
+int64_t fpl_stats_cycles(fpl_ctx* c) { return c ? c->C : 0; }
+
+int fpl_stats_reserve(fpl_ctx* c, int64_t cycles) {
+    if (!c) return fail("fpl_stats_reserve: null context");
+    CK(cudaSetDevice(c->device));
+    if (reserve_cycles(c, cycles)) return -1;
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int fpl_stats_download(fpl_ctx* c, int which, int64_t* out, int64_t n_words) {
+    if (!c || !out || which < 0 || which > 1) return fail("fpl_stats_download: bad argument");
+    if (n_words != FPL_STATS_WORDS(c->C)) return fail("fpl_stats_download: n_words %lld != FPL_STATS_WORDS(%lld)", (long long)n_words, (long long)c->C);
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(out, c->d_stats[which], sizeof(int64_t) * n_words, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int fpl_stats_device_ptr(fpl_ctx* c, int which, void** dptr, int64_t* n_words) {
+    if (!c || !dptr || !n_words || which < 0 || which > 1) return fail("fpl_stats_device_ptr: bad argument");
+    *dptr = c->d_stats[which];
+    *n_words = FPL_STATS_WORDS(c->C);
+    return 0;
+}
+
+int64_t fpl_counter_words(fpl_ctx* c) { return c ? c->counter_words : 0; }
+
+int fpl_counters_download(fpl_ctx* c, int64_t* out, int64_t n_words) {
+    if (!c || !out) return fail("fpl_counters_download: bad argument");
+    if (n_words != c->counter_words) return fail("fpl_counters_download: n_words %lld != %lld", (long long)n_words, (long long)c->counter_words);
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(out, c->d_counters, sizeof(int64_t) * n_words, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int fpl_counters_device_ptr(fpl_ctx* c, void** dptr, int64_t* n_words) {
+    if (!c || !dptr || !n_words) return fail("fpl_counters_device_ptr: bad argument");
+    *dptr = c->d_counters;
+    *n_words = c->counter_words;
+    return 0;
+}
+
+int fpl_reset(fpl_ctx* c) {
+    if (!c) return fail("fpl_reset: null context");
+    CK(cudaSetDevice(c->device));
+    for (int w = 0; w < 2; w++)
+        CK(cudaMemsetAsync(c->d_stats[w], 0, sizeof(unsigned long long) * FPL_STATS_WORDS(c->C), c->stream));
+    CK(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * c->counter_words, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int fpl_last_kernel_times(fpl_ctx* c, const char** names, float* ms, int cap) {
+    if (!c) return 0;
+    for (int k = 0; k < K_NKERNELS && k < cap; k++) {
+        if (names) names[k] = kKernelNames[k];
+        if (ms) ms[k] = c->kernel_ms[k];
+    }
+    return K_NKERNELS;
+}
+
+int64_t fpl_launch_count(fpl_ctx* c) { return c ? c->launches : 0; }
+
+int fpl_set_timing(fpl_ctx* c, int enabled) {
+    if (!c) return fail("fpl_set_timing: null context");
+    c->timing = enabled != 0;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,58 @@
+// Shared device-side definitions for libfplgpu.so (sm_100a).  See DESIGN.md for the kernel map.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "fplgpu.h"
+
+#define FPL_WINDOW 200       // AdapterTrimmer WINDOW (src/adaptertrimmer.cpp:169,239)
+#define FPL_PATTERN_LEN 16   // AdapterTrimmer PATTERN_LEN (:170,240)
+
+// Kernel parameter block: the options POD + device tables built once per context.
+struct DevParams {
+    fpl_options opt;
+    int n_adapters;
+    const uint8_t* adapters;  // [n][FPL_MAX_ADAPTER_LEN] adapter bytes
+    const int* alen;          // [n]
+    const uint4* peq;         // [n][256]: 128-bit match mask of the whole adapter for every byte value
+    const uint32_t* peq16;    // [n][256]: low 16 = mask of the first plen chars, high 16 = mask of the last plen chars
+    short thr[FPL_MAX_ADAPTER_LEN + 1];  // thr(n) = (int)round(ed_max*n), tabulated on the host with libm round
+};
+
+// Device view of a packed batch.
+struct DevBatch {
+    const uint8_t* seq;
+    const uint8_t* qual;
+    const int64_t* offsets;
+    const int32_t* lens;
+    int64_t n_reads;
+};
+
+// Per-read state handed from kernel to kernel (SoA would save little: it is 64 B/read, ~0.4% of the payload).
+struct ReadState {
+    int32_t lo, len;          // r1 window after trimAndCut / polyX / adapter trims
+    uint32_t alive;           // 0 if dropped by trimAndCut
+    uint32_t pad;
+    unsigned long long best[2];   // middle-adapter scan: (minHamming << 32) | pos, ~0ull = no position scanned
+    int32_t lowq, nn, totalq, diff;  // passFilter counts over the window
+    int32_t reserved[4];
+};
+
+// A segment to be fed to the Stats kernels: absolute byte offset into the batch buffers + length (0 = skip).
+struct StatSeg {
+    int64_t off;
+    int32_t len;
+    int32_t read;   // owning read (for writing the median back), -1 = none
+    int32_t slot;   // 0/1: which seg_median_qual slot, 2 = pre_median_qual
+    int32_t pad;
+};
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ int warp_incl_scan(int v) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane_id() >= d) v += t;
+    }
+    return v;
+}

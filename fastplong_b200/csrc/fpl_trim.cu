@@ -1,0 +1,424 @@
+// k_trim: the sequential, end-local part of processSingleEnd for one read per warp:
+//   Filter::trimAndCut (src/filter.cpp:130-232) -> PolyX::trimPolyX (src/polyx.cpp:11-78) ->
+//   AdapterTrimmer::trimBySequenceStart / trimBySequenceEnd for -s, -e and every FASTA adapter in order
+//   (src/adaptertrimmer.cpp:42-57,168-302).
+// Each stage is the parallel closed form of the reference's loop: the 32 lanes evaluate 32
+// candidate positions at once, a ballot / min-reduction picks what the sequential loop would have picked.
+// Work is O(window) per read, not O(read length), except for degenerate quality cuts.
+#include "fpl_device.cuh"
+
+namespace {
+
+__device__ __forceinline__ int sc(uint8_t b) { return (int)(signed char)b; }  // the reference reads `char`
+
+// ---- Levenshtein distance, Myers/Hyyro bit-parallel, pattern = adapter bits [shift, shift+m) ----
+// text = read bytes.  Equivalent to edit_distance() (src/editdistance.cpp:100-126): exact global distance.
+__device__ __forceinline__ void peq_sub(const uint4* peq, uint8_t c, int shift, int m, unsigned long long& lo,
+                                        unsigned long long& hi) {
+    uint4 v = __ldg(&peq[c]);
+    lo = ((unsigned long long)v.y << 32) | v.x;
+    hi = ((unsigned long long)v.w << 32) | v.z;
+    if (shift >= 64) { lo = hi >> (shift - 64); hi = 0; }
+    else if (shift > 0) { lo = (lo >> shift) | (hi << (64 - shift)); hi >>= shift; }
+    if (m < 64) { lo &= (1ull << m) - 1; hi = 0; }
+    else if (m < 128) { hi &= (1ull << (m - 64)) - 1; }
+}
+
+__device__ int myers128(const uint8_t* text, int n, const uint4* peq, int shift, int m) {
+    if (m == 0) return n;
+    if (n == 0) return m;
+    unsigned long long VPl, VPh, VNl = 0, VNh = 0;
+    if (m < 64) { VPl = (1ull << m) - 1; VPh = 0; }
+    else if (m == 64) { VPl = ~0ull; VPh = 0; }
+    else if (m < 128) { VPl = ~0ull; VPh = (1ull << (m - 64)) - 1; }
+    else { VPl = ~0ull; VPh = ~0ull; }
+    const bool topHi = m > 64;
+    const unsigned long long top = 1ull << ((m - 1) & 63);
+    int score = m;
+    for (int i = 0; i < n; i++) {
+        unsigned long long El, Eh;
+        peq_sub(peq, text[i], shift, m, El, Eh);
+        unsigned long long Xvl = El | VNl, Xvh = Eh | VNh;
+        // Xh = (((Eq & VP) + VP) ^ VP) | Eq, 128-bit add with carry
+        unsigned long long al = El & VPl, ah = Eh & VPh;
+        unsigned long long sl = al + VPl;
+        unsigned long long carry = sl < al ? 1ull : 0ull;
+        unsigned long long sh = ah + VPh + carry;
+        unsigned long long Xhl = (sl ^ VPl) | El, Xhh = (sh ^ VPh) | Eh;
+        unsigned long long HPl = VNl | ~(Xhl | VPl), HPh = VNh | ~(Xhh | VPh);
+        unsigned long long HNl = VPl & Xhl, HNh = VPh & Xhh;
+        unsigned long long hpTop = topHi ? HPh : HPl, hnTop = topHi ? HNh : HNl;
+        if (hpTop & top) score++;
+        else if (hnTop & top) score--;
+        HPh = (HPh << 1) | (HPl >> 63); HPl = (HPl << 1) | 1ull;
+        HNh = (HNh << 1) | (HNl >> 63); HNl = HNl << 1;
+        VPl = HNl | ~(Xvl | HPl); VPh = HNh | ~(Xvh | HPh);
+        VNl = HPl & Xvl; VNh = HPh & Xvh;
+    }
+    return score;
+}
+
+// 16-bit pattern variant for the probe loops (:202-216, :273-286); eq16 = precomputed masks, already shifted.
+__device__ __forceinline__ int myers16(const uint8_t* text, int n, const uint32_t* peq16, bool suffix, int m) {
+    uint32_t VP = (1u << m) - 1u, VN = 0;
+    const uint32_t top = 1u << (m - 1);
+    int score = m;
+    for (int i = 0; i < n; i++) {
+        uint32_t e = __ldg(&peq16[text[i]]);
+        uint32_t Eq = suffix ? (e >> 16) : (e & 0xFFFFu);
+        uint32_t Xv = Eq | VN;
+        uint32_t Xh = (((Eq & VP) + VP) ^ VP) | Eq;
+        uint32_t HP = VN | ~(Xh | VP);
+        uint32_t HN = VP & Xh;
+        if (HP & top) score++;
+        else if (HN & top) score--;
+        HP = (HP << 1) | 1u;
+        HN = HN << 1;
+        VP = HN | ~(Xv | HP);
+        VN = HP & Xv;
+    }
+    return score;
+}
+
+__device__ __forceinline__ int hamming(const uint8_t* r, const uint8_t* a, int alen) {
+    int mm = 0;
+    for (int i = 0; i < alen; i++) mm += r[i] != __ldg(&a[i]);
+    return mm;
+}
+
+// AdapterTrimmer::searchAdapter restricted to the two windowed modes (src/adaptertrimmer.cpp:84-134,156-165).
+// left: first p with H<=T, else the LAST arg-min;  right: last p with H<=T, else the FIRST arg-min.
+__device__ int search_window(const DevParams& P, const uint8_t* rdata, int rlen, int aidx, int searchStart,
+                             int searchLen, bool left) {
+    const int lane = lane_id();
+    const int alen = P.alen[aidx];
+    const uint8_t* adata = P.adapters + (size_t)aidx * FPL_MAX_ADAPTER_LEN;
+    const int T = P.thr[alen];
+    int searchEnd = rlen;
+    if (searchLen > 0) searchEnd = min(rlen, searchLen + searchStart);
+    if (searchStart + alen > rlen) return -1;
+    int p0, p1;  // inclusive range of positions
+    bool descending = false;
+    if (left) { p0 = searchStart; p1 = searchEnd - alen - 1; }
+    else if (searchEnd > alen) { p0 = searchStart; p1 = searchEnd - alen; descending = true; }
+    else { p0 = searchStart; p1 = searchEnd - alen - 1; }  // generic mode, empty or tiny range
+    unsigned accept = descending ? 0u : 0xFFFFFFFFu;
+    unsigned best = 0xFFFFFFFFu;  // (H << 16) | tie-break key, minimised
+    for (int p = p0 + lane; p <= p1; p += 32) {
+        int mm = hamming(rdata + p, adata, alen);
+        unsigned rel = (unsigned)(p - p0);
+        if (mm <= T) accept = descending ? max(accept, rel + 1u) : min(accept, rel);
+        // ascending loops keep the last minimum (<=), the descending loop also uses <= and so keeps the smallest p;
+        // the generic loop (<) keeps the smallest p
+        unsigned key = (left ? (0xFFFFu - rel) : rel);
+        best = min(best, ((unsigned)mm << 16) | key);
+    }
+    accept = descending ? __reduce_max_sync(0xffffffffu, accept) : __reduce_min_sync(0xffffffffu, accept);
+    best = __reduce_min_sync(0xffffffffu, best);
+    if (descending) { if (accept != 0u) return p0 + (int)accept - 1; }
+    else if (accept != 0xFFFFFFFFu && (left)) return p0 + (int)accept;
+    if (best == 0xFFFFFFFFu) return -1;
+    unsigned key = best & 0xFFFFu;
+    int pos = p0 + (int)(left ? (0xFFFFu - key) : key);
+    int ed = myers128(rdata + pos, alen, P.peq + (size_t)aidx * 256, 0, alen);
+    return ed <= T ? pos : -1;
+}
+
+struct Win { int lo, len; };
+
+__device__ __forceinline__ void trim_front(Win& w, int n) {  // Read::trimFront, src/read.cpp:69-73
+    n = min(w.len - 1, n);
+    if (n < 0) { w.lo += w.len; w.len = 0; return; }
+    w.lo += n; w.len -= n;
+}
+__device__ __forceinline__ void resize_(Win& w, int n) {     // Read::resize, src/read.cpp:62-67
+    if (n > w.len || n < 0) return;
+    w.len = n;
+}
+
+struct EventSink {
+    fpl_read_result* out;
+    unsigned long long* table;  // device event count table
+    int n;
+    __device__ __forceinline__ void add(int idx, int side, int cmplen) {
+        if (lane_id() == 0) {
+            if (n < FPL_INLINE_EVENTS) out->events[n] = FPL_EVENT(idx, side, cmplen);
+            atomicAdd(&table[((size_t)idx * 2 + side) * (FPL_MAX_ADAPTER_LEN + 1) + cmplen], 1ull);
+        }
+        n++;
+    }
+};
+
+// AdapterTrimmer::trimBySequenceStart (src/adaptertrimmer.cpp:168-236)
+__device__ int trim_start(const DevParams& P, const uint8_t* seq, Win& w, int aidx, EventSink& ev, uint8_t* scratch) {
+    const int lane = lane_id();
+    const int alen = P.alen[aidx], ext = P.opt.trimming_extension;
+    const uint8_t* rdata = seq + w.lo;
+    const int rlen = w.len;
+    if (rlen < FPL_PATTERN_LEN) return 0;
+    const int plen = min(FPL_PATTERN_LEN, alen);
+    int mpos = search_window(P, rdata, rlen, aidx, 0, FPL_WINDOW, false);
+    if (mpos >= 0) {
+        mpos = min(mpos + ext, rlen - alen);
+        ev.add(aidx, 0, alen);
+        trim_front(w, mpos + alen);
+        return mpos + alen;
+    }
+    // probe: best (smallest ed, earliest p) 16-mer hit of the adapter's last plen chars (:202-216)
+    const int np = min(rlen - plen, FPL_WINDOW - plen);
+    const int T16 = P.thr[plen];
+    unsigned best = 0xFFFFFFFFu;
+    const uint32_t* t16 = P.peq16 + (size_t)aidx * 256;
+    for (int p = lane; p < np; p += 32) {
+        int ed = myers16(rdata + p, plen, t16, true, plen);
+        if (ed <= T16) best = min(best, ((unsigned)ed << 16) | (unsigned)p);
+    }
+    best = __reduce_min_sync(0xffffffffu, best);
+    if (best != 0xFFFFFFFFu) {
+        int pos = (int)(best & 0xFFFFu);
+        int cmplen = min(pos + plen, alen);
+        int ed = myers128(rdata + pos + plen - cmplen, cmplen, P.peq + (size_t)aidx * 256, alen - cmplen, cmplen);
+        if (ed <= P.thr[cmplen]) {
+            pos = min(pos + ext, rlen - alen);
+            ev.add(aidx, 0, cmplen);
+            trim_front(w, pos + plen);
+            return pos + plen;
+        }
+    }
+    return 0;
+}
+
+// AdapterTrimmer::trimBySequenceEnd (src/adaptertrimmer.cpp:238-302)
+__device__ int trim_end(const DevParams& P, const uint8_t* seq, Win& w, int aidx, EventSink& ev, uint8_t* scratch) {
+    const int lane = lane_id();
+    const int alen = P.alen[aidx], ext = P.opt.trimming_extension;
+    const uint8_t* rdata = seq + w.lo;
+    const int rlen = w.len;
+    if (rlen < FPL_PATTERN_LEN) return 0;
+    const int plen = min(FPL_PATTERN_LEN, alen);
+    const int searchStart = max(0, rlen - FPL_WINDOW);
+    int mpos = search_window(P, rdata, rlen, aidx, searchStart, FPL_WINDOW, true);
+    if (mpos >= 0) {
+        mpos = max(0, mpos - ext);
+        ev.add(aidx, 1, alen);
+        resize_(w, mpos);
+        return rlen - mpos;
+    }
+    // probe from the tail with the "last best, stop at the first worse hit" rule (:273-286):
+    // all distances in parallel into scratch, then the (short) sequential selection.
+    const int np = min(rlen - plen, FPL_WINDOW - plen);
+    const int T16 = P.thr[plen];
+    const uint32_t* t16 = P.peq16 + (size_t)aidx * 256;
+    for (int p = lane; p < np; p += 32) {
+        int ed = myers16(rdata + rlen - plen - p, plen, t16, false, plen);
+        scratch[p] = (uint8_t)(ed <= T16 ? ed : 255);
+    }
+    __syncwarp();
+    int pos = -1, mined = -1;
+    // every lane walks the same <=184 bytes of shared memory (broadcast reads); the result is warp-uniform
+    for (int p = 0; p < np; p++) {
+        int ed = scratch[p];
+        if (ed == 255) continue;
+        if (pos < 0) { pos = p; mined = ed; }
+        else if (ed > mined) break;
+        else { pos = p; mined = ed; }
+    }
+    __syncwarp();
+    if (pos > 0) {
+        int cmplen = min(pos + plen, alen);
+        int ed = myers128(rdata + rlen - plen - pos, cmplen, P.peq + (size_t)aidx * 256, 0, cmplen);
+        if (ed <= P.thr[cmplen]) {
+            pos = min(pos + ext, rlen - plen);
+            ev.add(aidx, 1, cmplen);
+            resize_(w, rlen - plen - pos);
+            return pos + plen;
+        }
+    }
+    return 0;
+}
+
+// first s in [s_lo, s_hi) whose w-wide quality window sum reaches `need`; s_hi if none (filter.cpp:171-181)
+__device__ int first_good_window_fwd(const uint8_t* qual, int s_lo, int s_hi, int w, int need) {
+    const int lane = lane_id();
+    for (int s0 = s_lo; s0 < s_hi; s0 += 32) {
+        int s = s0 + lane;
+        int sum = 0;
+        if (s < s_hi)
+            for (int j = 0; j < w; j++) sum += sc(qual[s + j]);
+        unsigned m = __ballot_sync(0xffffffffu, s < s_hi && sum >= need);
+        if (m) return s0 + __ffs(m) - 1;
+    }
+    return s_hi;
+}
+// largest t in (t_lo, t_hi] whose window qual[t-w+1..t] reaches `need`; t_lo if none (filter.cpp:203-212)
+__device__ int first_good_window_bwd(const uint8_t* qual, int t_hi, int t_lo, int w, int need) {
+    const int lane = lane_id();
+    for (int t0 = t_hi; t0 > t_lo; t0 -= 32) {
+        int t = t0 - lane;
+        int sum = 0;
+        if (t > t_lo)
+            for (int j = 0; j < w; j++) sum += sc(qual[t - j]);
+        unsigned m = __ballot_sync(0xffffffffu, t > t_lo && sum >= need);
+        if (m) return t0 - (__ffs(m) - 1);
+    }
+    return t_lo;
+}
+
+// Filter::trimAndCut: returns false if the read is dropped (NULL)
+__device__ bool trim_and_cut(const DevParams& P, const uint8_t* seq, const uint8_t* qual, int l, Win& w) {
+    const fpl_options& o = P.opt;
+    const int lane = lane_id();
+    int front = o.trim_front, tail = o.trim_tail;
+    const bool cf = o.cut_front_enabled, ct = o.cut_tail_enabled;
+    w.lo = 0; w.len = l;
+    if (front == 0 && tail == 0 && !cf && !ct) return true;
+    int rlen = l - front - tail;
+    if (rlen < 0) return false;
+    if (front == 0 && !cf && !ct) { resize_(w, rlen); return true; }
+    if (!cf && !ct) { w.lo = front; w.len = rlen; return true; }
+    if (cf) {
+        const int ws = o.cut_front_window;
+        if (l - front - tail - ws <= 0) return false;
+        int s = first_good_window_fwd(qual, front, l - tail - ws, ws, (33 + o.cut_front_quality) * ws);
+        if (s > 0) s = s + ws - 1;
+        // while (s < l && seq[s] == 'N') s++
+        while (true) {
+            int i = s + lane;
+            unsigned m = __ballot_sync(0xffffffffu, !(i < l && seq[i] == 'N'));
+            if (m) { s += __ffs(m) - 1; break; }
+            s += 32;
+        }
+        front = s;
+        rlen = l - front - tail;
+    }
+    if (ct) {
+        const int ws = o.cut_tail_window;
+        if (l - front - tail - ws <= 0) return false;
+        int t = first_good_window_bwd(qual, l - tail - 1, front + ws - 1, ws, (33 + o.cut_tail_quality) * ws);
+        if (t < l - 1) t = t - ws + 1;
+        // while (t >= 0 && seq[t] == 'N') t--
+        while (true) {
+            int i = t - lane;
+            unsigned m = __ballot_sync(0xffffffffu, !(i >= 0 && seq[i] == 'N'));
+            if (m) { t -= __ffs(m) - 1; break; }
+            t -= 32;
+        }
+        rlen = t - front + 1;
+    }
+    if (rlen <= 0 || front >= l - 1) return false;
+    w.lo = front; w.len = rlen;
+    return true;
+}
+
+// PolyX::trimPolyX closed form: suffix counts by warp scan, first position where the stop rule fires.
+__device__ void trim_polyx(const DevParams& P, const uint8_t* data, Win& w, fpl_read_result* out,
+                           unsigned long long* counters) {
+    const int lane = lane_id();
+    const int rlen = w.len;
+    const int compareReq = P.opt.polyx_min_len;
+    int cA = 0, cT = 0, cC = 0, cG = 0;
+    int pos = rlen;
+    int nA = 0, nT = 0, nC = 0, nG = 0;
+    bool found = false;
+    for (int p0 = 0; p0 < rlen && !found; p0 += 32) {
+        int p = p0 + lane;
+        bool valid = p < rlen;
+        uint8_t ch = valid ? data[rlen - p - 1] : 0;
+        int a = (ch == 'A') | (ch == 'N'), t = (ch == 'T') | (ch == 'N');
+        int c = (ch == 'C') | (ch == 'N'), g = (ch == 'G') | (ch == 'N');
+        a = warp_incl_scan(a) + cA; t = warp_incl_scan(t) + cT;
+        c = warp_incl_scan(c) + cC; g = warp_incl_scan(g) + cG;
+        int cmp = p + 1;
+        int allowed = min(5, cmp / 8);
+        bool stop = valid && (cmp - a > allowed) && (cmp - t > allowed) && (cmp - c > allowed) && (cmp - g > allowed) &&
+                    (p >= 8 || p + 1 >= compareReq - 1);
+        unsigned m = __ballot_sync(0xffffffffu, stop);
+        int src = m ? __ffs(m) - 1 : 31;
+        nA = __shfl_sync(0xffffffffu, a, src); nT = __shfl_sync(0xffffffffu, t, src);
+        nC = __shfl_sync(0xffffffffu, c, src); nG = __shfl_sync(0xffffffffu, g, src);
+        if (m) { pos = p0 + src; found = true; }
+        else { cA = nA; cT = nT; cC = nC; cG = nG; }
+    }
+    if (!found) { nA = cA; nT = cT; nC = cC; nG = cG; pos = rlen; }
+    if (pos + 1 >= compareReq) {
+        int poly = 0, mx = nA;
+        if (nT > mx) { mx = nT; poly = 1; }
+        if (nC > mx) { mx = nC; poly = 2; }
+        if (nG > mx) { mx = nG; poly = 3; }
+        const uint8_t polyBase = poly == 0 ? 'A' : poly == 1 ? 'T' : poly == 2 ? 'C' : 'G';
+        // back off to the last matching base: first j >= max(0, rlen-pos-1) with data[j] == polyBase
+        int j = max(0, rlen - pos - 1);
+        int hit = -1;
+        for (; j < rlen; j += 32) {
+            int i = j + lane;
+            unsigned m = __ballot_sync(0xffffffffu, i < rlen && data[i] == polyBase);
+            if (m) { hit = j + __ffs(m) - 1; break; }
+        }
+        int newpos = hit >= 0 ? rlen - hit - 1 : -1;
+        resize_(w, rlen - newpos - 1);
+        if (lane == 0) {
+            out->flags |= FPL_FLAG_POLYX;
+            out->polyx_base = (uint8_t)poly;
+            out->polyx_len = newpos + 1;
+            atomicAdd(&counters[FPL_CNT_POLYX_READS + poly], 1ull);
+            atomicAdd(&counters[FPL_CNT_POLYX_BASES + poly], (unsigned long long)(long long)(newpos + 1));
+        }
+    }
+}
+
+}  // namespace
+
+#define TRIM_WARPS 4
+
+__global__ void __launch_bounds__(TRIM_WARPS * 32)
+k_trim(const __grid_constant__ DevParams P, DevBatch b, ReadState* __restrict__ st, fpl_read_result* __restrict__ res,
+       unsigned long long* __restrict__ counters) {
+    __shared__ uint8_t scratch_all[TRIM_WARPS][FPL_WINDOW];
+    const int wid = threadIdx.x >> 5, lane = lane_id();
+    const int64_t r = (int64_t)blockIdx.x * TRIM_WARPS + wid;
+    if (r >= b.n_reads) return;
+    uint8_t* scratch = scratch_all[wid];
+    const int64_t off = b.offsets[r];
+    const int L = b.lens[r];
+    const uint8_t* seq = b.seq + off;
+    const uint8_t* qual = b.qual + off;
+    fpl_read_result* out = &res[r];
+    if (lane == 0) {
+        // zero the record; later kernels fill segments / medians
+        uint4* o4 = reinterpret_cast<uint4*>(out);
+        o4[0] = make_uint4(0, 0, 0, 0); o4[1] = o4[0]; o4[2] = o4[0]; o4[3] = o4[0];
+    }
+    __syncwarp();
+    Win w;
+    bool alive = trim_and_cut(P, seq, qual, L, w);
+    if (alive && P.opt.polyx_enabled) trim_polyx(P, seq + w.lo, w, out, counters);
+    int trimmed = 0;
+    EventSink ev{out, counters + FPL_CNT_FIXED, 0};
+    if (alive && P.opt.adapter_enabled) {
+        if (P.alen[0] > 0) trimmed += trim_start(P, seq, w, 0, ev, scratch);
+        if (P.alen[1] > 0) trimmed += trim_end(P, seq, w, 1, ev, scratch);
+        for (int k = 2; k < P.n_adapters; k++) {
+            trimmed += trim_start(P, seq, w, k, ev, scratch);
+            trimmed += trim_end(P, seq, w, k, ev, scratch);
+        }
+    }
+    if (lane == 0) {
+        ReadState s;
+        s.lo = w.lo; s.len = w.len; s.alive = alive ? 1u : 0u; s.pad = 0;
+        s.best[0] = ~0ull; s.best[1] = ~0ull;
+        s.lowq = s.nn = s.totalq = s.diff = 0;
+        s.reserved[0] = s.reserved[1] = s.reserved[2] = s.reserved[3] = 0;
+        st[r] = s;
+        if (!alive) out->flags |= FPL_FLAG_DROPPED_BY_CUT;
+        else { out->trim_lo = w.lo; out->trim_len = w.len; }
+        out->n_events = (uint16_t)ev.n;
+        out->adapter_trimmed_bases = trimmed;
+    }
+}
+
+void launch_trim(const DevParams& P, const DevBatch& b, ReadState* st, fpl_read_result* res,
+                 unsigned long long* counters, cudaStream_t stream) {
+    if (b.n_reads == 0) return;
+    unsigned grid = (unsigned)((b.n_reads + TRIM_WARPS - 1) / TRIM_WARPS);
+    k_trim<<<grid, TRIM_WARPS * 32, 0, stream>>>(P, b, st, res, counters);
+}
