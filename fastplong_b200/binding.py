@@ -34,6 +34,8 @@ def load_library():
     lib.fpl_process_host.argtypes = [C.c_void_p, C.POINTER(FplBatch), C.c_void_p]
     lib.fpl_process_device.argtypes = [C.c_void_p, C.POINTER(FplBatch), C.c_void_p]
     lib.fpl_sync.argtypes = [C.c_void_p]
+    lib.fpl_stream.argtypes = [C.c_void_p]
+    lib.fpl_stream.restype = C.c_void_p
     lib.fpl_fetch_results.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     lib.fpl_stats_cycles.argtypes = [C.c_void_p]
     lib.fpl_stats_cycles.restype = C.c_int64
@@ -45,7 +47,8 @@ def load_library():
     lib.fpl_counters_download.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     lib.fpl_counters_device_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
     lib.fpl_reset.argtypes = [C.c_void_p]
-    lib.fpl_last_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
+    lib.fpl_last_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_float),
+                                          C.POINTER(C.c_int64), C.c_int]
     lib.fpl_launch_count.argtypes = [C.c_void_p]
     lib.fpl_launch_count.restype = C.c_int64
     lib.fpl_set_timing.argtypes = [C.c_void_p, C.c_int]
@@ -56,7 +59,7 @@ def load_library():
 
 
 EXPORTS = ["fpl_last_error", "fpl_abi_version", "fpl_create", "fpl_destroy", "fpl_process_host", "fpl_process_device",
-           "fpl_sync", "fpl_fetch_results", "fpl_stats_cycles", "fpl_stats_reserve", "fpl_stats_download",
+           "fpl_sync", "fpl_stream", "fpl_fetch_results", "fpl_stats_cycles", "fpl_stats_reserve", "fpl_stats_download",
            "fpl_stats_device_ptr", "fpl_counter_words", "fpl_counters_download", "fpl_counters_device_ptr",
            "fpl_reset", "fpl_last_kernel_times", "fpl_launch_count", "fpl_set_timing"]
 
@@ -114,6 +117,11 @@ class Engine:
     def sync(self):
         self._check(self.lib.fpl_sync(self.h))
 
+    @property
+    def stream_ptr(self):
+        """cudaStream_t of the context (wrap with torch.cuda.ExternalStream to record events / order collectives)."""
+        return int(self.lib.fpl_stream(self.h) or 0)
+
     def fetch_results(self, n):
         res = np.zeros(n, dtype=RESULT_DTYPE)
         self._check(self.lib.fpl_fetch_results(self.h, res.ctypes.data, n))
@@ -160,10 +168,12 @@ class Engine:
         self._check(self.lib.fpl_set_timing(self.h, int(on)))
 
     def kernel_times(self):
+        """{kernel name: (total device ms, timed launches)} since set_timing(True)."""
         names = (C.c_char_p * 16)()
         ms = (C.c_float * 16)()
-        k = self.lib.fpl_last_kernel_times(self.h, names, ms, 16)
-        return {names[i].decode(): float(ms[i]) for i in range(k)}
+        cnt = (C.c_int64 * 16)()
+        k = self.lib.fpl_last_kernel_times(self.h, names, ms, cnt, 16)
+        return {names[i].decode(): (float(ms[i]), int(cnt[i])) for i in range(k)}
 
     @property
     def launch_count(self):

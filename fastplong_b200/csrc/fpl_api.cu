@@ -81,6 +81,7 @@ struct fpl_ctx {
     int64_t tile_bases = 0;
     bool timing = false;
     float kernel_ms[K_NKERNELS];
+    int64_t kernel_n[K_NKERNELS];
     int64_t launches = 0;
     struct Ev { int k; cudaEvent_t a, b; };
     std::vector<Ev> events;
@@ -142,22 +143,24 @@ struct Timed {
     }
 };
 
+// Harvest the event pairs that have completed; pending ones stay queued (kernel_ms accumulates until
+// fpl_set_timing() resets it).
 static void collect_times(fpl_ctx* c) {
+    size_t keep = 0;
     for (auto& e : c->events) {
+        if (cudaEventQuery(e.b) != cudaSuccess) { c->events[keep++] = e; continue; }
         float ms = 0;
-        if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) c->kernel_ms[e.k] += ms;
+        if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) { c->kernel_ms[e.k] += ms; c->kernel_n[e.k]++; }
         c->pool.push_back(e.a); c->pool.push_back(e.b);
     }
-    c->events.clear();
+    c->events.resize(keep);
 }
 
 // Runs every kernel over reads [0, n) of a device-resident batch whose lens are known on the host.
 static int run_batch(fpl_ctx* c, const DevBatch& full, const int32_t* h_lens, fpl_read_result* d_res_out) {
     const int64_t n = full.n_reads;
     CK(cudaSetDevice(c->device));
-    for (int k = 0; k < K_NKERNELS; k++) c->kernel_ms[k] = 0;
     collect_times(c);
-    for (int k = 0; k < K_NKERNELS; k++) c->kernel_ms[k] = 0;
     c->last_n = n;
     if (ensure_reads(c, n)) return -1;
     fpl_read_result* d_res = d_res_out ? d_res_out : c->d_results;
@@ -269,7 +272,7 @@ int fpl_create(const fpl_options* opt, const fpl_adapters* ad, fpl_ctx** out) {
     CKC(cudaMemset(c->d_counters, 0, sizeof(unsigned long long) * c->counter_words));
     const char* tb = getenv("FPL_TILE_MBASES");
     c->tile_bases = (tb && atoll(tb) > 0 ? atoll(tb) : 24) * 1000000ll;
-    for (int k = 0; k < K_NKERNELS; k++) c->kernel_ms[k] = 0;
+    for (int k = 0; k < K_NKERNELS; k++) { c->kernel_ms[k] = 0; c->kernel_n[k] = 0; }
     if (reserve_cycles(c, 1024)) { fpl_destroy(c); return -1; }
     CKC(cudaStreamSynchronize(c->stream));
 #undef CKC
@@ -305,6 +308,8 @@ int fpl_process_device(fpl_ctx* c, const fpl_batch* b, fpl_read_result* results_
     DevBatch d = {b->seq, b->qual, b->offsets, b->lens, n};
     return run_batch(c, d, c->h_lens.data(), results_dev);
 }
+
+void* fpl_stream(fpl_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
 int fpl_sync(fpl_ctx* c) {
     if (!c) return fail("fpl_sync: null context");
@@ -419,15 +424,16 @@ int fpl_reset(fpl_ctx* c) {
     for (int w = 0; w < 2; w++)
         CK(cudaMemsetAsync(c->d_stats[w], 0, sizeof(unsigned long long) * FPL_STATS_WORDS(c->C), c->stream));
     CK(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * c->counter_words, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
     return 0;
 }
 
-int fpl_last_kernel_times(fpl_ctx* c, const char** names, float* ms, int cap) {
+int fpl_last_kernel_times(fpl_ctx* c, const char** names, float* ms, int64_t* launches, int cap) {
     if (!c) return 0;
+    collect_times(c);
     for (int k = 0; k < K_NKERNELS && k < cap; k++) {
         if (names) names[k] = kKernelNames[k];
         if (ms) ms[k] = c->kernel_ms[k];
+        if (launches) launches[k] = c->kernel_n[k];
     }
     return K_NKERNELS;
 }
@@ -437,6 +443,8 @@ int64_t fpl_launch_count(fpl_ctx* c) { return c ? c->launches : 0; }
 int fpl_set_timing(fpl_ctx* c, int enabled) {
     if (!c) return fail("fpl_set_timing: null context");
     c->timing = enabled != 0;
+    collect_times(c);
+    for (int k = 0; k < K_NKERNELS; k++) { c->kernel_ms[k] = 0; c->kernel_n[k] = 0; }
     return 0;
 }
 

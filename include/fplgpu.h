@@ -217,6 +217,8 @@ int fpl_process_host(fpl_ctx* ctx, const fpl_batch* host_batch, fpl_read_result*
  */
 int fpl_process_device(fpl_ctx* ctx, const fpl_batch* dev_batch, fpl_read_result* results_dev);
 int fpl_sync(fpl_ctx* ctx);
+/* The context's CUDA stream (a cudaStream_t), so a caller can order its own work / events against the kernels. */
+void* fpl_stream(fpl_ctx* ctx);
 
 /* Copy the context's last device results (n records) to host memory. */
 int fpl_fetch_results(fpl_ctx* ctx, fpl_read_result* results, int64_t n_reads);
@@ -238,15 +240,16 @@ int64_t fpl_counter_words(fpl_ctx* ctx);
 int fpl_counters_download(fpl_ctx* ctx, int64_t* out, int64_t n_words);
 int fpl_counters_device_ptr(fpl_ctx* ctx, void** dptr, int64_t* n_words);
 
-/* Zero all accumulators (a fresh ThreadConfig). */
+/* Zero all accumulators (a fresh ThreadConfig); stream-ordered, asynchronous. */
 int fpl_reset(fpl_ctx* ctx);
 
 /*
- * Measurement hooks: device time (ms, CUDA events on the context's stream) of each kernel of the last
- * fpl_process_* call, and the number of kernel launches it made.  names/ms hold up to cap entries;
- * returns the number of kernels.
+ * Measurement hooks.  fpl_set_timing(ctx, 1) brackets every kernel launch with CUDA events on the context's
+ * stream and zeroes the per-kernel totals; fpl_last_kernel_times returns, per kernel, the device time (ms) and
+ * the number of timed launches accumulated since then (call after fpl_sync).  names/ms/launches hold up to cap
+ * entries; returns the number of kernels.  fpl_launch_count = kernel launches made by the context so far.
  */
-int fpl_last_kernel_times(fpl_ctx* ctx, const char** names, float* ms, int cap);
+int fpl_last_kernel_times(fpl_ctx* ctx, const char** names, float* ms, int64_t* launches, int cap);
 int64_t fpl_launch_count(fpl_ctx* ctx);
 int fpl_set_timing(fpl_ctx* ctx, int enabled);
 
