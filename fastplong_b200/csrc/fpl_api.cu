@@ -9,6 +9,7 @@
 #include <string>
 #include <vector>
 #include "fpl_device.cuh"
+#include "fpl_scanplan.h"
 
 static_assert(sizeof(fpl_options) == 128, "fpl_options ABI size");
 static_assert(sizeof(fpl_read_result) == 64, "fpl_read_result ABI size");
@@ -18,6 +19,7 @@ static_assert(sizeof(StatSeg) == 24, "StatSeg size");
 // kernel launchers (fpl_trim.cu, fpl_scan.cu, fpl_stats.cu)
 void launch_trim(const DevParams&, const DevBatch&, ReadState*, fpl_read_result*, unsigned long long*, cudaStream_t);
 void launch_scan(const DevParams&, const DevBatch&, ReadState*, cudaStream_t);
+void launch_scan_fast(const DevParams&, const ScanPlan&, const DevBatch&, ReadState*, cudaStream_t);
 void launch_final(const DevParams&, const DevBatch&, const ReadState*, fpl_read_result*, StatSeg*, cudaStream_t);
 void launch_count(const fpl_read_result*, int64_t, unsigned long long*, cudaStream_t);
 void launch_cycle_stats(const uint8_t*, const uint8_t*, const StatSeg*, int64_t, int64_t, unsigned long long*, int64_t,
@@ -51,6 +53,7 @@ struct fpl_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     DevParams P;
+    ScanPlan plan;
     int n_adapters = 0;
     uint8_t* d_adapters = nullptr;
     int* d_alen = nullptr;
@@ -191,7 +194,7 @@ static int run_batch(fpl_ctx* c, const DevBatch& full, const int32_t* h_lens, fp
         { Timed t(c, K_TRIM); launch_trim(c->P, b, st, res, c->d_counters, s); }
         { Timed t(c, K_CYCLE_PRE); launch_cycle_stats(full.seq, full.qual, pre, b.n_reads, tmax, c->d_stats[0], c->C, s); }
         { Timed t(c, K_QUAL_PRE); launch_read_qual(full.qual, pre, b.n_reads, c->d_stats[0], c->C, res, s); }
-        { Timed t(c, K_SCAN); launch_scan(c->P, b, st, s); }
+        { Timed t(c, K_SCAN); if (c->plan.fast) launch_scan_fast(c->P, c->plan, b, st, s); else launch_scan(c->P, b, st, s); }
         { Timed t(c, K_FINAL); launch_final(c->P, b, st, res, post, s); }
         { Timed t(c, K_COUNT); launch_count(res, b.n_reads, c->d_counters, s); }
         { Timed t(c, K_CYCLE_POST); launch_cycle_stats(full.seq, full.qual, post, 2 * b.n_reads, tmax, c->d_stats[1], c->C, s); }
@@ -255,6 +258,29 @@ int fpl_create(const fpl_options* opt, const fpl_adapters* ad, fpl_ctx** out) {
     memset(&c->P, 0, sizeof(c->P));
     c->P.opt = *opt;
     c->P.n_adapters = n;
+    // plan for the bit-sliced middle-adapter scan (k_scan_fast); anything it cannot express uses k_scan
+    memset(&c->plan, 0, sizeof(c->plan));
+    {
+        bool fast = getenv("FPL_FORCE_GENERIC_SCAN") == nullptr;
+        int maxa = 1;
+        for (int k = 0; k < 2 && fast && opt->adapter_enabled; k++) {
+            const char* s = k == 0 ? ad->start : ad->end;
+            const int len = h_alen[k];
+            if (len < 1) { fast = false; break; }
+            if (len > maxa) maxa = len;
+            int nin = 0;
+            for (int i = 0; i < len; i++) {
+                int letter = s[i] == 'A' ? 0 : s[i] == 'C' ? 1 : s[i] == 'G' ? 2 : s[i] == 'T' ? 3 : -1;
+                if (letter < 0) { fast = false; break; }
+                c->plan.in[k][nin++] = (uint16_t)(0x8000u | ((uint32_t)(letter * SCANPLAN_MASK_WORDS + (i >> 5)) << 5) | (uint32_t)(i & 31));
+            }
+            while (nin % 8) c->plan.in[k][nin++] = 0;
+            c->plan.n_in[k] = nin;
+        }
+        c->plan.fast = fast ? 1 : 0;
+        c->plan.npl = maxa <= 31 ? 5 : maxa <= 63 ? 6 : maxa <= 127 ? 7 : 8;
+        c->plan.halo_words = ((maxa - 1) >> 5) + 1;
+    }
     for (int i = 0; i <= FPL_MAX_ADAPTER_LEN; i++) c->P.thr[i] = (short)(int)round(opt->ed_max * i);  // src/adaptertrimmer.cpp:73
 #define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail("%s failed: %s", #call, cudaGetErrorString(e_)); fpl_destroy(c); return -1; } } while (0)
     CKC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -271,7 +297,9 @@ int fpl_create(const fpl_options* opt, const fpl_adapters* ad, fpl_ctx** out) {
     CKC(cudaMalloc(&c->d_counters, sizeof(unsigned long long) * c->counter_words));
     CKC(cudaMemset(c->d_counters, 0, sizeof(unsigned long long) * c->counter_words));
     const char* tb = getenv("FPL_TILE_MBASES");
-    c->tile_bases = (tb && atoll(tb) > 0 ? atoll(tb) : 24) * 1000000ll;
+    // 0 (default) = no tiling: every kernel streams the whole batch from HBM (measured faster than L2-sized tiles,
+    // whose launches are too small to fill the GPU: profiles/README.md)
+    c->tile_bases = (tb && atoll(tb) > 0) ? atoll(tb) * 1000000ll : (1ll << 62);
     for (int k = 0; k < K_NKERNELS; k++) { c->kernel_ms[k] = 0; c->kernel_n[k] = 0; }
     if (reserve_cycles(c, 1024)) { fpl_destroy(c); return -1; }
     CKC(cudaStreamSynchronize(c->stream));

@@ -1,0 +1,308 @@
+// k_scan_fast: bit-sliced version of the per-base "adapter + quality" pass (same contract as k_scan in fpl_scan.cu,
+// selected by the host when both -s/-e adapters are non-empty, ACGT-only and <= 128 bp).
+//
+// Data layout per warp-tile: 32 lanes x 32 consecutive bytes (two 16-byte vector loads per lane, coalesced).
+//   1. each lane turns its 32 sequence bytes into four 32-bit bit-planes (bits 0,1,2,4 of every byte; one
+//      AND + IMAD + funnel-shift per word per plane) and checks (b & 0xE8) == 0x40 for all of them; under that
+//      check the planes decide exactly which bytes are A, C, G or T.  Lanes that fail it (N or any other
+//      byte) build their four letter masks byte by byte.
+//   2. the letter masks go to shared memory ([letter][lane], plus zero words for the halo), so that the mask of
+//      adapter letter a_i shifted by i positions is one funnel shift of two neighbouring words;
+//   3. the alen shifted masks are summed per bit position with carry-save adders (3:2 compressors are two LOP3
+//      each, Harley-Seal blocks of 8 inputs) into a bit-sliced match counter; H(p) = alen - matches(p);
+//   4. a bit-sliced arg-max (MSB-first candidate narrowing) gives each lane its best position of the tile; the
+//      first arg-min of the whole read falls out of a (H << 32 | pos) min-reduction (strict '<' of
+//      src/adaptertrimmer.cpp:148 == smallest position among equal H).
+// Quality bytes: sum via dp4a, #(q < qualified) via one SWAR compare per word; N count is zero by construction in
+// lanes that passed the alphabet check; the complexity count compares each word with itself shifted by one byte.
+#include "fpl_device.cuh"
+#include "fpl_scanplan.h"
+
+#define SF_WARPS 4
+#define SF_THREADS (SF_WARPS * 32)
+#define SF_MASK_WORDS SCANPLAN_MASK_WORDS   // 32 lanes + up to 4 halo words (+ pad)
+
+namespace {
+
+__device__ __forceinline__ uint32_t lop3_xor3(uint32_t a, uint32_t b, uint32_t c) { return a ^ b ^ c; }
+__device__ __forceinline__ uint32_t lop3_maj(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (c & (a | b)); }
+
+// carry-save adder: (h, l) = a + b + c per bit position
+#define CSA(h, l, a, b, c)                \
+    do {                                  \
+        uint32_t a_ = (a), b_ = (b), c_ = (c); \
+        l = lop3_xor3(a_, b_, c_);        \
+        h = lop3_maj(a_, b_, c_);         \
+    } while (0)
+
+__device__ __forceinline__ uint32_t plane_nibble(uint32_t w, uint32_t mask, uint32_t mul) { return (w & mask) * mul; }
+
+// exact per-byte "non-zero" flags in bit 7 of every byte
+__device__ __forceinline__ uint32_t nz7(uint32_t d) { return (((d & 0x7f7f7f7fu) + 0x7f7f7f7fu) | d) & 0x80808080u; }
+
+struct LaneSeq { uint32_t w[8]; };
+
+__device__ __forceinline__ void load32(const uint8_t* p, bool ok, LaneSeq& s) {
+    if (ok) {
+        const uint4* v = reinterpret_cast<const uint4*>(p);
+        uint4 a = __ldg(v), b = __ldg(v + 1);
+        s.w[0] = a.x; s.w[1] = a.y; s.w[2] = a.z; s.w[3] = a.w;
+        s.w[4] = b.x; s.w[5] = b.y; s.w[6] = b.z; s.w[7] = b.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; k++) s.w[k] = 0;
+    }
+}
+
+template <int NPL>
+__device__ __forceinline__ void scan_adapter(const ScanPlan& plan, int which, const uint32_t* smask, int lane,
+                                             uint32_t valid, int alen, int64_t pos0, int& bestM, int64_t& bestPos) {
+    // bit-sliced counter of matches: cnt[b] holds bit b of matches(p) for the lane's 32 positions
+    uint32_t cnt[NPL];
+#pragma unroll
+    for (int b = 0; b < NPL; b++) cnt[b] = 0;
+    uint32_t ones = 0, twos = 0, fours = 0;
+    const int nin = plan.n_in[which];
+    for (int k0 = 0; k0 < nin; k0 += 8) {
+        uint32_t x[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const uint32_t e = plan.in[which][k0 + j];   // uniform: (valid<<15) | smem word offset << 5 | shift
+            const uint32_t* wp = smask + (e >> 5 & 0x3FFu) + lane;
+            const uint32_t lo = wp[0], hi = wp[1];
+            const uint32_t v = __funnelshift_r(lo, hi, e & 31u);
+            x[j] = (e & 0x8000u) ? v : 0u;
+        }
+        uint32_t twosA, twosB, foursA, foursB, eight;
+        CSA(twosA, ones, ones, x[0], x[1]);
+        CSA(twosB, ones, ones, x[2], x[3]);
+        CSA(foursA, twos, twos, twosA, twosB);
+        CSA(twosA, ones, ones, x[4], x[5]);
+        CSA(twosB, ones, ones, x[6], x[7]);
+        CSA(foursB, twos, twos, twosA, twosB);
+        CSA(eight, fours, fours, foursA, foursB);
+        // ripple the weight-8 carry into planes 3..NPL-1
+        uint32_t carry = eight;
+#pragma unroll
+        for (int b = 3; b < NPL; b++) {
+            const uint32_t t = cnt[b] & carry;
+            cnt[b] ^= carry;
+            carry = t;
+        }
+    }
+    cnt[0] = ones; cnt[1] = twos; cnt[2] = fours;
+    if (valid) {
+        uint32_t cand = valid;
+        int val = 0;
+#pragma unroll
+        for (int b = NPL - 1; b >= 0; b--) {
+            const uint32_t t = cand & cnt[b];
+            if (t) { cand = t; val |= 1 << b; }
+        }
+        if (val > bestM) { bestM = val; bestPos = pos0 + (__ffs(cand) - 1); }
+    }
+    (void)alen;
+}
+
+}  // namespace
+
+template <int NPL>
+__global__ void __launch_bounds__(SF_THREADS)
+k_scan_fast(const __grid_constant__ DevParams P, const __grid_constant__ ScanPlan plan, DevBatch b,
+            ReadState* __restrict__ st) {
+    __shared__ uint32_t smask_all[SF_WARPS][4][SF_MASK_WORDS];
+    __shared__ unsigned long long sh64[2][SF_WARPS];
+    __shared__ int sh32[4][SF_WARPS];
+    const int wid = threadIdx.x >> 5, lane = lane_id();
+    const int64_t r = blockIdx.x;
+    const ReadState s = st[r];
+    if (!s.alive) return;
+    const int len = s.len;
+    const int64_t start = b.offsets[r] + s.lo;            // absolute byte offset of the window
+    const int pre = (int)(start & 15);                    // bytes between the 16-byte aligned base and the window
+    const uint8_t* sbase = b.seq + (start - pre);
+    const uint8_t* qbase = b.qual + (start - pre);
+    const int alen0 = P.alen[0], alen1 = P.alen[1];
+    const bool doAdapters = P.opt.adapter_enabled != 0;
+    const bool doCounts = (P.opt.qual_filter_enabled || P.opt.length_filter_enabled);
+    const bool doCplx = P.opt.complexity_enabled != 0;
+    const uint32_t qq4 = (uint32_t)(P.opt.qualified_qual & 0x7f) * 0x01010101u;
+    const int np0 = (doAdapters && alen0 <= len) ? len - alen0 : 0;
+    const int np1 = (doAdapters && alen1 <= len) ? len - alen1 : 0;
+    const int HL = plan.halo_words;
+    const int step = (32 - HL) * 32;                      // bytes advanced per warp-tile
+    const int total = pre + len;                          // bytes from the aligned base to the window end
+    uint32_t* smask = &smask_all[wid][0][0];
+    // zero the halo words once (words 32..39 of every letter)
+    for (int i = lane; i < 4 * SF_MASK_WORDS; i += 32) smask[i] = 0;
+    __syncwarp();
+
+    int bestM0 = -1, bestM1 = -1;
+    int64_t bestP0 = 0, bestP1 = 0;
+    int lowq_ge = 0, nn = 0, totalq = 0, diff = 0, nbytes = 0;
+
+    for (int64_t t0 = (int64_t)wid * step; t0 < total; t0 += (int64_t)SF_WARPS * step) {
+        const int64_t a0 = t0 + 32 * lane;                // this lane's first byte (relative to the aligned base)
+        const bool inrange = a0 < total && a0 + 32 > pre;
+        LaneSeq sq;
+        load32(sbase + a0, inrange, sq);
+        // ---- alphabet check + bit planes ----
+        uint32_t bad = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) bad |= (sq.w[k] & 0xE8E8E8E8u) ^ 0x40404040u;
+        // bytes outside the window may be anything: they are masked by `valid` below, but they must not send a
+        // clean lane to the slow path needlessly -> only the exactness matters, so no special casing here.
+        uint32_t MA, MC, MG, MT;
+        if (bad == 0) {
+            uint32_t B0 = 0, B1 = 0, B2 = 0, B4 = 0;
+#pragma unroll
+            for (int k = 7; k >= 0; k--) {
+                const uint32_t w = sq.w[k];
+                B0 = __funnelshift_l(plane_nibble(w, 0x01010101u, 0x10204080u), B0, 4);
+                B1 = __funnelshift_l(plane_nibble(w, 0x02020202u, 0x08102040u), B1, 4);
+                B2 = __funnelshift_l(plane_nibble(w, 0x04040404u, 0x04081020u), B2, 4);
+                B4 = __funnelshift_l(plane_nibble(w, 0x10101010u, 0x01020408u), B4, 4);
+            }
+            const uint32_t acg = ~B4 & B0;
+            MA = acg & ~B1 & ~B2;
+            MC = acg & B1 & ~B2;
+            MG = acg & B1 & B2;
+            MT = B4 & ~B0 & ~B1 & B2;
+        } else {
+            MA = MC = MG = MT = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t ch = (sq.w[k] >> (8 * j)) & 0xFFu;
+                    const uint32_t bit = 1u << (4 * k + j);
+                    MA |= ch == 'A' ? bit : 0u; MC |= ch == 'C' ? bit : 0u;
+                    MG |= ch == 'G' ? bit : 0u; MT |= ch == 'T' ? bit : 0u;
+                }
+            }
+        }
+        // ---- window masks for this lane: which of its 32 bytes are inside the window / are scan positions ----
+        // byte index a <-> window position p = a - pre
+        const int64_t p_first = a0 - pre;                 // window position of bit 0
+        const bool mine = lane < 32 - HL;                 // halo lanes are re-processed by the next tile
+        uint32_t inwin = 0, v0 = 0, v1 = 0;
+        if (mine && inrange) {
+            auto range_mask = [&](int64_t n) -> uint32_t {   // bits j with 0 <= p_first + j < n
+                int64_t lo = -p_first; if (lo < 0) lo = 0;
+                int64_t hi = n - p_first; if (hi > 32) hi = 32;
+                if (hi <= lo) return 0u;
+                const uint32_t upto_hi = hi >= 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u);
+                const uint32_t below_lo = lo >= 32 ? 0xFFFFFFFFu : ((1u << lo) - 1u);
+                return upto_hi & ~below_lo;
+            };
+            inwin = range_mask(len);
+            v0 = range_mask(np0);
+            v1 = range_mask(np1);
+        }
+        // ---- passFilter / complexity counts ----
+        if (inwin && (doCounts || doCplx)) {
+            if (doCounts) {
+                LaneSeq qv;
+                load32(qbase + a0, true, qv);
+                if (inwin == 0xFFFFFFFFu) {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const uint32_t q = qv.w[k];
+                        totalq = (int)__dp4a(q, 0x01010101u, (unsigned)totalq);
+                        const uint32_t ge = ((q | 0x80808080u) - qq4) & 0x80808080u;   // bit7: q >= qualified
+                        lowq_ge += __popc(ge);
+                    }
+                    nbytes += 32;
+                } else {
+                    for (int j = 0; j < 32; j++)
+                        if (inwin >> j & 1u) {
+                            const int q = (int)((qv.w[j >> 2] >> (8 * (j & 3))) & 0xFFu);
+                            totalq += q;
+                            lowq_ge += (q & 0x7f) >= (int)(qq4 & 0x7f);
+                            nbytes++;
+                        }
+                }
+                if (bad) {   // only lanes with a non-ACGT byte can hold an 'N'
+                    for (int j = 0; j < 32; j++)
+                        if (inwin >> j & 1u) nn += ((sq.w[j >> 2] >> (8 * (j & 3))) & 0xFFu) == 'N';
+                }
+            }
+        }
+        if (doCplx) {   // warp-uniform: pairs (i, i+1), i < len-1; byte 31's partner is the next lane's first byte
+            const uint32_t nxt = __shfl_down_sync(0xffffffffu, sq.w[0], 1);
+            if (inwin) {
+                // pair mask: positions p with p < len-1
+                uint32_t pm = inwin;
+                const int64_t last = (int64_t)len - 1 - p_first;   // bit index of the window's last byte
+                if (last >= 0 && last < 32) pm &= ~(1u << last);
+                if (pm == 0xFFFFFFFFu) {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const uint32_t w = sq.w[k], w2 = k < 7 ? sq.w[k + 1] : nxt;
+                        diff += __popc(nz7(w ^ __funnelshift_r(w, w2, 8)));
+                    }
+                } else {
+                    for (int j = 0; j < 32; j++)
+                        if (pm >> j & 1u) {
+                            const uint32_t c0 = (sq.w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+                            const uint32_t w2 = (j + 1) < 32 ? sq.w[(j + 1) >> 2] : nxt;
+                            const uint32_t c1 = (w2 >> (8 * ((j + 1) & 3))) & 0xFFu;
+                            diff += c0 != c1;
+                        }
+                }
+            }
+        }
+        // ---- Hamming scans ----
+        if (doAdapters) {
+            __syncwarp();
+            smask[0 * SF_MASK_WORDS + lane] = MA;
+            smask[1 * SF_MASK_WORDS + lane] = MC;
+            smask[2 * SF_MASK_WORDS + lane] = MG;
+            smask[3 * SF_MASK_WORDS + lane] = MT;
+            __syncwarp();
+            scan_adapter<NPL>(plan, 0, smask, lane, v0, alen0, p_first, bestM0, bestP0);
+            scan_adapter<NPL>(plan, 1, smask, lane, v1, alen1, p_first, bestM1, bestP1);
+        }
+    }
+    // ---- block reduction ----
+    unsigned long long k0 = bestM0 >= 0 ? (((unsigned long long)(unsigned)(alen0 - bestM0) << 32) | (unsigned)bestP0) : ~0ull;
+    unsigned long long k1 = bestM1 >= 0 ? (((unsigned long long)(unsigned)(alen1 - bestM1) << 32) | (unsigned)bestP1) : ~0ull;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        unsigned long long o0 = __shfl_xor_sync(0xffffffffu, k0, d), o1 = __shfl_xor_sync(0xffffffffu, k1, d);
+        k0 = o0 < k0 ? o0 : k0; k1 = o1 < k1 ? o1 : k1;
+    }
+    lowq_ge = __reduce_add_sync(0xffffffffu, lowq_ge); nn = __reduce_add_sync(0xffffffffu, nn);
+    totalq = __reduce_add_sync(0xffffffffu, totalq); diff = __reduce_add_sync(0xffffffffu, diff);
+    nbytes = __reduce_add_sync(0xffffffffu, nbytes);
+    if (lane == 0) {
+        sh64[0][wid] = k0; sh64[1][wid] = k1;
+        sh32[0][wid] = nbytes - lowq_ge;                  // #(q < qualified)
+        sh32[1][wid] = nn;
+        sh32[2][wid] = totalq - 33 * nbytes;              // sum(q - 33)
+        sh32[3][wid] = diff;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long m0 = sh64[0][0], m1 = sh64[1][0];
+        int c0 = sh32[0][0], c1 = sh32[1][0], c2 = sh32[2][0], c3 = sh32[3][0];
+        for (int i = 1; i < SF_WARPS; i++) {
+            m0 = sh64[0][i] < m0 ? sh64[0][i] : m0; m1 = sh64[1][i] < m1 ? sh64[1][i] : m1;
+            c0 += sh32[0][i]; c1 += sh32[1][i]; c2 += sh32[2][i]; c3 += sh32[3][i];
+        }
+        ReadState* o = &st[r];
+        o->best[0] = m0; o->best[1] = m1;
+        o->lowq = c0; o->nn = c1; o->totalq = c2; o->diff = c3;
+    }
+}
+
+void launch_scan_fast(const DevParams& P, const ScanPlan& plan, const DevBatch& b, ReadState* st, cudaStream_t stream) {
+    if (b.n_reads == 0) return;
+    const unsigned grid = (unsigned)b.n_reads;
+    switch (plan.npl) {
+        case 5: k_scan_fast<5><<<grid, SF_THREADS, 0, stream>>>(P, plan, b, st); break;
+        case 6: k_scan_fast<6><<<grid, SF_THREADS, 0, stream>>>(P, plan, b, st); break;
+        case 7: k_scan_fast<7><<<grid, SF_THREADS, 0, stream>>>(P, plan, b, st); break;
+        default: k_scan_fast<8><<<grid, SF_THREADS, 0, stream>>>(P, plan, b, st); break;
+    }
+}
