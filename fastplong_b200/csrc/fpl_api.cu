@@ -268,14 +268,12 @@ int fpl_create(const fpl_options* opt, const fpl_adapters* ad, fpl_ctx** out) {
             const int len = h_alen[k];
             if (len < 1) { fast = false; break; }
             if (len > maxa) maxa = len;
-            int nin = 0;
             for (int i = 0; i < len; i++) {
                 int letter = s[i] == 'A' ? 0 : s[i] == 'C' ? 1 : s[i] == 'G' ? 2 : s[i] == 'T' ? 3 : -1;
                 if (letter < 0) { fast = false; break; }
-                c->plan.in[k][nin++] = (uint16_t)(0x8000u | ((uint32_t)(letter * SCANPLAN_MASK_WORDS + (i >> 5)) << 5) | (uint32_t)(i & 31));
+                uint8_t& n = c->plan.cnt[k][letter][i >> 5];
+                c->plan.shift[k][letter][i >> 5][n++] = (uint8_t)(i & 31);
             }
-            while (nin % 8) c->plan.in[k][nin++] = 0;
-            c->plan.n_in[k] = nin;
         }
         c->plan.fast = fast ? 1 : 0;
         c->plan.npl = maxa <= 31 ? 5 : maxa <= 63 ? 6 : maxa <= 127 ? 7 : 8;

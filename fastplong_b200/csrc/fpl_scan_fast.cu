@@ -6,10 +6,11 @@
 //      AND + IMAD + funnel-shift per word per plane) and checks (b & 0xE8) == 0x40 for all of them; under that
 //      check the planes decide exactly which bytes are A, C, G or T.  Lanes that fail it (N or any other
 //      byte) build their four letter masks byte by byte.
-//   2. the letter masks go to shared memory ([letter][lane], plus zero words for the halo), so that the mask of
-//      adapter letter a_i shifted by i positions is one funnel shift of two neighbouring words;
+//   2. each lane fetches its neighbours' letter masks with warp shuffles, so that the mask of adapter letter a_i
+//      shifted by i positions is one funnel shift of two registers (the shift amounts per letter come from the
+//      host-built ScanPlan, four per 32-bit uniform load);
 //   3. the alen shifted masks are summed per bit position with carry-save adders (3:2 compressors are two LOP3
-//      each, Harley-Seal blocks of 8 inputs) into a bit-sliced match counter; H(p) = alen - matches(p);
+//      each, Harley-Seal blocks of 4 inputs) into a bit-sliced match counter; H(p) = alen - matches(p);
 //   4. a bit-sliced arg-max (MSB-first candidate narrowing) gives each lane its best position of the tile; the
 //      first arg-min of the whole read falls out of a (H << 32 | pos) min-reduction (strict '<' of
 //      src/adaptertrimmer.cpp:148 == smallest position among equal H).
@@ -20,7 +21,6 @@
 
 #define SF_WARPS 4
 #define SF_THREADS (SF_WARPS * 32)
-#define SF_MASK_WORDS SCANPLAN_MASK_WORDS   // 32 lanes + up to 4 halo words (+ pad)
 
 namespace {
 
@@ -54,43 +54,56 @@ __device__ __forceinline__ void load32(const uint8_t* p, bool ok, LaneSeq& s) {
     }
 }
 
+// One Harley-Seal block of four 1-bit inputs into the bit-sliced counter (ones, twos, cnt[2..NPL-1]).
 template <int NPL>
-__device__ __forceinline__ void scan_adapter(const ScanPlan& plan, int which, const uint32_t* smask, int lane,
-                                             uint32_t valid, int alen, int64_t pos0, int& bestM, int64_t& bestPos) {
-    // bit-sliced counter of matches: cnt[b] holds bit b of matches(p) for the lane's 32 positions
+__device__ __forceinline__ void add4(uint32_t& ones, uint32_t& twos, uint32_t (&cnt)[NPL], uint32_t x0, uint32_t x1,
+                                     uint32_t x2, uint32_t x3) {
+    uint32_t tA, tB, f;
+    CSA(tA, ones, ones, x0, x1);
+    CSA(tB, ones, ones, x2, x3);
+    CSA(f, twos, twos, tA, tB);
+    uint32_t carry = f;   // weight 4
+#pragma unroll
+    for (int b = 2; b < NPL; b++) {
+        const uint32_t t = cnt[b] & carry;
+        cnt[b] ^= carry;
+        carry = t;
+    }
+}
+
+// matches(p) for one adapter over the lane's 32 positions, then the lane-local arg-max (first position).
+// M[l][w] = letter-l mask of the 32 positions starting 32*w after this lane's first position.
+template <int NPL, int HL>
+__device__ __forceinline__ void scan_adapter(const ScanPlan& plan, int which, const uint32_t (&M)[4][HL + 1],
+                                             uint32_t valid, int64_t pos0, int& bestM, int64_t& bestPos) {
     uint32_t cnt[NPL];
 #pragma unroll
     for (int b = 0; b < NPL; b++) cnt[b] = 0;
-    uint32_t ones = 0, twos = 0, fours = 0;
-    const int nin = plan.n_in[which];
-    for (int k0 = 0; k0 < nin; k0 += 8) {
-        uint32_t x[8];
+    uint32_t ones = 0, twos = 0;
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const uint32_t e = plan.in[which][k0 + j];   // uniform: (valid<<15) | smem word offset << 5 | shift
-            const uint32_t* wp = smask + (e >> 5 & 0x3FFu) + lane;
-            const uint32_t lo = wp[0], hi = wp[1];
-            const uint32_t v = __funnelshift_r(lo, hi, e & 31u);
-            x[j] = (e & 0x8000u) ? v : 0u;
-        }
-        uint32_t twosA, twosB, foursA, foursB, eight;
-        CSA(twosA, ones, ones, x[0], x[1]);
-        CSA(twosB, ones, ones, x[2], x[3]);
-        CSA(foursA, twos, twos, twosA, twosB);
-        CSA(twosA, ones, ones, x[4], x[5]);
-        CSA(twosB, ones, ones, x[6], x[7]);
-        CSA(foursB, twos, twos, twosA, twosB);
-        CSA(eight, fours, fours, foursA, foursB);
-        // ripple the weight-8 carry into planes 3..NPL-1
-        uint32_t carry = eight;
+    for (int l = 0; l < 4; l++) {
 #pragma unroll
-        for (int b = 3; b < NPL; b++) {
-            const uint32_t t = cnt[b] & carry;
-            cnt[b] ^= carry;
-            carry = t;
+        for (int w = 0; w < HL; w++) {
+            const uint32_t lo = M[l][w], hi = M[l][w + 1];
+            const int n = plan.cnt[which][l][w];                       // warp-uniform
+            const uint32_t* sh4 = reinterpret_cast<const uint32_t*>(&plan.shift[which][l][w][0]);
+            int k = 0;
+            for (; k + 4 <= n; k += 4) {
+                const uint32_t v = sh4[k >> 2];                         // four shift amounts (funnel shift wraps at 32)
+                add4<NPL>(ones, twos, cnt, __funnelshift_r(lo, hi, v), __funnelshift_r(lo, hi, v >> 8),
+                          __funnelshift_r(lo, hi, v >> 16), __funnelshift_r(lo, hi, v >> 24));
+            }
+            if (k < n) {
+                const int r = n - k;
+                const uint32_t v = sh4[k >> 2];
+                const uint32_t x0 = __funnelshift_r(lo, hi, v);
+                const uint32_t x1 = r > 1 ? __funnelshift_r(lo, hi, v >> 8) : 0u;
+                const uint32_t x2 = r > 2 ? __funnelshift_r(lo, hi, v >> 16) : 0u;
+                add4<NPL>(ones, twos, cnt, x0, x1, x2, 0u);
+            }
         }
     }
-    cnt[0] = ones; cnt[1] = twos; cnt[2] = fours;
+    cnt[0] = ones; cnt[1] = twos;
     if (valid) {
         uint32_t cand = valid;
         int val = 0;
@@ -101,16 +114,14 @@ __device__ __forceinline__ void scan_adapter(const ScanPlan& plan, int which, co
         }
         if (val > bestM) { bestM = val; bestPos = pos0 + (__ffs(cand) - 1); }
     }
-    (void)alen;
 }
 
 }  // namespace
 
-template <int NPL>
+template <int NPL, int HL>
 __global__ void __launch_bounds__(SF_THREADS)
 k_scan_fast(const __grid_constant__ DevParams P, const __grid_constant__ ScanPlan plan, DevBatch b,
             ReadState* __restrict__ st) {
-    __shared__ uint32_t smask_all[SF_WARPS][4][SF_MASK_WORDS];
     __shared__ unsigned long long sh64[2][SF_WARPS];
     __shared__ int sh32[4][SF_WARPS];
     const int wid = threadIdx.x >> 5, lane = lane_id();
@@ -129,13 +140,8 @@ k_scan_fast(const __grid_constant__ DevParams P, const __grid_constant__ ScanPla
     const uint32_t qq4 = (uint32_t)(P.opt.qualified_qual & 0x7f) * 0x01010101u;
     const int np0 = (doAdapters && alen0 <= len) ? len - alen0 : 0;
     const int np1 = (doAdapters && alen1 <= len) ? len - alen1 : 0;
-    const int HL = plan.halo_words;
     const int step = (32 - HL) * 32;                      // bytes advanced per warp-tile
     const int total = pre + len;                          // bytes from the aligned base to the window end
-    uint32_t* smask = &smask_all[wid][0][0];
-    // zero the halo words once (words 32..39 of every letter)
-    for (int i = lane; i < 4 * SF_MASK_WORDS; i += 32) smask[i] = 0;
-    __syncwarp();
 
     int bestM0 = -1, bestM1 = -1;
     int64_t bestP0 = 0, bestP1 = 0;
@@ -254,14 +260,17 @@ k_scan_fast(const __grid_constant__ DevParams P, const __grid_constant__ ScanPla
         }
         // ---- Hamming scans ----
         if (doAdapters) {
-            __syncwarp();
-            smask[0 * SF_MASK_WORDS + lane] = MA;
-            smask[1 * SF_MASK_WORDS + lane] = MC;
-            smask[2 * SF_MASK_WORDS + lane] = MG;
-            smask[3 * SF_MASK_WORDS + lane] = MT;
-            __syncwarp();
-            scan_adapter<NPL>(plan, 0, smask, lane, v0, alen0, p_first, bestM0, bestP0);
-            scan_adapter<NPL>(plan, 1, smask, lane, v1, alen1, p_first, bestM1, bestP1);
+            // letter masks of this lane's word and of the HL following words (neighbour lanes; the last HL lanes of
+            // the tile read wrapped garbage, their results are masked out by `mine`)
+            uint32_t M[4][HL + 1];
+            M[0][0] = MA; M[1][0] = MC; M[2][0] = MG; M[3][0] = MT;
+#pragma unroll
+            for (int w = 1; w <= HL; w++) {
+                M[0][w] = __shfl_down_sync(0xffffffffu, MA, w); M[1][w] = __shfl_down_sync(0xffffffffu, MC, w);
+                M[2][w] = __shfl_down_sync(0xffffffffu, MG, w); M[3][w] = __shfl_down_sync(0xffffffffu, MT, w);
+            }
+            scan_adapter<NPL, HL>(plan, 0, M, v0, p_first, bestM0, bestP0);
+            scan_adapter<NPL, HL>(plan, 1, M, v1, p_first, bestM1, bestP1);
         }
     }
     // ---- block reduction ----
@@ -299,10 +308,16 @@ k_scan_fast(const __grid_constant__ DevParams P, const __grid_constant__ ScanPla
 void launch_scan_fast(const DevParams& P, const ScanPlan& plan, const DevBatch& b, ReadState* st, cudaStream_t stream) {
     if (b.n_reads == 0) return;
     const unsigned grid = (unsigned)b.n_reads;
-    switch (plan.npl) {
-        case 5: k_scan_fast<5><<<grid, SF_THREADS, 0, stream>>>(P, plan, b, st); break;
-        case 6: k_scan_fast<6><<<grid, SF_THREADS, 0, stream>>>(P, plan, b, st); break;
-        case 7: k_scan_fast<7><<<grid, SF_THREADS, 0, stream>>>(P, plan, b, st); break;
-        default: k_scan_fast<8><<<grid, SF_THREADS, 0, stream>>>(P, plan, b, st); break;
+#define SF_LAUNCH(N, H) k_scan_fast<N, H><<<grid, SF_THREADS, 0, stream>>>(P, plan, b, st)
+    const int key = plan.npl * 10 + plan.halo_words;
+    switch (key) {
+        case 51: SF_LAUNCH(5, 1); break;
+        case 61: SF_LAUNCH(6, 1); break;
+        case 62: SF_LAUNCH(6, 2); break;
+        case 72: SF_LAUNCH(7, 2); break;
+        case 73: SF_LAUNCH(7, 3); break;
+        case 74: SF_LAUNCH(7, 4); break;
+        default: SF_LAUNCH(8, 4); break;
     }
+#undef SF_LAUNCH
 }

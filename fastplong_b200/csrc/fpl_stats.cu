@@ -1,21 +1,22 @@
 // Stats::statRead (src/stats.cpp:265-375) as two kernels over a list of segments
 // (pre-filter Stats: every input read; post-filter Stats: every passing segment):
 //
-//  k_cycle_stats  column-tiled: a CTA owns a tile of 1024 cycles x a group of segments.  Every lane owns its
-//                 cycle columns exclusively, so the per-(base-bin, cycle) counters live in shared memory and are
-//                 updated with plain read-modify-write (no atomics, no bank conflicts: column j*32+lane).
-//                 One 32-bit word packs (count << 20 | sum of raw quality chars); the tile is flushed once to
-//                 the global int64 arrays mCycleBaseContents / mCycleBaseQual.  Also counts the 5-mers (mKmer).
-//  k_read_qual    row-shaped: a warp owns a segment, builds its quality histogram in lane-private shared memory
-//                 columns, adds it to mBaseQualHistogram and derives the per-read median quality
+//  k_cycle_stats  column-tiled: a CTA owns a tile of 512 cycles x a group of up to 4000 segments; its warps take the
+//                 segments that reach the tile round-robin, one 16-byte vector of sequence and of quality per
+//                 lane.  The per-(base-bin, cycle) counters live in shared memory (column j*32+lane: conflict-free)
+//                 and are updated with shared-memory atomics; one 32-bit word packs (count << 20 | sum of raw
+//                 quality chars).  The tile is flushed once to the global int64 arrays mCycleBaseContents /
+//                 mCycleBaseQual.  Also counts the 5-mers (mKmer) with a SWAR fast path for all-ACGTU vectors.
+//  k_read_qual    row-shaped: a warp owns a segment, builds its quality histogram with shared-memory atomics
+//                 (16-byte vector loads), adds it to mBaseQualHistogram and derives the per-read median quality
 //                 (mMedianReadQualHistogram / mMedianReadQualBases / mReads / mLengthSum).
 #include "fpl_device.cuh"
 
 #define CS_THREADS 256
 #define CS_WARPS (CS_THREADS / 32)
-#define CS_WARP_CYCLES 128                       // 4 bytes per lane
-#define CS_TILE (CS_WARPS * CS_WARP_CYCLES)      // 1024 cycles per CTA
-#define CS_GROUP 1024                            // segments per CTA; packed counter: count < 4096, sum < 2^20
+#define CS_TILE 512                              // cycles per CTA: one 16-byte vector per lane
+#define CS_GROUP 4000                            // segments per CTA; packed counter: count <= 4095, sum of q < 2^20
+#define CS_STAGE 1000                            // descriptors staged in shared memory at a time
 
 namespace {
 
@@ -29,15 +30,56 @@ __device__ __forceinline__ uint32_t kmer_code(uint32_t b) {
     return v;
 }
 
-// unaligned 4-byte fetch through two aligned 32-bit loads (segment starts are arbitrary byte offsets)
-__device__ __forceinline__ uint32_t load_u32_unaligned(const uint8_t* p) {
+// 16 bytes at an arbitrary address: two aligned 16-byte loads + a byte shift (sh = address & 15, warp-uniform)
+__device__ __forceinline__ void load16(const uint8_t* p, uint32_t (&o)[4]) {
     const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint4* v = reinterpret_cast<const uint4*>(a & ~(uintptr_t)15);
+    const unsigned sh = (unsigned)(a & 15);
+    const uint4 x = __ldg(v);
+    if (sh == 0) { o[0] = x.x; o[1] = x.y; o[2] = x.z; o[3] = x.w; return; }
+    const uint4 y = __ldg(v + 1);
+    const unsigned bs = (sh & 3) * 8;
+    switch (sh >> 2) {
+        case 0:
+            o[0] = __funnelshift_r(x.x, x.y, bs); o[1] = __funnelshift_r(x.y, x.z, bs);
+            o[2] = __funnelshift_r(x.z, x.w, bs); o[3] = __funnelshift_r(x.w, y.x, bs); break;
+        case 1:
+            o[0] = __funnelshift_r(x.y, x.z, bs); o[1] = __funnelshift_r(x.z, x.w, bs);
+            o[2] = __funnelshift_r(x.w, y.x, bs); o[3] = __funnelshift_r(y.x, y.y, bs); break;
+        case 2:
+            o[0] = __funnelshift_r(x.z, x.w, bs); o[1] = __funnelshift_r(x.w, y.x, bs);
+            o[2] = __funnelshift_r(y.x, y.y, bs); o[3] = __funnelshift_r(y.y, y.z, bs); break;
+        default:
+            o[0] = __funnelshift_r(x.w, y.x, bs); o[1] = __funnelshift_r(y.x, y.y, bs);
+            o[2] = __funnelshift_r(y.y, y.z, bs); o[3] = __funnelshift_r(y.z, y.w, bs); break;
+    }
+}
+
+__device__ __forceinline__ uint32_t load4_before(const uint8_t* p) {   // the 4 bytes ending just before p
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p) - 4;
     const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
     const unsigned sh = (unsigned)(a & 3) * 8;
-    uint32_t lo = __ldg(w);
+    const uint32_t lo = __ldg(w);
     if (sh == 0) return lo;
-    uint32_t hi = __ldg(w + 1);
-    return __funnelshift_r(lo, hi, sh);
+    return __funnelshift_r(lo, __ldg(w + 1), sh);
+}
+
+// 0x01 in every byte of w that is one of A, C, G, T, U (exact): b & 0xE8 == 0x40 and, on bits (b4,b2,b1,b0),
+// b4 ? (b2 & ~b1) : (b0 & (b1 | ~b2))
+__device__ __forceinline__ uint32_t valid_acgtu(uint32_t w) {
+    const uint32_t x1 = w >> 1, x2 = w >> 2, x4 = w >> 4;
+    const uint32_t g1 = w & (x1 | ~x2);
+    const uint32_t g2 = x2 & ~x1;
+    const uint32_t v = (x4 & g2) | (~x4 & g1);
+    const uint32_t t = (w & 0xE8E8E8E8u) ^ 0x40404040u;                         // zero byte <=> 010x0xxx
+    const uint32_t nz = (((t & 0x7f7f7f7fu) + 0x7f7f7f7fu) | t) >> 7;            // bit0 of each byte: t != 0
+    return v & ~nz & 0x01010101u;
+}
+
+// four 2-bit 5-mer codes of a word, oldest base in the top bits: code = bit1 << 1 | bit2 (A=0, T/U=1, C=2, G=3)
+__device__ __forceinline__ uint32_t pack_codes(uint32_t w) {
+    const uint32_t c = (w & 0x02020202u) | ((w >> 2) & 0x01010101u);
+    return (c * 0x40100401u) >> 24;
 }
 
 }  // namespace
@@ -45,72 +87,108 @@ __device__ __forceinline__ uint32_t load_u32_unaligned(const uint8_t* p) {
 __global__ void __launch_bounds__(CS_THREADS)
 k_cycle_stats(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qualbuf, const StatSeg* __restrict__ segs,
               int64_t nseg, unsigned long long* __restrict__ stats, int64_t C) {
-    // packed[bin][j*32 + lane] for the warp's 128 cycles: cycle c0w + 4*lane + j
-    __shared__ uint32_t packed[CS_WARPS][8][CS_WARP_CYCLES];
+    // packed[bin][j*32 + lane]: cycle c0 + 16*lane + j; one word = count << 20 | sum of quality chars
+    __shared__ uint32_t packed[8][CS_TILE];
     __shared__ uint32_t kmer[1024];
+    __shared__ int64_t d_off[CS_STAGE];
+    __shared__ int32_t d_len[CS_STAGE];
+    __shared__ int d_n;
     const int wid = threadIdx.x >> 5, lane = lane_id();
-    const int64_t c0w = (int64_t)blockIdx.x * CS_TILE + (int64_t)wid * CS_WARP_CYCLES;  // first cycle of this warp
+    const int64_t c0 = (int64_t)blockIdx.x * CS_TILE;      // first cycle of this CTA
     const int64_t g0 = (int64_t)blockIdx.y * CS_GROUP;
     const int64_t g1 = min(nseg, g0 + CS_GROUP);
     for (int i = threadIdx.x; i < 1024; i += CS_THREADS) kmer[i] = 0;
-    uint32_t (*mine)[CS_WARP_CYCLES] = packed[wid];
-    for (int i = lane; i < 8 * CS_WARP_CYCLES; i += 32) (&mine[0][0])[i] = 0;
-    __syncthreads();
-    const int64_t cl = c0w + 4 * lane;  // this lane's first cycle
-    for (int64_t s = g0; s < g1; s++) {
-        const StatSeg sg = segs[s];
-        if ((int64_t)sg.len <= c0w) continue;   // warp-uniform
-        const uint8_t* sp = seqbuf + sg.off;
-        const uint8_t* qp = qualbuf + sg.off;
-        uint32_t sw = 0, qw = 0, prev = 0;
-        const bool active = cl < sg.len;
-        if (active) {
-            sw = load_u32_unaligned(sp + cl);
-            qw = load_u32_unaligned(qp + cl);
+    for (int i = threadIdx.x; i < 8 * CS_TILE; i += CS_THREADS) (&packed[0][0])[i] = 0;
+    const int64_t cl = c0 + 16 * lane;                     // this lane's first cycle
+    bool any = false;
+    for (int64_t s0 = g0; s0 < g1; s0 += CS_STAGE) {
+        __syncthreads();
+        if (threadIdx.x == 0) d_n = 0;
+        __syncthreads();
+        // stage the descriptors of the segments that reach this tile
+        for (int64_t s = s0 + threadIdx.x; s < min(g1, s0 + CS_STAGE); s += CS_THREADS) {
+            const StatSeg sg = segs[s];
+            if ((int64_t)sg.len > c0) {
+                const int k = atomicAdd(&d_n, 1);
+                d_off[k] = sg.off; d_len[k] = sg.len;
+            }
         }
-        // the 4 bases before this lane's word, for the 5-mers: previous lane's word, or a load for lane 0
-        prev = __shfl_up_sync(0xffffffffu, sw, 1);
-        if (lane == 0) prev = c0w >= 4 ? load_u32_unaligned(sp + c0w - 4) : 0u;
-        if (!active) continue;
-        const int nvalid = (int)min((int64_t)4, (int64_t)sg.len - cl);
-        // codes of the 8 bases prev[0..3], sw[0..3]
-        uint32_t code[8];
+        __syncthreads();
+        const int n = d_n;
+        if (n) any = true;
+        for (int k = wid; k < n; k += CS_WARPS) {
+            const int64_t off = d_off[k];
+            const int len = d_len[k];
+            const uint8_t* sp = seqbuf + off + c0;
+            const uint8_t* qp = qualbuf + off + c0;
+            const bool active = cl < len;
+            uint32_t sw[4] = {0, 0, 0, 0}, qw[4] = {0, 0, 0, 0};
+            if (active) {
+                load16(sp + 16 * lane, sw);
+                load16(qp + 16 * lane, qw);
+            }
+            // the 4 bases before this lane's vector: previous lane's last word, or a load in front of the tile
+            uint32_t prev = __shfl_up_sync(0xffffffffu, sw[3], 1);
+            if (lane == 0) prev = c0 >= 4 ? load4_before(sp) : 0u;
+            if (!active) continue;
+            const int nvalid = (int)min((int64_t)16, (int64_t)len - cl);
+            if (nvalid == 16) {
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            code[j] = kmer_code((prev >> (8 * j)) & 0xFFu);
-            code[4 + j] = kmer_code((sw >> (8 * j)) & 0xFFu);
-        }
+                for (int w = 0; w < 4; w++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            if (j < nvalid) {
-                const uint32_t base = (sw >> (8 * j)) & 0xFFu;
-                const uint32_t q = (qw >> (8 * j)) & 0xFFu;
-                mine[base & 7u][j * 32 + lane] += (1u << 20) + q;
-                // 5-mer ending at cycle cl+j: needs cl+j >= 4 and five valid bases
-                if (cl + j >= 4) {
-                    const uint32_t c4 = code[j] , c3 = code[j + 1], c2 = code[j + 2], c1 = code[j + 3], c0 = code[j + 4];
-                    if (((c4 | c3 | c2 | c1 | c0) & 8u) == 0u)
-                        atomicAdd(&kmer[(c4 << 8) | (c3 << 6) | (c2 << 4) | (c1 << 2) | c0], 1u);
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t base = (sw[w] >> (8 * j)) & 0xFFu, q = (qw[w] >> (8 * j)) & 0xFFu;
+                        atomicAdd(&packed[base & 7u][(4 * w + j) * 32 + lane], (1u << 20) + q);
+                    }
+            } else {
+                for (int t = 0; t < nvalid; t++) {
+                    const uint32_t base = (sw[t >> 2] >> (8 * (t & 3))) & 0xFFu, q = (qw[t >> 2] >> (8 * (t & 3))) & 0xFFu;
+                    atomicAdd(&packed[base & 7u][t * 32 + lane], (1u << 20) + q);
+                }
+            }
+            // ---- 5-mers ending in this lane's 16 cycles (all five bases in ACGTU, cycle >= 4) ----
+            const uint32_t allv = valid_acgtu(prev) & valid_acgtu(sw[0]) & valid_acgtu(sw[1]) & valid_acgtu(sw[2]) &
+                                  valid_acgtu(sw[3]);
+            if (allv == 0x01010101u && nvalid == 16) {
+                // 20 codes, oldest first, 2 bits each: bits 39..0
+                const unsigned long long P = ((unsigned long long)pack_codes(prev) << 32) | (pack_codes(sw[0]) << 24) |
+                                             (pack_codes(sw[1]) << 16) | (pack_codes(sw[2]) << 8) | pack_codes(sw[3]);
+#pragma unroll
+                for (int t = 0; t < 16; t++)
+                    atomicAdd(&kmer[(uint32_t)(P >> (2 * (15 - t))) & 0x3FFu], 1u);
+            } else {
+                uint32_t code[20];
+#pragma unroll
+                for (int j = 0; j < 4; j++) code[j] = kmer_code((prev >> (8 * j)) & 0xFFu);
+#pragma unroll
+                for (int t = 0; t < 16; t++) code[4 + t] = kmer_code((sw[t >> 2] >> (8 * (t & 3))) & 0xFFu);
+#pragma unroll
+                for (int t = 0; t < 16; t++) {
+                    if (t < nvalid && cl + t >= 4) {
+                        const uint32_t c4 = code[t], c3 = code[t + 1], c2 = code[t + 2], c1 = code[t + 3], cc = code[t + 4];
+                        if (((c4 | c3 | c2 | c1 | cc) & 8u) == 0u)
+                            atomicAdd(&kmer[(c4 << 8) | (c3 << 6) | (c2 << 4) | (c1 << 2) | cc], 1u);
+                    }
                 }
             }
         }
     }
-    __syncwarp();
+    __syncthreads();
+    if (!any) return;   // block-uniform: d_n was read after a barrier by every thread
     // flush: content[b][c] += count ; qual[b][c] += sumq - 33*count
     unsigned long long* content = stats;
     unsigned long long* qualsum = stats + 8 * C;
-    for (int i = lane; i < 8 * CS_WARP_CYCLES; i += 32) {
-        const int bin = i / CS_WARP_CYCLES, col = i % CS_WARP_CYCLES;
-        const uint32_t v = mine[bin][col];
+    for (int i = threadIdx.x; i < 8 * CS_TILE; i += CS_THREADS) {
+        const int bin = i / CS_TILE, col = i % CS_TILE;
+        const uint32_t v = packed[bin][col];
         if (v) {
             const int j = col >> 5, ln = col & 31;
-            const int64_t c = c0w + 4 * ln + j;
+            const int64_t c = c0 + 16 * ln + j;
             const long long cnt = v >> 20, sq = v & 0xFFFFFu;
             atomicAdd(&content[(int64_t)bin * C + c], (unsigned long long)cnt);
             atomicAdd(&qualsum[(int64_t)bin * C + c], (unsigned long long)(sq - 33 * cnt));
         }
     }
-    __syncthreads();
     unsigned long long* tail = stats + 16 * C;
     for (int i = threadIdx.x; i < 1024; i += CS_THREADS)
         if (kmer[i]) atomicAdd(&tail[FPL_STATS_KMER + i], (unsigned long long)kmer[i]);
@@ -124,14 +202,14 @@ void launch_cycle_stats(const uint8_t* seq, const uint8_t* qual, const StatSeg* 
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-#define RQ_WARPS 4
-#define RQ_CHUNK (32 * 60000)   // bases per flush of the 16-bit lane-private counters (< 65536 per lane)
+#define RQ_WARPS 8
 
+// Shared-memory atomics are the fast way to histogram on this part (tools/ubench_hist.cu: a [128]-bin table updated
+// with atomicAdd by 8 warps streams quality bytes at HBM speed, 4x faster than lane-private read-modify-write).
 __global__ void __launch_bounds__(RQ_WARPS * 32)
 k_read_qual(const uint8_t* __restrict__ qualbuf, const StatSeg* __restrict__ segs, int64_t nseg,
             unsigned long long* __restrict__ stats, int64_t C, fpl_read_result* __restrict__ res) {
-    __shared__ uint16_t hist[RQ_WARPS][128][32];       // lane-private columns: no atomics
-    __shared__ uint32_t total[RQ_WARPS][128];          // per-segment histogram
+    __shared__ uint32_t hist[RQ_WARPS][128];           // per-warp: the current segment's histogram
     __shared__ uint32_t block_hist[128];               // all segments of this block -> one flush to mBaseQualHistogram
     __shared__ unsigned long long block_misc[2];       // reads, length sum
     const int wid = threadIdx.x >> 5, lane = lane_id();
@@ -139,62 +217,60 @@ k_read_qual(const uint8_t* __restrict__ qualbuf, const StatSeg* __restrict__ seg
     if (threadIdx.x < 2) block_misc[threadIdx.x] = 0;
     __syncthreads();
     unsigned long long* tail = stats + 16 * C;
-    const int64_t s = (int64_t)blockIdx.x * RQ_WARPS + wid;
-    if (s < nseg) {
+    uint32_t* h = hist[wid];
+    const int64_t nwarps = (int64_t)gridDim.x * RQ_WARPS;
+    for (int64_t s = (int64_t)blockIdx.x * RQ_WARPS + wid; s < nseg; s += nwarps) {
         const StatSeg sg = segs[s];
-        if (sg.read >= 0) {   // a real segment (pre: every read, even empty; post: passing segments only)
-            const uint8_t* qp = qualbuf + sg.off;
-            const int len = sg.len;
-            for (int b = lane; b < 128; b += 32) total[wid][b] = 0;
-            for (int base0 = 0; base0 < len; base0 += RQ_CHUNK) {
-                const int n = min(RQ_CHUNK, len - base0);
-                uint32_t* z = reinterpret_cast<uint32_t*>(&hist[wid][0][0]);
-                for (int i = lane; i < 128 * 32 / 2; i += 32) z[i] = 0;
-                __syncwarp();
-                for (int i = lane; i < n; i += 32) {
-                    const uint8_t q = qp[base0 + i];
-                    hist[wid][q & 127][lane]++;
-                }
-                __syncwarp();
-                // lane b sums bins b, b+32, b+64, b+96 over the 32 columns (rotated start: conflict-free)
-                for (int b = lane; b < 128; b += 32) {
-                    uint32_t acc = 0;
-                    for (int k = 0; k < 32; k++) acc += hist[wid][b][(k + lane) & 31];
-                    total[wid][b] += acc;
-                }
-                __syncwarp();
-            }
-            // median: smallest char m with sum_{c<=m} hist[c] > len>>1 (src/stats.cpp:351-361)
-            uint8_t median = 0;
-            if (len > 0) {
-                const int half = len >> 1;
-                // 4 bins per lane, in order: lane l owns bins 4l..4l+3
-                uint32_t h0 = total[wid][4 * lane], h1 = total[wid][4 * lane + 1], h2 = total[wid][4 * lane + 2],
-                         h3 = total[wid][4 * lane + 3];
-                int incl = warp_incl_scan((int)(h0 + h1 + h2 + h3));
-                int excl = incl - (int)(h0 + h1 + h2 + h3);
-                int m = 1 << 30;
-                int run = excl;
-                run += h0; if (run > half) m = min(m, 4 * lane);
-                run += h1; if (run > half) m = min(m, 4 * lane + 1);
-                run += h2; if (run > half) m = min(m, 4 * lane + 2);
-                run += h3; if (run > half) m = min(m, 4 * lane + 3);
-                m = __reduce_min_sync(0xffffffffu, m);
-                median = (uint8_t)m;
-            }
-            for (int b = lane; b < 128; b += 32)
-                if (total[wid][b]) atomicAdd(&block_hist[b], total[wid][b]);
-            if (lane == 0) {
-                atomicAdd(&block_misc[0], 1ull);
-                atomicAdd(&block_misc[1], (unsigned long long)len);
-                if (len > 0) {
-                    atomicAdd(&tail[FPL_STATS_MEDHIST + median], 1ull);
-                    atomicAdd(&tail[FPL_STATS_MEDBASES + median], (unsigned long long)len);
-                }
-                if (sg.slot == 2) res[sg.read].pre_median_qual = median;
-                else res[sg.read].seg_median_qual[sg.slot] = median;
-            }
+        if (sg.read < 0) continue;   // pre: every read, even empty; post: passing segments only
+        const uint8_t* qp = qualbuf + sg.off;
+        const int len = sg.len;
+        for (int b = lane; b < 128; b += 32) h[b] = 0;
+        __syncwarp();
+        // head bytes up to 16-byte alignment, vector body, tail bytes
+        const int head = min(len, (int)((16 - (reinterpret_cast<uintptr_t>(qp) & 15)) & 15));
+        if (lane < head) atomicAdd(&h[qp[lane] & 127], 1u);
+        const int nvec = (len - head) >> 4;
+        const uint4* vp = reinterpret_cast<const uint4*>(qp + head);
+        for (int i = lane; i < nvec; i += 32) {
+            const uint4 v = __ldg(vp + i);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) atomicAdd(&h[(w[k] >> (8 * j)) & 127u], 1u);
         }
+        const int done = head + (nvec << 4);
+        if (done + lane < len) atomicAdd(&h[qp[done + lane] & 127], 1u);   // < 16 tail bytes
+        __syncwarp();
+        // median: smallest char m with sum_{c<=m} hist[c] > len>>1 (src/stats.cpp:351-361); lane l owns bins 4l..4l+3
+        const uint32_t h0 = h[4 * lane], h1 = h[4 * lane + 1], h2 = h[4 * lane + 2], h3 = h[4 * lane + 3];
+        uint8_t median = 0;
+        if (len > 0) {
+            const int half = len >> 1;
+            const int incl = warp_incl_scan((int)(h0 + h1 + h2 + h3));
+            int run = incl - (int)(h0 + h1 + h2 + h3);
+            int m = 1 << 30;
+            run += h0; if (run > half) m = min(m, 4 * lane);
+            run += h1; if (run > half) m = min(m, 4 * lane + 1);
+            run += h2; if (run > half) m = min(m, 4 * lane + 2);
+            run += h3; if (run > half) m = min(m, 4 * lane + 3);
+            median = (uint8_t)__reduce_min_sync(0xffffffffu, m);
+        }
+        if (h0) atomicAdd(&block_hist[4 * lane], h0);
+        if (h1) atomicAdd(&block_hist[4 * lane + 1], h1);
+        if (h2) atomicAdd(&block_hist[4 * lane + 2], h2);
+        if (h3) atomicAdd(&block_hist[4 * lane + 3], h3);
+        if (lane == 0) {
+            atomicAdd(&block_misc[0], 1ull);
+            atomicAdd(&block_misc[1], (unsigned long long)len);
+            if (len > 0) {
+                atomicAdd(&tail[FPL_STATS_MEDHIST + median], 1ull);
+                atomicAdd(&tail[FPL_STATS_MEDBASES + median], (unsigned long long)len);
+            }
+            if (sg.slot == 2) res[sg.read].pre_median_qual = median;
+            else res[sg.read].seg_median_qual[sg.slot] = median;
+        }
+        __syncwarp();
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 128; i += blockDim.x)
@@ -208,7 +284,10 @@ k_read_qual(const uint8_t* __restrict__ qualbuf, const StatSeg* __restrict__ seg
 void launch_read_qual(const uint8_t* qual, const StatSeg* segs, int64_t nseg, unsigned long long* stats, int64_t C,
                       fpl_read_result* res, cudaStream_t stream) {
     if (nseg == 0) return;
-    k_read_qual<<<(unsigned)((nseg + RQ_WARPS - 1) / RQ_WARPS), RQ_WARPS * 32, 0, stream>>>(qual, segs, nseg, stats, C, res);
+    // persistent-ish grid: enough blocks to fill the GPU several times over, each warp strides over the segments
+    const int64_t want = (nseg + RQ_WARPS - 1) / RQ_WARPS;
+    const unsigned grid = (unsigned)(want < 148 * 64 ? want : 148 * 64);
+    k_read_qual<<<grid, RQ_WARPS * 32, 0, stream>>>(qual, segs, nseg, stats, C, res);
 }
 
 // pre-stats segment list: every input read, full length
