@@ -269,10 +269,10 @@ int fpl_create(const fpl_options* opt, const fpl_adapters* ad, fpl_ctx** out) {
             if (len < 1) { fast = false; break; }
             if (len > maxa) maxa = len;
             for (int i = 0; i < len; i++) {
-                int letter = s[i] == 'A' ? 0 : s[i] == 'C' ? 1 : s[i] == 'G' ? 2 : s[i] == 'T' ? 3 : -1;
-                if (letter < 0) { fast = false; break; }
-                uint8_t& n = c->plan.cnt[k][letter][i >> 5];
-                c->plan.shift[k][letter][i >> 5][n++] = (uint8_t)(i & 31);
+                const char ch = s[i];
+                if (ch != 'A' && ch != 'C' && ch != 'G' && ch != 'T') { fast = false; break; }
+                c->plan.hm[k][i] = (ch & 2) ? 0xFFFFFFFFu : 0u;   // code bit HI = byte bit 1
+                c->plan.lm[k][i] = (ch & 4) ? 0xFFFFFFFFu : 0u;   // code bit LO = byte bit 2
             }
         }
         c->plan.fast = fast ? 1 : 0;

@@ -56,3 +56,27 @@ __device__ __forceinline__ int warp_incl_scan(int v) {
     }
     return v;
 }
+
+// Levenshtein distance (Myers/Hyyro bit-parallel, global), pattern = adapter bits [shift, shift+m) with
+// shift+m <= 32, text = n read bytes.  Exact, == edit_distance() of src/editdistance.cpp:100-126.
+__device__ __forceinline__ int myers32(const uint8_t* text, int n, const uint4* peq, int shift, int m) {
+    if (m == 0) return n;
+    if (n == 0) return m;
+    const uint32_t mask = m >= 32 ? 0xFFFFFFFFu : ((1u << m) - 1u);
+    uint32_t VP = mask, VN = 0;
+    const uint32_t top = 1u << (m - 1);
+    int score = m;
+    for (int i = 0; i < n; i++) {
+        const uint32_t Eq = (__ldg(&peq[text[i]].x) >> shift) & mask;
+        const uint32_t Xv = Eq | VN;
+        const uint32_t Xh = (((Eq & VP) + VP) ^ VP) | Eq;
+        uint32_t HP = VN | ~(Xh | VP);
+        uint32_t HN = VP & Xh;
+        score += (HP & top) ? 1 : ((HN & top) ? -1 : 0);
+        HP = (HP << 1) | 1u;
+        HN = HN << 1;
+        VP = HN | ~(Xv | HP);
+        VN = HP & Xv;
+    }
+    return score;
+}

@@ -2,20 +2,20 @@
 // selected by the host when both -s/-e adapters are non-empty, ACGT-only and <= 128 bp).
 //
 // Data layout per warp-tile: 32 lanes x 32 consecutive bytes (two 16-byte vector loads per lane, coalesced).
-//   1. each lane turns its 32 sequence bytes into four 32-bit bit-planes (bits 0,1,2,4 of every byte; one
-//      AND + IMAD + funnel-shift per word per plane) and checks (b & 0xE8) == 0x40 for all of them; under that
-//      check the planes decide exactly which bytes are A, C, G or T.  Lanes that fail it (N or any other
-//      byte) build their four letter masks byte by byte.
-//   2. each lane fetches its neighbours' letter masks with warp shuffles, so that the mask of adapter letter a_i
-//      shifted by i positions is one funnel shift of two registers (the shift amounts per letter come from the
-//      host-built ScanPlan, four per 32-bit uniform load);
-//   3. the alen shifted masks are summed per bit position with carry-save adders (3:2 compressors are two LOP3
-//      each, Harley-Seal blocks of 4 inputs) into a bit-sliced match counter; H(p) = alen - matches(p);
+//   1. each lane turns its 32 sequence bytes into five 32-bit bit-planes (bits 0..4 of every byte; one
+//      AND + IMAD + funnel-shift per word per plane) and checks (b & 0xE0) == 0x40 for all of them (0x40..0x5F:
+//      every upper-case letter).  Under that check the planes decide exactly which bytes are A, C, G, T (plane V),
+//      their 2-bit code (HI = bit 1, LO = bit 2) and which are 'N'.  Lanes holding any other byte take a per-byte path.
+//   2. adapter letter a_i matches read position p+i iff V & (HI == h_i) & (LO == l_i) there: three funnel shifts by
+//      the static amount i (shared by both adapters) and two LOP3 whose third operands h_i / l_i come straight from
+//      the constant bank (ScanPlan.hm / lm), statically indexed because the loop over i is fully unrolled;
+//   3. the alen one-bit match vectors are summed per position with carry-save adders (3:2 compressors are two LOP3
+//      each, Harley-Seal blocks of 8) into a bit-sliced match counter; H(p) = alen - matches(p);
 //   4. a bit-sliced arg-max (MSB-first candidate narrowing) gives each lane its best position of the tile; the
 //      first arg-min of the whole read falls out of a (H << 32 | pos) min-reduction (strict '<' of
 //      src/adaptertrimmer.cpp:148 == smallest position among equal H).
-// Quality bytes: sum via dp4a, #(q < qualified) via one SWAR compare per word; N count is zero by construction in
-// lanes that passed the alphabet check; the complexity count compares each word with itself shifted by one byte.
+// Quality bytes: sum via dp4a, #(q < qualified) via one SWAR compare per word; N count = popcount of the N plane;
+// the complexity count compares each word with itself shifted by one byte.
 #include "fpl_device.cuh"
 #include "fpl_scanplan.h"
 
@@ -24,15 +24,12 @@
 
 namespace {
 
-__device__ __forceinline__ uint32_t lop3_xor3(uint32_t a, uint32_t b, uint32_t c) { return a ^ b ^ c; }
-__device__ __forceinline__ uint32_t lop3_maj(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (c & (a | b)); }
-
-// carry-save adder: (h, l) = a + b + c per bit position
-#define CSA(h, l, a, b, c)                \
-    do {                                  \
-        uint32_t a_ = (a), b_ = (b), c_ = (c); \
-        l = lop3_xor3(a_, b_, c_);        \
-        h = lop3_maj(a_, b_, c_);         \
+// carry-save adder: (h, l) = a + b + c per bit position (two LOP3)
+#define CSA(h, l, a, b, c)                       \
+    do {                                         \
+        const uint32_t a_ = (a), b_ = (b), c_ = (c); \
+        l = a_ ^ b_ ^ c_;                        \
+        h = (a_ & b_) | (c_ & (a_ | b_));        \
     } while (0)
 
 __device__ __forceinline__ uint32_t plane_nibble(uint32_t w, uint32_t mask, uint32_t mul) { return (w & mask) * mul; }
@@ -54,67 +51,54 @@ __device__ __forceinline__ void load32(const uint8_t* p, bool ok, LaneSeq& s) {
     }
 }
 
-// One Harley-Seal block of four 1-bit inputs into the bit-sliced counter (ones, twos, cnt[2..NPL-1]).
+// bit-sliced counter of matches for one adapter
 template <int NPL>
-__device__ __forceinline__ void add4(uint32_t& ones, uint32_t& twos, uint32_t (&cnt)[NPL], uint32_t x0, uint32_t x1,
-                                     uint32_t x2, uint32_t x3) {
-    uint32_t tA, tB, f;
-    CSA(tA, ones, ones, x0, x1);
-    CSA(tB, ones, ones, x2, x3);
-    CSA(f, twos, twos, tA, tB);
-    uint32_t carry = f;   // weight 4
+struct Counter {
+    uint32_t ones, twos, fours, hi[NPL > 3 ? NPL - 3 : 1];
+    __device__ __forceinline__ void clear() {
+        ones = twos = fours = 0;
 #pragma unroll
-    for (int b = 2; b < NPL; b++) {
-        const uint32_t t = cnt[b] & carry;
-        cnt[b] ^= carry;
-        carry = t;
+        for (int b = 0; b < NPL - 3; b++) hi[b] = 0;
     }
-}
-
-// matches(p) for one adapter over the lane's 32 positions, then the lane-local arg-max (first position).
-// M[l][w] = letter-l mask of the 32 positions starting 32*w after this lane's first position.
-template <int NPL, int HL>
-__device__ __forceinline__ void scan_adapter(const ScanPlan& plan, int which, const uint32_t (&M)[4][HL + 1],
-                                             uint32_t valid, int64_t pos0, int& bestM, int64_t& bestPos) {
-    uint32_t cnt[NPL];
+    __device__ __forceinline__ void add8(const uint32_t (&x)[8]) {
+        uint32_t twosA, twosB, foursA, foursB, eight;
+        CSA(twosA, ones, ones, x[0], x[1]);
+        CSA(twosB, ones, ones, x[2], x[3]);
+        CSA(foursA, twos, twos, twosA, twosB);
+        CSA(twosA, ones, ones, x[4], x[5]);
+        CSA(twosB, ones, ones, x[6], x[7]);
+        CSA(foursB, twos, twos, twosA, twosB);
+        CSA(eight, fours, fours, foursA, foursB);
+        uint32_t carry = eight;
 #pragma unroll
-    for (int b = 0; b < NPL; b++) cnt[b] = 0;
-    uint32_t ones = 0, twos = 0;
-#pragma unroll
-    for (int l = 0; l < 4; l++) {
-#pragma unroll
-        for (int w = 0; w < HL; w++) {
-            const uint32_t lo = M[l][w], hi = M[l][w + 1];
-            const int n = plan.cnt[which][l][w];                       // warp-uniform
-            const uint32_t* sh4 = reinterpret_cast<const uint32_t*>(&plan.shift[which][l][w][0]);
-            int k = 0;
-            for (; k + 4 <= n; k += 4) {
-                const uint32_t v = sh4[k >> 2];                         // four shift amounts (funnel shift wraps at 32)
-                add4<NPL>(ones, twos, cnt, __funnelshift_r(lo, hi, v), __funnelshift_r(lo, hi, v >> 8),
-                          __funnelshift_r(lo, hi, v >> 16), __funnelshift_r(lo, hi, v >> 24));
-            }
-            if (k < n) {
-                const int r = n - k;
-                const uint32_t v = sh4[k >> 2];
-                const uint32_t x0 = __funnelshift_r(lo, hi, v);
-                const uint32_t x1 = r > 1 ? __funnelshift_r(lo, hi, v >> 8) : 0u;
-                const uint32_t x2 = r > 2 ? __funnelshift_r(lo, hi, v >> 16) : 0u;
-                add4<NPL>(ones, twos, cnt, x0, x1, x2, 0u);
-            }
+        for (int b = 0; b < NPL - 3; b++) {
+            const uint32_t t = hi[b] & carry;
+            hi[b] ^= carry;
+            carry = t;
         }
     }
-    cnt[0] = ones; cnt[1] = twos;
-    if (valid) {
+    __device__ __forceinline__ void add1(uint32_t x) {   // ripple a single input (tail of an adapter, < 8 inputs)
+        uint32_t carry = x, t;
+        t = ones & carry; ones ^= carry; carry = t;
+        t = twos & carry; twos ^= carry; carry = t;
+        t = fours & carry; fours ^= carry; carry = t;
+#pragma unroll
+        for (int b = 0; b < NPL - 3; b++) { t = hi[b] & carry; hi[b] ^= carry; carry = t; }
+    }
+    __device__ __forceinline__ uint32_t plane(int b) const { return b == 0 ? ones : b == 1 ? twos : b == 2 ? fours : hi[b - 3]; }
+    // lane-local arg-max over the positions in `valid`, first position on ties
+    __device__ __forceinline__ void argmax(uint32_t valid, int64_t pos0, int& bestM, int64_t& bestPos) const {
+        if (!valid) return;
         uint32_t cand = valid;
         int val = 0;
 #pragma unroll
         for (int b = NPL - 1; b >= 0; b--) {
-            const uint32_t t = cand & cnt[b];
+            const uint32_t t = cand & plane(b);
             if (t) { cand = t; val |= 1 << b; }
         }
         if (val > bestM) { bestM = val; bestPos = pos0 + (__ffs(cand) - 1); }
     }
-}
+};
 
 }  // namespace
 
@@ -140,6 +124,7 @@ k_scan_fast(const __grid_constant__ DevParams P, const __grid_constant__ ScanPla
     const uint32_t qq4 = (uint32_t)(P.opt.qualified_qual & 0x7f) * 0x01010101u;
     const int np0 = (doAdapters && alen0 <= len) ? len - alen0 : 0;
     const int np1 = (doAdapters && alen1 <= len) ? len - alen1 : 0;
+    const int amax = max(alen0, alen1);
     const int step = (32 - HL) * 32;                      // bytes advanced per warp-tile
     const int total = pre + len;                          // bytes from the aligned base to the window end
 
@@ -155,40 +140,37 @@ k_scan_fast(const __grid_constant__ DevParams P, const __grid_constant__ ScanPla
         // ---- alphabet check + bit planes ----
         uint32_t bad = 0;
 #pragma unroll
-        for (int k = 0; k < 8; k++) bad |= (sq.w[k] & 0xE8E8E8E8u) ^ 0x40404040u;
-        // bytes outside the window may be anything: they are masked by `valid` below, but they must not send a
-        // clean lane to the slow path needlessly -> only the exactness matters, so no special casing here.
-        uint32_t MA, MC, MG, MT;
+        for (int k = 0; k < 8; k++) bad |= (sq.w[k] & 0xE0E0E0E0u) ^ 0x40404040u;
+        uint32_t V, HI, LO, NM;
         if (bad == 0) {
-            uint32_t B0 = 0, B1 = 0, B2 = 0, B4 = 0;
+            uint32_t B0 = 0, B1 = 0, B2 = 0, B3 = 0, B4 = 0;
 #pragma unroll
             for (int k = 7; k >= 0; k--) {
                 const uint32_t w = sq.w[k];
                 B0 = __funnelshift_l(plane_nibble(w, 0x01010101u, 0x10204080u), B0, 4);
                 B1 = __funnelshift_l(plane_nibble(w, 0x02020202u, 0x08102040u), B1, 4);
                 B2 = __funnelshift_l(plane_nibble(w, 0x04040404u, 0x04081020u), B2, 4);
+                B3 = __funnelshift_l(plane_nibble(w, 0x08080808u, 0x02040810u), B3, 4);
                 B4 = __funnelshift_l(plane_nibble(w, 0x10101010u, 0x01020408u), B4, 4);
             }
-            const uint32_t acg = ~B4 & B0;
-            MA = acg & ~B1 & ~B2;
-            MC = acg & B1 & ~B2;
-            MG = acg & B1 & B2;
-            MT = B4 & ~B0 & ~B1 & B2;
+            // bytes are 010 b4 b3 b2 b1 b0:  A 00001  C 00011  G 00111  T 10100  N 01110
+            V = ~B3 & ((~B4 & B0 & (B1 | ~B2)) | (B4 & B2 & ~B1 & ~B0));
+            HI = B1; LO = B2;
+            NM = B3 & B2 & B1 & ~B0 & ~B4;
         } else {
-            MA = MC = MG = MT = 0;
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const uint32_t ch = (sq.w[k] >> (8 * j)) & 0xFFu;
-                    const uint32_t bit = 1u << (4 * k + j);
-                    MA |= ch == 'A' ? bit : 0u; MC |= ch == 'C' ? bit : 0u;
-                    MG |= ch == 'G' ? bit : 0u; MT |= ch == 'T' ? bit : 0u;
+            V = HI = LO = NM = 0;
+            for (int j = 0; j < 32; j++) {
+                const uint32_t ch = (sq.w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+                const uint32_t bit = 1u << j;
+                if (ch == 'A' || ch == 'C' || ch == 'G' || ch == 'T') {
+                    V |= bit;
+                    if (ch & 2u) HI |= bit;
+                    if (ch & 4u) LO |= bit;
                 }
+                if (ch == 'N') NM |= bit;
             }
         }
         // ---- window masks for this lane: which of its 32 bytes are inside the window / are scan positions ----
-        // byte index a <-> window position p = a - pre
         const int64_t p_first = a0 - pre;                 // window position of bit 0
         const bool mine = lane < 32 - HL;                 // halo lanes are re-processed by the next tile
         uint32_t inwin = 0, v0 = 0, v1 = 0;
@@ -205,39 +187,32 @@ k_scan_fast(const __grid_constant__ DevParams P, const __grid_constant__ ScanPla
             v0 = range_mask(np0);
             v1 = range_mask(np1);
         }
-        // ---- passFilter / complexity counts ----
-        if (inwin && (doCounts || doCplx)) {
-            if (doCounts) {
-                LaneSeq qv;
-                load32(qbase + a0, true, qv);
-                if (inwin == 0xFFFFFFFFu) {
+        // ---- passFilter counts ----
+        if (inwin && doCounts) {
+            LaneSeq qv;
+            load32(qbase + a0, true, qv);
+            if (inwin == 0xFFFFFFFFu) {
 #pragma unroll
-                    for (int k = 0; k < 8; k++) {
-                        const uint32_t q = qv.w[k];
-                        totalq = (int)__dp4a(q, 0x01010101u, (unsigned)totalq);
-                        const uint32_t ge = ((q | 0x80808080u) - qq4) & 0x80808080u;   // bit7: q >= qualified
-                        lowq_ge += __popc(ge);
+                for (int k = 0; k < 8; k++) {
+                    const uint32_t q = qv.w[k];
+                    totalq = (int)__dp4a(q, 0x01010101u, (unsigned)totalq);
+                    lowq_ge += __popc(((q | 0x80808080u) - qq4) & 0x80808080u);   // bit7: q >= qualified
+                }
+                nbytes += 32;
+            } else {
+                for (int j = 0; j < 32; j++)
+                    if (inwin >> j & 1u) {
+                        const int q = (int)((qv.w[j >> 2] >> (8 * (j & 3))) & 0xFFu);
+                        totalq += q;
+                        lowq_ge += (q & 0x7f) >= (int)(qq4 & 0x7f);
+                        nbytes++;
                     }
-                    nbytes += 32;
-                } else {
-                    for (int j = 0; j < 32; j++)
-                        if (inwin >> j & 1u) {
-                            const int q = (int)((qv.w[j >> 2] >> (8 * (j & 3))) & 0xFFu);
-                            totalq += q;
-                            lowq_ge += (q & 0x7f) >= (int)(qq4 & 0x7f);
-                            nbytes++;
-                        }
-                }
-                if (bad) {   // only lanes with a non-ACGT byte can hold an 'N'
-                    for (int j = 0; j < 32; j++)
-                        if (inwin >> j & 1u) nn += ((sq.w[j >> 2] >> (8 * (j & 3))) & 0xFFu) == 'N';
-                }
             }
+            nn += __popc(NM & inwin);
         }
         if (doCplx) {   // warp-uniform: pairs (i, i+1), i < len-1; byte 31's partner is the next lane's first byte
             const uint32_t nxt = __shfl_down_sync(0xffffffffu, sq.w[0], 1);
             if (inwin) {
-                // pair mask: positions p with p < len-1
                 uint32_t pm = inwin;
                 const int64_t last = (int64_t)len - 1 - p_first;   // bit index of the window's last byte
                 if (last >= 0 && last < 32) pm &= ~(1u << last);
@@ -260,17 +235,71 @@ k_scan_fast(const __grid_constant__ DevParams P, const __grid_constant__ ScanPla
         }
         // ---- Hamming scans ----
         if (doAdapters) {
-            // letter masks of this lane's word and of the HL following words (neighbour lanes; the last HL lanes of
-            // the tile read wrapped garbage, their results are masked out by `mine`)
-            uint32_t M[4][HL + 1];
-            M[0][0] = MA; M[1][0] = MC; M[2][0] = MG; M[3][0] = MT;
+            // planes of this lane's word and of the HL following words (neighbour lanes; the last HL lanes of the tile
+            // read wrapped garbage, their results are masked out by `mine`)
+            uint32_t PV[HL + 1], P1[HL + 1], P2[HL + 1];
+            PV[0] = V; P1[0] = HI; P2[0] = LO;
 #pragma unroll
             for (int w = 1; w <= HL; w++) {
-                M[0][w] = __shfl_down_sync(0xffffffffu, MA, w); M[1][w] = __shfl_down_sync(0xffffffffu, MC, w);
-                M[2][w] = __shfl_down_sync(0xffffffffu, MG, w); M[3][w] = __shfl_down_sync(0xffffffffu, MT, w);
+                PV[w] = __shfl_down_sync(0xffffffffu, V, w);
+                P1[w] = __shfl_down_sync(0xffffffffu, HI, w);
+                P2[w] = __shfl_down_sync(0xffffffffu, LO, w);
             }
-            scan_adapter<NPL, HL>(plan, 0, M, v0, p_first, bestM0, bestP0);
-            scan_adapter<NPL, HL>(plan, 1, M, v1, p_first, bestM1, bestP1);
+            Counter<NPL> c0, c1;
+            c0.clear(); c1.clear();
+#pragma unroll
+            for (int i0 = 0; i0 < HL * 32; i0 += 8) {
+                if (i0 + 8 <= amax) {                      // warp-uniform
+                    uint32_t sv[8], s1[8], s2[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const int i = i0 + j, w = i >> 5, sh = i & 31;
+                        sv[j] = __funnelshift_r(PV[w], PV[w + 1], sh);
+                        s1[j] = __funnelshift_r(P1[w], P1[w + 1], sh);
+                        s2[j] = __funnelshift_r(P2[w], P2[w + 1], sh);
+                    }
+                    if (i0 + 8 <= alen0) {
+                        uint32_t x[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            const uint32_t u = sv[j] & ~(s1[j] ^ plan.hm[0][i0 + j]);
+                            x[j] = u & ~(s2[j] ^ plan.lm[0][i0 + j]);
+                        }
+                        c0.add8(x);
+                    }
+                    if (i0 + 8 <= alen1) {
+                        uint32_t x[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            const uint32_t u = sv[j] & ~(s1[j] ^ plan.hm[1][i0 + j]);
+                            x[j] = u & ~(s2[j] ^ plan.lm[1][i0 + j]);
+                        }
+                        c1.add8(x);
+                    }
+                }
+            }
+            // tails: the alen % 8 letters after the last full block, one at a time (runtime shift, runtime table index)
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const int alen = k ? alen1 : alen0;
+                const int i0 = alen & ~7;
+                if (i0 < alen) {
+                    const int w = i0 >> 5;                  // the whole tail lies in one 32-position word
+                    uint32_t tv = PV[0], tvn = PV[1], t1 = P1[0], t1n = P1[1], t2 = P2[0], t2n = P2[1];
+#pragma unroll
+                    for (int ww = 1; ww < HL; ww++)
+                        if (w == ww) { tv = PV[ww]; tvn = PV[ww + 1]; t1 = P1[ww]; t1n = P1[ww + 1]; t2 = P2[ww]; t2n = P2[ww + 1]; }
+                    for (int i = i0; i < alen; i++) {
+                        const uint32_t xv = __funnelshift_r(tv, tvn, i), x1 = __funnelshift_r(t1, t1n, i),
+                                       x2 = __funnelshift_r(t2, t2n, i);
+                        const uint32_t u = xv & ~(x1 ^ plan.hm[k][i]);
+                        const uint32_t x = u & ~(x2 ^ plan.lm[k][i]);
+                        if (k) c1.add1(x); else c0.add1(x);
+                    }
+                }
+            }
+            c0.argmax(v0, p_first, bestM0, bestP0);
+            c1.argmax(v1, p_first, bestM1, bestP1);
         }
     }
     // ---- block reduction ----

@@ -116,59 +116,70 @@ k_cycle_stats(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qu
         __syncthreads();
         const int n = d_n;
         if (n) any = true;
-        for (int k = wid; k < n; k += CS_WARPS) {
+        // software pipeline: the vectors of segment k+CS_WARPS are in flight while segment k is processed
+        uint32_t nsw[4] = {0, 0, 0, 0}, nqw[4] = {0, 0, 0, 0}, nprev0 = 0;
+        int nlen = 0;
+        auto fetch = [&](int k) {
             const int64_t off = d_off[k];
-            const int len = d_len[k];
+            nlen = d_len[k];
             const uint8_t* sp = seqbuf + off + c0;
-            const uint8_t* qp = qualbuf + off + c0;
-            const bool active = cl < len;
-            uint32_t sw[4] = {0, 0, 0, 0}, qw[4] = {0, 0, 0, 0};
-            if (active) {
-                load16(sp + 16 * lane, sw);
-                load16(qp + 16 * lane, qw);
+            if (cl < nlen) {
+                load16(sp + 16 * lane, nsw);
+                load16(qualbuf + off + c0 + 16 * lane, nqw);
+            } else {
+                nsw[0] = nsw[1] = nsw[2] = nsw[3] = 0;
             }
-            // the 4 bases before this lane's vector: previous lane's last word, or a load in front of the tile
-            uint32_t prev = __shfl_up_sync(0xffffffffu, sw[3], 1);
-            if (lane == 0) prev = c0 >= 4 ? load4_before(sp) : 0u;
+            if (lane == 0) nprev0 = c0 >= 4 ? load4_before(sp) : 0u;
+        };
+        if (wid < n) fetch(wid);
+        for (int k = wid; k < n; k += CS_WARPS) {
+            uint32_t sw[4], qw[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) { sw[i] = nsw[i]; qw[i] = nqw[i]; }
+            const int len = nlen;
+            const uint32_t prev0 = nprev0;
+            if (k + CS_WARPS < n) fetch(k + CS_WARPS);
+            const bool active = cl < len;
+            // per word: validity nibble (A,C,G,T,U) and four 2-bit codes; the previous lane's last word supplies the
+            // four bases in front of this lane's vector (lane 0: the word loaded in front of the tile)
+            uint32_t vn[4], pc[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                vn[i] = active ? (valid_acgtu(sw[i]) * 0x10204080u) >> 28 : 0u;
+                pc[i] = pack_codes(sw[i]);
+            }
+            uint32_t pvn = __shfl_up_sync(0xffffffffu, vn[3], 1), ppc = __shfl_up_sync(0xffffffffu, pc[3], 1);
+            if (lane == 0) { pvn = (valid_acgtu(prev0) * 0x10204080u) >> 28; ppc = pack_codes(prev0); }
             if (!active) continue;
             const int nvalid = (int)min((int64_t)16, (int64_t)len - cl);
-            if (nvalid == 16) {
+            // ---- per-(bin, cycle) counters: word = count << 20 | sum of quality chars ----
+            const uint32_t lane4 = (uint32_t)lane * 4u;
+            uint8_t* pk = reinterpret_cast<uint8_t*>(&packed[0][0]);
 #pragma unroll
-                for (int w = 0; w < 4; w++)
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const uint32_t base = (sw[w] >> (8 * j)) & 0xFFu, q = (qw[w] >> (8 * j)) & 0xFFu;
-                        atomicAdd(&packed[base & 7u][(4 * w + j) * 32 + lane], (1u << 20) + q);
-                    }
-            } else {
-                for (int t = 0; t < nvalid; t++) {
-                    const uint32_t base = (sw[t >> 2] >> (8 * (t & 3))) & 0xFFu, q = (qw[t >> 2] >> (8 * (t & 3))) & 0xFFu;
-                    atomicAdd(&packed[base & 7u][t * 32 + lane], (1u << 20) + q);
+            for (int t = 0; t < 16; t++) {
+                if (t < nvalid) {
+                    const uint32_t w = sw[t >> 2];
+                    const int j = t & 3;
+                    // byte offset of packed[base & 7][t*32 + lane]: (base & 7) << 11 | t << 7 | lane << 2
+                    const uint32_t binoff = j == 0 ? (w << 11) : j == 1 ? (w << 3) : j == 2 ? (w >> 5) : (w >> 13);
+                    const uint32_t addr = (binoff & 0x3800u) | ((uint32_t)t << 7) | lane4;
+                    const uint32_t val = __byte_perm(qw[t >> 2], 0x00100000u, 0x7650 + j);   // q | 1 << 20
+                    atomicAdd(reinterpret_cast<uint32_t*>(pk + addr), val);
                 }
             }
-            // ---- 5-mers ending in this lane's 16 cycles (all five bases in ACGTU, cycle >= 4) ----
-            const uint32_t allv = valid_acgtu(prev) & valid_acgtu(sw[0]) & valid_acgtu(sw[1]) & valid_acgtu(sw[2]) &
-                                  valid_acgtu(sw[3]);
-            if (allv == 0x01010101u && nvalid == 16) {
-                // 20 codes, oldest first, 2 bits each: bits 39..0
-                const unsigned long long P = ((unsigned long long)pack_codes(prev) << 32) | (pack_codes(sw[0]) << 24) |
-                                             (pack_codes(sw[1]) << 16) | (pack_codes(sw[2]) << 8) | pack_codes(sw[3]);
-#pragma unroll
-                for (int t = 0; t < 16; t++)
-                    atomicAdd(&kmer[(uint32_t)(P >> (2 * (15 - t))) & 0x3FFu], 1u);
-            } else {
-                uint32_t code[20];
-#pragma unroll
-                for (int j = 0; j < 4; j++) code[j] = kmer_code((prev >> (8 * j)) & 0xFFu);
-#pragma unroll
-                for (int t = 0; t < 16; t++) code[4 + t] = kmer_code((sw[t >> 2] >> (8 * (t & 3))) & 0xFFu);
+            // ---- 5-mers ending in this lane's 16 cycles: all five bases in ACGTU ----
+            const uint32_t V20 = pvn | (vn[0] << 4) | (vn[1] << 8) | (vn[2] << 12) | (vn[3] << 16);
+            uint32_t ok = V20 & (V20 >> 1) & (V20 >> 2) & (V20 >> 3) & (V20 >> 4);   // bit t: bytes t-4..t all valid
+            if (nvalid < 16) ok &= (1u << nvalid) - 1u;
+            if (ok) {
+                // 20 codes, oldest first, 2 bits each: Phi = codes of bytes -4..11 (32 bits), Plo = bytes 4..15 low part
+                const uint32_t Phi = (ppc << 24) | (pc[0] << 16) | (pc[1] << 8) | pc[2];   // bytes -4..11
+                const uint32_t Plo = (pc[1] << 24) | (pc[2] << 16) | (pc[3] << 8);         // bytes 4..15, then 8 zero bits
 #pragma unroll
                 for (int t = 0; t < 16; t++) {
-                    if (t < nvalid && cl + t >= 4) {
-                        const uint32_t c4 = code[t], c3 = code[t + 1], c2 = code[t + 2], c1 = code[t + 3], cc = code[t + 4];
-                        if (((c4 | c3 | c2 | c1 | cc) & 8u) == 0u)
-                            atomicAdd(&kmer[(c4 << 8) | (c3 << 6) | (c2 << 4) | (c1 << 2) | cc], 1u);
-                    }
+                    // 5-mer ending at byte t = codes of bytes t-4..t
+                    const uint32_t idx = t <= 11 ? (Phi >> (2 * (11 - t))) & 0x3FFu : (Plo >> (2 * (15 - t) + 8)) & 0x3FFu;
+                    if (ok >> t & 1u) atomicAdd(&kmer[idx], 1u);
                 }
             }
         }

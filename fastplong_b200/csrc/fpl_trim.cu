@@ -58,6 +58,10 @@ __device__ int myers128(const uint8_t* text, int n, const uint4* peq, int shift,
     return score;
 }
 
+__device__ __forceinline__ int ed_adapter(const uint8_t* text, int n, const uint4* peq, int shift, int m, int alen) {
+    return alen <= 32 ? myers32(text, n, peq, shift, m) : myers128(text, n, peq, shift, m);
+}
+
 // 16-bit pattern variant for the probe loops (:202-216, :273-286); eq16 = precomputed masks, already shifted.
 __device__ __forceinline__ int myers16(const uint8_t* text, int n, const uint32_t* peq16, bool suffix, int m) {
     uint32_t VP = (1u << m) - 1u, VN = 0;
@@ -120,7 +124,7 @@ __device__ int search_window(const DevParams& P, const uint8_t* rdata, int rlen,
     if (best == 0xFFFFFFFFu) return -1;
     unsigned key = best & 0xFFFFu;
     int pos = p0 + (int)(left ? (0xFFFFu - key) : key);
-    int ed = myers128(rdata + pos, alen, P.peq + (size_t)aidx * 256, 0, alen);
+    int ed = ed_adapter(rdata + pos, alen, P.peq + (size_t)aidx * 256, 0, alen, alen);
     return ed <= T ? pos : -1;
 }
 
@@ -177,7 +181,7 @@ __device__ int trim_start(const DevParams& P, const uint8_t* seq, Win& w, int ai
     if (best != 0xFFFFFFFFu) {
         int pos = (int)(best & 0xFFFFu);
         int cmplen = min(pos + plen, alen);
-        int ed = myers128(rdata + pos + plen - cmplen, cmplen, P.peq + (size_t)aidx * 256, alen - cmplen, cmplen);
+        int ed = ed_adapter(rdata + pos + plen - cmplen, cmplen, P.peq + (size_t)aidx * 256, alen - cmplen, cmplen, alen);
         if (ed <= P.thr[cmplen]) {
             pos = min(pos + ext, rlen - alen);
             ev.add(aidx, 0, cmplen);
@@ -226,7 +230,7 @@ __device__ int trim_end(const DevParams& P, const uint8_t* seq, Win& w, int aidx
     __syncwarp();
     if (pos > 0) {
         int cmplen = min(pos + plen, alen);
-        int ed = myers128(rdata + rlen - plen - pos, cmplen, P.peq + (size_t)aidx * 256, 0, cmplen);
+        int ed = ed_adapter(rdata + rlen - plen - pos, cmplen, P.peq + (size_t)aidx * 256, 0, cmplen, alen);
         if (ed <= P.thr[cmplen]) {
             pos = min(pos + ext, rlen - plen);
             ev.add(aidx, 1, cmplen);
