@@ -273,6 +273,7 @@ int fpl_create(const fpl_options* opt, const fpl_adapters* ad, fpl_ctx** out) {
                 if (ch != 'A' && ch != 'C' && ch != 'G' && ch != 'T') { fast = false; break; }
                 c->plan.hm[k][i] = (ch & 2) ? 0xFFFFFFFFu : 0u;   // code bit HI = byte bit 1
                 c->plan.lm[k][i] = (ch & 4) ? 0xFFFFFFFFu : 0u;   // code bit LO = byte bit 2
+                c->plan.vm[k][i] = 0xFFFFFFFFu;
             }
         }
         c->plan.fast = fast ? 1 : 0;

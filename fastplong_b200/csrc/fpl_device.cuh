@@ -48,6 +48,13 @@ struct StatSeg {
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
+// Shared-memory reduction (no return value) on a 32-bit shared-window address: avoids the generic-address
+// conversion the compiler emits around atomicAdd(&smem[i], v) and never needs a convergence barrier.
+__device__ __forceinline__ void red_shared_add(uint32_t saddr, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t shared_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
 __device__ __forceinline__ int warp_incl_scan(int v) {
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {

@@ -77,14 +77,6 @@ struct Counter {
             carry = t;
         }
     }
-    __device__ __forceinline__ void add1(uint32_t x) {   // ripple a single input (tail of an adapter, < 8 inputs)
-        uint32_t carry = x, t;
-        t = ones & carry; ones ^= carry; carry = t;
-        t = twos & carry; twos ^= carry; carry = t;
-        t = fours & carry; fours ^= carry; carry = t;
-#pragma unroll
-        for (int b = 0; b < NPL - 3; b++) { t = hi[b] & carry; hi[b] ^= carry; carry = t; }
-    }
     __device__ __forceinline__ uint32_t plane(int b) const { return b == 0 ? ones : b == 1 ? twos : b == 2 ? fours : hi[b - 3]; }
     // lane-local arg-max over the positions in `valid`, first position on ties
     __device__ __forceinline__ void argmax(uint32_t valid, int64_t pos0, int& bestM, int64_t& bestPos) const {
@@ -103,7 +95,7 @@ struct Counter {
 }  // namespace
 
 template <int NPL, int HL>
-__global__ void __launch_bounds__(SF_THREADS)
+__global__ void __launch_bounds__(SF_THREADS, 6)
 k_scan_fast(const __grid_constant__ DevParams P, const __grid_constant__ ScanPlan plan, DevBatch b,
             ReadState* __restrict__ st) {
     __shared__ unsigned long long sh64[2][SF_WARPS];
@@ -175,13 +167,12 @@ k_scan_fast(const __grid_constant__ DevParams P, const __grid_constant__ ScanPla
         const bool mine = lane < 32 - HL;                 // halo lanes are re-processed by the next tile
         uint32_t inwin = 0, v0 = 0, v1 = 0;
         if (mine && inrange) {
-            auto range_mask = [&](int64_t n) -> uint32_t {   // bits j with 0 <= p_first + j < n
-                int64_t lo = -p_first; if (lo < 0) lo = 0;
-                int64_t hi = n - p_first; if (hi > 32) hi = 32;
-                if (hi <= lo) return 0u;
-                const uint32_t upto_hi = hi >= 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u);
-                const uint32_t below_lo = lo >= 32 ? 0xFFFFFFFFu : ((1u << lo) - 1u);
-                return upto_hi & ~below_lo;
+            // bits j with 0 <= p_first + j < n  (p_first > -32 here because the lane is in range)
+            const uint32_t from0 = p_first >= 0 ? 0xFFFFFFFFu : (0xFFFFFFFFu << (int)(-p_first));
+            auto range_mask = [&](int n) -> uint32_t {
+                const int64_t hi = (int64_t)n - p_first;   // bits below hi are < n
+                const uint32_t upto = hi >= 32 ? 0xFFFFFFFFu : hi <= 0 ? 0u : ((1u << (int)hi) - 1u);
+                return upto & from0;
             };
             inwin = range_mask(len);
             v0 = range_mask(np0);
@@ -249,7 +240,7 @@ k_scan_fast(const __grid_constant__ DevParams P, const __grid_constant__ ScanPla
             c0.clear(); c1.clear();
 #pragma unroll
             for (int i0 = 0; i0 < HL * 32; i0 += 8) {
-                if (i0 + 8 <= amax) {                      // warp-uniform
+                if (i0 < amax) {                           // warp-uniform
                     uint32_t sv[8], s1[8], s2[8];
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
@@ -258,43 +249,26 @@ k_scan_fast(const __grid_constant__ DevParams P, const __grid_constant__ ScanPla
                         s1[j] = __funnelshift_r(P1[w], P1[w + 1], sh);
                         s2[j] = __funnelshift_r(P2[w], P2[w + 1], sh);
                     }
-                    if (i0 + 8 <= alen0) {
-                        uint32_t x[8];
 #pragma unroll
-                        for (int j = 0; j < 8; j++) {
-                            const uint32_t u = sv[j] & ~(s1[j] ^ plan.hm[0][i0 + j]);
-                            x[j] = u & ~(s2[j] ^ plan.lm[0][i0 + j]);
+                    for (int k = 0; k < 2; k++) {
+                        const int alen = k ? alen1 : alen0;
+                        if (i0 < alen) {                   // warp-uniform
+                            uint32_t x[8];
+                            if (i0 + 8 <= alen) {
+#pragma unroll
+                                for (int j = 0; j < 8; j++) {
+                                    const uint32_t u = sv[j] & ~(s1[j] ^ plan.hm[k][i0 + j]);
+                                    x[j] = u & ~(s2[j] ^ plan.lm[k][i0 + j]);
+                                }
+                            } else {                       // last block of an adapter whose length is not a multiple of 8
+#pragma unroll
+                                for (int j = 0; j < 8; j++) {
+                                    const uint32_t u = sv[j] & ~(s1[j] ^ plan.hm[k][i0 + j]);
+                                    x[j] = u & ~(s2[j] ^ plan.lm[k][i0 + j]) & plan.vm[k][i0 + j];
+                                }
+                            }
+                            if (k) c1.add8(x); else c0.add8(x);
                         }
-                        c0.add8(x);
-                    }
-                    if (i0 + 8 <= alen1) {
-                        uint32_t x[8];
-#pragma unroll
-                        for (int j = 0; j < 8; j++) {
-                            const uint32_t u = sv[j] & ~(s1[j] ^ plan.hm[1][i0 + j]);
-                            x[j] = u & ~(s2[j] ^ plan.lm[1][i0 + j]);
-                        }
-                        c1.add8(x);
-                    }
-                }
-            }
-            // tails: the alen % 8 letters after the last full block, one at a time (runtime shift, runtime table index)
-#pragma unroll
-            for (int k = 0; k < 2; k++) {
-                const int alen = k ? alen1 : alen0;
-                const int i0 = alen & ~7;
-                if (i0 < alen) {
-                    const int w = i0 >> 5;                  // the whole tail lies in one 32-position word
-                    uint32_t tv = PV[0], tvn = PV[1], t1 = P1[0], t1n = P1[1], t2 = P2[0], t2n = P2[1];
-#pragma unroll
-                    for (int ww = 1; ww < HL; ww++)
-                        if (w == ww) { tv = PV[ww]; tvn = PV[ww + 1]; t1 = P1[ww]; t1n = P1[ww + 1]; t2 = P2[ww]; t2n = P2[ww + 1]; }
-                    for (int i = i0; i < alen; i++) {
-                        const uint32_t xv = __funnelshift_r(tv, tvn, i), x1 = __funnelshift_r(t1, t1n, i),
-                                       x2 = __funnelshift_r(t2, t2n, i);
-                        const uint32_t u = xv & ~(x1 ^ plan.hm[k][i]);
-                        const uint32_t x = u & ~(x2 ^ plan.lm[k][i]);
-                        if (k) c1.add1(x); else c0.add1(x);
                     }
                 }
             }

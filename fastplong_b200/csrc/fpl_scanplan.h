@@ -12,4 +12,5 @@ struct ScanPlan {
     // lm = code bit "LO" (byte bit 2).  A=(0,0) C=(1,0) G=(1,1) T=(0,1).
     uint32_t hm[2][128];
     uint32_t lm[2][128];
+    uint32_t vm[2][128];   // all-ones for i < alen, zero beyond (only read in the last, partial block of 8)
 };

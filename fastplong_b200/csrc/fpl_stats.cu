@@ -89,7 +89,7 @@ k_cycle_stats(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qu
               int64_t nseg, unsigned long long* __restrict__ stats, int64_t C) {
     // packed[bin][j*32 + lane]: cycle c0 + 16*lane + j; one word = count << 20 | sum of quality chars
     __shared__ uint32_t packed[8][CS_TILE];
-    __shared__ uint32_t kmer[1024];
+    __shared__ uint32_t kmer[1024 + 32];   // [1024..1055]: sink for the lanes whose 5-mer is not valid
     __shared__ int64_t d_off[CS_STAGE];
     __shared__ int32_t d_len[CS_STAGE];
     __shared__ int d_n;
@@ -100,6 +100,9 @@ k_cycle_stats(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qu
     for (int i = threadIdx.x; i < 1024; i += CS_THREADS) kmer[i] = 0;
     for (int i = threadIdx.x; i < 8 * CS_TILE; i += CS_THREADS) (&packed[0][0])[i] = 0;
     const int64_t cl = c0 + 16 * lane;                     // this lane's first cycle
+    const uint32_t pk_lane = shared_addr(&packed[0][0]) + (uint32_t)lane * 4u;
+    const uint32_t km_base = shared_addr(&kmer[0]);
+    const uint32_t km_sink = km_base + (1024u + (uint32_t)lane) * 4u;
     bool any = false;
     for (int64_t s0 = g0; s0 < g1; s0 += CS_STAGE) {
         __syncthreads();
@@ -153,19 +156,21 @@ k_cycle_stats(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qu
             if (!active) continue;
             const int nvalid = (int)min((int64_t)16, (int64_t)len - cl);
             // ---- per-(bin, cycle) counters: word = count << 20 | sum of quality chars ----
-            const uint32_t lane4 = (uint32_t)lane * 4u;
-            uint8_t* pk = reinterpret_cast<uint8_t*>(&packed[0][0]);
+            // shared byte address of packed[base & 7][t*32 + lane] = pk_lane + ((base & 7) << 11) + (t << 7)
+            auto count = [&](int t) {
+                const uint32_t w = sw[t >> 2];
+                const int j = t & 3;
+                const uint32_t binoff = j == 0 ? (w << 11) : j == 1 ? (w << 3) : j == 2 ? (w >> 5) : (w >> 13);
+                const uint32_t val = __byte_perm(qw[t >> 2], 0x00100000u, 0x7650 + j);   // q | 1 << 20
+                red_shared_add(pk_lane + (binoff & 0x3800u) + ((uint32_t)t << 7), val);
+            };
+            if (nvalid == 16) {
 #pragma unroll
-            for (int t = 0; t < 16; t++) {
-                if (t < nvalid) {
-                    const uint32_t w = sw[t >> 2];
-                    const int j = t & 3;
-                    // byte offset of packed[base & 7][t*32 + lane]: (base & 7) << 11 | t << 7 | lane << 2
-                    const uint32_t binoff = j == 0 ? (w << 11) : j == 1 ? (w << 3) : j == 2 ? (w >> 5) : (w >> 13);
-                    const uint32_t addr = (binoff & 0x3800u) | ((uint32_t)t << 7) | lane4;
-                    const uint32_t val = __byte_perm(qw[t >> 2], 0x00100000u, 0x7650 + j);   // q | 1 << 20
-                    atomicAdd(reinterpret_cast<uint32_t*>(pk + addr), val);
-                }
+                for (int t = 0; t < 16; t++) count(t);
+            } else {
+#pragma unroll
+                for (int t = 0; t < 16; t++)
+                    if (t < nvalid) count(t);
             }
             // ---- 5-mers ending in this lane's 16 cycles: all five bases in ACGTU ----
             const uint32_t V20 = pvn | (vn[0] << 4) | (vn[1] << 8) | (vn[2] << 12) | (vn[3] << 16);
@@ -179,7 +184,8 @@ k_cycle_stats(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qu
                 for (int t = 0; t < 16; t++) {
                     // 5-mer ending at byte t = codes of bytes t-4..t
                     const uint32_t idx = t <= 11 ? (Phi >> (2 * (11 - t))) & 0x3FFu : (Plo >> (2 * (15 - t) + 8)) & 0x3FFu;
-                    if (ok >> t & 1u) atomicAdd(&kmer[idx], 1u);
+                    // invalid 5-mers go to a per-lane sink slot instead of branching around the reduction
+                    red_shared_add((ok >> t & 1u) ? km_base + idx * 4u : km_sink, 1u);
                 }
             }
         }

@@ -1,0 +1,483 @@
+// Drop-in definition of the reference's class SingleEndProcessor (declared in /root/reference/src/seprocessor.h:23-50)
+// whose per-pack hot loop runs on the GPU through the C ABI of include/fplgpu.h.
+//
+// Built by fastplong_b200/host/Makefile together with the UNMODIFIED reference translation units (everything in
+// /root/reference/src except seprocessor.cpp, compiled where they lie) into build/fastplong_gpu: same CLI, same
+// FastqReader / ReadPool / WriterThread / Options / JsonReporter / HtmlReporter, this file in the middle.
+//
+// What stays host-side here is bookkeeping only:
+//   * reader thread -> per-worker pack lists -> worker threads -> writer threads, with the writer's
+//     one-string-per-pack, round-robin-over-workers contract (src/writerthread.cpp:37-48);
+//   * each worker gathers the packs it is dealt into one packed batch (pinned host buffers), calls
+//     fpl_process_host() on its own fpl_ctx, then walks the per-read records in pack order to assemble the output
+//     strings (Read::appendToString, Read::breakByGap names) and to feed FilterResult / Stats exactly what
+//     processSingleEnd would have fed them;
+//   * at the end the device-accumulated Stats blocks and the adapter event table are added into each worker's
+//     Stats / FilterResult objects so that Stats::merge, summarize and the reporters run unchanged.
+// No per-base decision is taken on the host.
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <thread>
+#include <vector>
+#include <unistd.h>
+#include <cuda_runtime_api.h>
+
+// Stats / FilterResult keep their accumulators private and offer no setters (src/stats.h:56-113,
+// src/filterresult.h:58-64); this adapter TU is compiled with the class keys opened so that it can ADD the
+// device-accumulated arrays into them.  The reference's own TUs are compiled untouched.
+#define private public
+#include "stats.h"
+#include "filterresult.h"
+#undef private
+#include "seprocessor.h"
+#include "fastqreader.h"
+#include "jsonreporter.h"
+#include "htmlreporter.h"
+#include "util.h"
+#include "fplgpu.h"
+
+namespace {
+
+// ---- pinned, growable host buffer ----
+template <typename T>
+struct Pinned {
+    T* p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t n) {
+        if (n <= cap) return;
+        size_t want = cap ? cap : 1024;
+        while (want < n) want *= 2;
+        T* q = nullptr;
+        if (cudaMallocHost((void**)&q, want * sizeof(T)) != cudaSuccess) error_exit("fastplong_gpu: cudaMallocHost failed");
+        if (p) cudaFreeHost(p);
+        p = q; cap = want;
+    }
+    ~Pinned() { if (p) cudaFreeHost(p); }
+};
+
+struct GpuWorker {
+    fpl_ctx* ctx = nullptr;
+    Pinned<uint8_t> seq, qual;
+    Pinned<int64_t> offsets;
+    Pinned<int32_t> lens;
+    Pinned<fpl_read_result> results;
+    std::vector<ReadPack*> packs;
+};
+
+// how many bases a worker gathers before it submits (bounded so that host memory stays bounded like the reference's
+// PACK_IN_MEM_LIMIT does, src/common.h:38)
+const int64_t kBatchBases = 48ll << 20;
+const size_t kSlotAlign = 128;
+
+fpl_options makeAbiOptions(Options* o, int device) {
+    fpl_options a;
+    memset(&a, 0, sizeof(a));
+    a.struct_size = sizeof(a);
+    a.device = device;
+    a.trim_front = o->trim.front;
+    a.trim_tail = o->trim.tail;
+    a.cut_front_enabled = o->qualityCut.enabledFront;
+    a.cut_front_window = o->qualityCut.windowSizeFront;
+    a.cut_front_quality = o->qualityCut.qualityFront;
+    a.cut_tail_enabled = o->qualityCut.enabledTail;
+    a.cut_tail_window = o->qualityCut.windowSizeTail;
+    a.cut_tail_quality = o->qualityCut.qualityTail;
+    a.polyx_enabled = o->polyXTrim.enabled;
+    a.polyx_min_len = o->polyXTrim.minLen;
+    a.adapter_enabled = o->adapter.enabled;
+    a.trimming_extension = o->adapter.trimmingExtension;
+    a.ed_max = o->adapter.edMax;
+    a.qual_filter_enabled = o->qualfilter.enabled;
+    a.qualified_qual = o->qualfilter.qualifiedQual;
+    a.unqualified_percent_limit = o->qualfilter.unqualifiedPercentLimit;
+    a.avg_qual_req = o->qualfilter.avgQualReq;
+    a.n_base_percent_limit = o->qualfilter.nBasePercentLimit;
+    a.n_base_limit = o->qualfilter.nBaseLimit;
+    a.length_filter_enabled = o->lengthFilter.enabled;
+    a.length_required = o->lengthFilter.requiredLength;
+    a.length_max = o->lengthFilter.maxLength;
+    a.complexity_enabled = o->complexityFilter.enabled;
+    a.complexity_threshold_pct = (int)(o->complexityFilter.threshold * 100.0 + 0.5);  // src/main.cpp:205 divided an int by 100.0
+    return a;
+}
+
+void check(int rc, const char* what) {
+    if (rc != 0) error_exit(std::string("fastplong_gpu: ") + what + ": " + fpl_last_error());
+}
+
+// "@name" -> "@split-by-adapter-left-name" (Read::breakByGap, src/read.cpp:199-200, 208-209)
+void appendRecord(std::string& out, const std::string& name, const char* tagAfterAt, const char* nameSuffix,
+                  const char* seq, const char* qual, int n, const std::string& strand) {
+    if (tagAfterAt && !name.empty()) {
+        out.append(name, 0, 1);
+        out.append(tagAfterAt);
+        out.append(name, 1, std::string::npos);
+    } else {
+        out.append(name);
+    }
+    if (nameSuffix) { out.push_back(' '); out.append(nameSuffix); }
+    out.push_back('\n');
+    out.append(seq, n);
+    out.push_back('\n');
+    out.append(strand);
+    out.push_back('\n');
+    out.append(qual, n);
+    out.push_back('\n');
+}
+
+void addStatsBlock(Stats* s, const std::vector<int64_t>& blk, int64_t C) {
+    int64_t used = 0;
+    for (int64_t c = 0; c < C; c++)
+        for (int b = 0; b < 8; b++)
+            if (blk[b * C + c]) used = c + 1;
+    if (used > s->mBufLen) s->extendBuffer((int)used);
+    for (int b = 0; b < 8; b++)
+        for (int64_t c = 0; c < used; c++) {
+            const long n = blk[b * C + c], q = blk[8 * C + b * C + c];
+            s->mCycleBaseContents[b][c] += n;
+            s->mCycleBaseQual[b][c] += q;
+            s->mCycleTotalBase[c] += n;      // the two row-sum arrays of src/stats.cpp:306-307
+            s->mCycleTotalQual[c] += q;
+        }
+    const int64_t* t = blk.data() + 16 * C;
+    for (int k = 0; k < 1024; k++) s->mKmer[k] += t[FPL_STATS_KMER + k];
+    for (int k = 0; k < 128; k++) {
+        s->mBaseQualHistogram[k] += t[FPL_STATS_QUALHIST + k];
+        s->mMedianReadQualHistogram[k] += t[FPL_STATS_MEDHIST + k];
+        s->mMedianReadQualBases[k] += t[FPL_STATS_MEDBASES + k];
+    }
+    s->mReads += t[FPL_STATS_READS];
+    s->mLengthSum += t[FPL_STATS_LENSUM];
+}
+
+}  // namespace
+
+// -------------------------------------------------------------------------------------------------------------------
+// The per-worker GPU state lives outside the class (its layout is fixed by the reference header).
+static std::vector<std::unique_ptr<GpuWorker>> g_workers;
+static std::vector<std::string> g_adapters;   // fpl_adapters order
+
+SingleEndProcessor::SingleEndProcessor(Options* opt) {
+    mOptions = opt;
+    mReaderFinished = false;
+    mFinishedThreads = 0;
+    mFilter = new Filter(opt);
+    mLeftWriter = NULL;
+    mFailedWriter = NULL;
+    mInputLists = NULL;
+    mPackReadCounter = 0;
+    mPackProcessedCounter = 0;
+    mReadPool = new ReadPool(mOptions);
+    if (opt->mask.enabled || opt->breakOpt.enabled)
+        error_exit("fastplong_gpu: --mask / --break are not implemented on the GPU path (SURVEY §8f); use the reference binary for them");
+}
+
+SingleEndProcessor::~SingleEndProcessor() {
+    delete mFilter;
+    delete mReadPool;
+    delete[] mInputLists;
+}
+
+void SingleEndProcessor::initOutput() {
+    if (!mOptions->failedOut.empty()) mFailedWriter = new WriterThread(mOptions, mOptions->failedOut);
+    if (mOptions->out.empty() && !mOptions->outputToSTDOUT) return;
+    mLeftWriter = new WriterThread(mOptions, mOptions->out, mOptions->outputToSTDOUT);
+}
+
+void SingleEndProcessor::closeOutput() {
+    delete mLeftWriter; mLeftWriter = NULL;
+    delete mFailedWriter; mFailedWriter = NULL;
+}
+
+void SingleEndProcessor::initConfig(ThreadConfig* config) {
+    if (mOptions->out.empty()) return;
+    if (mOptions->split.enabled) config->initWriterForSplit();
+}
+
+void SingleEndProcessor::recycleToPool(int tid, Read* r) {
+    if (!mReadPool->input(tid, r)) delete r;
+}
+
+void SingleEndProcessor::writerTask(WriterThread* w) {
+    while (true) {
+        if (w->isCompleted()) { w->output(); break; }   // drain what is left, as the reference's loop does
+        w->output();
+    }
+    if (mOptions->verbose) loginfo(w->getFilename() + " writer finished");
+}
+
+// Reader: identical contract to the reference's (16-read packs dealt round-robin, src/seprocessor.cpp:331-429).
+void SingleEndProcessor::readerTask() {
+    if (mOptions->verbose) loginfo("start to load data");
+    FastqReader reader(mOptions->in, true);
+    reader.setReadPool(mReadPool);
+    const int T = mOptions->thread;
+    long total = 0, reported = 0;
+    bool stop = false;
+    while (!stop) {
+        ReadPack* pack = new ReadPack;
+        pack->data = new Read*[PACK_SIZE];
+        pack->count = 0;
+        while (pack->count < PACK_SIZE) {
+            Read* r = reader.read();
+            if (!r) { stop = true; break; }
+            pack->data[pack->count++] = r;
+            total++;
+            if (mOptions->readsToProcess > 0 && total >= mOptions->readsToProcess) { stop = true; break; }
+        }
+        // the reference always emits a final (possibly empty) pack when the input ends on a pack boundary
+        if (pack->count == 0 && !stop) { delete[] pack->data; delete pack; continue; }
+        mInputLists[mPackReadCounter % T]->produce(pack);
+        mPackReadCounter++;
+        if (mOptions->verbose && total >= reported + 1000000) {
+            reported = total;
+            loginfo("loaded " + to_string(reported / 1000000) + "M reads");
+        }
+        // back-pressure: do not run further ahead of the workers than they can hold
+        while (!stop && (long)mPackReadCounter - mPackProcessedCounter > 4L * PACK_IN_MEM_LIMIT * T) usleep(200);
+        if (mLeftWriter)
+            while (!stop && mLeftWriter->bufferLength() > 4L * PACK_IN_MEM_LIMIT * T) usleep(1000);
+    }
+    for (int t = 0; t < T; t++) mInputLists[t]->setProducerFinished();
+    mReaderFinished = true;
+    if (mOptions->verbose) loginfo("Loading completed with " + to_string(mPackReadCounter) + " packs");
+}
+
+// processSingleEnd for a whole batch of packs at once; `pack` == NULL flushes config's pending packs.
+// (The reference calls it once per pack; the GPU path gathers packs, see processorTask.)
+bool SingleEndProcessor::processSingleEnd(ReadPack* pack, ThreadConfig* config) {
+    const int tid = config->getThreadId();
+    GpuWorker& w = *g_workers[tid];
+    if (pack) { w.packs.push_back(pack); return true; }
+    if (w.packs.empty()) return true;
+
+    // ---- gather: packed batch in pinned memory ----
+    size_t nreads = 0, nbytes = 0;
+    for (ReadPack* p : w.packs)
+        for (int i = 0; i < p->count; i++) {
+            nreads++;
+            nbytes += (p->data[i]->mSeq->length() + kSlotAlign - 1) / kSlotAlign * kSlotAlign;
+        }
+    w.seq.reserve(nbytes + 256); w.qual.reserve(nbytes + 256);
+    w.offsets.reserve(nreads + 1); w.lens.reserve(nreads + 1); w.results.reserve(nreads + 1);
+    size_t k = 0, off = 0;
+    for (ReadPack* p : w.packs)
+        for (int i = 0; i < p->count; i++) {
+            Read* r = p->data[i];
+            const size_t n = r->mSeq->length();
+            if (r->mQuality->length() != n) error_exit("sequence and quality have different lengths: " + *r->mName);
+            memcpy(w.seq.p + off, r->mSeq->data(), n);
+            memcpy(w.qual.p + off, r->mQuality->data(), n);
+            w.offsets.p[k] = (int64_t)off;
+            w.lens.p[k] = (int32_t)n;
+            off += (n + kSlotAlign - 1) / kSlotAlign * kSlotAlign;
+            k++;
+        }
+    fpl_batch b;
+    b.seq = w.seq.p; b.qual = w.qual.p; b.offsets = w.offsets.p; b.lens = w.lens.p;
+    b.n_reads = (int64_t)nreads; b.n_bytes = (int64_t)off;
+    check(fpl_process_host(w.ctx, &b, w.results.p), "fpl_process_host");
+
+    // ---- scatter: walk the records in pack order (src/seprocessor.cpp:186-326) ----
+    Stats* pre = config->getPreStats1();
+    Stats* post = config->getPostStats1();
+    FilterResult* fr = config->getFilterResult();
+    k = 0;
+    for (ReadPack* p : w.packs) {
+        string* outstr = new string();
+        string* failedOut = new string();
+        int readPassed = 0;
+        for (int i = 0; i < p->count; i++, k++) {
+            Read* or1 = p->data[i];
+            const fpl_read_result& rr = w.results.p[k];
+            const int L = (int)or1->mSeq->length();
+            const char* seq = or1->mSeq->data();
+            const char* qual = or1->mQuality->data();
+            // per-read lists of Stats::statRead (src/stats.cpp:268-271, 362-368); the arrays come from the device
+            pre->mLengthVec.push_back(L);
+            pre->mNeedCalcLength = true;
+            if (L > 0) pre->mQualLength[(char)rr.pre_median_qual].push_back(L);
+            if (rr.flags & FPL_FLAG_POLYX) fr->addPolyXTrimmed(rr.polyx_base, rr.polyx_len);
+            if (rr.adapter_trimmed_bases > 0) fr->addReadTrimmed(rr.adapter_trimmed_bases);
+            bool passed = false;
+            for (int sgi = 0; sgi < rr.n_segments; sgi++) {
+                const int code = rr.seg_result[sgi];
+                config->addFilterResult(code, 1);
+                if (code == PASS_FILTER) {
+                    const char* tag = NULL;
+                    if (rr.flags & FPL_FLAG_MIDDLE_ADAPTER)
+                        tag = (sgi == 1 || (rr.flags & FPL_FLAG_SEG0_IS_RIGHT)) ? "split-by-adapter-right-" : "split-by-adapter-left-";
+                    appendRecord(*outstr, *or1->mName, tag, NULL, seq + rr.seg_lo[sgi], qual + rr.seg_lo[sgi],
+                                 rr.seg_len[sgi], *or1->mStrand);
+                    passed = true;
+                    post->mLengthVec.push_back(rr.seg_len[sgi]);
+                    post->mNeedCalcLength = true;
+                    if (rr.seg_len[sgi] > 0) post->mQualLength[(char)rr.seg_median_qual[sgi]].push_back(rr.seg_len[sgi]);
+                } else if (mFailedWriter && rr.n_segments == 1) {
+                    // the reference prints the trimmed or1 with the reason tag (src/seprocessor.cpp:278-280)
+                    appendRecord(*failedOut, *or1->mName, NULL, FAILED_TYPES[code], seq + rr.trim_lo, qual + rr.trim_lo,
+                                 rr.trim_len, *or1->mStrand);
+                }
+            }
+            if (passed) readPassed++;
+            recycleToPool(tid, or1);
+        }
+        if (mOptions->split.enabled) {
+            if (!mOptions->out.empty()) config->getWriter1()->writeString(outstr);
+        }
+        if (mLeftWriter) { mLeftWriter->input(tid, outstr); outstr = NULL; }
+        if (mFailedWriter) { mFailedWriter->input(tid, failedOut); failedOut = NULL; }
+        if (mOptions->split.byFileLines) config->markProcessed(readPassed);
+        else config->markProcessed(p->count);
+        delete outstr;
+        delete failedOut;
+        delete[] p->data;
+        delete p;
+    }
+    w.packs.clear();
+    return true;
+}
+
+void SingleEndProcessor::processorTask(ThreadConfig* config) {
+    SingleProducerSingleConsumerList<ReadPack*>* input = config->getInput();
+    int64_t pending = 0;
+    while (true) {
+        if (config->canBeStopped()) break;
+        bool idle = true;
+        while (input->canBeConsumed()) {
+            ReadPack* pack = input->consume();
+            for (int i = 0; i < pack->count; i++) pending += (int64_t)pack->data[i]->mSeq->length();
+            processSingleEnd(pack, config);   // gathers
+            mPackProcessedCounter++;           // "taken": lets the reader run ahead by a bounded number of packs
+            idle = false;
+            if (pending >= kBatchBases) break;
+        }
+        if (pending >= kBatchBases || (idle && pending > 0) || (input->isProducerFinished() && !input->canBeConsumed())) {
+            processSingleEnd(NULL, config);   // submit + scatter
+            pending = 0;
+        }
+        if (input->isProducerFinished() && !input->canBeConsumed()) {
+            if (mOptions->verbose) loginfo("thread " + to_string(config->getThreadId() + 1) + " data processing completed");
+            break;
+        }
+        if (idle) usleep(100);
+    }
+    input->setConsumerFinished();
+    mFinishedThreads++;
+    if (mFinishedThreads == mOptions->thread) {
+        if (mLeftWriter) mLeftWriter->setInputCompleted();
+        if (mFailedWriter) mFailedWriter->setInputCompleted();
+    }
+    if (mOptions->verbose) loginfo("thread " + to_string(config->getThreadId() + 1) + " finished");
+}
+
+bool SingleEndProcessor::process() {
+    if (!mOptions->split.enabled) initOutput();
+    const int T = mOptions->thread;
+
+    // one GPU context per worker thread; workers are spread over the visible devices
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        error_exit("fastplong_gpu: no CUDA device available (this build has no CPU fallback for the hot path)");
+    g_adapters.clear();
+    g_adapters.push_back(mOptions->adapter.sequenceStart);
+    g_adapters.push_back(mOptions->adapter.sequenceEnd);
+    if (mOptions->adapter.hasFasta)
+        for (auto& s : mOptions->adapter.seqsInFasta) g_adapters.push_back(s);
+    std::vector<const char*> fasta;
+    for (size_t i = 2; i < g_adapters.size(); i++) fasta.push_back(g_adapters[i].c_str());
+    fpl_adapters ad;
+    ad.start = g_adapters[0].c_str(); ad.end = g_adapters[1].c_str();
+    ad.n_fasta = (int)fasta.size(); ad.fasta = fasta.empty() ? NULL : fasta.data();
+    g_workers.clear();
+    for (int t = 0; t < T; t++) {
+        g_workers.emplace_back(new GpuWorker());
+        fpl_options o = makeAbiOptions(mOptions, t % ndev);
+        check(fpl_create(&o, &ad, &g_workers[t]->ctx), "fpl_create");
+    }
+
+    mInputLists = new SingleProducerSingleConsumerList<ReadPack*>*[T];
+    std::vector<ThreadConfig*> configs(T);
+    for (int t = 0; t < T; t++) {
+        mInputLists[t] = new SingleProducerSingleConsumerList<ReadPack*>();
+        configs[t] = new ThreadConfig(mOptions, t, false);
+        configs[t]->setInputList(mInputLists[t]);
+        initConfig(configs[t]);
+    }
+
+    std::thread reader(std::bind(&SingleEndProcessor::readerTask, this));
+    std::vector<std::thread> workers;
+    for (int t = 0; t < T; t++) workers.emplace_back(std::bind(&SingleEndProcessor::processorTask, this, configs[t]));
+    std::unique_ptr<std::thread> leftWriter, failedWriter;
+    if (mLeftWriter) leftWriter.reset(new std::thread(std::bind(&SingleEndProcessor::writerTask, this, mLeftWriter)));
+    if (mFailedWriter) failedWriter.reset(new std::thread(std::bind(&SingleEndProcessor::writerTask, this, mFailedWriter)));
+
+    reader.join();
+    for (auto& th : workers) th.join();
+    if (!mOptions->split.enabled) {
+        if (leftWriter) leftWriter->join();
+        if (failedWriter) failedWriter->join();
+    }
+    if (mOptions->verbose) loginfo("start to generate reports\n");
+
+    // ---- device accumulators -> the workers' Stats / FilterResult objects (replaces what statRead / the trimmers
+    //      would have added), then the reference's own merge + reporters ----
+    std::vector<Stats*> preStats, postStats;
+    std::vector<FilterResult*> filterResults;
+    for (int t = 0; t < T; t++) {
+        GpuWorker& w = *g_workers[t];
+        const int64_t C = fpl_stats_cycles(w.ctx);
+        std::vector<int64_t> blk((size_t)FPL_STATS_WORDS(C));
+        check(fpl_stats_download(w.ctx, FPL_STATS_PRE, blk.data(), (int64_t)blk.size()), "fpl_stats_download");
+        addStatsBlock(configs[t]->getPreStats1(), blk, C);
+        check(fpl_stats_download(w.ctx, FPL_STATS_POST, blk.data(), (int64_t)blk.size()), "fpl_stats_download");
+        addStatsBlock(configs[t]->getPostStats1(), blk, C);
+        // adapter (sub)string counts: FilterResult::addAdapterTrimmed (src/filterresult.cpp:69-77)
+        std::vector<int64_t> cnt((size_t)fpl_counter_words(w.ctx));
+        check(fpl_counters_download(w.ctx, cnt.data(), (int64_t)cnt.size()), "fpl_counters_download");
+        FilterResult* fr = configs[t]->getFilterResult();
+        for (size_t a = 0; a < g_adapters.size(); a++)
+            for (int side = 0; side < 2; side++)
+                for (int c = 1; c <= FPL_MAX_ADAPTER_LEN && c <= (int)g_adapters[a].length(); c++) {
+                    const int64_t n = cnt[FPL_CNT_FIXED + (a * 2 + side) * (FPL_MAX_ADAPTER_LEN + 1) + c];
+                    if (!n) continue;
+                    const std::string& ad_ = g_adapters[a];
+                    fr->mAdapter[side == 0 ? ad_.substr(ad_.length() - c, c) : ad_.substr(0, c)] += n;
+                }
+        preStats.push_back(configs[t]->getPreStats1());
+        postStats.push_back(configs[t]->getPostStats1());
+        filterResults.push_back(fr);
+    }
+    Stats* finalPreStats = Stats::merge(preStats);
+    finalPreStats->calcLengthHistogram();
+    Stats* finalPostStats = Stats::merge(postStats);
+    finalPostStats->calcLengthHistogram();
+    FilterResult* finalFilterResult = FilterResult::merge(filterResults);
+
+    cerr << "Before filtering:" << endl;
+    finalPreStats->print();
+    cerr << endl << "After filtering:" << endl;
+    finalPostStats->print();
+    cerr << endl << "Filtering result:" << endl;
+    finalFilterResult->print();
+
+    JsonReporter jr(mOptions);
+    jr.report(finalFilterResult, finalPreStats, finalPostStats);
+    HtmlReporter hr(mOptions);
+    hr.report(finalFilterResult, finalPreStats, finalPostStats);
+
+    for (int t = 0; t < T; t++) {
+        fpl_destroy(g_workers[t]->ctx);
+        g_workers[t]->ctx = nullptr;
+        delete configs[t];
+    }
+    g_workers.clear();
+    delete finalPreStats;
+    delete finalPostStats;
+    delete finalFilterResult;
+    if (!mOptions->split.enabled) closeOutput();
+    return true;
+}
