@@ -1,0 +1,84 @@
+"""Whole-binary parity: build/fastplong_gpu (the reference CLI with our SingleEndProcessor + libfplgpu.so) against
+oracle/_ref/fastplong_ref (the unmodified reference) and against the committed golden runs: md5 of --out and
+--failed_out, and the JSON report text minus its "command" line."""
+import hashlib
+import json
+import os
+import subprocess
+
+import pytest
+
+import cases
+from fastplong_b200 import synth
+from oracle_lib import REF_BIN
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GPU_BIN = os.path.join(ROOT, "build", "fastplong_gpu")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def md5(path):
+    return hashlib.md5(open(path, "rb").read()).hexdigest()
+
+
+def json_text_md5(path):
+    lines = [ln for ln in open(path, "rb").read().split(b"\n") if b'"command"' not in ln]
+    return hashlib.md5(b"\n".join(lines)).hexdigest()
+
+
+def run(binary, opt, fq, outdir, tag, threads=3, extra=()):
+    out, failed, js, html = (os.path.join(outdir, f"{tag}.{n}") for n in ("out.fq", "failed.fq", "json", "html"))
+    cmd = [binary, "-i", fq, "-o", out, "--failed_out", failed, "-j", js, "-h", html, "-w", str(threads)]
+    cmd += opt.cli_flags() + list(extra)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return {"out_md5": md5(out), "failed_md5": md5(failed), "json_text_md5": json_text_md5(js), "json": js}
+
+
+needs_bin = pytest.mark.skipif(not os.path.exists(GPU_BIN), reason="build/fastplong_gpu not built")
+
+
+@needs_bin
+@pytest.mark.parametrize("name", ["c1_small", "cut_polyx", "loose"])
+def test_gpu_binary_matches_golden_reference_run(name, tmp_path):
+    g = json.load(open(os.path.join(GOLDEN, f"binary_{name}.json")))
+    batch = synth.ont_like(g["n_reads"], g["mean_len"], g["seed"], **g["synth_kwargs"])
+    fq = str(tmp_path / "in.fq")
+    synth.to_fastq(batch, fq)
+    if md5(fq) != g["input_md5"]:
+        pytest.skip("synthetic input differs from the fixture's")
+    got = run(GPU_BIN, cases.OPTION_SETS[g["options"]], fq, str(tmp_path), "gpu")
+    assert got["out_md5"] == g["out_md5"]
+    assert got["failed_md5"] == g["failed_md5"]
+    assert got["json_text_md5"] == g["json_text_md5"]
+
+
+@needs_bin
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/fastplong_ref not built")
+@pytest.mark.parametrize("name,threads", [("default_se", 1), ("cut_polyx_cplx", 4), ("fasta5", 3), ("literal_auto", 2),
+                                          ("trims_limits", 3), ("end_only_wide_window", 8)])
+def test_gpu_binary_matches_reference_binary(name, threads, tmp_path):
+    """Fresh input, both binaries side by side (config-1 shape: ONT-like reads, known 30 bp adapters)."""
+    opt = cases.OPTION_SETS[name]
+    batch = synth.ont_like(700, 4000, 31 + threads, p_chimera=0.03, p_polya=0.03, q_mean=17.0)
+    fq = str(tmp_path / "in.fq")
+    synth.to_fastq(batch, fq)
+    extra = []
+    if opt.adapter_fasta:
+        fa = str(tmp_path / "adapters.fa")
+        with open(fa, "w") as f:   # headers chosen so that std::map order == list order (src/options.cpp:50-59)
+            for i, s in enumerate(opt.adapter_fasta):
+                f.write(f">a{i:03d}\n{s}\n")
+        extra = ["-a", fa]
+    ref = run(REF_BIN, opt, fq, str(tmp_path), "ref", threads, extra)
+    got = run(GPU_BIN, opt, fq, str(tmp_path), "gpu", threads, extra)
+    assert got["out_md5"] == ref["out_md5"]
+    assert got["failed_md5"] == ref["failed_md5"]
+    if got["json_text_md5"] != ref["json_text_md5"]:
+        a, b = json.load(open(got["json"])), json.load(open(ref["json"]))
+        a.pop("command"); b.pop("command")
+        for k in b:
+            assert a[k] == b[k], k
+        raise AssertionError("JSON text differs although the parsed content is equal")
