@@ -10,6 +10,7 @@
 #include <vector>
 #include "fpl_device.cuh"
 #include "fpl_scanplan.h"
+#include "fpl_jit.h"
 
 static_assert(sizeof(fpl_options) == 128, "fpl_options ABI size");
 static_assert(sizeof(fpl_read_result) == 64, "fpl_read_result ABI size");
@@ -54,6 +55,7 @@ struct fpl_ctx {
     cudaStream_t stream = nullptr;
     DevParams P;
     ScanPlan plan;
+    FplJitKernel jit;   // specialised scan kernel (NVRTC), fn == nullptr if not used
     int n_adapters = 0;
     uint8_t* d_adapters = nullptr;
     int* d_alen = nullptr;
@@ -194,7 +196,12 @@ static int run_batch(fpl_ctx* c, const DevBatch& full, const int32_t* h_lens, fp
         { Timed t(c, K_TRIM); launch_trim(c->P, b, st, res, c->d_counters, s); }
         { Timed t(c, K_CYCLE_PRE); launch_cycle_stats(full.seq, full.qual, pre, b.n_reads, tmax, c->d_stats[0], c->C, s); }
         { Timed t(c, K_QUAL_PRE); launch_read_qual(full.qual, pre, b.n_reads, c->d_stats[0], c->C, res, s); }
-        { Timed t(c, K_SCAN); if (c->plan.fast) launch_scan_fast(c->P, c->plan, b, st, s); else launch_scan(c->P, b, st, s); }
+        {
+            Timed t(c, K_SCAN);
+            if (c->jit.fn) { if (fpl_jit_launch_scan(&c->jit, b, st, s)) return fail("launching k_scan_jit failed"); }
+            else if (c->plan.fast) launch_scan_fast(c->P, c->plan, b, st, s);
+            else launch_scan(c->P, b, st, s);
+        }
         { Timed t(c, K_FINAL); launch_final(c->P, b, st, res, post, s); }
         { Timed t(c, K_COUNT); launch_count(res, b.n_reads, c->d_counters, s); }
         { Timed t(c, K_CYCLE_POST); launch_cycle_stats(full.seq, full.qual, post, 2 * b.n_reads, tmax, c->d_stats[1], c->C, s); }
@@ -295,6 +302,16 @@ int fpl_create(const fpl_options* opt, const fpl_adapters* ad, fpl_ctx** out) {
     c->counter_words = FPL_COUNTER_WORDS(n);
     CKC(cudaMalloc(&c->d_counters, sizeof(unsigned long long) * c->counter_words));
     CKC(cudaMemset(c->d_counters, 0, sizeof(unsigned long long) * c->counter_words));
+    // specialise the scan kernel on the adapters (NVRTC); FPL_NO_JIT=1 keeps the precompiled k_scan_fast
+    if (c->plan.fast && getenv("FPL_NO_JIT") == nullptr) {
+        char jerr[512] = "";
+        const bool doCounts = opt->qual_filter_enabled || opt->length_filter_enabled;
+        if (fpl_jit_build_scan(c->device, ad->start ? ad->start : "", ad->end ? ad->end : "", opt->adapter_enabled != 0,
+                               doCounts, opt->complexity_enabled != 0, opt->qualified_qual, &c->jit, jerr, sizeof(jerr))) {
+            fprintf(stderr, "libfplgpu: run-time specialisation unavailable (%s); using the precompiled k_scan_fast\n", jerr);
+            c->jit.fn = nullptr;
+        }
+    }
     const char* tb = getenv("FPL_TILE_MBASES");
     // 0 (default) = no tiling: every kernel streams the whole batch from HBM (measured faster than L2-sized tiles,
     // whose launches are too small to fill the GPU: profiles/README.md)
