@@ -24,9 +24,9 @@ void launch_scan_fast(const DevParams&, const ScanPlan&, const DevBatch&, ReadSt
 void launch_final(const DevParams&, const DevBatch&, const ReadState*, fpl_read_result*, StatSeg*, cudaStream_t);
 void launch_count(const fpl_read_result*, int64_t, unsigned long long*, cudaStream_t);
 void launch_cycle_stats(const uint8_t*, const uint8_t*, const StatSeg*, int64_t, int64_t, unsigned long long*, int64_t,
-                        cudaStream_t);
-void launch_read_qual(const uint8_t*, const StatSeg*, int64_t, unsigned long long*, int64_t, fpl_read_result*,
-                      cudaStream_t);
+                        bool, unsigned long long*, cudaStream_t);
+void launch_kmer_fix(const DevBatch&, const fpl_read_result*, unsigned long long*, cudaStream_t);
+void launch_read_qual(const DevBatch&, unsigned long long*, unsigned long long*, int64_t, fpl_read_result*, cudaStream_t);
 void launch_make_preseg(const DevBatch&, StatSeg*, cudaStream_t);
 
 static thread_local char g_err[512] = "";
@@ -45,10 +45,10 @@ static int fail(const char* fmt, ...) {
         if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-enum { K_PRESEG, K_CYCLE_PRE, K_QUAL_PRE, K_TRIM, K_SCAN, K_FINAL, K_COUNT, K_CYCLE_POST, K_QUAL_POST, K_NKERNELS };
-static const char* const kKernelNames[K_NKERNELS] = {"k_make_preseg", "k_cycle_stats(pre)", "k_read_qual(pre)",
+enum { K_PRESEG, K_CYCLE_PRE, K_QUAL_PRE, K_TRIM, K_SCAN, K_FINAL, K_COUNT, K_CYCLE_POST, K_QUAL_POST, K_KMER_FIX, K_NKERNELS };
+static const char* const kKernelNames[K_NKERNELS] = {"k_make_preseg", "k_cycle_stats(pre)", "k_read_qual(pre+post)",
                                                      "k_trim", "k_scan", "k_final", "k_count",
-                                                     "k_cycle_stats(post)", "k_read_qual(post)"};
+                                                     "k_cycle_stats(post)", "k_read_qual(post)", "k_kmer_fix"};
 
 struct fpl_ctx {
     int device = 0;
@@ -194,8 +194,8 @@ static int run_batch(fpl_ctx* c, const DevBatch& full, const int32_t* h_lens, fp
         cudaStream_t s = c->stream;
         { Timed t(c, K_PRESEG); launch_make_preseg(b, pre, s); }
         { Timed t(c, K_TRIM); launch_trim(c->P, b, st, res, c->d_counters, s); }
-        { Timed t(c, K_CYCLE_PRE); launch_cycle_stats(full.seq, full.qual, pre, b.n_reads, tmax, c->d_stats[0], c->C, s); }
-        { Timed t(c, K_QUAL_PRE); launch_read_qual(full.qual, pre, b.n_reads, c->d_stats[0], c->C, res, s); }
+        { Timed t(c, K_CYCLE_PRE); launch_cycle_stats(full.seq, full.qual, pre, b.n_reads, tmax, c->d_stats[0], c->C, true,
+                                                       c->d_stats[1] + 16 * c->C + FPL_STATS_KMER, s); }
         {
             Timed t(c, K_SCAN);
             if (c->jit.fn) { if (fpl_jit_launch_scan(&c->jit, b, st, s)) return fail("launching k_scan_jit failed"); }
@@ -204,8 +204,9 @@ static int run_batch(fpl_ctx* c, const DevBatch& full, const int32_t* h_lens, fp
         }
         { Timed t(c, K_FINAL); launch_final(c->P, b, st, res, post, s); }
         { Timed t(c, K_COUNT); launch_count(res, b.n_reads, c->d_counters, s); }
-        { Timed t(c, K_CYCLE_POST); launch_cycle_stats(full.seq, full.qual, post, 2 * b.n_reads, tmax, c->d_stats[1], c->C, s); }
-        { Timed t(c, K_QUAL_POST); launch_read_qual(full.qual, post, 2 * b.n_reads, c->d_stats[1], c->C, res, s); }
+        { Timed t(c, K_CYCLE_POST); launch_cycle_stats(full.seq, full.qual, post, 2 * b.n_reads, tmax, c->d_stats[1], c->C, false, nullptr, s); }
+        { Timed t(c, K_KMER_FIX); launch_kmer_fix(b, res, c->d_stats[1] + 16 * c->C + FPL_STATS_KMER, s); }
+        { Timed t(c, K_QUAL_PRE); launch_read_qual(b, c->d_stats[0], c->d_stats[1], c->C, res, s); }
         r0 = r1;
     }
     CK(cudaGetLastError());

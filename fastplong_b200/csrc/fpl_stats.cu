@@ -7,9 +7,11 @@
 //                 and are updated with shared-memory atomics; one 32-bit word packs (count << 20 | sum of raw
 //                 quality chars).  The tile is flushed once to the global int64 arrays mCycleBaseContents /
 //                 mCycleBaseQual.  Also counts the 5-mers (mKmer) with a SWAR fast path for all-ACGTU vectors.
-//  k_read_qual    row-shaped: a warp owns a segment, builds its quality histogram with shared-memory atomics
+//  k_read_qual    row-shaped: a warp owns a read, builds its quality histogram with shared-memory atomics
 //                 (16-byte vector loads), adds it to mBaseQualHistogram and derives the per-read median quality
-//                 (mMedianReadQualHistogram / mMedianReadQualBases / mReads / mLengthSum).
+//                 (mMedianReadQualHistogram / mMedianReadQualBases / mReads / mLengthSum) for BOTH Stats objects:
+//                 a passing segment's histogram is the read's minus the removed ends.
+//  k_kmer_fix     post-filter 5-mer table = pre-filter table - the 5-mers outside the passing segments.
 #include "fpl_device.cuh"
 
 #define CS_THREADS 256
@@ -84,9 +86,12 @@ __device__ __forceinline__ uint32_t pack_codes(uint32_t w) {
 
 }  // namespace
 
+// DO_KMER: also count the 5-mers; their table is flushed to `stats` and, if given, to `kmer_also` (the post-filter
+// block: post 5-mers = pre 5-mers - the ones k_kmer_fix finds outside the passing segments).
+template <bool DO_KMER>
 __global__ void __launch_bounds__(CS_THREADS)
 k_cycle_stats(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qualbuf, const StatSeg* __restrict__ segs,
-              int64_t nseg, unsigned long long* __restrict__ stats, int64_t C) {
+              int64_t nseg, unsigned long long* __restrict__ stats, int64_t C, unsigned long long* __restrict__ kmer_also) {
     // packed[bin][j*32 + lane]: cycle c0 + 16*lane + j; one word = count << 20 | sum of quality chars
     __shared__ uint32_t packed[8][CS_TILE];
     __shared__ uint32_t kmer[1024 + 32];   // [1024..1055]: sink for the lanes whose 5-mer is not valid
@@ -132,7 +137,7 @@ k_cycle_stats(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qu
             } else {
                 nsw[0] = nsw[1] = nsw[2] = nsw[3] = 0;
             }
-            if (lane == 0) nprev0 = c0 >= 4 ? load4_before(sp) : 0u;
+            if (DO_KMER && lane == 0) nprev0 = c0 >= 4 ? load4_before(sp) : 0u;
         };
         if (wid < n) fetch(wid);
         for (int k = wid; k < n; k += CS_WARPS) {
@@ -145,14 +150,16 @@ k_cycle_stats(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qu
             const bool active = cl < len;
             // per word: validity nibble (A,C,G,T,U) and four 2-bit codes; the previous lane's last word supplies the
             // four bases in front of this lane's vector (lane 0: the word loaded in front of the tile)
-            uint32_t vn[4], pc[4];
+            uint32_t vn[4] = {0, 0, 0, 0}, pc[4] = {0, 0, 0, 0}, pvn = 0, ppc = 0;
+            if (DO_KMER) {
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                vn[i] = active ? (valid_acgtu(sw[i]) * 0x10204080u) >> 28 : 0u;
-                pc[i] = pack_codes(sw[i]);
+                for (int i = 0; i < 4; i++) {
+                    vn[i] = active ? (valid_acgtu(sw[i]) * 0x10204080u) >> 28 : 0u;
+                    pc[i] = pack_codes(sw[i]);
+                }
+                pvn = __shfl_up_sync(0xffffffffu, vn[3], 1); ppc = __shfl_up_sync(0xffffffffu, pc[3], 1);
+                if (lane == 0) { pvn = (valid_acgtu(prev0) * 0x10204080u) >> 28; ppc = pack_codes(prev0); }
             }
-            uint32_t pvn = __shfl_up_sync(0xffffffffu, vn[3], 1), ppc = __shfl_up_sync(0xffffffffu, pc[3], 1);
-            if (lane == 0) { pvn = (valid_acgtu(prev0) * 0x10204080u) >> 28; ppc = pack_codes(prev0); }
             if (!active) continue;
             const int nvalid = (int)min((int64_t)16, (int64_t)len - cl);
             // ---- per-(bin, cycle) counters: word = count << 20 | sum of quality chars ----
@@ -172,6 +179,7 @@ k_cycle_stats(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qu
                 for (int t = 0; t < 16; t++)
                     if (t < nvalid) count(t);
             }
+            if (!DO_KMER) continue;
             // ---- 5-mers ending in this lane's 16 cycles: all five bases in ACGTU ----
             const uint32_t V20 = pvn | (vn[0] << 4) | (vn[1] << 8) | (vn[2] << 12) | (vn[3] << 16);
             uint32_t ok = V20 & (V20 >> 1) & (V20 >> 2) & (V20 >> 3) & (V20 >> 4);   // bit t: bytes t-4..t all valid
@@ -206,105 +214,211 @@ k_cycle_stats(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qu
             atomicAdd(&qualsum[(int64_t)bin * C + c], (unsigned long long)(sq - 33 * cnt));
         }
     }
-    unsigned long long* tail = stats + 16 * C;
-    for (int i = threadIdx.x; i < 1024; i += CS_THREADS)
-        if (kmer[i]) atomicAdd(&tail[FPL_STATS_KMER + i], (unsigned long long)kmer[i]);
+    if (DO_KMER) {
+        unsigned long long* tail = stats + 16 * C;
+        for (int i = threadIdx.x; i < 1024; i += CS_THREADS)
+            if (kmer[i]) {
+                atomicAdd(&tail[FPL_STATS_KMER + i], (unsigned long long)kmer[i]);
+                if (kmer_also) atomicAdd(&kmer_also[i], (unsigned long long)kmer[i]);
+            }
+    }
 }
 
+// kmer_to: where the 5-mer counts of this launch go besides `stats` (nullptr = nowhere else); do_kmer = false skips them
 void launch_cycle_stats(const uint8_t* seq, const uint8_t* qual, const StatSeg* segs, int64_t nseg, int64_t max_len,
-                        unsigned long long* stats, int64_t C, cudaStream_t stream) {
+                        unsigned long long* stats, int64_t C, bool do_kmer, unsigned long long* kmer_also,
+                        cudaStream_t stream) {
     if (nseg == 0 || max_len <= 0) return;
     dim3 grid((unsigned)((max_len + CS_TILE - 1) / CS_TILE), (unsigned)((nseg + CS_GROUP - 1) / CS_GROUP));
-    k_cycle_stats<<<grid, CS_THREADS, 0, stream>>>(seq, qual, segs, nseg, stats, C);
+    if (do_kmer) k_cycle_stats<true><<<grid, CS_THREADS, 0, stream>>>(seq, qual, segs, nseg, stats, C, kmer_also);
+    else k_cycle_stats<false><<<grid, CS_THREADS, 0, stream>>>(seq, qual, segs, nseg, stats, C, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_kmer_fix: the post-filter 5-mer table is the pre-filter one minus the 5-mers that do not lie inside a passing
+// segment (trimmed ends, split gaps, failed or dropped reads).  A 5-mer ending at read position e (e >= 4) survives
+// iff a passing segment [a, b) has a + 4 <= e < b (Stats::statRead skips the first four cycles of every read it is
+// given, src/stats.cpp:309-311).  The removed ranges are short for almost every read.
+// ------------------------------------------------------------------------------------------------------------------
+#define KF_WARPS 8
+__global__ void __launch_bounds__(KF_WARPS * 32)
+k_kmer_fix(DevBatch b, const fpl_read_result* __restrict__ res, unsigned long long* __restrict__ post_kmer) {
+    __shared__ uint32_t rem[1024];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) rem[i] = 0;
+    __syncthreads();
+    const int wid = threadIdx.x >> 5, lane = lane_id();
+    const uint32_t rem_base = shared_addr(&rem[0]);
+    const int64_t nwarps = (int64_t)gridDim.x * KF_WARPS;
+    for (int64_t r = (int64_t)blockIdx.x * KF_WARPS + wid; r < b.n_reads; r += nwarps) {
+        const int L = b.lens[r];
+        if (L < 5) continue;
+        const uint8_t* seq = b.seq + b.offsets[r];
+        const fpl_read_result* o = &res[r];
+        // kept intervals of ending positions, in read order
+        int ks[2], ke[2], nk = 0;
+        const int nseg = o->n_segments;
+        for (int k = 0; k < nseg; k++)
+            if (o->seg_result[k] == FPL_PASS_FILTER) { ks[nk] = o->seg_lo[k] + 4; ke[nk] = o->seg_lo[k] + o->seg_len[k]; nk++; }
+        // removed ranges: [4, ks0) [ke0, ks1) [ke1, L)
+        int from = 4;
+        for (int k = 0; k <= nk; k++) {
+            const int to = k < nk ? min(ks[k], L) : L;
+            for (int e0 = from; e0 < to; e0 += 32) {
+                const int e = e0 + lane;
+                if (e < to) {
+                    const uint32_t c4 = kmer_code(seq[e - 4]), c3 = kmer_code(seq[e - 3]), c2 = kmer_code(seq[e - 2]),
+                                   c1 = kmer_code(seq[e - 1]), c0 = kmer_code(seq[e]);
+                    if (((c4 | c3 | c2 | c1 | c0) & 8u) == 0u)
+                        red_shared_add(rem_base + (((c4 << 8) | (c3 << 6) | (c2 << 4) | (c1 << 2) | c0) << 2), 1u);
+                }
+            }
+            if (k < nk) from = max(from, ke[k]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x)
+        if (rem[i]) atomicAdd(&post_kmer[i], 0ull - (unsigned long long)rem[i]);
+}
+
+void launch_kmer_fix(const DevBatch& b, const fpl_read_result* res, unsigned long long* post_kmer, cudaStream_t stream) {
+    if (b.n_reads == 0) return;
+    const int64_t want = (b.n_reads + KF_WARPS - 1) / KF_WARPS;
+    const unsigned grid = (unsigned)(want < 148 * 16 ? want : 148 * 16);
+    k_kmer_fix<<<grid, KF_WARPS * 32, 0, stream>>>(b, res, post_kmer);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
 #define RQ_WARPS 8
 
-// Shared-memory atomics are the fast way to histogram on this part (tools/ubench_hist.cu: a [128]-bin table updated
+namespace {
+// median: smallest char m with sum_{c<=m} hist[c] > len>>1 (src/stats.cpp:351-361); lane l owns bins 4l..4l+3
+__device__ __forceinline__ uint8_t hist_median(const uint32_t* h, int len, int lane, uint32_t (&own)[4]) {
+    own[0] = h[4 * lane]; own[1] = h[4 * lane + 1]; own[2] = h[4 * lane + 2]; own[3] = h[4 * lane + 3];
+    if (len <= 0) return 0;
+    const int half = len >> 1;
+    const int tot = (int)(own[0] + own[1] + own[2] + own[3]);
+    int run = warp_incl_scan(tot) - tot;
+    int m = 1 << 30;
+    run += own[0]; if (run > half) m = min(m, 4 * lane);
+    run += own[1]; if (run > half) m = min(m, 4 * lane + 1);
+    run += own[2]; if (run > half) m = min(m, 4 * lane + 2);
+    run += own[3]; if (run > half) m = min(m, 4 * lane + 3);
+    return (uint8_t)__reduce_min_sync(0xffffffffu, m);
+}
+
+// h[q] += delta for the bytes qp[0..n): 16-byte vector body, byte head/tail (delta = 1 or 0xFFFFFFFF)
+__device__ __forceinline__ void hist_bytes(uint32_t hbase, const uint8_t* qp, int n, uint32_t delta, int lane) {
+    const int head = min(n, (int)((16 - (reinterpret_cast<uintptr_t>(qp) & 15)) & 15));
+    if (lane < head) red_shared_add(hbase + ((uint32_t)(qp[lane] & 127) << 2), delta);
+    const int nvec = (n - head) >> 4;
+    const uint4* vp = reinterpret_cast<const uint4*>(qp + head);
+    for (int i = lane; i < nvec; i += 32) {
+        const uint4 v = __ldg(vp + i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) red_shared_add(hbase + (((w[k] >> (8 * j)) & 127u) << 2), delta);
+    }
+    const int done = head + (nvec << 4);
+    if (done + lane < n) red_shared_add(hbase + ((uint32_t)(qp[done + lane] & 127) << 2), delta);   // < 16 tail bytes
+}
+}  // namespace
+
+// Shared-memory atomics are the fast way to histogram on this part (tools/ubench_hist.cu: a 128-bin table updated
 // with atomicAdd by 8 warps streams quality bytes at HBM speed, 4x faster than lane-private read-modify-write).
+//
+// One warp per input read: the histogram of the whole read gives the pre-filter median and mBaseQualHistogram; the
+// histogram of each passing segment is derived from it by subtracting the (short) removed ends — or counted directly
+// when the segment is the smaller part — and gives the post-filter median and histogram.  One pass over the
+// quality bytes serves both Stats objects.
 __global__ void __launch_bounds__(RQ_WARPS * 32)
-k_read_qual(const uint8_t* __restrict__ qualbuf, const StatSeg* __restrict__ segs, int64_t nseg,
-            unsigned long long* __restrict__ stats, int64_t C, fpl_read_result* __restrict__ res) {
-    __shared__ uint32_t hist[RQ_WARPS][128];           // per-warp: the current segment's histogram
-    __shared__ uint32_t block_hist[128];               // all segments of this block -> one flush to mBaseQualHistogram
-    __shared__ unsigned long long block_misc[2];       // reads, length sum
+k_read_qual(DevBatch b, unsigned long long* __restrict__ stats_pre, unsigned long long* __restrict__ stats_post, int64_t C,
+            fpl_read_result* __restrict__ res) {
+    __shared__ uint32_t hist[RQ_WARPS][2][128];        // per warp: [0] whole read, [1] current segment
+    __shared__ uint32_t block_hist[2][128];            // this block's reads -> one flush per Stats block
+    __shared__ unsigned long long block_misc[2][2];    // reads, length sum
     const int wid = threadIdx.x >> 5, lane = lane_id();
-    for (int i = threadIdx.x; i < 128; i += blockDim.x) block_hist[i] = 0;
-    if (threadIdx.x < 2) block_misc[threadIdx.x] = 0;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) (&block_hist[0][0])[i] = 0;
+    if (threadIdx.x < 4) (&block_misc[0][0])[threadIdx.x] = 0;
     __syncthreads();
-    unsigned long long* tail = stats + 16 * C;
-    uint32_t* h = hist[wid];
+    unsigned long long* tail[2] = {stats_pre + 16 * C, stats_post + 16 * C};
+    uint32_t* hfull = hist[wid][0];
+    uint32_t* hseg = hist[wid][1];
+    const uint32_t hfull_s = shared_addr(hfull), hseg_s = shared_addr(hseg);
     const int64_t nwarps = (int64_t)gridDim.x * RQ_WARPS;
-    for (int64_t s = (int64_t)blockIdx.x * RQ_WARPS + wid; s < nseg; s += nwarps) {
-        const StatSeg sg = segs[s];
-        if (sg.read < 0) continue;   // pre: every read, even empty; post: passing segments only
-        const uint8_t* qp = qualbuf + sg.off;
-        const int len = sg.len;
-        for (int b = lane; b < 128; b += 32) h[b] = 0;
+    for (int64_t r = (int64_t)blockIdx.x * RQ_WARPS + wid; r < b.n_reads; r += nwarps) {
+        const uint8_t* qp = b.qual + b.offsets[r];
+        const int L = b.lens[r];
+        fpl_read_result* o = &res[r];
+        for (int i = lane; i < 128; i += 32) hfull[i] = 0;
         __syncwarp();
-        // head bytes up to 16-byte alignment, vector body, tail bytes
-        const int head = min(len, (int)((16 - (reinterpret_cast<uintptr_t>(qp) & 15)) & 15));
-        if (lane < head) atomicAdd(&h[qp[lane] & 127], 1u);
-        const int nvec = (len - head) >> 4;
-        const uint4* vp = reinterpret_cast<const uint4*>(qp + head);
-        for (int i = lane; i < nvec; i += 32) {
-            const uint4 v = __ldg(vp + i);
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-#pragma unroll
-                for (int j = 0; j < 4; j++) atomicAdd(&h[(w[k] >> (8 * j)) & 127u], 1u);
-        }
-        const int done = head + (nvec << 4);
-        if (done + lane < len) atomicAdd(&h[qp[done + lane] & 127], 1u);   // < 16 tail bytes
+        hist_bytes(hfull_s, qp, L, 1u, lane);
         __syncwarp();
-        // median: smallest char m with sum_{c<=m} hist[c] > len>>1 (src/stats.cpp:351-361); lane l owns bins 4l..4l+3
-        const uint32_t h0 = h[4 * lane], h1 = h[4 * lane + 1], h2 = h[4 * lane + 2], h3 = h[4 * lane + 3];
-        uint8_t median = 0;
-        if (len > 0) {
-            const int half = len >> 1;
-            const int incl = warp_incl_scan((int)(h0 + h1 + h2 + h3));
-            int run = incl - (int)(h0 + h1 + h2 + h3);
-            int m = 1 << 30;
-            run += h0; if (run > half) m = min(m, 4 * lane);
-            run += h1; if (run > half) m = min(m, 4 * lane + 1);
-            run += h2; if (run > half) m = min(m, 4 * lane + 2);
-            run += h3; if (run > half) m = min(m, 4 * lane + 3);
-            median = (uint8_t)__reduce_min_sync(0xffffffffu, m);
-        }
-        if (h0) atomicAdd(&block_hist[4 * lane], h0);
-        if (h1) atomicAdd(&block_hist[4 * lane + 1], h1);
-        if (h2) atomicAdd(&block_hist[4 * lane + 2], h2);
-        if (h3) atomicAdd(&block_hist[4 * lane + 3], h3);
+        uint32_t own[4];
+        const uint8_t med = hist_median(hfull, L, lane, own);
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (own[k]) atomicAdd(&block_hist[0][4 * lane + k], own[k]);
         if (lane == 0) {
-            atomicAdd(&block_misc[0], 1ull);
-            atomicAdd(&block_misc[1], (unsigned long long)len);
-            if (len > 0) {
-                atomicAdd(&tail[FPL_STATS_MEDHIST + median], 1ull);
-                atomicAdd(&tail[FPL_STATS_MEDBASES + median], (unsigned long long)len);
+            atomicAdd(&block_misc[0][0], 1ull);
+            atomicAdd(&block_misc[0][1], (unsigned long long)L);
+            if (L > 0) {
+                atomicAdd(&tail[0][FPL_STATS_MEDHIST + med], 1ull);
+                atomicAdd(&tail[0][FPL_STATS_MEDBASES + med], (unsigned long long)L);
             }
-            if (sg.slot == 2) res[sg.read].pre_median_qual = median;
-            else res[sg.read].seg_median_qual[sg.slot] = median;
+            o->pre_median_qual = med;
+        }
+        const int nseg = o->n_segments;
+        for (int k = 0; k < nseg; k++) {
+            if (o->seg_result[k] != FPL_PASS_FILTER) continue;      // warp-uniform
+            const int a = o->seg_lo[k], n = o->seg_len[k];
+            __syncwarp();
+            if (L - n <= n) {            // copy the read's histogram and take the removed ends out
+                for (int i = lane; i < 128; i += 32) hseg[i] = hfull[i];
+                __syncwarp();
+                hist_bytes(hseg_s, qp, a, 0xFFFFFFFFu, lane);
+                hist_bytes(hseg_s, qp + a + n, L - a - n, 0xFFFFFFFFu, lane);
+            } else {
+                for (int i = lane; i < 128; i += 32) hseg[i] = 0;
+                __syncwarp();
+                hist_bytes(hseg_s, qp + a, n, 1u, lane);
+            }
+            __syncwarp();
+            const uint8_t smed = hist_median(hseg, n, lane, own);
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (own[j]) atomicAdd(&block_hist[1][4 * lane + j], own[j]);
+            if (lane == 0) {
+                atomicAdd(&block_misc[1][0], 1ull);
+                atomicAdd(&block_misc[1][1], (unsigned long long)n);
+                if (n > 0) {
+                    atomicAdd(&tail[1][FPL_STATS_MEDHIST + smed], 1ull);
+                    atomicAdd(&tail[1][FPL_STATS_MEDBASES + smed], (unsigned long long)n);
+                }
+                o->seg_median_qual[k] = smed;
+            }
         }
         __syncwarp();
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 128; i += blockDim.x)
-        if (block_hist[i]) atomicAdd(&tail[FPL_STATS_QUALHIST + i], (unsigned long long)block_hist[i]);
-    if (threadIdx.x == 0 && block_misc[0]) {
-        atomicAdd(&tail[FPL_STATS_READS], block_misc[0]);
-        atomicAdd(&tail[FPL_STATS_LENSUM], block_misc[1]);
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        const int which = i >> 7, bin = i & 127;
+        if (block_hist[which][bin]) atomicAdd(&tail[which][FPL_STATS_QUALHIST + bin], (unsigned long long)block_hist[which][bin]);
+    }
+    if (threadIdx.x < 2 && block_misc[threadIdx.x][0]) {
+        atomicAdd(&tail[threadIdx.x][FPL_STATS_READS], block_misc[threadIdx.x][0]);
+        atomicAdd(&tail[threadIdx.x][FPL_STATS_LENSUM], block_misc[threadIdx.x][1]);
     }
 }
 
-void launch_read_qual(const uint8_t* qual, const StatSeg* segs, int64_t nseg, unsigned long long* stats, int64_t C,
+void launch_read_qual(const DevBatch& b, unsigned long long* stats_pre, unsigned long long* stats_post, int64_t C,
                       fpl_read_result* res, cudaStream_t stream) {
-    if (nseg == 0) return;
-    // persistent-ish grid: enough blocks to fill the GPU several times over, each warp strides over the segments
-    const int64_t want = (nseg + RQ_WARPS - 1) / RQ_WARPS;
+    if (b.n_reads == 0) return;
+    // persistent-ish grid: enough blocks to fill the GPU several times over, each warp strides over the reads
+    const int64_t want = (b.n_reads + RQ_WARPS - 1) / RQ_WARPS;
     const unsigned grid = (unsigned)(want < 148 * 64 ? want : 148 * 64);
-    k_read_qual<<<grid, RQ_WARPS * 32, 0, stream>>>(qual, segs, nseg, stats, C, res);
+    k_read_qual<<<grid, RQ_WARPS * 32, 0, stream>>>(b, stats_pre, stats_post, C, res);
 }
 
 // pre-stats segment list: every input read, full length
