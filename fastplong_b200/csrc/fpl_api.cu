@@ -61,6 +61,7 @@ struct fpl_ctx {
     int* d_alen = nullptr;
     uint4* d_peq = nullptr;
     uint32_t* d_peq16 = nullptr;
+    uint32_t* d_acode = nullptr;
     // accumulators
     int64_t C = 0;
     unsigned long long* d_stats[2] = {nullptr, nullptr};
@@ -244,6 +245,7 @@ int fpl_create(const fpl_options* opt, const fpl_adapters* ad, fpl_ctx** out) {
     std::vector<int> h_alen(n, 0);
     std::vector<uint4> h_peq((size_t)n * 256, make_uint4(0, 0, 0, 0));
     std::vector<uint32_t> h_peq16((size_t)n * 256, 0);
+    std::vector<uint32_t> h_acode((size_t)n * 4, 0);
     for (int k = 0; k < n; k++) {
         const char* s = k == 0 ? ad->start : k == 1 ? ad->end : ad->fasta[k - 2];
         if (!s) s = "";
@@ -255,6 +257,20 @@ int fpl_create(const fpl_options* opt, const fpl_adapters* ad, fpl_ctx** out) {
         h_alen[k] = (int)len;
         memcpy(&h_ad[(size_t)k * FPL_MAX_ADAPTER_LEN], s, len);
         const int plen = (int)len < FPL_PATTERN_LEN ? (int)len : FPL_PATTERN_LEN;
+        {   // packed 2-bit form for the windowed Hamming search (k_trim), only for ACGT-only adapters of <= 32 bp
+            bool ok = len >= 1 && len <= 32;
+            unsigned long long code = 0, mask = 0;
+            for (size_t j = 0; j < len && ok; j++) {
+                const char ch = s[j];
+                if (ch != 'A' && ch != 'C' && ch != 'G' && ch != 'T') ok = false;
+                code |= (unsigned long long)((ch >> 1) & 3) << (2 * j);
+                mask |= 1ull << (2 * j);
+            }
+            if (ok) {
+                h_acode[(size_t)k * 4 + 0] = (uint32_t)code; h_acode[(size_t)k * 4 + 1] = (uint32_t)(code >> 32);
+                h_acode[(size_t)k * 4 + 2] = (uint32_t)mask; h_acode[(size_t)k * 4 + 3] = (uint32_t)(mask >> 32);
+            }
+        }
         for (size_t j = 0; j < len; j++) {
             uint8_t ch = (uint8_t)s[j];
             uint32_t* w = reinterpret_cast<uint32_t*>(&h_peq[(size_t)k * 256 + ch]);
@@ -295,11 +311,13 @@ int fpl_create(const fpl_options* opt, const fpl_adapters* ad, fpl_ctx** out) {
     CKC(cudaMalloc(&c->d_alen, sizeof(int) * n));
     CKC(cudaMalloc(&c->d_peq, sizeof(uint4) * h_peq.size()));
     CKC(cudaMalloc(&c->d_peq16, sizeof(uint32_t) * h_peq16.size()));
+    CKC(cudaMalloc(&c->d_acode, sizeof(uint32_t) * h_acode.size()));
+    CKC(cudaMemcpy(c->d_acode, h_acode.data(), sizeof(uint32_t) * h_acode.size(), cudaMemcpyHostToDevice));
     CKC(cudaMemcpy(c->d_adapters, h_ad.data(), h_ad.size(), cudaMemcpyHostToDevice));
     CKC(cudaMemcpy(c->d_alen, h_alen.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
     CKC(cudaMemcpy(c->d_peq, h_peq.data(), sizeof(uint4) * h_peq.size(), cudaMemcpyHostToDevice));
     CKC(cudaMemcpy(c->d_peq16, h_peq16.data(), sizeof(uint32_t) * h_peq16.size(), cudaMemcpyHostToDevice));
-    c->P.adapters = c->d_adapters; c->P.alen = c->d_alen; c->P.peq = c->d_peq; c->P.peq16 = c->d_peq16;
+    c->P.adapters = c->d_adapters; c->P.alen = c->d_alen; c->P.peq = c->d_peq; c->P.peq16 = c->d_peq16; c->P.acode = c->d_acode;
     c->counter_words = FPL_COUNTER_WORDS(n);
     CKC(cudaMalloc(&c->d_counters, sizeof(unsigned long long) * c->counter_words));
     CKC(cudaMemset(c->d_counters, 0, sizeof(unsigned long long) * c->counter_words));
@@ -331,7 +349,7 @@ void fpl_destroy(fpl_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     collect_times(c);
     for (auto e : c->pool) cudaEventDestroy(e);
-    cudaFree(c->d_adapters); cudaFree(c->d_alen); cudaFree(c->d_peq); cudaFree(c->d_peq16);
+    cudaFree(c->d_adapters); cudaFree(c->d_alen); cudaFree(c->d_peq); cudaFree(c->d_peq16); cudaFree(c->d_acode);
     cudaFree(c->d_stats[0]); cudaFree(c->d_stats[1]); cudaFree(c->d_counters);
     cudaFree(c->d_state); cudaFree(c->d_results); cudaFree(c->d_preseg); cudaFree(c->d_postseg);
     cudaFree(c->d_seq); cudaFree(c->d_qual); cudaFree(c->d_offsets); cudaFree(c->d_lens);

@@ -32,14 +32,20 @@ __device__ __forceinline__ uint32_t kmer_code(uint32_t b) {
     return v;
 }
 
-// 16 bytes at an arbitrary address: two aligned 16-byte loads + a byte shift (sh = address & 15, warp-uniform)
-__device__ __forceinline__ void load16(const uint8_t* p, uint32_t (&o)[4]) {
+// 16 bytes at an arbitrary address: two aligned 16-byte loads (load16_raw, issued early) + a byte shift
+// (assemble16, at the point of use so that the loads stay in flight; sh = address & 15 is warp-uniform)
+struct Raw16 { uint4 x, y; };
+__device__ __forceinline__ Raw16 load16_raw(const uint8_t* p) {
     const uintptr_t a = reinterpret_cast<uintptr_t>(p);
     const uint4* v = reinterpret_cast<const uint4*>(a & ~(uintptr_t)15);
-    const unsigned sh = (unsigned)(a & 15);
-    const uint4 x = __ldg(v);
+    Raw16 r;
+    r.x = __ldg(v);
+    r.y = (a & 15) ? __ldg(v + 1) : make_uint4(0, 0, 0, 0);
+    return r;
+}
+__device__ __forceinline__ void assemble16(const Raw16& r, unsigned sh, uint32_t (&o)[4]) {
+    const uint4 x = r.x, y = r.y;
     if (sh == 0) { o[0] = x.x; o[1] = x.y; o[2] = x.z; o[3] = x.w; return; }
-    const uint4 y = __ldg(v + 1);
     const unsigned bs = (sh & 3) * 8;
     switch (sh >> 2) {
         case 0:
@@ -89,7 +95,7 @@ __device__ __forceinline__ uint32_t pack_codes(uint32_t w) {
 // DO_KMER: also count the 5-mers; their table is flushed to `stats` and, if given, to `kmer_also` (the post-filter
 // block: post 5-mers = pre 5-mers - the ones k_kmer_fix finds outside the passing segments).
 template <bool DO_KMER>
-__global__ void __launch_bounds__(CS_THREADS)
+__global__ void __launch_bounds__(CS_THREADS, 4)
 k_cycle_stats(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qualbuf, const StatSeg* __restrict__ segs,
               int64_t nseg, unsigned long long* __restrict__ stats, int64_t C, unsigned long long* __restrict__ kmer_also) {
     // packed[bin][j*32 + lane]: cycle c0 + 16*lane + j; one word = count << 20 | sum of quality chars
@@ -125,29 +131,32 @@ k_cycle_stats(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qu
         const int n = d_n;
         if (n) any = true;
         // software pipeline: the vectors of segment k+CS_WARPS are in flight while segment k is processed
-        uint32_t nsw[4] = {0, 0, 0, 0}, nqw[4] = {0, 0, 0, 0}, nprev0 = 0;
+        Raw16 nrs, nrq;
+        nrs.x = nrs.y = nrq.x = nrq.y = make_uint4(0, 0, 0, 0);
+        uint32_t nprev0 = 0;
+        unsigned nsh = 0;
         int nlen = 0;
         auto fetch = [&](int k) {
             const int64_t off = d_off[k];
             nlen = d_len[k];
             const uint8_t* sp = seqbuf + off + c0;
+            nsh = (unsigned)(reinterpret_cast<uintptr_t>(sp) & 15);   // same for the quality buffer (both 16-byte aligned bases)
             if (cl < nlen) {
-                load16(sp + 16 * lane, nsw);
-                load16(qualbuf + off + c0 + 16 * lane, nqw);
-            } else {
-                nsw[0] = nsw[1] = nsw[2] = nsw[3] = 0;
+                nrs = load16_raw(sp + 16 * lane);
+                nrq = load16_raw(qualbuf + off + c0 + 16 * lane);
             }
             if (DO_KMER && lane == 0) nprev0 = c0 >= 4 ? load4_before(sp) : 0u;
         };
         if (wid < n) fetch(wid);
         for (int k = wid; k < n; k += CS_WARPS) {
-            uint32_t sw[4], qw[4];
-#pragma unroll
-            for (int i = 0; i < 4; i++) { sw[i] = nsw[i]; qw[i] = nqw[i]; }
+            const Raw16 rs = nrs, rq = nrq;
+            const unsigned sh = nsh;
             const int len = nlen;
             const uint32_t prev0 = nprev0;
             if (k + CS_WARPS < n) fetch(k + CS_WARPS);
             const bool active = cl < len;
+            uint32_t sw[4] = {0, 0, 0, 0}, qw[4] = {0, 0, 0, 0};
+            if (active) { assemble16(rs, sh, sw); assemble16(rq, sh, qw); }
             // per word: validity nibble (A,C,G,T,U) and four 2-bit codes; the previous lane's last word supplies the
             // four bases in front of this lane's vector (lane 0: the word loaded in front of the tile)
             uint32_t vn[4] = {0, 0, 0, 0}, pc[4] = {0, 0, 0, 0}, pvn = 0, ppc = 0;

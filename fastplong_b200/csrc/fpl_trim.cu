@@ -92,8 +92,12 @@ __device__ __forceinline__ int hamming(const uint8_t* r, const uint8_t* a, int a
 
 // AdapterTrimmer::searchAdapter restricted to the two windowed modes (src/adaptertrimmer.cpp:84-134,156-165).
 // left: first p with H<=T, else the LAST arg-min;  right: last p with H<=T, else the FIRST arg-min.
+__device__ __forceinline__ bool is_acgt(uint32_t b) {   // exact: A 0x41, C 0x43, G 0x47, T 0x54
+    return (b >> 5) == 2u && ((0x0010008Au >> (b & 31u)) & 1u);
+}
+
 __device__ int search_window(const DevParams& P, const uint8_t* rdata, int rlen, int aidx, int searchStart,
-                             int searchLen, bool left) {
+                             int searchLen, bool left, uint32_t* pk) {
     const int lane = lane_id();
     const int alen = P.alen[aidx];
     const uint8_t* adata = P.adapters + (size_t)aidx * FPL_MAX_ADAPTER_LEN;
@@ -108,8 +112,40 @@ __device__ int search_window(const DevParams& P, const uint8_t* rdata, int rlen,
     else { p0 = searchStart; p1 = searchEnd - alen - 1; }  // generic mode, empty or tiny range
     unsigned accept = descending ? 0u : 0xFFFFFFFFu;
     unsigned best = 0xFFFFFFFFu;  // (H << 16) | tie-break key, minimised
+    // Packed form of the window for ACGT-only adapters of <= 32 bp: 2-bit codes and "not ACGT" flags, 16 bases per
+    // word, in shared memory (pk[0..17] codes, pk[18..35] flags); H(p) = popcount over the adapter's positions of
+    // (code differs | base invalid), exactly the byte-wise count of src/adaptertrimmer.cpp:93-96.
+    const uint4 ac = __ldg(reinterpret_cast<const uint4*>(P.acode) + aidx);
+    const int nbytes = p1 - p0 + alen;
+    const bool packed = (ac.z | ac.w) != 0u && nbytes <= 256 && p1 >= p0;
+    if (packed) {
+        uint32_t codes = 0, inv = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int idx = 8 * lane + j;
+            const uint32_t b = idx < nbytes ? rdata[p0 + idx] : 0u;
+            codes |= ((b >> 1) & 3u) << (2 * j);
+            inv |= (is_acgt(b) ? 0u : 1u) << (2 * j);
+        }
+        __syncwarp();
+        reinterpret_cast<uint16_t*>(pk)[lane] = (uint16_t)codes;
+        reinterpret_cast<uint16_t*>(pk + 18)[lane] = (uint16_t)inv;
+        if (lane < 2) { pk[16 + lane] = 0; pk[34 + lane] = 0x55555555u; }
+        __syncwarp();
+    }
     for (int p = p0 + lane; p <= p1; p += 32) {
-        int mm = hamming(rdata + p, adata, alen);
+        int mm;
+        if (packed) {
+            const int q = p - p0, wi = q >> 4, sh = (q & 15) * 2;
+            const uint32_t c0 = pk[wi], c1 = pk[wi + 1], c2 = pk[wi + 2];
+            const uint32_t i0 = pk[18 + wi], i1 = pk[19 + wi], i2 = pk[20 + wi];
+            const uint32_t dlo = __funnelshift_r(c0, c1, sh) ^ ac.x, dhi = __funnelshift_r(c1, c2, sh) ^ ac.y;
+            const uint32_t mlo = (dlo | (dlo >> 1) | __funnelshift_r(i0, i1, sh)) & ac.z;
+            const uint32_t mhi = (dhi | (dhi >> 1) | __funnelshift_r(i1, i2, sh)) & ac.w;
+            mm = __popc(mlo) + __popc(mhi);
+        } else {
+            mm = hamming(rdata + p, adata, alen);
+        }
         unsigned rel = (unsigned)(p - p0);
         if (mm <= T) accept = descending ? max(accept, rel + 1u) : min(accept, rel);
         // ascending loops keep the last minimum (<=), the descending loop also uses <= and so keeps the smallest p;
@@ -161,7 +197,7 @@ __device__ int trim_start(const DevParams& P, const uint8_t* seq, Win& w, int ai
     const int rlen = w.len;
     if (rlen < FPL_PATTERN_LEN) return 0;
     const int plen = min(FPL_PATTERN_LEN, alen);
-    int mpos = search_window(P, rdata, rlen, aidx, 0, FPL_WINDOW, false);
+    int mpos = search_window(P, rdata, rlen, aidx, 0, FPL_WINDOW, false, reinterpret_cast<uint32_t*>(scratch));
     if (mpos >= 0) {
         mpos = min(mpos + ext, rlen - alen);
         ev.add(aidx, 0, alen);
@@ -201,7 +237,7 @@ __device__ int trim_end(const DevParams& P, const uint8_t* seq, Win& w, int aidx
     if (rlen < FPL_PATTERN_LEN) return 0;
     const int plen = min(FPL_PATTERN_LEN, alen);
     const int searchStart = max(0, rlen - FPL_WINDOW);
-    int mpos = search_window(P, rdata, rlen, aidx, searchStart, FPL_WINDOW, true);
+    int mpos = search_window(P, rdata, rlen, aidx, searchStart, FPL_WINDOW, true, reinterpret_cast<uint32_t*>(scratch));
     if (mpos >= 0) {
         mpos = max(0, mpos - ext);
         ev.add(aidx, 1, alen);
@@ -218,15 +254,32 @@ __device__ int trim_end(const DevParams& P, const uint8_t* seq, Win& w, int aidx
         scratch[p] = (uint8_t)(ed <= T16 ? ed : 255);
     }
     __syncwarp();
-    int pos = -1, mined = -1;
-    // every lane walks the same <=184 bytes of shared memory (broadcast reads); the result is warp-uniform
-    for (int p = 0; p < np; p++) {
-        int ed = scratch[p];
-        if (ed == 255) continue;
-        if (pos < 0) { pos = p; mined = ed; }
-        else if (ed > mined) break;
-        else { pos = p; mined = ed; }
+    // sequential rule of :273-286 in closed form: walk the hits in order, stop at the first hit whose
+    // distance exceeds the previous hit's, keep the hit before it; 32 positions per step.
+    int pos = -1, carryE = -1, carryPos = -1;
+    bool done = false;
+    for (int c0 = 0; c0 < np && !done; c0 += 32) {
+        const int p = c0 + lane;
+        const int e = p < np ? (int)scratch[p] : 255;
+        const bool hit = e != 255;
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        const unsigned lower = m & ((1u << lane) - 1u);
+        const int src = lower ? 31 - __clz(lower) : -1;
+        int pe = __shfl_sync(0xffffffffu, e, src >= 0 ? src : 0);
+        if (src < 0) pe = carryE;
+        const unsigned bm = __ballot_sync(0xffffffffu, hit && pe >= 0 && e > pe);
+        if (bm) {
+            const int bl = __ffs(bm) - 1;
+            const unsigned lowerb = m & ((1u << bl) - 1u);
+            pos = lowerb ? c0 + 31 - __clz(lowerb) : carryPos;
+            done = true;
+        } else if (m) {
+            const int last = 31 - __clz(m);
+            carryE = __shfl_sync(0xffffffffu, e, last);
+            carryPos = c0 + last;
+        }
     }
+    if (!done) pos = carryPos;
     __syncwarp();
     if (pos > 0) {
         int cmplen = min(pos + plen, alen);
@@ -377,7 +430,7 @@ __device__ void trim_polyx(const DevParams& P, const uint8_t* data, Win& w, fpl_
 __global__ void __launch_bounds__(TRIM_WARPS * 32)
 k_trim(const __grid_constant__ DevParams P, DevBatch b, ReadState* __restrict__ st, fpl_read_result* __restrict__ res,
        unsigned long long* __restrict__ counters) {
-    __shared__ uint8_t scratch_all[TRIM_WARPS][FPL_WINDOW];
+    __shared__ __align__(16) uint8_t scratch_all[TRIM_WARPS][208];   // probe distances / packed window (36 words)
     const int wid = threadIdx.x >> 5, lane = lane_id();
     const int64_t r = (int64_t)blockIdx.x * TRIM_WARPS + wid;
     if (r >= b.n_reads) return;
