@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <nvrtc.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <map>
 #include <mutex>
@@ -53,6 +54,8 @@ int fpl_jit_build_scan(int device, const char* a0, const char* a1, bool doAdapte
     defs += std::string("#define FPL_DO_COUNTS ") + (doCounts ? "true" : "false") + "\n";
     defs += std::string("#define FPL_DO_CPLX ") + (doCplx ? "true" : "false") + "\n";
     defs += "#define FPL_QQ " + std::to_string(qq & 0x7f) + "\n";
+    const char* mb = getenv("FPL_JIT_MINBLOCKS");   // occupancy knob (registers per thread); 8 (64 registers) measured best on B200: 4/5/6/8 blocks -> 17.8/15.7/14.5/13.7 ms
+    defs += std::string("#define FPL_MINBLOCKS ") + (mb && atoi(mb) > 0 ? std::to_string(atoi(mb)) : std::string("8")) + "\n";
     const std::string key = std::to_string(device) + "|" + defs;
     std::lock_guard<std::mutex> lock(g_mu);
     auto it = g_cache.find(key);

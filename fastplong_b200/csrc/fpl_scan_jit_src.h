@@ -116,7 +116,7 @@ __device__ __forceinline__ void argmax(const Counter& c, uint32_t valid, int64_t
     if (val > bestM) { bestM = val; bestPos = pos0 + (__ffs(cand) - 1); }
 }
 
-extern "C" __global__ void __launch_bounds__(SF_THREADS, 6)
+extern "C" __global__ void __launch_bounds__(SF_THREADS, FPL_MINBLOCKS)
 k_scan_jit(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qualbuf, const int64_t* __restrict__ offsets,
            ReadState* __restrict__ st, int64_t n_reads) {
     __shared__ unsigned long long sh64[2][SF_WARPS];
@@ -139,22 +139,32 @@ k_scan_jit(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qualb
     const int np1 = (doAdapters && ALEN1 <= len) ? len - ALEN1 : 0;
     constexpr int step = (32 - HL) * 32;
     const int total = pre + len;
+    const int np_min = min(np0, np1);                          // < len; 0 when the scans are off
 
     int bestM0 = -1, bestM1 = -1;
     int64_t bestP0 = 0, bestP1 = 0;
     int lowq_ge = 0, nn = 0, totalq = 0, diff = 0, nbytes = 0;
 
+    // software pipeline: the sequence vectors of the warp's next tile are requested before this tile is processed
+    uint4 nx = make_uint4(0, 0, 0, 0), ny = nx;
+    {
+        const int64_t a0 = (int64_t)wid * step + 32 * lane;
+        if (a0 < total && a0 + 32 > pre) {
+            const uint4* v = reinterpret_cast<const uint4*>(sbase + a0);
+            nx = __ldg(v); ny = __ldg(v + 1);
+        }
+    }
     for (int64_t t0 = (int64_t)wid * step; t0 < total; t0 += (int64_t)SF_WARPS * step) {
         const int64_t a0 = t0 + 32 * lane;
         const bool inrange = a0 < total && a0 + 32 > pre;
-        uint32_t w[8];
-        if (inrange) {
-            const uint4* v = reinterpret_cast<const uint4*>(sbase + a0);
-            const uint4 x = __ldg(v), y = __ldg(v + 1);
-            w[0] = x.x; w[1] = x.y; w[2] = x.z; w[3] = x.w; w[4] = y.x; w[5] = y.y; w[6] = y.z; w[7] = y.w;
-        } else {
-#pragma unroll
-            for (int k = 0; k < 8; k++) w[k] = 0;
+        const uint32_t w[8] = {nx.x, nx.y, nx.z, nx.w, ny.x, ny.y, ny.z, ny.w};
+        {
+            const int64_t a1 = a0 + (int64_t)SF_WARPS * step;
+            nx = make_uint4(0, 0, 0, 0); ny = nx;
+            if (a1 < total && a1 + 32 > pre) {
+                const uint4* v = reinterpret_cast<const uint4*>(sbase + a1);
+                nx = __ldg(v); ny = __ldg(v + 1);
+            }
         }
         uint32_t bad = 0;
 #pragma unroll
@@ -191,15 +201,19 @@ k_scan_jit(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qualb
         const bool mine = lane < 32 - HL;
         uint32_t inwin = 0, v0 = 0, v1 = 0;
         if (mine && inrange) {
-            const uint32_t from0 = p_first >= 0 ? 0xFFFFFFFFu : (0xFFFFFFFFu << (int)(-p_first));
-            auto range_mask = [&](int n) -> uint32_t {
-                const int64_t hi = (int64_t)n - p_first;
-                const uint32_t upto = hi >= 32 ? 0xFFFFFFFFu : hi <= 0 ? 0u : ((1u << (int)hi) - 1u);
-                return upto & from0;
-            };
-            inwin = range_mask(len);
-            v0 = range_mask(np0);
-            v1 = range_mask(np1);
+            if (p_first >= 0 && p_first + 32 <= np_min) {       // interior lane: everything is in range
+                inwin = v0 = v1 = 0xFFFFFFFFu;
+            } else {
+                const uint32_t from0 = p_first >= 0 ? 0xFFFFFFFFu : (0xFFFFFFFFu << (int)(-p_first));
+                auto range_mask = [&](int n) -> uint32_t {
+                    const int64_t hi = (int64_t)n - p_first;
+                    const uint32_t upto = hi >= 32 ? 0xFFFFFFFFu : hi <= 0 ? 0u : ((1u << (int)hi) - 1u);
+                    return upto & from0;
+                };
+                inwin = range_mask(len);
+                v0 = range_mask(np0);
+                v1 = range_mask(np1);
+            }
         }
         if constexpr (doCounts) {
             if (inwin) {
