@@ -104,8 +104,18 @@ __device__ __forceinline__ void add_blocks(Counter& c, const Masks& m) {
     }
 }
 
-__device__ __forceinline__ void argmax(const Counter& c, uint32_t valid, int64_t pos0, int& bestM, int64_t& bestPos) {
+// gbest = best match count any lane of the CTA has seen for this adapter (shared memory): a position can only be the
+// read's first arg-max if its count is >= gbest, which the top planes rule out for almost every lane.
+__device__ __forceinline__ void argmax(const Counter& c, uint32_t valid, int64_t pos0, int& bestM, int64_t& bestPos,
+                                       volatile int* gbest) {
     if (!valid) return;
+    const int g = *gbest;
+    if constexpr (NPL >= 2) {
+        const uint32_t top = c.p[NPL - 1], nxt = c.p[NPL - 2];
+        constexpr int T1 = 1 << (NPL - 1), T0 = 1 << (NPL - 2);
+        const uint32_t f = g >= T1 + T0 ? (top & nxt) : g >= T1 ? top : g >= T0 ? (top | nxt) : 0xFFFFFFFFu;
+        if (!(valid & f)) return;
+    }
     uint32_t cand = valid;
     int val = 0;
 #pragma unroll
@@ -113,7 +123,10 @@ __device__ __forceinline__ void argmax(const Counter& c, uint32_t valid, int64_t
         const uint32_t t = cand & c.p[b];
         if (t) { cand = t; val |= 1 << b; }
     }
-    if (val > bestM) { bestM = val; bestPos = pos0 + (__ffs(cand) - 1); }
+    if (val > bestM) {
+        bestM = val; bestPos = pos0 + (__ffs(cand) - 1);
+        if (val > g) atomicMax((int*)gbest, val);
+    }
 }
 
 extern "C" __global__ void __launch_bounds__(SF_THREADS, FPL_MINBLOCKS)
@@ -121,11 +134,14 @@ k_scan_jit(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qualb
            ReadState* __restrict__ st, int64_t n_reads) {
     __shared__ unsigned long long sh64[2][SF_WARPS];
     __shared__ int sh32[4][SF_WARPS];
+    __shared__ int gbest[2];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t r = blockIdx.x;
     if (r >= n_reads) return;
     const ReadState s = st[r];
     if (!s.alive) return;
+    if (threadIdx.x < 2) gbest[threadIdx.x] = -1;
+    __syncthreads();
     const int len = s.len;
     const int64_t start = offsets[r] + s.lo;
     const int pre = (int)(start & 15);
@@ -143,7 +159,8 @@ k_scan_jit(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qualb
 
     int bestM0 = -1, bestM1 = -1;
     int64_t bestP0 = 0, bestP1 = 0;
-    int lowq_ge = 0, nn = 0, totalq = 0, diff = 0, nbytes = 0;
+    int nn = 0, totalq = 0, diff = 0, nbytes = 0;
+    unsigned ge128 = 0;   // 128 * #(q >= qualified)
 
     // software pipeline: the sequence vectors of the warp's next tile are requested before this tile is processed
     uint4 nx = make_uint4(0, 0, 0, 0), ny = nx;
@@ -166,11 +183,12 @@ k_scan_jit(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qualb
                 nx = __ldg(v); ny = __ldg(v + 1);
             }
         }
-        uint32_t bad = 0;
+        // every byte in 0x40..0x5F  <=>  bits 7..5 of (byte ^ 0xA0) are all ones: one LOP3 per word
+        uint32_t okacc = 0xFFFFFFFFu;
 #pragma unroll
-        for (int k = 0; k < 8; k++) bad |= (w[k] & 0xE0E0E0E0u) ^ 0x40404040u;
+        for (int k = 0; k < 8; k++) okacc &= w[k] ^ 0xA0A0A0A0u;
         uint32_t MA, MC, MG, MT, NM;
-        if (bad == 0) {
+        if ((okacc | 0x1F1F1F1Fu) == 0xFFFFFFFFu) {
             uint32_t B0 = 0, B1 = 0, B2 = 0, B3 = 0, B4 = 0;
 #pragma unroll
             for (int k = 7; k >= 0; k--) {
@@ -224,7 +242,8 @@ k_scan_jit(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qualb
 #pragma unroll
                     for (int k = 0; k < 8; k++) {
                         totalq = (int)__dp4a(q[k], 0x01010101u, (unsigned)totalq);
-                        lowq_ge += __popc(((q[k] | 0x80808080u) - qq4) & 0x80808080u);
+                        // bytes are 0x80 where q >= qualified: their dp4a sum is 128 * count (divided out at the end)
+                        ge128 = __dp4a(((q[k] | 0x80808080u) - qq4) & 0x80808080u, 0x01010101u, ge128);
                     }
                     nbytes += 32;
                 } else {
@@ -232,7 +251,7 @@ k_scan_jit(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qualb
                         if (inwin >> j & 1u) {
                             const int qv = (int)((q[j >> 2] >> (8 * (j & 3))) & 0xFFu);
                             totalq += qv;
-                            lowq_ge += (qv & 0x7f) >= (int)(qq4 & 0x7f);
+                            ge128 += ((qv & 0x7f) >= (int)(qq4 & 0x7f)) ? 128u : 0u;
                             nbytes++;
                         }
                 }
@@ -273,10 +292,10 @@ k_scan_jit(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qualb
             Counter c0, c1;
             c0.clear();
             add_blocks<0, 0>(c0, m);
-            argmax(c0, v0, p_first, bestM0, bestP0);
+            argmax(c0, v0, p_first, bestM0, bestP0, &gbest[0]);
             c1.clear();
             add_blocks<1, 0>(c1, m);
-            argmax(c1, v1, p_first, bestM1, bestP1);
+            argmax(c1, v1, p_first, bestM1, bestP1, &gbest[1]);
         }
     }
     unsigned long long k0 = bestM0 >= 0 ? (((unsigned long long)(unsigned)(ALEN0 - bestM0) << 32) | (unsigned)bestP0) : ~0ull;
@@ -286,6 +305,7 @@ k_scan_jit(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qualb
         const unsigned long long o0 = __shfl_xor_sync(0xffffffffu, k0, d), o1 = __shfl_xor_sync(0xffffffffu, k1, d);
         k0 = o0 < k0 ? o0 : k0; k1 = o1 < k1 ? o1 : k1;
     }
+    int lowq_ge = (int)(ge128 >> 7);
     lowq_ge = __reduce_add_sync(0xffffffffu, lowq_ge); nn = __reduce_add_sync(0xffffffffu, nn);
     totalq = __reduce_add_sync(0xffffffffu, totalq); diff = __reduce_add_sync(0xffffffffu, diff);
     nbytes = __reduce_add_sync(0xffffffffu, nbytes);
