@@ -34,6 +34,23 @@ OPTION_SETS = {
 }
 
 
+def _rand_adapter(n, seed):
+    rng = np.random.default_rng(seed)
+    return "".join("ACGT"[i] for i in rng.integers(0, 4, size=n))
+
+
+# -s/-e adapters of every word-count class of the scan kernels (halo 1..4 words, 5..8 counter planes)
+LONG_ADAPTERS = {n: (_rand_adapter(n, 100 + n), _rand_adapter(max(4, n - 3), 200 + n)) for n in (31, 32, 33, 45, 64, 65, 96, 97, 127, 128)}
+for _n, (_s, _e) in LONG_ADAPTERS.items():
+    OPTION_SETS[f"long_adapter_{_n}"] = Options(start_adapter=_s, end_adapter=_e, low_complexity_filter=(_n % 2 == 0))
+
+
+def long_adapter_batch(n_adapter, seed, n=160):
+    """Reads with the long adapters planted at the ends and in the middle (chimeras), noisy."""
+    s, e = LONG_ADAPTERS[n_adapter]
+    return synth.ont_like(n, 1500, seed, adapter_start=s, adapter_end=e, p_chimera=0.15, p_n=0.002)
+
+
 def planted_fasta_reads(seed, n=120):
     """Reads with FASTA5 entries planted at either end (noisy), for the fasta5 option set."""
     rng = np.random.default_rng(seed)

@@ -54,6 +54,26 @@ def test_ont_like_vs_oracle(name):
                          cases.ont_batch(91, n=400, mean=3000, p_chimera=0.05, p_polya=0.05), name + "/ont")
 
 
+@pytest.mark.parametrize("n", sorted(cases.LONG_ADAPTERS))
+def test_long_adapters_vs_oracle(n):
+    """-s/-e adapters of 31..128 bp: every halo-word / counter-plane class of k_scan_jit and k_scan_fast."""
+    check_against_oracle(cases.OPTION_SETS[f"long_adapter_{n}"], cases.long_adapter_batch(n, 900 + n), f"long{n}")
+
+
+@pytest.mark.parametrize("n", [30, 64, 128])
+def test_precompiled_scan_matches_jit(n, monkeypatch):
+    """FPL_NO_JIT=1 selects the precompiled k_scan_fast; FPL_FORCE_GENERIC_SCAN=1 the byte-wise k_scan."""
+    if n == 30:
+        opt, batch = cases.OPTION_SETS["default_se"], cases.ont_batch(17, n=300, mean=2500, p_chimera=0.1)
+    else:
+        opt, batch = cases.OPTION_SETS[f"long_adapter_{n}"], cases.long_adapter_batch(n, 5)
+    ref = gpu_engine(opt).process(batch)
+    monkeypatch.setenv("FPL_NO_JIT", "1")
+    compare_results(gpu_engine(opt).process(batch), ref, "k_scan_fast")
+    monkeypatch.setenv("FPL_FORCE_GENERIC_SCAN", "1")
+    compare_results(gpu_engine(opt).process(batch), ref, "k_scan")
+
+
 def test_config1_shape_vs_oracle():
     """BASELINE config 1 shape (ONT reads, mean 8 kb, known 30 bp adapters, default filters), 1500 reads."""
     opt = Options(start_adapter=synth.ADAPTER_START)

@@ -30,6 +30,11 @@ def test_ont_like(name):
     check(cases.OPTION_SETS[name], cases.ont_batch(77, n=150, mean=2500, p_chimera=0.05, p_polya=0.05), name + "/ont")
 
 
+@pytest.mark.parametrize("n", sorted(cases.LONG_ADAPTERS))
+def test_long_adapters(n):
+    check(cases.OPTION_SETS[f"long_adapter_{n}"], cases.long_adapter_batch(n, 900 + n), f"long{n}")
+
+
 def test_edit_distance_random_pairs():
     rng = np.random.default_rng(5)
     o, r = OracleEngine(Options()), RefEngine(Options())
