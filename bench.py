@@ -34,10 +34,31 @@ SEED = 20260924
 ALG_BYTES_PER_BASE = 2      # 1 sequence byte + 1 quality byte, each read once
 ALG_BYTES_PER_READ = 64     # offset, length, result record
 HBM_FALLBACK_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
+# CPU arm: a sample large enough that the binary's fixed costs (start-up, adapter detection pre-pass, report writing)
+# do not dominate: 20k reads x 15 kb = 0.3 Gbases, a few seconds of reference CPU time per run with 16 workers
+REF_SAMPLE_READS = 20000
 
 
-def workload_options():
+WORKLOADS = {
+    # name: (reads per tile, replicas, mean length, description)
+    "c2": (TILE_READS, REPLICAS, MEAN_LEN, "configs[1]: 1M ONT reads mean 15 kb, auto-detected adapters + --cut_front --cut_tail "
+                                           "-W 10, default filters, pre+post stats"),
+    "c3": (8192, 8, 20000, "configs[2] shape at 1/76 scale: 65k HiFi-like reads mean 20 kb, 64-entry adapter FASTA + polyX"),
+    "c5": (512, 8, 500000, "configs[4] shape: 4k ultra-long reads mean 500 kb, adapter trim only (-Q -L)"),
+}
+
+
+def workload_options(name="c2"):
     from fastplong_b200 import Options, synth
+    if name == "c3":
+        import numpy as np
+        rng = np.random.default_rng(64)
+        fasta = ["".join("ACGT"[i] for i in rng.integers(0, 4, size=int(rng.integers(20, 45)))) for _ in range(64)]
+        return Options(start_adapter=synth.ADAPTER_START, end_adapter=synth.ADAPTER_END, adapter_fasta=sorted(fasta),
+                       trim_poly_x=True)
+    if name == "c5":
+        return Options(start_adapter=synth.ADAPTER_START, end_adapter=synth.ADAPTER_END, disable_quality_filtering=True,
+                       disable_length_filtering=True)
     # -s/-e left at "auto" on the CLI; the strings below are what Evaluator::evalAdapterAndReadNum detects on this
     # generator's reads (verified with oracle/_ref/fastplong_ref) — the pre-pass itself is
     # outside the hot path.
@@ -127,13 +148,17 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    opt = workload_options()
+    opt = workload_options(args.workload)
     opt.device = local
-    tile_reads = args.tile_reads
-    replicas = args.replicas
+    wl_reads, wl_reps, mean_len, wl_desc = WORKLOADS[args.workload]
+    tile_reads = args.tile_reads or wl_reads
+    replicas = args.replicas or wl_reps
     # ---- synthetic workload: seeded host tile (per rank: independent shards, weak scaling) ----
     t0 = time.time()
-    tile = synth.ont_like(tile_reads, MEAN_LEN, SEED + rank)
+    kw = {}
+    if args.workload == "c3":
+        kw = dict(q_mean=33.0, q_sd=6.0, q_clip=60, p_polya=0.05, planted=opt.adapter_fasta[:4], p_planted=0.2)
+    tile = synth.ont_like(tile_reads, mean_len, SEED + rank, **kw)
     gen_s = time.time() - t0
     tile_bytes = tile.n_bytes - 256            # drop the tail pad: replicas are laid back to back (multiple of 128)
     n_reads = tile_reads * replicas
@@ -283,7 +308,7 @@ def run_ours(args):
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_baseline = reference_cpu_run(sample_reads=1000, repeats=1)
+        cpu_baseline = reference_cpu_run(sample_reads=REF_SAMPLE_READS, repeats=1)
 
     if world > 1:
         dist.barrier()
@@ -295,9 +320,8 @@ def run_ours(args):
         "unit": "Gbases/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "configs[1]: 1M ONT reads mean 15 kb, auto-detected adapters + --cut_front --cut_tail "
-                               "-W 10, default filters, pre+post stats",
-                   "reads_per_gpu": n_reads, "bases_per_gpu": n_bases, "mean_len": MEAN_LEN,
+        "config": {"workload": wl_desc,
+                   "reads_per_gpu": n_reads, "bases_per_gpu": n_bases, "mean_len": mean_len,
                    "tile": f"{tile_reads} seeded reads x {replicas} replicas in HBM",
                    "adapters": "as auto-detected by the reference evaluator on this generator (30 bp start + revcomp end)",
                    "l2": "inputs (2 x %.1f GB) larger than L2; no flush needed" % (d_seq.numel() / 1e9),
@@ -314,6 +338,9 @@ def run_ours(args):
 
 
 # ----------------------------------------------------------------------------------------------------------------
+_SAMPLE_CACHE = {}
+
+
 def reference_cpu_run(sample_reads, repeats):
     """fastplong_ref (the unmodified reference, oracle/_ref) on a bounded sample of the same workload, plain FASTQ
     on tmpfs, all the worker threads it accepts (-w min(16, nproc)).  Returns the cpu_baseline object."""
@@ -323,9 +350,15 @@ def reference_cpu_run(sample_reads, repeats):
         return {"value": None, "unit": "Gbases/s", "cores": 0, "kind": "reference",
                 "sample": "oracle/_ref/fastplong_ref not built"}
     tmp = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
-    fq = os.path.join(tmp, f"fpl_bench_{os.getpid()}.fq")
-    batch = synth.ont_like(sample_reads, MEAN_LEN, SEED)
-    synth.to_fastq(batch, fq)
+    fq = os.path.join(tmp, f"fpl_bench_{os.getpid()}_{sample_reads}.fq")
+    if fq in _SAMPLE_CACHE:
+        n_bases = _SAMPLE_CACHE[fq]
+    else:
+        batch = synth.ont_like(sample_reads, MEAN_LEN, SEED)
+        synth.to_fastq(batch, fq)
+        n_bases = _SAMPLE_CACHE[fq] = batch.n_bases
+        import atexit
+        atexit.register(lambda: os.path.exists(fq) and os.remove(fq))
     cores = min(16, os.cpu_count() or 1)
     opt = workload_options()
     opt.start_adapter = opt.end_adapter = "auto"   # the binary runs its own detection pre-pass
@@ -345,22 +378,22 @@ def reference_cpu_run(sample_reads, repeats):
             if best is None or wall < best:
                 best = wall
     finally:
-        for suffix in ("", ".out", ".json", ".html"):
+        for suffix in (".out", ".json", ".html"):
             try:
                 os.remove(fq + suffix)
             except OSError:
                 pass
-    return {"value": round(batch.n_bases / best / 1e9, 5), "unit": "Gbases/s", "cores": cores, "kind": "reference",
-            "sample": f"{sample_reads} reads / {batch.n_bases} bases of the same generator, fastplong_ref -w {cores} "
+    return {"value": round(n_bases / best / 1e9, 5), "unit": "Gbases/s", "cores": cores, "kind": "reference",
+            "sample": f"{sample_reads} reads / {n_bases} bases of the same generator, fastplong_ref -w {cores} "
                       f"whole-binary wall {best:.2f} s (plain FASTQ on tmpfs, incl. detection pre-pass and reports)",
-            "wall_s": round(best, 3), "bases": batch.n_bases}
+            "wall_s": round(best, 3), "bases": n_bases}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_reads = 1000
+    sample_reads = REF_SAMPLE_READS
     for _ in range(max(args.warmup, 1)):
         reference_cpu_run(sample_reads, 1)
     walls, base = [], None
@@ -378,7 +411,7 @@ def run_reference(args):
             "value": round(value, 5), "unit": "Gbases/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
             "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": round(ms, 2), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "configs[1] shape, bounded sample: %d ONT reads mean 15 kb per step, auto-detected "
+            "config": {"workload": "configs[1] shape, bounded sample: %d ONT reads mean 15 kb (0.3 Gbases) per step, auto-detected "
                                    "adapters + --cut_front --cut_tail -W 10 (reference CPU build, host cores only)" % sample_reads},
             "cpu_baseline": cb,
             "e2e": {"value": round(value, 5), "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -392,8 +425,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--tile-reads", type=int, default=TILE_READS)
-    ap.add_argument("--replicas", type=int, default=REPLICAS)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS),
+                    help="c2 = BASELINE configs[1] (the bench line); c3/c5 = other BASELINE config shapes, informational")
+    ap.add_argument("--tile-reads", type=int, default=0)
+    ap.add_argument("--replicas", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

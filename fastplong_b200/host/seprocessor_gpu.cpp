@@ -46,9 +46,10 @@ template <typename T>
 struct Pinned {
     T* p = nullptr;
     size_t cap = 0;
-    void reserve(size_t n) {
+    // page-locking is slow (tens of ms per call): grow rarely, never shrink
+    void reserve(size_t n, size_t at_least = 0) {
         if (n <= cap) return;
-        size_t want = cap ? cap : 1024;
+        size_t want = cap ? cap : (at_least ? at_least : 1024);
         while (want < n) want *= 2;
         T* q = nullptr;
         if (cudaMallocHost((void**)&q, want * sizeof(T)) != cudaSuccess) error_exit("fastplong_gpu: cudaMallocHost failed");
@@ -261,8 +262,9 @@ bool SingleEndProcessor::processSingleEnd(ReadPack* pack, ThreadConfig* config) 
             nreads++;
             nbytes += (p->data[i]->mSeq->length() + kSlotAlign - 1) / kSlotAlign * kSlotAlign;
         }
-    w.seq.reserve(nbytes + 256); w.qual.reserve(nbytes + 256);
-    w.offsets.reserve(nreads + 1); w.lens.reserve(nreads + 1); w.results.reserve(nreads + 1);
+    // first use sizes the pinned buffers for a full batch, so that later batches do not re-pin memory
+    w.seq.reserve(nbytes + 256, (size_t)kBatchBases + (8u << 20)); w.qual.reserve(nbytes + 256, (size_t)kBatchBases + (8u << 20));
+    w.offsets.reserve(nreads + 1, 1u << 16); w.lens.reserve(nreads + 1, 1u << 16); w.results.reserve(nreads + 1, 1u << 16);
     size_t k = 0, off = 0;
     for (ReadPack* p : w.packs)
         for (int i = 0; i < p->count; i++) {

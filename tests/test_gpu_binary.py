@@ -82,3 +82,31 @@ def test_gpu_binary_matches_reference_binary(name, threads, tmp_path):
         for k in b:
             assert a[k] == b[k], k
         raise AssertionError("JSON text differs although the parsed content is equal")
+
+
+@needs_bin
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/fastplong_ref not built")
+def test_config1_full_size_bit_exact(tmp_path):
+    """BASELINE configs[0] at full size: 10k ONT reads mean 8 kb, known 30 bp start/end adapters, default Q-filter —
+    reference CPU run vs the GPU binary, bit-exact FASTQ outputs and JSON report; prints both wall times."""
+    import time
+    opt = cases.OPTION_SETS["default_se"]
+    batch = synth.ont_like(10000, 8000, 1)
+    fq = "/dev/shm/fpl_c1.fq" if os.path.isdir("/dev/shm") else str(tmp_path / "c1.fq")
+    synth.to_fastq(batch, fq)
+    try:
+        t0 = time.perf_counter()
+        ref = run(REF_BIN, opt, fq, str(tmp_path), "ref", threads=16)
+        t1 = time.perf_counter()
+        got = run(GPU_BIN, opt, fq, str(tmp_path), "gpu", threads=4)
+        t2 = time.perf_counter()
+    finally:
+        if fq.startswith("/dev/shm"):
+            os.remove(fq)
+    print(f"\nconfig 1 ({batch.n_bases / 1e6:.1f} Mbases): fastplong_ref -w 16 {t1 - t0:.2f} s, fastplong_gpu -w 4 {t2 - t1:.2f} s")
+    open(os.path.join(ROOT, "gpurun_out", "c1_binary_times.txt"), "w").write(
+        f"config1 {batch.n_reads} reads {batch.n_bases} bases ref_w16_s {t1 - t0:.3f} gpu_w4_s {t2 - t1:.3f}\n") \
+        if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else None
+    assert got["out_md5"] == ref["out_md5"]
+    assert got["failed_md5"] == ref["failed_md5"]
+    assert got["json_text_md5"] == ref["json_text_md5"]
