@@ -65,6 +65,9 @@ RESULT_DTYPE = np.dtype([
     ("pre_median_qual", "u1"), ("polyx_base", "u1"), ("n_events", "<u2"),
     ("polyx_len", "<i4"), ("adapter_trimmed_bases", "<i4"), ("events", "<u4", (INLINE_EVENTS,))], align=False)
 assert RESULT_DTYPE.itemsize == 64
+FASTQ_RECORD_DTYPE = np.dtype([("name_off", "<i8"), ("seq_off", "<i8"), ("plus_off", "<i8"), ("qual_off", "<i8"),
+                               ("name_len", "<i4"), ("seq_len", "<i4"), ("plus_len", "<i4"), ("reserved", "<i4")])
+assert FASTQ_RECORD_DTYPE.itemsize == 48
 assert C.sizeof(FplOptions) == 128, C.sizeof(FplOptions)
 
 

@@ -34,6 +34,8 @@ def load_library():
     lib.fpl_process_host.argtypes = [C.c_void_p, C.POINTER(FplBatch), C.c_void_p]
     lib.fpl_process_device.argtypes = [C.c_void_p, C.POINTER(FplBatch), C.c_void_p]
     lib.fpl_sync.argtypes = [C.c_void_p]
+    lib.fpl_process_fastq_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
+                                           C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.fpl_stream.argtypes = [C.c_void_p]
     lib.fpl_stream.restype = C.c_void_p
     lib.fpl_fetch_results.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
@@ -58,7 +60,7 @@ def load_library():
     return lib
 
 
-EXPORTS = ["fpl_last_error", "fpl_abi_version", "fpl_create", "fpl_destroy", "fpl_process_host", "fpl_process_device",
+EXPORTS = ["fpl_last_error", "fpl_abi_version", "fpl_create", "fpl_destroy", "fpl_process_host", "fpl_process_device", "fpl_process_fastq_host",
            "fpl_sync", "fpl_stream", "fpl_fetch_results", "fpl_stats_cycles", "fpl_stats_reserve", "fpl_stats_download",
            "fpl_stats_device_ptr", "fpl_counter_words", "fpl_counters_download", "fpl_counters_device_ptr",
            "fpl_reset", "fpl_last_kernel_times", "fpl_launch_count", "fpl_set_timing"]
@@ -109,6 +111,22 @@ class Engine:
         b = batch.to_abi()
         self._check(self.lib.fpl_process_host(self.h, C.byref(b), res.ctypes.data))
         return res
+
+    def process_fastq(self, text, is_last=True, max_records=None):
+        """A chunk of plain FASTQ text (bytes / uint8 array) -> (record table, per-read results, bytes consumed), or None
+        if the chunk is not in the strict layout (the caller then uses the reference reader)."""
+        from .abi import FASTQ_RECORD_DTYPE
+        buf = np.frombuffer(text, dtype=np.uint8) if not isinstance(text, np.ndarray) else text
+        cap = int(max_records if max_records is not None else max(16, buf.size // 8))
+        recs = np.zeros(cap, dtype=FASTQ_RECORD_DTYPE)
+        res = np.zeros(cap, dtype=RESULT_DTYPE)
+        n, used = C.c_int64(), C.c_int64()
+        rc = self.lib.fpl_process_fastq_host(self.h, buf.ctypes.data if buf.size else None, buf.size, int(is_last),
+                                             recs.ctypes.data, res.ctypes.data, cap, C.byref(n), C.byref(used))
+        if rc == 1:
+            return None
+        self._check(rc)
+        return recs[:n.value], res[:n.value], used.value
 
     def process_device(self, seq_ptr, qual_ptr, offsets_ptr, lens_ptr, n_reads, n_bytes, results_ptr=None):
         b = FplBatch(seq_ptr, qual_ptr, offsets_ptr, lens_ptr, n_reads, n_bytes)

@@ -11,6 +11,7 @@
 #include "fpl_device.cuh"
 #include "fpl_scanplan.h"
 #include "fpl_jit.h"
+#include "fpl_ingest.h"
 
 static_assert(sizeof(fpl_options) == 128, "fpl_options ABI size");
 static_assert(sizeof(fpl_read_result) == 64, "fpl_read_result ABI size");
@@ -56,6 +57,7 @@ struct fpl_ctx {
     DevParams P;
     ScanPlan plan;
     FplJitKernel jit;   // specialised scan kernel (NVRTC), fn == nullptr if not used
+    FplIngest ingest;   // device-side FASTQ parsing state
     int n_adapters = 0;
     uint8_t* d_adapters = nullptr;
     int* d_alen = nullptr;
@@ -353,6 +355,7 @@ void fpl_destroy(fpl_ctx* c) {
     cudaFree(c->d_stats[0]); cudaFree(c->d_stats[1]); cudaFree(c->d_counters);
     cudaFree(c->d_state); cudaFree(c->d_results); cudaFree(c->d_preseg); cudaFree(c->d_postseg);
     cudaFree(c->d_seq); cudaFree(c->d_qual); cudaFree(c->d_offsets); cudaFree(c->d_lens);
+    fpl_ingest_free(&c->ingest);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -422,6 +425,45 @@ int fpl_process_host(fpl_ctx* c, const fpl_batch* b, fpl_read_result* results) {
     DevBatch d = {c->d_seq, c->d_qual, c->d_offsets, c->d_lens, n};
     if (run_batch(c, d, b->lens, nullptr)) return -1;
     if (n) CK(cudaMemcpyAsync(results, c->d_results, sizeof(fpl_read_result) * n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    collect_times(c);
+    return 0;
+}
+
+int fpl_process_fastq_host(fpl_ctx* c, const uint8_t* text, int64_t n_bytes, int is_last, fpl_fastq_record* records,
+                           fpl_read_result* results, int64_t max_records, int64_t* n_records, int64_t* consumed) {
+    g_err[0] = 0;
+    if (!c || !n_records || !consumed || (n_bytes > 0 && !text)) return fail("fpl_process_fastq_host: null argument");
+    if (n_bytes < 0 || n_bytes >= (1ll << 40)) return fail("fpl_process_fastq_host: bad chunk size");
+    CK(cudaSetDevice(c->device));
+    char err[256] = "";
+    int64_t nrec = 0;
+    int rc = fpl_ingest_index(&c->ingest, text, n_bytes, is_last, c->stream, &nrec, consumed, err, sizeof(err));
+    if (rc < 0) return fail("fpl_process_fastq_host: %s", err);
+    if (rc > 0) return 1;
+    *n_records = nrec;
+    if (nrec == 0) return 0;
+    if (nrec > max_records) return 1;
+    if (!records || !results) return fail("fpl_process_fastq_host: records/results is null");
+    FplIngest& g = c->ingest;
+    const int64_t need = g.packed_bytes + 64;
+    if (need > c->cap_bytes) {
+        cudaFree(c->d_seq); cudaFree(c->d_qual); c->d_seq = c->d_qual = nullptr; c->cap_bytes = 0;
+        CK(cudaMalloc(&c->d_seq, need));
+        CK(cudaMalloc(&c->d_qual, need));
+        c->cap_bytes = need;
+    }
+    // slot padding is never interpreted, but keep it defined for whole-vector reads past a read's end
+    CK(cudaMemsetAsync(c->d_seq, 0, need, c->stream));
+    CK(cudaMemsetAsync(c->d_qual, 0, need, c->stream));
+    if (fpl_ingest_pack(&g, nrec, c->d_seq, c->d_qual, c->stream, err, sizeof(err))) return fail("fpl_process_fastq_host: %s", err);
+    c->h_lens.resize((size_t)nrec);
+    CK(cudaMemcpyAsync(c->h_lens.data(), g.d_lens, sizeof(int32_t) * nrec, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(records, g.d_rec, sizeof(fpl_fastq_record) * nrec, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    DevBatch d = {c->d_seq, c->d_qual, g.d_offsets, g.d_lens, nrec};
+    if (run_batch(c, d, c->h_lens.data(), nullptr)) return -1;
+    CK(cudaMemcpyAsync(results, c->d_results, sizeof(fpl_read_result) * nrec, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     collect_times(c);
     return 0;

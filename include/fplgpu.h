@@ -220,6 +220,33 @@ int fpl_sync(fpl_ctx* ctx);
 /* The context's CUDA stream (a cudaStream_t), so a caller can order its own work / events against the kernels. */
 void* fpl_stream(fpl_ctx* ctx);
 
+/*
+ * One FASTQ record located in a chunk of plain FASTQ text (byte offsets from the start of the chunk).
+ * The quality line has seq_len bytes.
+ */
+typedef struct fpl_fastq_record {
+    int64_t name_off;                 /* the '@' of the name line */
+    int64_t seq_off;
+    int64_t plus_off;                 /* the '+' line (kept verbatim in the output, src/read.cpp:119-143) */
+    int64_t qual_off;
+    int32_t name_len, seq_len, plus_len, reserved;
+} fpl_fastq_record;
+
+/*
+ * FastqReader::getLine / FastqReader::read (src/fastqreader.cpp:219-347) + the pack->batch staging
+ * + processSingleEnd, for one chunk of plain-text FASTQ held in HOST memory: the text is copied to the device, the
+ * newline index, the record table and the packed batch are built there, every kernel of fpl_process_host runs, and
+ * the record table (records[]) and the per-read results (results[]) come back.  *n_records = complete records found,
+ * *bytes_consumed = bytes of the chunk they span (the caller prepends the rest to its next chunk); is_last_chunk != 0
+ * lets an unterminated last line count.
+ * Returns 0 on success; 1 if the chunk is not in the strict layout this path handles (LF line ends, exactly four lines
+ * per record, '@' / '+' in place, |sequence| == |quality|, or more than max_records records) — nothing has been
+ * accumulated then and the caller must parse this input with the reference reader instead; < 0 on error.
+ */
+int fpl_process_fastq_host(fpl_ctx* ctx, const uint8_t* text, int64_t n_bytes, int is_last_chunk,
+                           fpl_fastq_record* records, fpl_read_result* results, int64_t max_records,
+                           int64_t* n_records, int64_t* bytes_consumed);
+
 /* Copy the context's last device results (n records) to host memory. */
 int fpl_fetch_results(fpl_ctx* ctx, fpl_read_result* results, int64_t n_reads);
 
