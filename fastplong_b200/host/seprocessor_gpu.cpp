@@ -15,8 +15,12 @@
 //   * at the end the device-accumulated Stats blocks and the adapter event table are added into each worker's
 //     Stats / FilterResult objects so that Stats::merge, summarize and the reporters run unchanged.
 // No per-base decision is taken on the host.
+#include <condition_variable>
+#include <cstdio>
 #include <cstring>
+#include <deque>
 #include <functional>
+#include <mutex>
 #include <map>
 #include <memory>
 #include <string>
@@ -152,6 +156,74 @@ void addStatsBlock(Stats* s, const std::vector<int64_t>& blk, int64_t C) {
     }
     s->mReads += t[FPL_STATS_READS];
     s->mLengthSum += t[FPL_STATS_LENSUM];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Raw-text path: for a plain (not gzipped) FASTQ file the device finds the records itself
+// (fpl_process_fastq_host) and the output strings are cut straight out of the file chunk; the reference's
+// FastqReader / ReadPool are not involved.  Chunks are cut on the host at record boundaries so that they are
+// independent; chunk k goes to worker k % T and its output string to writer list k % T, which is exactly the order the
+// writer threads consume (src/writerthread.cpp:37-48).
+// ---------------------------------------------------------------------------------------------------------------
+struct TextChunk {
+    uint8_t* p = nullptr;      // pinned
+    size_t cap = 0, n = 0;
+    bool last = false;
+};
+
+struct ChunkQueue {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<TextChunk*> q;
+    bool done = false;
+    void push(TextChunk* c) { { std::lock_guard<std::mutex> l(mu); q.push_back(c); } cv.notify_all(); }
+    void finish() { { std::lock_guard<std::mutex> l(mu); done = true; } cv.notify_all(); }
+    TextChunk* pop() {   // nullptr when finished
+        std::unique_lock<std::mutex> l(mu);
+        cv.wait(l, [&] { return !q.empty() || done; });
+        if (q.empty()) return nullptr;
+        TextChunk* c = q.front(); q.pop_front();
+        return c;
+    }
+};
+
+TextChunk* newChunk(size_t cap) {
+    TextChunk* c = new TextChunk();
+    if (cudaMallocHost((void**)&c->p, cap) != cudaSuccess) error_exit("fastplong_gpu: cudaMallocHost failed");
+    c->cap = cap;
+    return c;
+}
+void growChunk(TextChunk* c, size_t cap) {
+    uint8_t* q = nullptr;
+    if (cudaMallocHost((void**)&q, cap) != cudaSuccess) error_exit("fastplong_gpu: cudaMallocHost failed");
+    memcpy(q, c->p, c->n);
+    cudaFreeHost(c->p);
+    c->p = q; c->cap = cap;
+}
+
+// Largest prefix of buf[0..n) that ends at a record boundary: a newline followed by an '@' line whose line-after-next
+// starts with '+' (a quality line may start with '@', but then the line two below it is a sequence, not a '+' line).
+size_t recordBoundary(const uint8_t* buf, size_t n) {
+    size_t end = n;
+    while (end > 0) {
+        const uint8_t* nl = (const uint8_t*)memrchr(buf, '\n', end);
+        if (!nl) return 0;
+        const size_t p = (size_t)(nl - buf) + 1;                 // candidate: a record starts at p
+        if (p < n && buf[p] == '@') {
+            const uint8_t* l1 = (const uint8_t*)memchr(buf + p, '\n', n - p);
+            const uint8_t* l2 = l1 ? (const uint8_t*)memchr(l1 + 1, '\n', n - (size_t)(l1 + 1 - buf)) : nullptr;
+            if (l2 && (size_t)(l2 + 1 - buf) < n && l2[1] == '+') return p;
+        }
+        end = (size_t)(nl - buf);
+    }
+    return 0;
+}
+
+bool rawTextEligible(Options* o) {
+    if (getenv("FPL_HOST_PARSE")) return false;
+    if (o->inputFromSTDIN || o->in == "/dev/stdin" || ends_with(o->in, ".gz")) return false;
+    if (o->readsToProcess > 0 || o->split.enabled) return false;
+    return true;
 }
 
 }  // namespace
@@ -410,15 +482,142 @@ bool SingleEndProcessor::process() {
         initConfig(configs[t]);
     }
 
-    std::thread reader(std::bind(&SingleEndProcessor::readerTask, this));
-    std::vector<std::thread> workers;
-    for (int t = 0; t < T; t++) workers.emplace_back(std::bind(&SingleEndProcessor::processorTask, this, configs[t]));
     std::unique_ptr<std::thread> leftWriter, failedWriter;
     if (mLeftWriter) leftWriter.reset(new std::thread(std::bind(&SingleEndProcessor::writerTask, this, mLeftWriter)));
     if (mFailedWriter) failedWriter.reset(new std::thread(std::bind(&SingleEndProcessor::writerTask, this, mFailedWriter)));
 
-    reader.join();
-    for (auto& th : workers) th.join();
+    bool rawText = rawTextEligible(mOptions);
+    if (rawText) {
+        // ---- raw-text path: chunk reader -> T workers (device ingest + processSingleEnd + output assembly) ----
+        const size_t kChunk = 32u << 20;
+        std::vector<ChunkQueue> queues(T);
+        ChunkQueue freeList;
+        for (int i = 0; i < T + 2; i++) freeList.push(newChunk(kChunk + (8u << 20)));
+        FILE* fp = fopen(mOptions->in.c_str(), "rb");
+        if (!fp) error_exit("Failed to open file: " + mOptions->in);
+        WriterThread* left = mLeftWriter;
+        WriterThread* failedW = mFailedWriter;
+        Options* opt = mOptions;
+        std::atomic<int> notStrict(0);
+        if (mOptions->verbose) loginfo("start to load data");
+        std::thread reader([&] {
+            TextChunk* cur = freeList.pop();
+            cur->n = 0;
+            long k = 0;
+            bool eof = false;
+            while (!eof) {
+                if (cur->cap - cur->n < kChunk) growChunk(cur, cur->cap * 2);
+                const size_t got = fread(cur->p + cur->n, 1, kChunk, fp);
+                cur->n += got;
+                eof = got < kChunk;
+                size_t cut = eof ? cur->n : recordBoundary(cur->p, cur->n);
+                if (!eof && cut == 0) continue;                       // one record larger than the chunk: keep reading
+                TextChunk* next = nullptr;
+                if (!eof) {
+                    next = freeList.pop();
+                    if (next->cap < cur->n - cut + kChunk) growChunk(next, cur->n - cut + kChunk + (8u << 20));
+                    next->n = cur->n - cut;
+                    memcpy(next->p, cur->p + cut, next->n);
+                }
+                cur->n = cut; cur->last = eof;
+                queues[k % T].push(cur);
+                k++;
+                cur = next;
+            }
+            for (int t = 0; t < T; t++) queues[t].finish();
+        });
+        std::vector<std::thread> workers;
+        for (int t = 0; t < T; t++) workers.emplace_back([&, t] {
+            GpuWorker& w = *g_workers[t];
+            ThreadConfig* config = configs[t];
+            Stats* pre = config->getPreStats1();
+            Stats* post = config->getPostStats1();
+            FilterResult* fr = config->getFilterResult();
+            std::vector<fpl_fastq_record> recs;
+            std::vector<fpl_read_result> res;
+            while (TextChunk* c = queues[t].pop()) {
+                // at most one record per 4 bytes ("@\n\n+\n\n" is 6); size the tables from the text, generously
+                const size_t cap = c->n / 6 + 16;
+                if (recs.size() < cap) { recs.resize(cap); res.resize(cap); }
+                int64_t n = 0, used = 0;
+                const int rc = fpl_process_fastq_host(w.ctx, c->p, (int64_t)c->n, c->last ? 1 : 0, recs.data(), res.data(),
+                                                      (int64_t)cap, &n, &used);
+                if (rc < 0) check(rc, "fpl_process_fastq_host");
+                if (rc == 1 || (size_t)used != c->n) { notStrict = 1; n = 0; }
+                string* outstr = new string();
+                string* failedOut = new string();
+                const char* text = (const char*)c->p;
+                outstr->reserve(c->n);
+                for (int64_t i = 0; i < n; i++) {
+                    const fpl_fastq_record& fq = recs[i];
+                    const fpl_read_result& rr = res[i];
+                    const int L = fq.seq_len;
+                    pre->mLengthVec.push_back(L);
+                    pre->mNeedCalcLength = true;
+                    if (L > 0) pre->mQualLength[(char)rr.pre_median_qual].push_back(L);
+                    if (rr.flags & FPL_FLAG_POLYX) fr->addPolyXTrimmed(rr.polyx_base, rr.polyx_len);
+                    if (rr.adapter_trimmed_bases > 0) fr->addReadTrimmed(rr.adapter_trimmed_bases);
+                    for (int sgi = 0; sgi < rr.n_segments; sgi++) {
+                        const int code = rr.seg_result[sgi];
+                        config->addFilterResult(code, 1);
+                        const bool pass = code == PASS_FILTER;
+                        if (!pass && !(failedW && rr.n_segments == 1)) continue;
+                        string& dst = pass ? *outstr : *failedOut;
+                        const int lo = pass ? rr.seg_lo[sgi] : rr.trim_lo, ln = pass ? rr.seg_len[sgi] : rr.trim_len;
+                        if (pass && (rr.flags & FPL_FLAG_MIDDLE_ADAPTER)) {
+                            dst.push_back('@');
+                            dst.append((sgi == 1 || (rr.flags & FPL_FLAG_SEG0_IS_RIGHT)) ? "split-by-adapter-right-" : "split-by-adapter-left-");
+                            dst.append(text + fq.name_off + 1, fq.name_len - 1);
+                        } else {
+                            dst.append(text + fq.name_off, fq.name_len);
+                        }
+                        if (!pass) { dst.push_back(' '); dst.append(FAILED_TYPES[code]); }
+                        dst.push_back('\n');
+                        dst.append(text + fq.seq_off + lo, ln);
+                        dst.push_back('\n');
+                        dst.append(text + fq.plus_off, fq.plus_len);
+                        dst.push_back('\n');
+                        dst.append(text + fq.qual_off + lo, ln);
+                        dst.push_back('\n');
+                        if (pass) {
+                            post->mLengthVec.push_back(ln);
+                            post->mNeedCalcLength = true;
+                            if (ln > 0) post->mQualLength[(char)rr.seg_median_qual[sgi]].push_back(ln);
+                        }
+                    }
+                }
+                if (left) { left->input(t, outstr); outstr = NULL; }
+                if (failedW) { failedW->input(t, failedOut); failedOut = NULL; }
+                delete outstr;
+                delete failedOut;
+                freeList.push(c);
+            }
+            (void)opt;
+        });
+        reader.join();
+        for (auto& th : workers) th.join();
+        fclose(fp);
+        while (true) {
+            // drain the free list
+            std::unique_lock<std::mutex> l(freeList.mu);
+            if (freeList.q.empty()) break;
+            TextChunk* c = freeList.q.front(); freeList.q.pop_front();
+            l.unlock();
+            cudaFreeHost(c->p);
+            delete c;
+        }
+        if (notStrict)
+            error_exit("fastplong_gpu: the input is not in the strict 4-line FASTQ layout the device parser handles "
+                       "(CR line ends, blank lines or a malformed record); rerun with FPL_HOST_PARSE=1 to use the reference reader");
+        if (mLeftWriter) mLeftWriter->setInputCompleted();
+        if (mFailedWriter) mFailedWriter->setInputCompleted();
+    } else {
+        std::thread reader(std::bind(&SingleEndProcessor::readerTask, this));
+        std::vector<std::thread> workers;
+        for (int t = 0; t < T; t++) workers.emplace_back(std::bind(&SingleEndProcessor::processorTask, this, configs[t]));
+        reader.join();
+        for (auto& th : workers) th.join();
+    }
     if (!mOptions->split.enabled) {
         if (leftWriter) leftWriter->join();
         if (failedWriter) failedWriter->join();

@@ -28,11 +28,11 @@ def json_text_md5(path):
     return hashlib.md5(b"\n".join(lines)).hexdigest()
 
 
-def run(binary, opt, fq, outdir, tag, threads=3, extra=()):
+def run(binary, opt, fq, outdir, tag, threads=3, extra=(), env=None):
     out, failed, js, html = (os.path.join(outdir, f"{tag}.{n}") for n in ("out.fq", "failed.fq", "json", "html"))
     cmd = [binary, "-i", fq, "-o", out, "--failed_out", failed, "-j", js, "-h", html, "-w", str(threads)]
     cmd += opt.cli_flags() + list(extra)
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, **(env or {})))
     assert r.returncode == 0, r.stderr[-2000:]
     return {"out_md5": md5(out), "failed_md5": md5(failed), "json_text_md5": json_text_md5(js), "json": js}
 
@@ -57,10 +57,12 @@ def test_gpu_binary_matches_golden_reference_run(name, tmp_path):
 
 @needs_bin
 @pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/fastplong_ref not built")
+@pytest.mark.parametrize("parse", ["device", "host"])
 @pytest.mark.parametrize("name,threads", [("default_se", 1), ("cut_polyx_cplx", 4), ("fasta5", 3), ("literal_auto", 2),
                                           ("trims_limits", 3), ("end_only_wide_window", 8)])
-def test_gpu_binary_matches_reference_binary(name, threads, tmp_path):
-    """Fresh input, both binaries side by side (config-1 shape: ONT-like reads, known 30 bp adapters)."""
+def test_gpu_binary_matches_reference_binary(name, threads, parse, tmp_path):
+    """Fresh input, both binaries side by side (config-1 shape: ONT-like reads, known 30 bp adapters), with the FASTQ
+    parsed on the device (default for plain files) and by the reference's FastqReader (FPL_HOST_PARSE=1)."""
     opt = cases.OPTION_SETS[name]
     batch = synth.ont_like(700, 4000, 31 + threads, p_chimera=0.03, p_polya=0.03, q_mean=17.0)
     fq = str(tmp_path / "in.fq")
@@ -73,7 +75,7 @@ def test_gpu_binary_matches_reference_binary(name, threads, tmp_path):
                 f.write(f">a{i:03d}\n{s}\n")
         extra = ["-a", fa]
     ref = run(REF_BIN, opt, fq, str(tmp_path), "ref", threads, extra)
-    got = run(GPU_BIN, opt, fq, str(tmp_path), "gpu", threads, extra)
+    got = run(GPU_BIN, opt, fq, str(tmp_path), "gpu", threads, extra, env={"FPL_HOST_PARSE": "1"} if parse == "host" else None)
     assert got["out_md5"] == ref["out_md5"]
     assert got["failed_md5"] == ref["failed_md5"]
     if got["json_text_md5"] != ref["json_text_md5"]:
@@ -100,12 +102,17 @@ def test_config1_full_size_bit_exact(tmp_path):
         t1 = time.perf_counter()
         got = run(GPU_BIN, opt, fq, str(tmp_path), "gpu", threads=4)
         t2 = time.perf_counter()
+        got_host = run(GPU_BIN, opt, fq, str(tmp_path), "gpuh", threads=4, env={"FPL_HOST_PARSE": "1"})
+        t3 = time.perf_counter()
     finally:
         if fq.startswith("/dev/shm"):
             os.remove(fq)
-    print(f"\nconfig 1 ({batch.n_bases / 1e6:.1f} Mbases): fastplong_ref -w 16 {t1 - t0:.2f} s, fastplong_gpu -w 4 {t2 - t1:.2f} s")
+    print(f"\nconfig 1 ({batch.n_bases / 1e6:.1f} Mbases): fastplong_ref -w 16 {t1 - t0:.2f} s, fastplong_gpu -w 4 {t2 - t1:.2f} s "
+          f"(device FASTQ parse), {t3 - t2:.2f} s (reference reader)")
+    assert got_host["out_md5"] == ref["out_md5"] and got_host["json_text_md5"] == ref["json_text_md5"]
     open(os.path.join(ROOT, "gpurun_out", "c1_binary_times.txt"), "w").write(
-        f"config1 {batch.n_reads} reads {batch.n_bases} bases ref_w16_s {t1 - t0:.3f} gpu_w4_s {t2 - t1:.3f}\n") \
+        f"config1 {batch.n_reads} reads {batch.n_bases} bases ref_w16_s {t1 - t0:.3f} gpu_w4_device_parse_s {t2 - t1:.3f} "
+        f"gpu_w4_host_parse_s {t3 - t2:.3f}\n") \
         if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else None
     assert got["out_md5"] == ref["out_md5"]
     assert got["failed_md5"] == ref["failed_md5"]
