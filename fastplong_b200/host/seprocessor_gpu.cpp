@@ -26,6 +26,7 @@
 #include <string>
 #include <thread>
 #include <vector>
+#include <time.h>
 #include <unistd.h>
 #include <cuda_runtime_api.h>
 
@@ -448,7 +449,16 @@ void SingleEndProcessor::processorTask(ThreadConfig* config) {
     if (mOptions->verbose) loginfo("thread " + to_string(config->getThreadId() + 1) + " finished");
 }
 
+static double nowSec() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + ts.tv_nsec * 1e-9;
+}
+#define FPL_STAMP(what) do { if (timing) { double t_ = nowSec(); fprintf(stderr, "[fastplong_gpu] %-34s %8.3f s\n", what, t_ - t_last); t_last = t_; } } while (0)
+
 bool SingleEndProcessor::process() {
+    const bool timing = getenv("FPL_TIMING") != nullptr;
+    double t_last = nowSec();
     if (!mOptions->split.enabled) initOutput();
     const int T = mOptions->thread;
 
@@ -473,6 +483,7 @@ bool SingleEndProcessor::process() {
         check(fpl_create(&o, &ad, &g_workers[t]->ctx), "fpl_create");
     }
 
+    FPL_STAMP("CUDA init + contexts + JIT");
     mInputLists = new SingleProducerSingleConsumerList<ReadPack*>*[T];
     std::vector<ThreadConfig*> configs(T);
     for (int t = 0; t < T; t++) {
@@ -486,6 +497,7 @@ bool SingleEndProcessor::process() {
     if (mLeftWriter) leftWriter.reset(new std::thread(std::bind(&SingleEndProcessor::writerTask, this, mLeftWriter)));
     if (mFailedWriter) failedWriter.reset(new std::thread(std::bind(&SingleEndProcessor::writerTask, this, mFailedWriter)));
 
+    FPL_STAMP("thread configs (Stats objects)");
     bool rawText = rawTextEligible(mOptions);
     if (rawText) {
         // ---- raw-text path: chunk reader -> T workers (device ingest + processSingleEnd + output assembly) ----
@@ -536,8 +548,10 @@ bool SingleEndProcessor::process() {
             std::vector<fpl_fastq_record> recs;
             std::vector<fpl_read_result> res;
             while (TextChunk* c = queues[t].pop()) {
-                // at most one record per 4 bytes ("@\n\n+\n\n" is 6); size the tables from the text, generously
-                const size_t cap = c->n / 6 + 16;
+                // four newlines per record: count them to size the record tables
+                size_t nl = 0;
+                for (const uint8_t* q = c->p, *e = c->p + c->n; (q = (const uint8_t*)memchr(q, '\n', (size_t)(e - q))) != nullptr; q++) nl++;
+                const size_t cap = nl / 4 + 16;
                 if (recs.size() < cap) { recs.resize(cap); res.resize(cap); }
                 int64_t n = 0, used = 0;
                 const int rc = fpl_process_fastq_host(w.ctx, c->p, (int64_t)c->n, c->last ? 1 : 0, recs.data(), res.data(),
@@ -597,8 +611,8 @@ bool SingleEndProcessor::process() {
         reader.join();
         for (auto& th : workers) th.join();
         fclose(fp);
-        while (true) {
-            // drain the free list
+        while (getenv("FPL_TIDY")) {
+            // drain the free list (otherwise left to process teardown, see the note at the end of process())
             std::unique_lock<std::mutex> l(freeList.mu);
             if (freeList.q.empty()) break;
             TextChunk* c = freeList.q.front(); freeList.q.pop_front();
@@ -622,6 +636,7 @@ bool SingleEndProcessor::process() {
         if (leftWriter) leftWriter->join();
         if (failedWriter) failedWriter->join();
     }
+    FPL_STAMP("read + GPU + write");
     if (mOptions->verbose) loginfo("start to generate reports\n");
 
     // ---- device accumulators -> the workers' Stats / FilterResult objects (replaces what statRead / the trimmers
@@ -652,6 +667,7 @@ bool SingleEndProcessor::process() {
         postStats.push_back(configs[t]->getPostStats1());
         filterResults.push_back(fr);
     }
+    FPL_STAMP("device accumulators -> Stats");
     Stats* finalPreStats = Stats::merge(preStats);
     finalPreStats->calcLengthHistogram();
     Stats* finalPostStats = Stats::merge(postStats);
@@ -665,20 +681,29 @@ bool SingleEndProcessor::process() {
     cerr << endl << "Filtering result:" << endl;
     finalFilterResult->print();
 
+    FPL_STAMP("merge + summary");
     JsonReporter jr(mOptions);
     jr.report(finalFilterResult, finalPreStats, finalPostStats);
     HtmlReporter hr(mOptions);
     hr.report(finalFilterResult, finalPreStats, finalPostStats);
 
+    FPL_STAMP("JSON + HTML reports");
+    // The process ends right after process() returns (src/main.cpp:295-305): device buffers, pinned memory and contexts
+    // are left to process teardown instead of being released one by one (cudaFree / cudaFreeHost of hundreds of MB each
+    // cost more than processing a small input).  FPL_TIDY=1 releases everything (leak checkers, embedding in a library).
+    const bool tidy = getenv("FPL_TIDY") != nullptr;
     for (int t = 0; t < T; t++) {
-        fpl_destroy(g_workers[t]->ctx);
-        g_workers[t]->ctx = nullptr;
+        if (tidy) { fpl_destroy(g_workers[t]->ctx); g_workers[t]->ctx = nullptr; }
         delete configs[t];
     }
-    g_workers.clear();
+    FPL_STAMP("contexts + thread configs released");
+    if (tidy) g_workers.clear();
+    else for (auto& w : g_workers) w.release();
     delete finalPreStats;
     delete finalPostStats;
     delete finalFilterResult;
+    FPL_STAMP("final Stats released");
     if (!mOptions->split.enabled) closeOutput();
+    FPL_STAMP("outputs closed");
     return true;
 }
