@@ -2,7 +2,7 @@
 import ctypes as C
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_ADAPTER_LEN = 128
 MAX_ADAPTERS = 1024
 INLINE_EVENTS = 4
@@ -45,7 +45,8 @@ class FplOptions(C.Structure):
         ("ed_max", C.c_double)] + [(n, C.c_int32) for n in (
             "qual_filter_enabled", "qualified_qual", "unqualified_percent_limit", "avg_qual_req",
             "n_base_percent_limit", "n_base_limit", "length_filter_enabled", "length_required", "length_max",
-            "complexity_enabled", "complexity_threshold_pct")] + [("reserved", C.c_int32 * 5)]
+            "complexity_enabled", "complexity_threshold_pct", "mask_enabled", "mask_window", "mask_quality",
+            "break_enabled", "break_window", "break_quality")] + [("reserved", C.c_int32 * 3)]
 
 
 class FplAdapters(C.Structure):
@@ -68,7 +69,11 @@ assert RESULT_DTYPE.itemsize == 64
 FASTQ_RECORD_DTYPE = np.dtype([("name_off", "<i8"), ("seq_off", "<i8"), ("plus_off", "<i8"), ("qual_off", "<i8"),
                                ("name_len", "<i4"), ("seq_len", "<i4"), ("plus_len", "<i4"), ("reserved", "<i4")])
 assert FASTQ_RECORD_DTYPE.itemsize == 48
-assert C.sizeof(FplOptions) == 128, C.sizeof(FplOptions)
+SEGMENT_DTYPE = np.dtype([("read", "<i4"), ("lo", "<i4"), ("len", "<i4"), ("result", "u1"), ("median_qual", "u1"),
+                          ("split_side", "u1"), ("is_r1", "u1"), ("break_index", "<i4")])
+assert SEGMENT_DTYPE.itemsize == 20
+REGION_DTYPE = np.dtype([("read", "<i4"), ("lo", "<i4"), ("len", "<i4")])
+assert C.sizeof(FplOptions) == 144, C.sizeof(FplOptions)
 
 
 def make_adapters(start, end, fasta=()):

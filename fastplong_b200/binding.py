@@ -39,6 +39,8 @@ def load_library():
     lib.fpl_stream.argtypes = [C.c_void_p]
     lib.fpl_stream.restype = C.c_void_p
     lib.fpl_fetch_results.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    lib.fpl_last_segments.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+    lib.fpl_last_mask_regions.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
     lib.fpl_stats_cycles.argtypes = [C.c_void_p]
     lib.fpl_stats_cycles.restype = C.c_int64
     lib.fpl_stats_reserve.argtypes = [C.c_void_p, C.c_int64]
@@ -61,7 +63,7 @@ def load_library():
 
 
 EXPORTS = ["fpl_last_error", "fpl_abi_version", "fpl_create", "fpl_destroy", "fpl_process_host", "fpl_process_device", "fpl_process_fastq_host",
-           "fpl_sync", "fpl_stream", "fpl_fetch_results", "fpl_stats_cycles", "fpl_stats_reserve", "fpl_stats_download",
+           "fpl_sync", "fpl_stream", "fpl_last_segments", "fpl_last_mask_regions", "fpl_fetch_results", "fpl_stats_cycles", "fpl_stats_reserve", "fpl_stats_download",
            "fpl_stats_device_ptr", "fpl_counter_words", "fpl_counters_download", "fpl_counters_device_ptr",
            "fpl_reset", "fpl_last_kernel_times", "fpl_launch_count", "fpl_set_timing"]
 
@@ -139,6 +141,23 @@ class Engine:
     def stream_ptr(self):
         """cudaStream_t of the context (wrap with torch.cuda.ExternalStream to record events / order collectives)."""
         return int(self.lib.fpl_stream(self.h) or 0)
+
+    def _list(self, fn, dtype):
+        n = C.c_int64()
+        self._check(fn(self.h, None, 0, C.byref(n)) if False else 0)
+        # ask for the count first (a call with cap 0 fails only when there are entries)
+        fn(self.h, None, 0, C.byref(n))
+        out = np.zeros(n.value, dtype=dtype)
+        if n.value:
+            self._check(fn(self.h, out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+    def segments(self):
+        """--mask/--break: every output read of the last process() call (abi.SEGMENT_DTYPE)."""
+        return self._list(self.lib.fpl_last_segments, abi.SEGMENT_DTYPE)
+
+    def mask_regions(self):
+        return self._list(self.lib.fpl_last_mask_regions, abi.REGION_DTYPE)
 
     def fetch_results(self, n):
         res = np.zeros(n, dtype=RESULT_DTYPE)

@@ -12,8 +12,10 @@
 #include "fpl_scanplan.h"
 #include "fpl_jit.h"
 #include "fpl_ingest.h"
+#include "fpl_ext.h"
 
-static_assert(sizeof(fpl_options) == 128, "fpl_options ABI size");
+static_assert(sizeof(fpl_options) == 144, "fpl_options ABI size");
+static_assert(sizeof(fpl_segment) == 20 && sizeof(fpl_region) == 12, "segment / region ABI size");
 static_assert(sizeof(fpl_read_result) == 64, "fpl_read_result ABI size");
 static_assert(sizeof(ReadState) == 64, "ReadState size");
 static_assert(sizeof(StatSeg) == 24, "StatSeg size");
@@ -23,11 +25,11 @@ void launch_trim(const DevParams&, const DevBatch&, ReadState*, fpl_read_result*
 void launch_scan(const DevParams&, const DevBatch&, ReadState*, cudaStream_t);
 void launch_scan_fast(const DevParams&, const ScanPlan&, const DevBatch&, ReadState*, cudaStream_t);
 void launch_final(const DevParams&, const DevBatch&, const ReadState*, fpl_read_result*, StatSeg*, cudaStream_t);
-void launch_count(const fpl_read_result*, int64_t, unsigned long long*, cudaStream_t);
+void launch_count(const fpl_read_result*, int64_t, unsigned long long*, bool, cudaStream_t);
 void launch_cycle_stats(const uint8_t*, const uint8_t*, const StatSeg*, int64_t, int64_t, unsigned long long*, int64_t,
                         bool, unsigned long long*, cudaStream_t);
 void launch_kmer_fix(const DevBatch&, const fpl_read_result*, unsigned long long*, cudaStream_t);
-void launch_read_qual(const DevBatch&, unsigned long long*, unsigned long long*, int64_t, fpl_read_result*, cudaStream_t);
+void launch_read_qual(const DevBatch&, unsigned long long*, unsigned long long*, int64_t, fpl_read_result*, bool, cudaStream_t);
 void launch_make_preseg(const DevBatch&, StatSeg*, cudaStream_t);
 
 static thread_local char g_err[512] = "";
@@ -58,6 +60,8 @@ struct fpl_ctx {
     ScanPlan plan;
     FplJitKernel jit;   // specialised scan kernel (NVRTC), fn == nullptr if not used
     FplIngest ingest;   // device-side FASTQ parsing state
+    FplExt ext;         // --mask / --break state (variable number of output reads)
+    int64_t last_bytes = 0;
     int n_adapters = 0;
     uint8_t* d_adapters = nullptr;
     int* d_alen = nullptr;
@@ -165,7 +169,7 @@ static void collect_times(fpl_ctx* c) {
 }
 
 // Runs every kernel over reads [0, n) of a device-resident batch whose lens are known on the host.
-static int run_batch(fpl_ctx* c, const DevBatch& full, const int32_t* h_lens, fpl_read_result* d_res_out) {
+static int run_batch(fpl_ctx* c, const DevBatch& full, const int32_t* h_lens, fpl_read_result* d_res_out, int64_t n_bytes) {
     const int64_t n = full.n_reads;
     CK(cudaSetDevice(c->device));
     collect_times(c);
@@ -180,10 +184,12 @@ static int run_batch(fpl_ctx* c, const DevBatch& full, const int32_t* h_lens, fp
     }
     if (reserve_cycles(c, max_len > 0 ? max_len : 1)) return -1;
     // tiles of reads whose payload stays L2-resident across the kernels that revisit it
+    const bool ext = c->P.opt.mask_enabled || c->P.opt.break_enabled;   // variable number of output reads: one tile
+    c->ext.n_segs = 0; c->ext.n_regs = 0;
     int64_t r0 = 0;
     while (r0 < n) {
         int64_t r1 = r0, bases = 0, tmax = 0;
-        while (r1 < n && (r1 == r0 || bases + h_lens[r1] <= c->tile_bases)) {
+        while (r1 < n && (r1 == r0 || ext || bases + h_lens[r1] <= c->tile_bases)) {
             bases += h_lens[r1];
             if (h_lens[r1] > tmax) tmax = h_lens[r1];
             r1++;
@@ -198,7 +204,7 @@ static int run_batch(fpl_ctx* c, const DevBatch& full, const int32_t* h_lens, fp
         { Timed t(c, K_PRESEG); launch_make_preseg(b, pre, s); }
         { Timed t(c, K_TRIM); launch_trim(c->P, b, st, res, c->d_counters, s); }
         { Timed t(c, K_CYCLE_PRE); launch_cycle_stats(full.seq, full.qual, pre, b.n_reads, tmax, c->d_stats[0], c->C, true,
-                                                       c->d_stats[1] + 16 * c->C + FPL_STATS_KMER, s); }
+                                                       ext ? nullptr : c->d_stats[1] + 16 * c->C + FPL_STATS_KMER, s); }
         {
             Timed t(c, K_SCAN);
             if (c->jit.fn) { if (fpl_jit_launch_scan(&c->jit, b, st, s)) return fail("launching k_scan_jit failed"); }
@@ -206,10 +212,22 @@ static int run_batch(fpl_ctx* c, const DevBatch& full, const int32_t* h_lens, fp
             else launch_scan(c->P, b, st, s);
         }
         { Timed t(c, K_FINAL); launch_final(c->P, b, st, res, post, s); }
-        { Timed t(c, K_COUNT); launch_count(res, b.n_reads, c->d_counters, s); }
-        { Timed t(c, K_CYCLE_POST); launch_cycle_stats(full.seq, full.qual, post, 2 * b.n_reads, tmax, c->d_stats[1], c->C, false, nullptr, s); }
-        { Timed t(c, K_KMER_FIX); launch_kmer_fix(b, res, c->d_stats[1] + 16 * c->C + FPL_STATS_KMER, s); }
-        { Timed t(c, K_QUAL_PRE); launch_read_qual(b, c->d_stats[0], c->d_stats[1], c->C, res, s); }
+        if (!ext) {
+            { Timed t(c, K_COUNT); launch_count(res, b.n_reads, c->d_counters, true, s); }
+            { Timed t(c, K_CYCLE_POST); launch_cycle_stats(full.seq, full.qual, post, 2 * b.n_reads, tmax, c->d_stats[1], c->C, false, nullptr, s); }
+            { Timed t(c, K_KMER_FIX); launch_kmer_fix(b, res, c->d_stats[1] + 16 * c->C + FPL_STATS_KMER, s); }
+            { Timed t(c, K_QUAL_PRE); launch_read_qual(b, c->d_stats[0], c->d_stats[1], c->C, res, false, s); }
+        } else {
+            // --mask / --break: k_final left the output reads of the adapter stage in the records; fpl_ext_run breaks /
+            // masks / filters them (variable count) and the post-filter Stats run over its segment list
+            char xerr[256] = "";
+            const uint8_t* fseq = full.seq;
+            { Timed t(c, K_QUAL_PRE); launch_read_qual(b, c->d_stats[0], c->d_stats[1], c->C, res, true, s); }
+            { Timed t(c, K_COUNT); launch_count(res, b.n_reads, c->d_counters, false, s); }
+            if (fpl_ext_run(&c->ext, c->P, b, n_bytes, res, c->d_counters, c->d_stats[1], c->C, &fseq, s, xerr, sizeof(xerr)))
+                return fail("--mask/--break stage: %s", xerr);
+            { Timed t(c, K_CYCLE_POST); launch_cycle_stats(fseq, full.qual, c->ext.d_stat, c->ext.n_segs, tmax, c->d_stats[1], c->C, true, nullptr, s); }
+        }
         r0 = r1;
     }
     CK(cudaGetLastError());
@@ -356,6 +374,7 @@ void fpl_destroy(fpl_ctx* c) {
     cudaFree(c->d_state); cudaFree(c->d_results); cudaFree(c->d_preseg); cudaFree(c->d_postseg);
     cudaFree(c->d_seq); cudaFree(c->d_qual); cudaFree(c->d_offsets); cudaFree(c->d_lens);
     fpl_ingest_free(&c->ingest);
+    fpl_ext_free(&c->ext);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -372,7 +391,7 @@ int fpl_process_device(fpl_ctx* c, const fpl_batch* b, fpl_read_result* results_
         CK(cudaStreamSynchronize(c->stream));
     }
     DevBatch d = {b->seq, b->qual, b->offsets, b->lens, n};
-    return run_batch(c, d, c->h_lens.data(), results_dev);
+    return run_batch(c, d, c->h_lens.data(), results_dev, b->n_bytes);
 }
 
 void* fpl_stream(fpl_ctx* c) { return c ? (void*)c->stream : nullptr; }
@@ -423,7 +442,7 @@ int fpl_process_host(fpl_ctx* c, const fpl_batch* b, fpl_read_result* results) {
         CK(cudaMemcpyAsync(c->d_lens, b->lens, sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream));
     }
     DevBatch d = {c->d_seq, c->d_qual, c->d_offsets, c->d_lens, n};
-    if (run_batch(c, d, b->lens, nullptr)) return -1;
+    if (run_batch(c, d, b->lens, nullptr, b->n_bytes)) return -1;
     if (n) CK(cudaMemcpyAsync(results, c->d_results, sizeof(fpl_read_result) * n, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     collect_times(c);
@@ -462,10 +481,32 @@ int fpl_process_fastq_host(fpl_ctx* c, const uint8_t* text, int64_t n_bytes, int
     CK(cudaMemcpyAsync(records, g.d_rec, sizeof(fpl_fastq_record) * nrec, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     DevBatch d = {c->d_seq, c->d_qual, g.d_offsets, g.d_lens, nrec};
-    if (run_batch(c, d, c->h_lens.data(), nullptr)) return -1;
+    if (run_batch(c, d, c->h_lens.data(), nullptr, g.packed_bytes)) return -1;
     CK(cudaMemcpyAsync(results, c->d_results, sizeof(fpl_read_result) * nrec, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     collect_times(c);
+    return 0;
+}
+
+int fpl_last_segments(fpl_ctx* c, fpl_segment* out, int64_t cap, int64_t* n) {
+    if (!c || !n) return fail("fpl_last_segments: null argument");
+    *n = c->ext.n_segs;
+    if (*n == 0) return 0;
+    if (!out || cap < *n) return fail("fpl_last_segments: %lld entries, capacity %lld", (long long)*n, (long long)cap);
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(out, c->ext.d_segs, sizeof(fpl_segment) * *n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int fpl_last_mask_regions(fpl_ctx* c, fpl_region* out, int64_t cap, int64_t* n) {
+    if (!c || !n) return fail("fpl_last_mask_regions: null argument");
+    *n = c->ext.n_regs;
+    if (*n == 0) return 0;
+    if (!out || cap < *n) return fail("fpl_last_mask_regions: %lld entries, capacity %lld", (long long)*n, (long long)cap);
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(out, c->ext.d_regs, sizeof(fpl_region) * *n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     return 0;
 }
 

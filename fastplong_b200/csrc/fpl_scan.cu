@@ -322,7 +322,7 @@ void launch_final(const DevParams& P, const DevBatch& b, const ReadState* st, fp
 // aggregation in shared memory, one global atomic per non-zero counter per block.
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_count(const fpl_read_result* __restrict__ res, int64_t n, unsigned long long* __restrict__ counters) {
+k_count(const fpl_read_result* __restrict__ res, int64_t n, unsigned long long* __restrict__ counters, bool count_segments) {
     __shared__ unsigned long long sh[FPL_CNT_FIXED];
     for (int i = threadIdx.x; i < FPL_CNT_FIXED; i += blockDim.x) sh[i] = 0;
     __syncthreads();
@@ -331,7 +331,8 @@ k_count(const fpl_read_result* __restrict__ res, int64_t n, unsigned long long* 
         const fpl_read_result* o = &res[r];
         const uint32_t flags = o->flags;
         const int nseg = o->n_segments;
-        for (int k = 0; k < nseg; k++) atomicAdd(&sh[FPL_CNT_FILTER + o->seg_result[k]], 1ull);
+        if (count_segments)
+            for (int k = 0; k < nseg; k++) atomicAdd(&sh[FPL_CNT_FILTER + o->seg_result[k]], 1ull);
         const int tb = o->adapter_trimmed_bases;
         if (tb > 0) {
             atomicAdd(&sh[FPL_CNT_ADAPTER_READS], 1ull);
@@ -345,7 +346,8 @@ k_count(const fpl_read_result* __restrict__ res, int64_t n, unsigned long long* 
         if (sh[i]) atomicAdd(&counters[i], sh[i]);
 }
 
-void launch_count(const fpl_read_result* res, int64_t n, unsigned long long* counters, cudaStream_t stream) {
+// count_segments = false: --mask/--break, where the output reads are counted by k_ext_filter instead
+void launch_count(const fpl_read_result* res, int64_t n, unsigned long long* counters, bool count_segments, cudaStream_t stream) {
     if (n == 0) return;
-    k_count<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(res, n, counters);
+    k_count<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(res, n, counters, count_segments);
 }

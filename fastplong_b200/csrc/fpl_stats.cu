@@ -343,7 +343,7 @@ __device__ __forceinline__ void hist_bytes(uint32_t hbase, const uint8_t* qp, in
 // quality bytes serves both Stats objects.
 __global__ void __launch_bounds__(RQ_WARPS * 32)
 k_read_qual(DevBatch b, unsigned long long* __restrict__ stats_pre, unsigned long long* __restrict__ stats_post, int64_t C,
-            fpl_read_result* __restrict__ res) {
+            fpl_read_result* __restrict__ res, bool pre_only) {
     __shared__ uint32_t hist[RQ_WARPS][2][128];        // per warp: [0] whole read, [1] current segment
     __shared__ uint32_t block_hist[2][128];            // this block's reads -> one flush per Stats block
     __shared__ unsigned long long block_misc[2][2];    // reads, length sum
@@ -378,7 +378,7 @@ k_read_qual(DevBatch b, unsigned long long* __restrict__ stats_pre, unsigned lon
             }
             o->pre_median_qual = med;
         }
-        const int nseg = o->n_segments;
+        const int nseg = pre_only ? 0 : o->n_segments;   // --mask/--break: the post-filter part is k_ext_seg_qual's
         for (int k = 0; k < nseg; k++) {
             if (o->seg_result[k] != FPL_PASS_FILTER) continue;      // warp-uniform
             const int a = o->seg_lo[k], n = o->seg_len[k];
@@ -422,12 +422,12 @@ k_read_qual(DevBatch b, unsigned long long* __restrict__ stats_pre, unsigned lon
 }
 
 void launch_read_qual(const DevBatch& b, unsigned long long* stats_pre, unsigned long long* stats_post, int64_t C,
-                      fpl_read_result* res, cudaStream_t stream) {
+                      fpl_read_result* res, bool pre_only, cudaStream_t stream) {
     if (b.n_reads == 0) return;
     // persistent-ish grid: enough blocks to fill the GPU several times over, each warp strides over the reads
     const int64_t want = (b.n_reads + RQ_WARPS - 1) / RQ_WARPS;
     const unsigned grid = (unsigned)(want < 148 * 64 ? want : 148 * 64);
-    k_read_qual<<<grid, RQ_WARPS * 32, 0, stream>>>(b, stats_pre, stats_post, C, res);
+    k_read_qual<<<grid, RQ_WARPS * 32, 0, stream>>>(b, stats_pre, stats_post, C, res, pre_only);
 }
 
 // pre-stats segment list: every input read, full length

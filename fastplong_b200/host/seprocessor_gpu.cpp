@@ -107,6 +107,8 @@ fpl_options makeAbiOptions(Options* o, int device) {
     a.length_max = o->lengthFilter.maxLength;
     a.complexity_enabled = o->complexityFilter.enabled;
     a.complexity_threshold_pct = (int)(o->complexityFilter.threshold * 100.0 + 0.5);  // src/main.cpp:205 divided an int by 100.0
+    a.mask_enabled = o->mask.enabled; a.mask_window = o->mask.windowSize; a.mask_quality = o->mask.quality;
+    a.break_enabled = o->breakOpt.enabled; a.break_window = o->breakOpt.windowSize; a.break_quality = o->breakOpt.quality;
     return a;
 }
 

@@ -60,6 +60,13 @@ class Options:
     length_limit: int = 0
     low_complexity_filter: bool = False
     complexity_threshold: int = 30
+    # --mask / --break (src/main.cpp:62-70, 207-215)
+    mask: bool = False
+    mask_window_size: int = 50
+    mask_mean_quality: int = 10
+    break_reads: bool = False
+    break_window_size: int = 100
+    break_mean_quality: int = 10
     device: int = 0
 
     def resolve_adapters(self):
@@ -97,6 +104,9 @@ class Options:
         o.length_max = self.length_limit
         o.complexity_enabled = int(self.low_complexity_filter)
         o.complexity_threshold_pct = min(100, max(0, self.complexity_threshold))
+        o.mask_enabled, o.mask_window, o.mask_quality = int(self.mask), self.mask_window_size, self.mask_mean_quality
+        o.break_enabled, o.break_window, o.break_quality = (int(self.break_reads), self.break_window_size,
+                                                            self.break_mean_quality)
         s, e = self.resolve_adapters()
         ad, keep = make_adapters(s, e, self.adapter_fasta)
         return o, ad, keep
@@ -144,4 +154,9 @@ class Options:
         f += ["-l", str(self.length_required), "--length_limit", str(self.length_limit)]
         if self.low_complexity_filter:
             f += ["-y", "-Y", str(self.complexity_threshold)]
+        if self.mask:
+            f += ["-N", "--mask_window_size", str(self.mask_window_size), "--mask_mean_quality", str(self.mask_mean_quality)]
+        if self.break_reads:
+            f += ["-b", "--break_window_size", str(self.break_window_size), "--break_mean_quality",
+                  str(self.break_mean_quality)]
         return f

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define FPL_ABI_VERSION 1
+#define FPL_ABI_VERSION 2
 
 /* Filter result codes — identical to src/common.h:43-50 (they index FilterResult::mFilterReadStats[32]). */
 enum {
@@ -78,7 +78,15 @@ typedef struct fpl_options {
     int32_t length_max;               /* 0 = no limit */
     int32_t complexity_enabled;       /* opt.complexityFilter.enabled */
     int32_t complexity_threshold_pct; /* opt.complexityFilter.threshold * 100 (src/main.cpp:205) */
-    int32_t reserved[5];
+    /* --mask / --break: Filter::detectLowQualityRegions + Read::maskRegionWithN / breakByRegions
+       (src/seprocessor.cpp:235-262, src/filter.cpp:83-128, src/read.cpp:217-262) */
+    int32_t mask_enabled;             /* opt.mask.enabled */
+    int32_t mask_window;              /* opt.mask.windowSize */
+    int32_t mask_quality;             /* opt.mask.quality (phred) */
+    int32_t break_enabled;            /* opt.breakOpt.enabled */
+    int32_t break_window;
+    int32_t break_quality;
+    int32_t reserved[3];
 } fpl_options;
 
 /*
@@ -145,6 +153,27 @@ typedef struct fpl_read_result {
     int32_t adapter_trimmed_bases;    /* 'trimmed' at src/seprocessor.cpp:206-216; >0 => addReadTrimmed(trimmed) */
     uint32_t events[FPL_INLINE_EVENTS]; /* first FPL_INLINE_EVENTS events in application order */
 } fpl_read_result;
+
+/*
+ * With --break a read can end up in any number of output reads, and with --mask their bases change: in those modes
+ * (only) the full list of output reads and of masked regions of the last fpl_process_* call is available through
+ * fpl_last_segments / fpl_last_mask_regions; fpl_read_result.n_segments counts a read's entries, which are contiguous
+ * and in read order; the record's inline seg_* fields hold the first two.
+ */
+typedef struct fpl_segment {          /* one element of outReads (src/seprocessor.cpp:222-262) */
+    int32_t read;                     /* index of the input read in the batch */
+    int32_t lo, len;                  /* window on the ORIGINAL read's bytes */
+    uint8_t result;                   /* Filter::passFilter code */
+    uint8_t median_qual;              /* post-filter Stats median char of a passing segment, else 0 */
+    uint8_t split_side;               /* 0 none, 1 "split-by-adapter-left-", 2 "split-by-adapter-right-" (Read::breakByGap) */
+    uint8_t is_r1;                    /* 1 if this output read IS r1 (not a copy): --failed_out then shows its masked bases */
+    int32_t break_index;              /* 0: not made by Read::breakByRegions; k > 0: name prefix "r<k>-" (src/read.cpp:240,255) */
+} fpl_segment;
+
+typedef struct fpl_region {           /* Read::maskRegionWithN: bases [lo, lo+len) of the ORIGINAL read become 'N' */
+    int32_t read;
+    int32_t lo, len;
+} fpl_region;
 
 /* Which of the two Stats objects (ThreadConfig::getPreStats1 / getPostStats1, src/threadconfig.h:20-23). */
 enum { FPL_STATS_PRE = 0, FPL_STATS_POST = 1 };
@@ -246,6 +275,10 @@ typedef struct fpl_fastq_record {
 int fpl_process_fastq_host(fpl_ctx* ctx, const uint8_t* text, int64_t n_bytes, int is_last_chunk,
                            fpl_fastq_record* records, fpl_read_result* results, int64_t max_records,
                            int64_t* n_records, int64_t* bytes_consumed);
+
+/* Output reads / masked regions of the last fpl_process_* call (--mask / --break only; *n = 0 otherwise). */
+int fpl_last_segments(fpl_ctx* ctx, fpl_segment* out, int64_t cap, int64_t* n);
+int fpl_last_mask_regions(fpl_ctx* ctx, fpl_region* out, int64_t cap, int64_t* n);
 
 /* Copy the context's last device results (n records) to host memory. */
 int fpl_fetch_results(fpl_ctx* ctx, fpl_read_result* results, int64_t n_reads);

@@ -17,6 +17,8 @@ typedef struct {
 } orc_stats;
 
 struct orc_ctx {
+    fpl_segment* segs; int64_t n_segs, cap_segs;       /* --mask/--break: output reads of the last orc_process call */
+    fpl_region* regs; int64_t n_regs, cap_regs;        /* --mask: masked regions of the last call */
     fpl_options opt;
     int n_adapters;
     char** adapter;
@@ -428,9 +430,145 @@ static int pass_filter(const orc_ctx* c, const char* seqstr, const char* qualstr
     return FPL_PASS_FILTER;
 }
 
+/* ---- Filter::detectLowQualityRegions: src/filter.cpp:83-128, transcribed literally (the pre-sum loop
+ *      bound `i < windowSize-1` is absolute, so after the first region the running sum restarts from 0).
+ *      Calls emit(first, last) (0-based, inclusive) per region; returns the number of regions. ---- */
+typedef void (*region_cb)(void* u, int first, int last);
+static int detect_low_quality_regions(const char* qualstr, int l, int windowSize, int quality, region_cb emit, void* u) {
+    int n = 0;
+    if (l == 0 || windowSize <= 0) return 0;
+    int start = 0;
+    while (start + windowSize <= l) {
+        int totalQual = 0;
+        for (int i = start; i < windowSize - 1 && i < l; i++) totalQual += qualstr[i];
+        int windowStart = -1;
+        for (int s = start; s + windowSize < l; s++) {
+            if (totalQual < (33 + quality) * windowSize) { windowStart = s; break; }
+            totalQual += qualstr[s + windowSize];
+            totalQual -= qualstr[s];
+        }
+        if (windowStart == -1) break;
+        int e;
+        for (e = windowStart; e + windowSize < l; e++) {
+            totalQual += qualstr[e + windowSize];
+            totalQual -= qualstr[e];
+            if (totalQual >= (33 + quality) * windowSize) break;
+        }
+        if (emit) emit(u, windowStart, e + windowSize - 1);
+        n++;
+        start = e + windowSize;
+    }
+    return n;
+}
+
+typedef struct { int lo, len, split_side, is_r1, break_index; } piece;
+typedef struct { piece* v; int n, cap; } piece_list;
+static void pl_push(piece_list* l, piece p) {
+    if (l->n == l->cap) { l->cap = l->cap ? 2 * l->cap : 8; l->v = (piece*)realloc(l->v, sizeof(piece) * (size_t)l->cap); }
+    l->v[l->n++] = p;
+}
+typedef struct { int (*v)[2]; int n, cap; } region_list;
+static void rl_emit(void* u, int first, int last) {
+    region_list* l = (region_list*)u;
+    if (l->n == l->cap) { l->cap = l->cap ? 2 * l->cap : 8; l->v = (int(*)[2])realloc(l->v, sizeof(int[2]) * (size_t)l->cap); }
+    l->v[l->n][0] = first; l->v[l->n][1] = last; l->n++;
+}
+
+/* Read::breakByRegions: src/read.cpp:227-262 */
+static void break_by_regions(const piece* rr, const region_list* regions, piece_list* out) {
+    int lastEnd = -1, length = rr->len;
+    for (int i = 0; i < regions->n; i++) {
+        int start = regions->v[i][0], end = regions->v[i][1];
+        if (start < 0) start = 0;
+        if (end >= length) end = length - 1;
+        if (start > end || start >= length) continue;
+        if (start > lastEnd + 1) {
+            piece p = {rr->lo + lastEnd + 1, start - lastEnd - 1, rr->split_side, 0, i + 1};
+            pl_push(out, p);
+        }
+        lastEnd = end;
+    }
+    if (lastEnd < length - 1) {
+        piece p = {rr->lo + lastEnd + 1, length - lastEnd - 1, rr->split_side, 0, regions->n + 1};
+        pl_push(out, p);
+    }
+}
+
+static void push_segment(orc_ctx* c, fpl_segment sg) {
+    if (c->n_segs == c->cap_segs) { c->cap_segs = c->cap_segs ? 2 * c->cap_segs : 1024; c->segs = (fpl_segment*)realloc(c->segs, sizeof(fpl_segment) * (size_t)c->cap_segs); }
+    c->segs[c->n_segs++] = sg;
+}
+static void push_region(orc_ctx* c, fpl_region r) {
+    if (c->n_regs == c->cap_regs) { c->cap_regs = c->cap_regs ? 2 * c->cap_regs : 1024; c->regs = (fpl_region*)realloc(c->regs, sizeof(fpl_region) * (size_t)c->cap_regs); }
+    c->regs[c->n_regs++] = r;
+}
+
+/* --mask / --break variant of the tail of processSingleEnd (src/seprocessor.cpp:235-288) for one read whose outReads
+ * after the adapter stage are seg[0..nseg).  seq is the read's ORIGINAL bases; masking works on a private copy. */
+static void finish_read_ext(orc_ctx* c, int64_t ri, const char* seq, const char* qual, int L, const window* seg, int nseg,
+                            int split, int seg0right, fpl_read_result* out) {
+    const fpl_options* o = &c->opt;
+    piece_list reads = {0, 0, 0};
+    for (int k = 0; k < nseg; k++) {
+        piece p = {seg[k].lo, seg[k].len, split ? ((k == 1 || seg0right) ? 2 : 1) : 0, split ? 0 : 1, 0};
+        pl_push(&reads, p);
+    }
+    if (o->break_enabled && reads.n > 0) {                                                   /* :235-252 */
+        piece_list tmp = {0, 0, 0};
+        for (int i = 0; i < reads.n; i++) {
+            region_list regions = {0, 0, 0};
+            detect_low_quality_regions(qual + reads.v[i].lo, reads.v[i].len, o->break_window, o->break_quality, rl_emit, &regions);
+            if (regions.n > 0) break_by_regions(&reads.v[i], &regions, &tmp);
+            else pl_push(&tmp, reads.v[i]);
+            free(regions.v);
+        }
+        free(reads.v);
+        reads = tmp;
+    }
+    char* mseq = NULL;
+    if (o->mask_enabled && reads.n > 0) {                                                    /* :254-262 */
+        mseq = (char*)malloc((size_t)L + 1);
+        memcpy(mseq, seq, (size_t)L);
+        for (int i = 0; i < reads.n; i++) {
+            region_list regions = {0, 0, 0};
+            detect_low_quality_regions(qual + reads.v[i].lo, reads.v[i].len, o->mask_window, o->mask_quality, rl_emit, &regions);
+            for (int j = 0; j < regions.n; j++) {                                            /* Read::maskRegionWithN, src/read.cpp:217-225 */
+                int start = regions.v[j][0], len = regions.v[j][1] - regions.v[j][0] + 1, length = reads.v[i].len;
+                if (start < 0 || len <= 0 || start >= length) continue;
+                if (start + len > length) len = length - start;
+                memset(mseq + reads.v[i].lo + start, 'N', (size_t)len);
+                fpl_region r = {(int32_t)ri, reads.v[i].lo + start, len};
+                push_region(c, r);
+            }
+            free(regions.v);
+        }
+    }
+    const char* fseq = mseq ? mseq : seq;
+    out->n_segments = reads.n;
+    for (int k = 0; k < reads.n; k++) {                                                      /* :264-288 */
+        const piece* p = &reads.v[k];
+        int result = pass_filter(c, fseq + p->lo, qual + p->lo, p->len);
+        c->counters[FPL_CNT_FILTER + result]++;
+        fpl_segment sg;
+        memset(&sg, 0, sizeof(sg));
+        sg.read = (int32_t)ri; sg.lo = p->lo; sg.len = p->len; sg.result = (uint8_t)result;
+        sg.split_side = (uint8_t)p->split_side; sg.is_r1 = (uint8_t)p->is_r1; sg.break_index = p->break_index;
+        if (result == FPL_PASS_FILTER) sg.median_qual = (uint8_t)stat_read(&c->st[1], fseq + p->lo, qual + p->lo, p->len);
+        push_segment(c, sg);
+        if (k < 2) {
+            out->seg_lo[k] = p->lo; out->seg_len[k] = p->len; out->seg_result[k] = (uint8_t)result;
+            out->seg_median_qual[k] = sg.median_qual;
+        }
+    }
+    free(reads.v);
+    free(mseq);
+}
+
 /* ---- SingleEndProcessor::processSingleEnd per-read body: src/seprocessor.cpp:186-295 ---- */
 int orc_process(orc_ctx* c, const fpl_batch* b, fpl_read_result* results) {
     const fpl_options* o = &c->opt;
+    const int ext = o->mask_enabled || o->break_enabled;
+    c->n_segs = 0; c->n_regs = 0;
     for (int64_t i = 0; i < b->n_reads; i++) {
         fpl_read_result* out = &results[i];
         memset(out, 0, sizeof(*out));
@@ -454,7 +592,7 @@ int orc_process(orc_ctx* c, const fpl_batch* b, fpl_read_result* results) {
             }
         }
         window seg[2];
-        int nseg = 0;
+        int nseg = 0, split = 0, seg0right = 0;
         if (alive && o->adapter_enabled) {                                                   /* :205-229 */
             int trimmed = 0;
             if (c->alen[0] > 0) trimmed += trim_start(c, seq, &w, 0, out);
@@ -476,6 +614,7 @@ int orc_process(orc_ctx* c, const fpl_batch* b, fpl_read_result* results) {
                 if (len1 > 0) { seg[nseg].lo = w.lo; seg[nseg].len = len1; nseg++; }
                 if (len2 > 0) { seg[nseg].lo = w.lo + start + len; seg[nseg].len = len2; nseg++; }
                 if (nseg == 1 && len1 <= 0) out->flags |= FPL_FLAG_SEG0_IS_RIGHT;
+                split = 1; seg0right = (nseg == 1 && len1 <= 0);
             } else {
                 seg[nseg++] = w;
             }
@@ -483,6 +622,7 @@ int orc_process(orc_ctx* c, const fpl_batch* b, fpl_read_result* results) {
             seg[nseg++] = w;
         }
         if (alive) { out->trim_lo = w.lo; out->trim_len = w.len; }
+        if (ext) { finish_read_ext(c, i, seq, qual, L, seg, nseg, split, seg0right, out); continue; }
         out->n_segments = nseg;
         for (int k = 0; k < nseg; k++) {                                                     /* :264-288 */
             int result = pass_filter(c, seq + seg[k].lo, qual + seg[k].lo, seg[k].len);
@@ -517,9 +657,22 @@ orc_ctx* orc_create(const fpl_options* opt, const fpl_adapters* ad) {
 void orc_destroy(orc_ctx* c) {
     if (!c) return;
     for (int k = 0; k < c->n_adapters; k++) free(c->adapter[k]);
-    free(c->adapter); free(c->alen); free(c->counters);
+    free(c->adapter); free(c->alen); free(c->counters); free(c->segs); free(c->regs);
     for (int k = 0; k < 2; k++) { free(c->st[k].content); free(c->st[k].qual); }
     free(c);
+}
+
+int orc_last_segments(orc_ctx* c, fpl_segment* out, int64_t cap, int64_t* n) {
+    *n = c->n_segs;
+    if (c->n_segs > cap) return -1;
+    if (c->n_segs) memcpy(out, c->segs, sizeof(fpl_segment) * (size_t)c->n_segs);
+    return 0;
+}
+int orc_last_mask_regions(orc_ctx* c, fpl_region* out, int64_t cap, int64_t* n) {
+    *n = c->n_regs;
+    if (c->n_regs > cap) return -1;
+    if (c->n_regs) memcpy(out, c->regs, sizeof(fpl_region) * (size_t)c->n_regs);
+    return 0;
 }
 
 int64_t orc_stats_cycles(orc_ctx* c) { return c->st[0].C > c->st[1].C ? c->st[0].C : c->st[1].C; }

@@ -26,6 +26,9 @@ int orc_process(orc_ctx* c, const fpl_batch* batch, fpl_read_result* results);
 int64_t orc_stats_cycles(orc_ctx* c);
 int orc_stats_download(orc_ctx* c, int which, int64_t* out, int64_t C);
 int orc_counters_download(orc_ctx* c, int64_t* out, int64_t n_words);
+/* --mask/--break: output reads / masked regions of the last orc_process call (returns -1 if cap is too small) */
+int orc_last_segments(orc_ctx* c, fpl_segment* out, int64_t cap, int64_t* n);
+int orc_last_mask_regions(orc_ctx* c, fpl_region* out, int64_t cap, int64_t* n);
 
 /* single operators, for known-answer tests */
 int orc_edit_distance(const char* a, int alen, const char* b, int blen);

@@ -45,6 +45,8 @@ struct Harness {
     std::vector<std::string> adapters;  // fpl_adapters order
     int64_t dropped = 0, split = 0;
     std::map<uint32_t, int64_t> events;  // packed event -> count
+    std::vector<fpl_segment> segs;       // --mask/--break: outReads of the last ref_process call
+    std::vector<fpl_region> regs;        // --mask: regions handed to Read::maskRegionWithN (clamped like it does)
 };
 
 int medianOfLast(Stats* s, const long* before) {
@@ -109,8 +111,12 @@ void* ref_create(const fpl_options* o, const fpl_adapters* ad) {
     opt.lengthFilter.maxLength = o->length_max;
     opt.complexityFilter.enabled = o->complexity_enabled;
     opt.complexityFilter.threshold = o->complexity_threshold_pct / 100.0;  // src/main.cpp:205
-    opt.mask.enabled = false;
-    opt.breakOpt.enabled = false;
+    opt.mask.enabled = o->mask_enabled;
+    opt.mask.windowSize = o->mask_window;
+    opt.mask.quality = o->mask_quality;
+    opt.breakOpt.enabled = o->break_enabled;
+    opt.breakOpt.windowSize = o->break_window;
+    opt.breakOpt.quality = o->break_quality;
     h->adapters.push_back(opt.adapter.sequenceStart);
     h->adapters.push_back(opt.adapter.sequenceEnd);
     for (auto& s : opt.adapter.seqsInFasta) h->adapters.push_back(s);
@@ -132,6 +138,8 @@ int ref_process(void* hh, const fpl_batch* b, fpl_read_result* results) {
     Harness* h = (Harness*)hh;
     Options* opt = &h->opt;
     long before[128];
+    const bool ext = opt->mask.enabled || opt->breakOpt.enabled;
+    h->segs.clear(); h->regs.clear();
     for (int64_t i = 0; i < b->n_reads; i++) {
         fpl_read_result* out = &results[i];
         memset(out, 0, sizeof(*out));
@@ -214,6 +222,91 @@ int ref_process(void* hh, const fpl_batch* b, fpl_read_result* results) {
         out->n_events = (uint16_t)ev.size();
         for (size_t k = 0; k < ev.size() && k < FPL_INLINE_EVENTS; k++) out->events[k] = ev[k];
 
+        if (ext) {
+            // ---- src/seprocessor.cpp:235-288 with the reference's own detectLowQualityRegions / breakByRegions /
+            //      maskRegionWithN; our bookkeeping only tracks where each output read sits in the original bytes ----
+            struct Piece { Read* r; int lo; int side; int is_r1; int bidx; };
+            std::vector<Piece> reads;
+            const bool wasSplit = (out->flags & FPL_FLAG_MIDDLE_ADAPTER) != 0;
+            for (size_t k = 0; k < outReads.size(); k++) {
+                int side = wasSplit ? ((k == 1 || (out->flags & FPL_FLAG_SEG0_IS_RIGHT)) ? 2 : 1) : 0;
+                reads.push_back({outReads[k], segLo[k], side, outReads[k] == r1 ? 1 : 0, 0});
+            }
+            if (opt->breakOpt.enabled && !reads.empty()) {
+                std::vector<Piece> tmp;
+                for (auto& p : reads) {
+                    vector<pair<int, int>> regions = h->filter->detectLowQualityRegions(p.r, opt->breakOpt.windowSize, opt->breakOpt.quality);
+                    if (!regions.empty()) {
+                        vector<Read*> brs = p.r->breakByRegions(regions);
+                        // offsets of the pieces: the arithmetic of Read::breakByRegions (src/read.cpp:227-262), checked
+                        // against the bytes of the pieces the reference actually made
+                        int lastEnd = -1, length = p.r->length();
+                        size_t bi = 0;
+                        for (size_t ri = 0; ri <= regions.size(); ri++) {
+                            int start, end;
+                            if (ri < regions.size()) {
+                                start = regions[ri].first < 0 ? 0 : regions[ri].first;
+                                end = regions[ri].second >= length ? length - 1 : regions[ri].second;
+                                if (start > end || start >= length) continue;
+                                if (start > lastEnd + 1) {
+                                    if (bi >= brs.size()) { std::cerr << "ref_harness: breakByRegions bookkeeping" << std::endl; abort(); }
+                                    tmp.push_back({brs[bi++], p.lo + lastEnd + 1, p.side, 0, (int)ri + 1});
+                                }
+                                lastEnd = end;
+                            } else if (lastEnd < length - 1) {
+                                if (bi >= brs.size()) { std::cerr << "ref_harness: breakByRegions bookkeeping" << std::endl; abort(); }
+                                tmp.push_back({brs[bi++], p.lo + lastEnd + 1, p.side, 0, (int)regions.size() + 1});
+                            }
+                        }
+                        if (bi != brs.size()) { std::cerr << "ref_harness: breakByRegions piece count" << std::endl; abort(); }
+                        if (p.r != or1 && p.r != r1) delete p.r;
+                    } else {
+                        tmp.push_back(p);
+                    }
+                }
+                reads = tmp;
+            }
+            if (opt->mask.enabled && !reads.empty()) {
+                for (auto& p : reads) {
+                    vector<pair<int, int>> regions = h->filter->detectLowQualityRegions(p.r, opt->mask.windowSize, opt->mask.quality);
+                    for (auto& rg : regions) {
+                        int start = rg.first, len = rg.second - rg.first + 1, length = p.r->length();
+                        p.r->maskRegionWithN(start, len);
+                        if (start < 0 || len <= 0 || start >= length) continue;      // what maskRegionWithN itself skips
+                        if (start + len > length) len = length - start;
+                        h->regs.push_back({(int32_t)i, p.lo + start, len});
+                    }
+                }
+            }
+            out->n_segments = (int32_t)reads.size();
+            for (size_t k = 0; k < reads.size(); k++) {
+                Piece& p = reads[k];
+                int result = h->filter->passFilter(p.r);
+                h->fr->addFilterResult(result, 1);
+                fpl_segment sg;
+                memset(&sg, 0, sizeof(sg));
+                sg.read = (int32_t)i; sg.lo = p.lo; sg.len = p.r->length(); sg.result = (uint8_t)result;
+                sg.split_side = (uint8_t)p.side; sg.is_r1 = (uint8_t)p.is_r1; sg.break_index = p.bidx;
+                if (result == PASS_FILTER) {
+                    memcpy(before, h->post->mMedianReadQualHistogram, sizeof(before));
+                    h->post->statRead(p.r);
+                    sg.median_qual = (uint8_t)medianOfLast(h->post, before);
+                }
+                // the piece's QUALITY bytes are never modified: they must equal the original window
+                if (sg.len > 0 && memcmp(p.r->mQuality->data(), b->qual + b->offsets[i] + p.lo, sg.len) != 0) {
+                    std::cerr << "ref_harness: piece window mismatch on read " << i << std::endl; abort();
+                }
+                h->segs.push_back(sg);
+                if (k < 2) {
+                    out->seg_lo[k] = sg.lo; out->seg_len[k] = sg.len; out->seg_result[k] = sg.result;
+                    out->seg_median_qual[k] = sg.median_qual;
+                }
+                if (p.r != or1 && p.r != r1) delete p.r;
+            }
+            delete or1;
+            continue;
+        }
+
         out->n_segments = (int32_t)outReads.size();
         for (size_t k = 0; k < outReads.size(); k++) {                     // :264-288
             Read* outr = outReads[k];
@@ -236,6 +329,21 @@ int ref_process(void* hh, const fpl_batch* b, fpl_read_result* results) {
         }
         delete or1;
     }
+    return 0;
+}
+
+int ref_last_segments(void* hh, fpl_segment* out, int64_t cap, int64_t* n) {
+    Harness* h = (Harness*)hh;
+    *n = (int64_t)h->segs.size();
+    if (*n > cap) return -1;
+    if (*n) memcpy(out, h->segs.data(), sizeof(fpl_segment) * h->segs.size());
+    return 0;
+}
+int ref_last_mask_regions(void* hh, fpl_region* out, int64_t cap, int64_t* n) {
+    Harness* h = (Harness*)hh;
+    *n = (int64_t)h->regs.size();
+    if (*n > cap) return -1;
+    if (*n) memcpy(out, h->regs.data(), sizeof(fpl_region) * h->regs.size());
     return 0;
 }
 

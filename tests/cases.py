@@ -83,3 +83,35 @@ def adversarial_batch(seed):
 
 def ont_batch(seed, n=300, mean=2000, **kw):
     return synth.ont_like(n, mean, seed, **kw)
+
+
+# ---- --mask / --break ----
+MASK_BREAK_SETS = {
+    "break_default": Options(start_adapter=S, break_reads=True),
+    "break_w20": Options(start_adapter=S, break_reads=True, break_window_size=20, break_mean_quality=16),
+    "mask_default": Options(start_adapter=S, mask=True),
+    "mask_cplx": Options(start_adapter=S, mask=True, mask_window_size=10, mask_mean_quality=17, low_complexity_filter=True,
+                         n_percent_limit=20),
+    "mask_and_break": Options(start_adapter=S, mask=True, mask_window_size=12, mask_mean_quality=15, break_reads=True,
+                              break_window_size=30, break_mean_quality=14, cut_front=True, cut_tail=True,
+                              n_base_limit=50, n_percent_limit=5),
+    "break_no_adapter": Options(disable_adapter_trimming=True, break_reads=True, break_window_size=25,
+                                break_mean_quality=12, disable_quality_filtering=True),
+}
+
+
+def blocky_quality_batch(seed, n=150):
+    """Reads whose quality alternates between good (~Q30) and bad (~Q5) stretches of random length, some with
+    adapters and chimeras: --break cuts them into several pieces, --mask paints the bad stretches."""
+    rng = np.random.default_rng(seed)
+    b = synth.ont_like(n, 1200, seed, p_chimera=0.1, q_mean=30.0, q_sd=3.0)
+    q = b.qual.copy()
+    for i in range(b.n_reads):
+        o, L = int(b.offsets[i]), int(b.lens[i])
+        pos = int(rng.integers(0, 300))
+        while pos < L:
+            bad = int(rng.integers(5, 260))
+            q[o + pos:o + min(L, pos + bad)] = (np.rint(rng.normal(5, 2, size=min(L, pos + bad) - pos)).clip(1, 40).astype(np.uint8) + 33)
+            pos += bad + int(rng.integers(20, 900))
+    from fastplong_b200 import PackedBatch
+    return PackedBatch(b.seq, q, b.offsets, b.lens)

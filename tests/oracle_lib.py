@@ -50,6 +50,10 @@ class _CpuEngine:
         self._stats_dl.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]
         self._cnt_dl = getattr(lib, p + "_counters_download")
         self._cnt_dl.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+        self._segs = getattr(lib, p + "_last_segments")
+        self._segs.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+        self._regs = getattr(lib, p + "_last_mask_regions")
+        self._regs.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
         self.lib = lib
         self.options = options
         o, ad, keep = options.to_abi()
@@ -77,6 +81,21 @@ class _CpuEngine:
         if batch.n_reads:
             self.max_len = max(self.max_len, int(batch.lens.max()))
         return res
+
+    def _list(self, fn, dtype):
+        n = C.c_int64()
+        fn(self.h, None, 0, C.byref(n))
+        out = np.zeros(n.value, dtype=dtype)
+        if n.value:
+            assert fn(self.h, out.ctypes.data, n.value, C.byref(n)) == 0
+        return out
+
+    def segments(self):
+        """--mask/--break: every output read of the last process() call."""
+        return self._list(self._segs, abi.SEGMENT_DTYPE)
+
+    def mask_regions(self):
+        return self._list(self._regs, abi.REGION_DTYPE)
 
     def stats(self, which, cycles=None):
         cyc = int(cycles if cycles is not None else max(self.max_len, 1))
@@ -152,6 +171,14 @@ def compare_results(a, b, what="results"):
             i = int(bad[0])
             raise AssertionError(f"{what}: field {name} differs on {len(bad)} reads, first read {i}: "
                                  f"{a[i]} vs {b[i]}")
+
+
+def compare_lists(a, b, what):
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    for name in a.dtype.names:
+        if not np.array_equal(a[name], b[name]):
+            i = int(np.nonzero(a[name] != b[name])[0][0])
+            raise AssertionError(f"{what}: field {name} differs first at {i}: {a[i]} vs {b[i]}")
 
 
 def compare_stats(a, b, what="stats"):

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_mirror_sizes():
-    assert C.sizeof(abi.FplOptions) == 128
+    assert C.sizeof(abi.FplOptions) == 144
     assert abi.RESULT_DTYPE.itemsize == 64
     hdr = open(os.path.join(ROOT, "include", "fplgpu.h")).read()
     assert int(re.search(r"#define FPL_MAX_ADAPTER_LEN (\d+)", hdr).group(1)) == abi.MAX_ADAPTER_LEN
