@@ -136,6 +136,109 @@ void appendRecord(std::string& out, const std::string& name, const char* tagAfte
     out.push_back('\n');
 }
 
+// One input read as the host sees it (Read object or extents in a raw FASTQ chunk).
+struct ReadView {
+    const char* name; size_t name_len;
+    const char* seq; const char* qual; int len;
+    const char* strand; size_t strand_len;
+};
+
+void appendView(std::string& out, const ReadView& v, const char* seq, const std::string& prefixAfterAt, const char* nameSuffix,
+                int lo, int n) {
+    if (!prefixAfterAt.empty() && v.name_len > 0) {
+        out.append(v.name, 1);
+        out.append(prefixAfterAt);
+        out.append(v.name + 1, v.name_len - 1);
+    } else {
+        out.append(v.name, v.name_len);
+    }
+    if (nameSuffix) { out.push_back(' '); out.append(nameSuffix); }
+    out.push_back('\n');
+    out.append(seq + lo, n);
+    out.push_back('\n');
+    out.append(v.strand, v.strand_len);
+    out.push_back('\n');
+    out.append(v.qual + lo, n);
+    out.push_back('\n');
+}
+
+// Everything processSingleEnd does with one read AFTER the per-base work (src/seprocessor.cpp:264-288 and the
+// FilterResult / Stats side effects), driven by the device's record.  segs/regs: this read's entries of the
+// --mask/--break lists (nullptr in the plain mode, where the record's inline segments are used).
+bool scatterRead(const ReadView& v, const fpl_read_result& rr, const fpl_segment* segs, const fpl_region* regs, int nregs,
+                 ThreadConfig* config, bool haveFailedWriter, std::string& outstr, std::string& failedOut, std::string& scratch) {
+    Stats* pre = config->getPreStats1();
+    Stats* post = config->getPostStats1();
+    FilterResult* fr = config->getFilterResult();
+    const int L = v.len;
+    pre->mLengthVec.push_back(L);
+    pre->mNeedCalcLength = true;
+    if (L > 0) pre->mQualLength[(char)rr.pre_median_qual].push_back(L);
+    if (rr.flags & FPL_FLAG_POLYX) fr->addPolyXTrimmed(rr.polyx_base, rr.polyx_len);
+    if (rr.adapter_trimmed_bases > 0) fr->addReadTrimmed(rr.adapter_trimmed_bases);
+    const char* mseq = v.seq;          // masked view of the bases (Read::maskRegionWithN), only materialised if needed
+    if (nregs > 0) {
+        scratch.assign(v.seq, (size_t)L);
+        for (int k = 0; k < nregs; k++) memset(&scratch[regs[k].lo], 'N', (size_t)regs[k].len);
+        mseq = scratch.data();
+    }
+    bool passed = false;
+    for (int k = 0; k < rr.n_segments; k++) {
+        int lo, ln, code, median, side, bidx, isR1;
+        if (segs) {
+            lo = segs[k].lo; ln = segs[k].len; code = segs[k].result; median = segs[k].median_qual;
+            side = segs[k].split_side; bidx = segs[k].break_index; isR1 = segs[k].is_r1;
+        } else {
+            lo = rr.seg_lo[k]; ln = rr.seg_len[k]; code = rr.seg_result[k]; median = rr.seg_median_qual[k];
+            side = (rr.flags & FPL_FLAG_MIDDLE_ADAPTER) ? ((k == 1 || (rr.flags & FPL_FLAG_SEG0_IS_RIGHT)) ? 2 : 1) : 0;
+            bidx = 0; isR1 = side == 0;
+        }
+        config->addFilterResult(code, 1);
+        if (code == PASS_FILTER) {
+            std::string prefix;          // "r<k>-" (Read::breakByRegions) goes in front of the breakByGap tag
+            if (bidx) prefix = "r" + std::to_string(bidx) + "-";
+            if (side) prefix += side == 2 ? "split-by-adapter-right-" : "split-by-adapter-left-";
+            appendView(outstr, v, mseq, prefix, NULL, lo, ln);
+            passed = true;
+            post->mLengthVec.push_back(ln);
+            post->mNeedCalcLength = true;
+            if (ln > 0) post->mQualLength[(char)median].push_back(ln);
+        } else if (haveFailedWriter && rr.n_segments == 1) {
+            // the reference prints or1, trimmed in place — and masked in place only if the output read IS r1 (:278-280)
+            appendView(failedOut, v, isR1 ? mseq : v.seq, std::string(), FAILED_TYPES[code], rr.trim_lo, rr.trim_len);
+        }
+    }
+    return passed;
+}
+
+// the --mask/--break lists of the last call on this context, grouped per read while walking the records in order
+struct ExtLists {
+    std::vector<fpl_segment> segs;
+    std::vector<fpl_region> regs;
+    size_t sp = 0, rp = 0;
+    bool on = false;
+    void fetch(fpl_ctx* ctx, bool enabled) {
+        on = enabled; sp = rp = 0;
+        if (!on) return;
+        int64_t n = 0;
+        fpl_last_segments(ctx, NULL, 0, &n);
+        segs.resize((size_t)n);
+        if (n) check(fpl_last_segments(ctx, segs.data(), n, &n), "fpl_last_segments");
+        fpl_last_mask_regions(ctx, NULL, 0, &n);
+        regs.resize((size_t)n);
+        if (n) check(fpl_last_mask_regions(ctx, regs.data(), n, &n), "fpl_last_mask_regions");
+    }
+    // entries of read i (records are walked in order, the lists are in read order)
+    const fpl_segment* segsOf(int nseg) { const fpl_segment* p = on ? segs.data() + sp : NULL; if (on) sp += (size_t)nseg; return p; }
+    const fpl_region* regsOf(int64_t read, int& n) {
+        n = 0;
+        if (!on) return NULL;
+        const fpl_region* p = regs.data() + rp;
+        while (rp < regs.size() && regs[rp].read == read) { rp++; n++; }
+        return p;
+    }
+};
+
 void addStatsBlock(Stats* s, const std::vector<int64_t>& blk, int64_t C) {
     int64_t used = 0;
     for (int64_t c = 0; c < C; c++)
@@ -247,8 +350,6 @@ SingleEndProcessor::SingleEndProcessor(Options* opt) {
     mPackReadCounter = 0;
     mPackProcessedCounter = 0;
     mReadPool = new ReadPool(mOptions);
-    if (opt->mask.enabled || opt->breakOpt.enabled)
-        error_exit("fastplong_gpu: --mask / --break are not implemented on the GPU path (SURVEY §8f); use the reference binary for them");
 }
 
 SingleEndProcessor::~SingleEndProcessor() {
@@ -359,9 +460,9 @@ bool SingleEndProcessor::processSingleEnd(ReadPack* pack, ThreadConfig* config) 
     check(fpl_process_host(w.ctx, &b, w.results.p), "fpl_process_host");
 
     // ---- scatter: walk the records in pack order (src/seprocessor.cpp:186-326) ----
-    Stats* pre = config->getPreStats1();
-    Stats* post = config->getPostStats1();
-    FilterResult* fr = config->getFilterResult();
+    ExtLists ext;
+    ext.fetch(w.ctx, mOptions->mask.enabled || mOptions->breakOpt.enabled);
+    std::string scratch;
     k = 0;
     for (ReadPack* p : w.packs) {
         string* outstr = new string();
@@ -370,36 +471,12 @@ bool SingleEndProcessor::processSingleEnd(ReadPack* pack, ThreadConfig* config) 
         for (int i = 0; i < p->count; i++, k++) {
             Read* or1 = p->data[i];
             const fpl_read_result& rr = w.results.p[k];
-            const int L = (int)or1->mSeq->length();
-            const char* seq = or1->mSeq->data();
-            const char* qual = or1->mQuality->data();
-            // per-read lists of Stats::statRead (src/stats.cpp:268-271, 362-368); the arrays come from the device
-            pre->mLengthVec.push_back(L);
-            pre->mNeedCalcLength = true;
-            if (L > 0) pre->mQualLength[(char)rr.pre_median_qual].push_back(L);
-            if (rr.flags & FPL_FLAG_POLYX) fr->addPolyXTrimmed(rr.polyx_base, rr.polyx_len);
-            if (rr.adapter_trimmed_bases > 0) fr->addReadTrimmed(rr.adapter_trimmed_bases);
-            bool passed = false;
-            for (int sgi = 0; sgi < rr.n_segments; sgi++) {
-                const int code = rr.seg_result[sgi];
-                config->addFilterResult(code, 1);
-                if (code == PASS_FILTER) {
-                    const char* tag = NULL;
-                    if (rr.flags & FPL_FLAG_MIDDLE_ADAPTER)
-                        tag = (sgi == 1 || (rr.flags & FPL_FLAG_SEG0_IS_RIGHT)) ? "split-by-adapter-right-" : "split-by-adapter-left-";
-                    appendRecord(*outstr, *or1->mName, tag, NULL, seq + rr.seg_lo[sgi], qual + rr.seg_lo[sgi],
-                                 rr.seg_len[sgi], *or1->mStrand);
-                    passed = true;
-                    post->mLengthVec.push_back(rr.seg_len[sgi]);
-                    post->mNeedCalcLength = true;
-                    if (rr.seg_len[sgi] > 0) post->mQualLength[(char)rr.seg_median_qual[sgi]].push_back(rr.seg_len[sgi]);
-                } else if (mFailedWriter && rr.n_segments == 1) {
-                    // the reference prints the trimmed or1 with the reason tag (src/seprocessor.cpp:278-280)
-                    appendRecord(*failedOut, *or1->mName, NULL, FAILED_TYPES[code], seq + rr.trim_lo, qual + rr.trim_lo,
-                                 rr.trim_len, *or1->mStrand);
-                }
-            }
-            if (passed) readPassed++;
+            ReadView v = {or1->mName->data(), or1->mName->length(), or1->mSeq->data(), or1->mQuality->data(),
+                          (int)or1->mSeq->length(), or1->mStrand->data(), or1->mStrand->length()};
+            int nregs = 0;
+            const fpl_segment* sg = ext.segsOf(rr.n_segments);
+            const fpl_region* rg = ext.regsOf((int64_t)k, nregs);
+            if (scatterRead(v, rr, sg, rg, nregs, config, mFailedWriter != NULL, *outstr, *failedOut, scratch)) readPassed++;
             recycleToPool(tid, or1);
         }
         if (mOptions->split.enabled) {
@@ -564,43 +641,17 @@ bool SingleEndProcessor::process() {
                 string* failedOut = new string();
                 const char* text = (const char*)c->p;
                 outstr->reserve(c->n);
+                ExtLists ext;
+                ext.fetch(w.ctx, n > 0 && (opt->mask.enabled || opt->breakOpt.enabled));
+                std::string scratch;
                 for (int64_t i = 0; i < n; i++) {
                     const fpl_fastq_record& fq = recs[i];
-                    const fpl_read_result& rr = res[i];
-                    const int L = fq.seq_len;
-                    pre->mLengthVec.push_back(L);
-                    pre->mNeedCalcLength = true;
-                    if (L > 0) pre->mQualLength[(char)rr.pre_median_qual].push_back(L);
-                    if (rr.flags & FPL_FLAG_POLYX) fr->addPolyXTrimmed(rr.polyx_base, rr.polyx_len);
-                    if (rr.adapter_trimmed_bases > 0) fr->addReadTrimmed(rr.adapter_trimmed_bases);
-                    for (int sgi = 0; sgi < rr.n_segments; sgi++) {
-                        const int code = rr.seg_result[sgi];
-                        config->addFilterResult(code, 1);
-                        const bool pass = code == PASS_FILTER;
-                        if (!pass && !(failedW && rr.n_segments == 1)) continue;
-                        string& dst = pass ? *outstr : *failedOut;
-                        const int lo = pass ? rr.seg_lo[sgi] : rr.trim_lo, ln = pass ? rr.seg_len[sgi] : rr.trim_len;
-                        if (pass && (rr.flags & FPL_FLAG_MIDDLE_ADAPTER)) {
-                            dst.push_back('@');
-                            dst.append((sgi == 1 || (rr.flags & FPL_FLAG_SEG0_IS_RIGHT)) ? "split-by-adapter-right-" : "split-by-adapter-left-");
-                            dst.append(text + fq.name_off + 1, fq.name_len - 1);
-                        } else {
-                            dst.append(text + fq.name_off, fq.name_len);
-                        }
-                        if (!pass) { dst.push_back(' '); dst.append(FAILED_TYPES[code]); }
-                        dst.push_back('\n');
-                        dst.append(text + fq.seq_off + lo, ln);
-                        dst.push_back('\n');
-                        dst.append(text + fq.plus_off, fq.plus_len);
-                        dst.push_back('\n');
-                        dst.append(text + fq.qual_off + lo, ln);
-                        dst.push_back('\n');
-                        if (pass) {
-                            post->mLengthVec.push_back(ln);
-                            post->mNeedCalcLength = true;
-                            if (ln > 0) post->mQualLength[(char)rr.seg_median_qual[sgi]].push_back(ln);
-                        }
-                    }
+                    ReadView v = {text + fq.name_off, (size_t)fq.name_len, text + fq.seq_off, text + fq.qual_off, fq.seq_len,
+                                  text + fq.plus_off, (size_t)fq.plus_len};
+                    int nregs = 0;
+                    const fpl_segment* sg = ext.segsOf(res[i].n_segments);
+                    const fpl_region* rg = ext.regsOf(i, nregs);
+                    scatterRead(v, res[i], sg, rg, nregs, config, failedW != NULL, *outstr, *failedOut, scratch);
                 }
                 if (left) { left->input(t, outstr); outstr = NULL; }
                 if (failedW) { failedW->input(t, failedOut); failedOut = NULL; }

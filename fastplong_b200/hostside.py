@@ -40,6 +40,48 @@ def emit_fastq(batch, names, results, strand=b"+"):
     return b"".join(out), b"".join(failed)
 
 
+def emit_fastq_ext(batch, names, results, segments, regions, strand=b"+"):
+    """--mask/--break variant (src/seprocessor.cpp:235-288): `segments` is the full list of output reads (read order),
+    `regions` the masked regions.  Names get "r<k>-" (Read::breakByRegions) in front of the split tag."""
+    out, failed = [], []
+    reg_by_read = {}
+    for rg in regions:
+        reg_by_read.setdefault(int(rg["read"]), []).append((int(rg["lo"]), int(rg["len"])))
+    ptr = 0
+    for i in range(batch.n_reads):
+        r = results[i]
+        o, L = int(batch.offsets[i]), int(batch.lens[i])
+        n = int(r["n_segments"])
+        pieces = segments[ptr:ptr + n]
+        ptr += n
+        assert all(int(p["read"]) == i for p in pieces)
+        seq = batch.seq[o:o + L]
+        mseq = seq
+        if i in reg_by_read:
+            mseq = seq.copy()
+            for lo, ln in reg_by_read[i]:
+                mseq[lo:lo + ln] = ord("N")
+        qual = batch.qual[o:o + L]
+        name = names[i]
+        for p in pieces:
+            lo, ln, code = int(p["lo"]), int(p["len"]), int(p["result"])
+            if code == abi.PASS_FILTER:
+                nm = name[1:]
+                if p["split_side"]:
+                    nm = (b"split-by-adapter-right-" if p["split_side"] == 2 else b"split-by-adapter-left-") + nm
+                if p["break_index"]:
+                    nm = b"r%d-" % int(p["break_index"]) + nm
+                out.append(name[:1] + nm + b"\n" + mseq[lo:lo + ln].tobytes() + b"\n" + strand + b"\n" +
+                           qual[lo:lo + ln].tobytes() + b"\n")
+            elif n == 1:
+                tl, tn = int(r["trim_lo"]), int(r["trim_len"])
+                src = mseq if p["is_r1"] else seq
+                failed.append(name + b" " + abi.FAILED_TYPES[code].encode() + b"\n" + src[tl:tl + tn].tobytes() + b"\n" +
+                              strand + b"\n" + qual[tl:tl + tn].tobytes() + b"\n")
+    assert ptr == len(segments)
+    return b"".join(out), b"".join(failed)
+
+
 def default_names(batch, prefix=b"read"):
     return [b"@%s%d len=%d" % (prefix, i, int(batch.lens[i])) for i in range(batch.n_reads)]
 

@@ -5,6 +5,8 @@ where /root/reference exists and oracle/_ref has been built by `make -C oracle`)
                                  numpy's generator staying bit-stable
   ref_<optionset>.npz            per-read records, pre/post Stats blocks and FilterResult counters produced by the
                                  reference's own operators (oracle/_ref/libfplref.so) for each tests/cases.py option set
+  blocky_input.npz               the packed blocky-quality batch (seed 88) for the --mask/--break fixtures
+  ref_mb_<set>.npz               the same for tests/cases.py MASK_BREAK_SETS, plus the output-read and masked-region lists
   binary_<name>.json             whole-binary runs of oracle/_ref/fastplong_ref on a seeded FASTQ: md5 of --out and
                                  --failed_out, md5 of the JSON report text minus its "command" line, the report's
                                  scalar sections (curves replaced by their md5), and the input md5
@@ -34,6 +36,12 @@ BINARY_RUNS = {
     "c1_small": (11, 160, 1500, "default_se", {"p_chimera": 0.05, "q_mean": 17.0}),
     "cut_polyx": (12, 160, 1500, "cut_polyx_cplx", {"p_polya": 0.05, "p_chimera": 0.05, "q_mean": 17.0}),
     "loose": (13, 120, 1200, "loose_ed", {"p_chimera": 0.04}),
+}
+# --mask / --break whole-binary runs on cases.blocky_quality_batch(seed, n)
+BINARY_MB_RUNS = {
+    "mb_break": (21, 120, "break_default"),
+    "mb_mask": (22, 120, "mask_cplx"),
+    "mb_both": (23, 120, "mask_and_break"),
 }
 
 
@@ -75,6 +83,24 @@ def main():
         res = r.process(b)
         np.savez_compressed(os.path.join(HERE, f"ref_{name}.npz"), results=res, pre=r.stats(0, cyc),
                             post=r.stats(1, cyc), counters=r.counters(), cycles=cyc)
+    bb = cases.blocky_quality_batch(88, n=120)
+    np.savez_compressed(os.path.join(HERE, "blocky_input.npz"), seq=bb.seq, qual=bb.qual, offsets=bb.offsets, lens=bb.lens)
+    cyc = int(bb.lens.max())
+    for name, opt in cases.MASK_BREAK_SETS.items():
+        r = RefEngine(opt)
+        res = r.process(bb)
+        np.savez_compressed(os.path.join(HERE, f"ref_mb_{name}.npz"), results=res, pre=r.stats(0, cyc),
+                            post=r.stats(1, cyc), counters=r.counters(), cycles=cyc, segments=r.segments(),
+                            regions=r.mask_regions())
+    for name, (seed, n, optname) in BINARY_MB_RUNS.items():
+        opt = cases.MASK_BREAK_SETS[optname]
+        batch = cases.blocky_quality_batch(seed, n=n)
+        with tempfile.TemporaryDirectory() as d:
+            fq = os.path.join(d, "in.fq")
+            synth.to_fastq(batch, fq)
+            g = run_binary(REF_BIN, opt, fq, d)
+            g.update({"input_md5": md5(fq), "seed": seed, "n_reads": n, "options": optname})
+        json.dump(g, open(os.path.join(HERE, f"binary_{name}.json"), "w"), indent=1, sort_keys=True)
     for name, (seed, n, mean, optname, kw) in BINARY_RUNS.items():
         opt = cases.OPTION_SETS[optname]
         batch = synth.ont_like(n, mean, seed, **kw)

@@ -87,6 +87,39 @@ def test_gpu_binary_matches_reference_binary(name, threads, parse, tmp_path):
 
 
 @needs_bin
+@pytest.mark.parametrize("name", ["mb_break", "mb_mask", "mb_both"])
+def test_gpu_binary_mask_break_matches_golden_reference_run(name, tmp_path):
+    g = json.load(open(os.path.join(GOLDEN, f"binary_{name}.json")))
+    batch = cases.blocky_quality_batch(g["seed"], n=g["n_reads"])
+    fq = str(tmp_path / "in.fq")
+    synth.to_fastq(batch, fq)
+    if md5(fq) != g["input_md5"]:
+        pytest.skip("synthetic input differs from the fixture's")
+    got = run(GPU_BIN, cases.MASK_BREAK_SETS[g["options"]], fq, str(tmp_path), "gpu")
+    assert got["out_md5"] == g["out_md5"]
+    assert got["failed_md5"] == g["failed_md5"]
+    assert got["json_text_md5"] == g["json_text_md5"]
+
+
+@needs_bin
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/fastplong_ref not built")
+@pytest.mark.parametrize("parse", ["device", "host"])
+@pytest.mark.parametrize("name,threads", [("break_default", 2), ("break_w20", 3), ("mask_default", 1), ("mask_cplx", 4),
+                                          ("mask_and_break", 3), ("break_no_adapter", 2)])
+def test_gpu_binary_mask_break_matches_reference_binary(name, threads, parse, tmp_path):
+    """-N / -b: both binaries side by side on blocky-quality reads, both parse paths."""
+    opt = cases.MASK_BREAK_SETS[name]
+    batch = cases.blocky_quality_batch(40 + threads, n=400)
+    fq = str(tmp_path / "in.fq")
+    synth.to_fastq(batch, fq)
+    ref = run(REF_BIN, opt, fq, str(tmp_path), "ref", threads)
+    got = run(GPU_BIN, opt, fq, str(tmp_path), "gpu", threads, env={"FPL_HOST_PARSE": "1"} if parse == "host" else None)
+    assert got["out_md5"] == ref["out_md5"]
+    assert got["failed_md5"] == ref["failed_md5"]
+    assert got["json_text_md5"] == ref["json_text_md5"]
+
+
+@needs_bin
 @pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/fastplong_ref not built")
 def test_config1_full_size_bit_exact(tmp_path):
     """BASELINE configs[0] at full size: 10k ONT reads mean 8 kb, known 30 bp start/end adapters, default Q-filter —

@@ -67,3 +67,52 @@ def test_oracle_reproduces_reference_binary_outputs(name):
     for k, v in ref_counts.items():
         assert amap[k] == v, k
     assert sum(v for k, v in amap.items() if k not in ref_counts) == others
+
+
+# ---- --mask / --break ----
+from oracle_lib import compare_lists  # noqa: E402
+
+
+def blocky_input():
+    z = np.load(os.path.join(GOLDEN, "blocky_input.npz"))
+    return PackedBatch(z["seq"], z["qual"], z["offsets"], z["lens"])
+
+
+@pytest.mark.parametrize("name", sorted(cases.MASK_BREAK_SETS))
+def test_oracle_matches_reference_fixture_mask_break(name):
+    b = blocky_input()
+    z = np.load(os.path.join(GOLDEN, f"ref_mb_{name}.npz"))
+    o = OracleEngine(cases.MASK_BREAK_SETS[name])
+    compare_results(o.process(b), z["results"], name)
+    compare_lists(o.segments(), z["segments"], name + "/segments")
+    compare_lists(o.mask_regions(), z["regions"], name + "/regions")
+    cyc = int(z["cycles"])
+    compare_stats(o.stats(0, cyc), z["pre"], name + "/pre")
+    compare_stats(o.stats(1, cyc), z["post"], name + "/post")
+    compare_stats(o.counters(), z["counters"], name + "/counters")
+
+
+@pytest.mark.parametrize("name", ["mb_break", "mb_mask", "mb_both"])
+def test_oracle_reproduces_reference_binary_outputs_mask_break(name):
+    """Oracle records + output-read list + masked regions -> host FASTQ assembly == fastplong_ref -N / -b outputs
+    ("r<k>-" names, masked bases, the failed-out rule of src/seprocessor.cpp:264-288)."""
+    g = json.load(open(os.path.join(GOLDEN, f"binary_{name}.json")))
+    opt = cases.MASK_BREAK_SETS[g["options"]]
+    batch = cases.blocky_quality_batch(g["seed"], n=g["n_reads"])
+    fq = b"".join(b"@read%d len=%d\n%s\n+\n%s\n" % (i, len(s), s, q) for i, (s, q) in
+                  enumerate(batch.read(i) for i in range(batch.n_reads)))
+    if hashlib.md5(fq).hexdigest() != g["input_md5"]:
+        pytest.skip("numpy generator produced a different synthetic input than when the fixture was made")
+    o = OracleEngine(opt)
+    res = o.process(batch)
+    out, failed = hostside.emit_fastq_ext(batch, hostside.default_names(batch), res, o.segments(), o.mask_regions())
+    assert hashlib.md5(out).hexdigest() == g["out_md5"]
+    assert hashlib.md5(failed).hexdigest() == g["failed_md5"]
+    cyc = int(batch.lens.max())
+    rep = hostside.report_summary(o.stats(0, cyc), o.stats(1, cyc), o.counters(), cyc)
+    j = g["json"]
+    for ours, key in ((rep["before"], "read_before_filtering"), (rep["after"], "read_after_filtering")):
+        for f in ("total_reads", "total_bases", "q20_bases", "q30_bases", "total_cycles"):
+            assert ours[f] == j[key][f], (key, f)
+    for f, v in rep["filtering_result"].items():
+        assert v == j["filtering_result"][f], f

@@ -5,7 +5,7 @@ import pytest
 
 import cases
 from fastplong_b200 import Options, pack_reads, synth
-from oracle_lib import OracleEngine, RefEngine, compare_results, compare_stats, have_ref
+from oracle_lib import OracleEngine, RefEngine, compare_lists, compare_results, compare_stats, have_ref
 
 pytestmark = pytest.mark.skipif(not have_ref(), reason="oracle/_ref/libfplref.so not built")
 
@@ -53,3 +53,21 @@ def test_edit_distance_random_pairs():
 
 def test_empty_batch():
     check(cases.OPTION_SETS["default_se"], pack_reads([]), "empty")
+
+
+@pytest.mark.parametrize("name", sorted(cases.MASK_BREAK_SETS))
+@pytest.mark.parametrize("kind", ["blocky", "adversarial", "ont"])
+def test_mask_break(name, kind):
+    """--mask / --break: records, the output-read list, the masked regions, both Stats blocks, counters."""
+    opt = cases.MASK_BREAK_SETS[name]
+    batch = {"blocky": lambda: cases.blocky_quality_batch(5, n=100), "adversarial": lambda: cases.adversarial_batch(4),
+             "ont": lambda: cases.ont_batch(6, n=80, mean=2000, p_chimera=0.05)}[kind]()
+    o, r = OracleEngine(opt), RefEngine(opt)
+    what = f"{name}/{kind}"
+    compare_results(o.process(batch), r.process(batch), what)
+    compare_lists(o.segments(), r.segments(), what + "/segments")
+    compare_lists(o.mask_regions(), r.mask_regions(), what + "/regions")
+    cyc = max(1, int(batch.lens.max()))
+    for w in (0, 1):
+        compare_stats(o.stats(w, cyc), r.stats(w, cyc), f"{what}/stats{w}")
+    compare_stats(o.counters(), r.counters(), what + "/counters")
