@@ -10,6 +10,7 @@
 #include <vector>
 #include "fpl_device.cuh"
 #include "fpl_scanplan.h"
+#include "fpl_stats.h"
 #include "fpl_jit.h"
 #include "fpl_ingest.h"
 #include "fpl_ext.h"
@@ -26,7 +27,7 @@ void launch_scan(const DevParams&, const DevBatch&, ReadState*, cudaStream_t);
 void launch_scan_fast(const DevParams&, const ScanPlan&, const DevBatch&, ReadState*, cudaStream_t);
 void launch_final(const DevParams&, const DevBatch&, const ReadState*, fpl_read_result*, StatSeg*, cudaStream_t);
 void launch_count(const fpl_read_result*, int64_t, unsigned long long*, bool, cudaStream_t);
-void launch_cycle_stats(const uint8_t*, const uint8_t*, const StatSeg*, int64_t, int64_t, unsigned long long*, int64_t,
+int launch_cycle_stats(CycleWs*, const uint8_t*, const uint8_t*, const StatSeg*, int64_t, int64_t, unsigned long long*, int64_t,
                         bool, unsigned long long*, cudaStream_t);
 void launch_kmer_fix(const DevBatch&, const fpl_read_result*, unsigned long long*, cudaStream_t);
 void launch_read_qual(const DevBatch&, unsigned long long*, unsigned long long*, int64_t, fpl_read_result*, bool, cudaStream_t);
@@ -77,6 +78,7 @@ struct fpl_ctx {
     int64_t cap_reads = 0;
     ReadState* d_state = nullptr;
     fpl_read_result* d_results = nullptr;
+    CycleWs cycle_ws;
     StatSeg* d_preseg = nullptr;
     StatSeg* d_postseg = nullptr;
     int64_t last_n = 0;
@@ -203,8 +205,9 @@ static int run_batch(fpl_ctx* c, const DevBatch& full, const int32_t* h_lens, fp
         cudaStream_t s = c->stream;
         { Timed t(c, K_PRESEG); launch_make_preseg(b, pre, s); }
         { Timed t(c, K_TRIM); launch_trim(c->P, b, st, res, c->d_counters, s); }
-        { Timed t(c, K_CYCLE_PRE); launch_cycle_stats(full.seq, full.qual, pre, b.n_reads, tmax, c->d_stats[0], c->C, true,
-                                                       ext ? nullptr : c->d_stats[1] + 16 * c->C + FPL_STATS_KMER, s); }
+        { Timed t(c, K_CYCLE_PRE);
+          if (launch_cycle_stats(&c->cycle_ws, full.seq, full.qual, pre, b.n_reads, tmax, c->d_stats[0], c->C, true,
+                                 ext ? nullptr : c->d_stats[1] + 16 * c->C + FPL_STATS_KMER, s)) return fail("out of device memory (cycle stats workspace)"); }
         {
             Timed t(c, K_SCAN);
             if (c->jit.fn) { if (fpl_jit_launch_scan(&c->jit, b, st, s)) return fail("launching k_scan_jit failed"); }
@@ -214,7 +217,9 @@ static int run_batch(fpl_ctx* c, const DevBatch& full, const int32_t* h_lens, fp
         { Timed t(c, K_FINAL); launch_final(c->P, b, st, res, post, s); }
         if (!ext) {
             { Timed t(c, K_COUNT); launch_count(res, b.n_reads, c->d_counters, true, s); }
-            { Timed t(c, K_CYCLE_POST); launch_cycle_stats(full.seq, full.qual, post, 2 * b.n_reads, tmax, c->d_stats[1], c->C, false, nullptr, s); }
+            { Timed t(c, K_CYCLE_POST);
+              if (launch_cycle_stats(&c->cycle_ws, full.seq, full.qual, post, 2 * b.n_reads, tmax, c->d_stats[1], c->C, false, nullptr, s))
+                  return fail("out of device memory (cycle stats workspace)"); }
             { Timed t(c, K_KMER_FIX); launch_kmer_fix(b, res, c->d_stats[1] + 16 * c->C + FPL_STATS_KMER, s); }
             { Timed t(c, K_QUAL_PRE); launch_read_qual(b, c->d_stats[0], c->d_stats[1], c->C, res, false, s); }
         } else {
@@ -226,7 +231,9 @@ static int run_batch(fpl_ctx* c, const DevBatch& full, const int32_t* h_lens, fp
             { Timed t(c, K_COUNT); launch_count(res, b.n_reads, c->d_counters, false, s); }
             if (fpl_ext_run(&c->ext, c->P, b, n_bytes, res, c->d_counters, c->d_stats[1], c->C, &fseq, s, xerr, sizeof(xerr)))
                 return fail("--mask/--break stage: %s", xerr);
-            { Timed t(c, K_CYCLE_POST); launch_cycle_stats(fseq, full.qual, c->ext.d_stat, c->ext.n_segs, tmax, c->d_stats[1], c->C, true, nullptr, s); }
+            { Timed t(c, K_CYCLE_POST);
+              if (launch_cycle_stats(&c->cycle_ws, fseq, full.qual, c->ext.d_stat, c->ext.n_segs, tmax, c->d_stats[1], c->C, true, nullptr, s))
+                  return fail("out of device memory (cycle stats workspace)"); }
         }
         r0 = r1;
     }
@@ -371,6 +378,7 @@ void fpl_destroy(fpl_ctx* c) {
     for (auto e : c->pool) cudaEventDestroy(e);
     cudaFree(c->d_adapters); cudaFree(c->d_alen); cudaFree(c->d_peq); cudaFree(c->d_peq16); cudaFree(c->d_acode);
     cudaFree(c->d_stats[0]); cudaFree(c->d_stats[1]); cudaFree(c->d_counters);
+    fpl_cycle_ws_free(&c->cycle_ws);
     cudaFree(c->d_state); cudaFree(c->d_results); cudaFree(c->d_preseg); cudaFree(c->d_postseg);
     cudaFree(c->d_seq); cudaFree(c->d_qual); cudaFree(c->d_offsets); cudaFree(c->d_lens);
     fpl_ingest_free(&c->ingest);

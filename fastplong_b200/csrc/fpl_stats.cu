@@ -13,12 +13,19 @@
 //                 a passing segment's histogram is the read's minus the removed ends.
 //  k_kmer_fix     post-filter 5-mer table = pre-filter table - the 5-mers outside the passing segments.
 #include "fpl_device.cuh"
+#include "fpl_stats.h"
 
-#define CS_THREADS 256
-#define CS_WARPS (CS_THREADS / 32)
-#define CS_TILE 512                              // cycles per CTA: one 16-byte vector per lane
+#include <cub/cub.cuh>
+
+#define CS_NT_KMER 1024                          // threads per CTA with the 5-mer tables (one CTA per SM: 145 KB of shared memory)
+#define CS_NT_PLAIN 512
+#define CS_TILE 512                              // bytes of every segment a CTA looks at: one 16-byte vector per lane
+#define CS_ROWW 33                               // words per counter row: 32 lanes + the carry column
+#define CS_BINW (16 * CS_ROWW + 16)              // words per base bin: a multiple of 32, so the bank is the lane's whatever the bin
 #define CS_GROUP 4000                            // segments per CTA; packed counter: count <= 4095, sum of q < 2^20
 #define CS_STAGE 1000                            // descriptors staged in shared memory at a time
+#define CS_SMEM_BASE (8 * CS_BINW * 4 + CS_STAGE * 16)            // counters + staged descriptors
+#define CS_SMEM_KMER (CS_SMEM_BASE + 1024 * 32 * 4)               // + lane-private 5-mer tables
 
 namespace {
 
@@ -32,192 +39,232 @@ __device__ __forceinline__ uint32_t kmer_code(uint32_t b) {
     return v;
 }
 
-// 16 bytes at an arbitrary address: two aligned 16-byte loads (load16_raw, issued early) + a byte shift
-// (assemble16, at the point of use so that the loads stay in flight; sh = address & 15 is warp-uniform)
-struct Raw16 { uint4 x, y; };
-__device__ __forceinline__ Raw16 load16_raw(const uint8_t* p) {
-    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-    const uint4* v = reinterpret_cast<const uint4*>(a & ~(uintptr_t)15);
-    Raw16 r;
-    r.x = __ldg(v);
-    r.y = (a & 15) ? __ldg(v + 1) : make_uint4(0, 0, 0, 0);
-    return r;
-}
-__device__ __forceinline__ void assemble16(const Raw16& r, unsigned sh, uint32_t (&o)[4]) {
-    const uint4 x = r.x, y = r.y;
-    if (sh == 0) { o[0] = x.x; o[1] = x.y; o[2] = x.z; o[3] = x.w; return; }
-    const unsigned bs = (sh & 3) * 8;
-    switch (sh >> 2) {
-        case 0:
-            o[0] = __funnelshift_r(x.x, x.y, bs); o[1] = __funnelshift_r(x.y, x.z, bs);
-            o[2] = __funnelshift_r(x.z, x.w, bs); o[3] = __funnelshift_r(x.w, y.x, bs); break;
-        case 1:
-            o[0] = __funnelshift_r(x.y, x.z, bs); o[1] = __funnelshift_r(x.z, x.w, bs);
-            o[2] = __funnelshift_r(x.w, y.x, bs); o[3] = __funnelshift_r(y.x, y.y, bs); break;
-        case 2:
-            o[0] = __funnelshift_r(x.z, x.w, bs); o[1] = __funnelshift_r(x.w, y.x, bs);
-            o[2] = __funnelshift_r(y.x, y.y, bs); o[3] = __funnelshift_r(y.y, y.z, bs); break;
-        default:
-            o[0] = __funnelshift_r(x.w, y.x, bs); o[1] = __funnelshift_r(y.x, y.y, bs);
-            o[2] = __funnelshift_r(y.y, y.z, bs); o[3] = __funnelshift_r(y.z, y.w, bs); break;
-    }
+// 0x80 in every byte of w that is NOT one of A, C, G, T, U (exact, any byte value).  With g = b2 & ~b1 (set for
+// T/U: 0x54/0x55), the valid bytes are exactly those with ((b & 0xF9) | g) == 0x41 ^ (g << 4).
+__device__ __forceinline__ uint32_t invalid_acgtu(uint32_t w, uint32_t x1) {
+    const uint32_t g = (w >> 2) & ~x1 & 0x01010101u;
+    const uint32_t d = ((w & 0xF9F9F9F9u) | g) ^ 0x41414141u ^ (g * 16u);
+    return (((d & 0x7f7f7f7fu) + 0x7f7f7f7fu) | d) & 0x80808080u;
 }
 
-__device__ __forceinline__ uint32_t load4_before(const uint8_t* p) {   // the 4 bytes ending just before p
-    const uintptr_t a = reinterpret_cast<uintptr_t>(p) - 4;
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-    const unsigned sh = (unsigned)(a & 3) * 8;
-    const uint32_t lo = __ldg(w);
-    if (sh == 0) return lo;
-    return __funnelshift_r(lo, __ldg(w + 1), sh);
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {   // PTX semantics: selector bit 3 = sign fill
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+__device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c) {  // keeps the work on the IMAD pipe
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
 }
 
-// 0x01 in every byte of w that is one of A, C, G, T, U (exact): b & 0xE8 == 0x40 and, on bits (b4,b2,b1,b0),
-// b4 ? (b2 & ~b1) : (b0 & (b1 | ~b2))
-__device__ __forceinline__ uint32_t valid_acgtu(uint32_t w) {
-    const uint32_t x1 = w >> 1, x2 = w >> 2, x4 = w >> 4;
-    const uint32_t g1 = w & (x1 | ~x2);
-    const uint32_t g2 = x2 & ~x1;
-    const uint32_t v = (x4 & g2) | (~x4 & g1);
-    const uint32_t t = (w & 0xE8E8E8E8u) ^ 0x40404040u;                         // zero byte <=> 010x0xxx
-    const uint32_t nz = (((t & 0x7f7f7f7fu) + 0x7f7f7f7fu) | t) >> 7;            // bit0 of each byte: t != 0
-    return v & ~nz & 0x01010101u;
+template <int IMM>
+__device__ __forceinline__ void red_shared_add_imm(uint32_t saddr, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0 + %2], %1;" ::"r"(saddr), "r"(v), "n"(IMM) : "memory");
 }
 
-// four 2-bit 5-mer codes of a word, oldest base in the top bits: code = bit1 << 1 | bit2 (A=0, T/U=1, C=2, G=3)
-__device__ __forceinline__ uint32_t pack_codes(uint32_t w) {
-    const uint32_t c = (w & 0x02020202u) | ((w >> 2) & 0x01010101u);
-    return (c * 0x40100401u) >> 24;
+// Counter word of (bin, column): the CTA's columns are the cycles 512*tile - 15 + col, col in [0, 527).  Column col lives
+// in row col & 15 at position col >> 4 (33 positions per row), so that the 32 lanes of one instruction — which hold the
+// columns 16*lane + m for one m — hit 32 different banks (the bin stride is a multiple of 32 words).
+// A lane's vector starts S columns into its 16-column stripe (S = 15 - (segment address & 15), warp-uniform): byte J
+// is column 16*lane + J + S = row (J+S)&15, position lane + ((J+S)>>4).
+//   wm: base & 7 in every byte; qm: quality chars; cw: 0x10 in every byte that counts (0 elsewhere, with qm = 0 there)
+// Per base: one PRMT for the bin, one for the value (quality | 1 << 20), one IMAD for the address, one reduction.
+template <int S, int J>
+__device__ __forceinline__ void count1(const uint32_t (&wm)[4], const uint32_t (&qm)[4], const uint32_t (&cw)[4], uint32_t pk_lane) {
+    constexpr int jj = J & 3, m = J + S, z = 8 | jj;                      // selector z: sign fill of a 7-bit byte = 0
+    const uint32_t bin = prmt(wm[J >> 2], 0u, jj | z << 4 | z << 8 | z << 12);
+    const uint32_t val = prmt(qm[J >> 2], cw[J >> 2], jj | z << 4 | (4 + jj) << 8 | z << 12);
+    red_shared_add_imm<4 * ((m & 15) * CS_ROWW + (m >> 4))>(mad_u32(bin, CS_BINW * 4u, pk_lane), val);
+}
+template <int S>
+__device__ __forceinline__ void count16(const uint32_t (&wm)[4], const uint32_t (&qm)[4], const uint32_t (&cw)[4], uint32_t pk) {
+    count1<S, 0>(wm, qm, cw, pk); count1<S, 1>(wm, qm, cw, pk); count1<S, 2>(wm, qm, cw, pk); count1<S, 3>(wm, qm, cw, pk);
+    count1<S, 4>(wm, qm, cw, pk); count1<S, 5>(wm, qm, cw, pk); count1<S, 6>(wm, qm, cw, pk); count1<S, 7>(wm, qm, cw, pk);
+    count1<S, 8>(wm, qm, cw, pk); count1<S, 9>(wm, qm, cw, pk); count1<S, 10>(wm, qm, cw, pk); count1<S, 11>(wm, qm, cw, pk);
+    count1<S, 12>(wm, qm, cw, pk); count1<S, 13>(wm, qm, cw, pk); count1<S, 14>(wm, qm, cw, pk); count1<S, 15>(wm, qm, cw, pk);
+}
+
+// 0xFF in byte k of the result iff bit k of the nibble n
+__device__ __forceinline__ uint32_t nibble_to_bytes(uint32_t n) { return ((n * 0x00204081u) & 0x01010101u) * 0xFFu; }
+
+// 5-mer ending at byte T of the lane's vector.  P: 2-bit codes, oldest first, the 5-mer's in bits [22+2*SH .. 32); the
+// table word is [code][lane] (no bank conflicts); an invalid 5-mer adds 0 (no branch around the reduction).
+template <int SHL, int T>
+__device__ __forceinline__ void kmer1(uint32_t P, uint32_t ok, uint32_t km_lane) {
+    const uint32_t idx = (P << SHL) >> 22;
+    red_shared_add(mad_u32(idx, 128u, km_lane), (ok << (31 - T)) >> 31);
 }
 
 }  // namespace
 
+// Sorted segment descriptor (by length, longest first): 16 bytes.
+struct SegD {
+    int64_t off;
+    int32_t len;
+    int32_t pad;
+};
+// The same as a CTA stages it for its tile: a = 16-byte aligned byte offset of the tile's first vector, lim = how many
+// of the tile's bytes lie in front of the segment's end (> 0), sh = segment address & 15.
+struct __align__(16) TileSeg {
+    int64_t a;
+    int32_t lim;
+    int32_t sh;
+};
+
 // DO_KMER: also count the 5-mers; their table is flushed to `stats` and, if given, to `kmer_also` (the post-filter
 // block: post 5-mers = pre 5-mers - the ones k_kmer_fix finds outside the passing segments).
-template <bool DO_KMER>
-__global__ void __launch_bounds__(CS_THREADS, 4)
-k_cycle_stats(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qualbuf, const StatSeg* __restrict__ segs,
+//
+// Grid: x = 512-byte tile of the segments' 16-byte-aligned byte ranges, y = group of CS_GROUP segments of the list
+// sorted by length (so a group's segments end in the same few tiles and the CTAs beyond the longest one leave at once).
+// Every load is an aligned 16-byte vector: the misalignment of a segment (its address & 15, different for every
+// post-filter segment) moves the COLUMNS its bytes count into instead of the bytes (count16<S>).
+template <bool DO_KMER, int NT>
+__global__ void __launch_bounds__(NT, DO_KMER ? 1 : 2048 / NT / 2)
+k_cycle_stats(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qualbuf, const SegD* __restrict__ segs,
               int64_t nseg, unsigned long long* __restrict__ stats, int64_t C, unsigned long long* __restrict__ kmer_also) {
-    // packed[bin][j*32 + lane]: cycle c0 + 16*lane + j; one word = count << 20 | sum of quality chars
-    __shared__ uint32_t packed[8][CS_TILE];
-    __shared__ uint32_t kmer[1024 + 32];   // [1024..1055]: sink for the lanes whose 5-mer is not valid
-    __shared__ int64_t d_off[CS_STAGE];
-    __shared__ int32_t d_len[CS_STAGE];
-    __shared__ int d_n;
+    extern __shared__ __align__(16) uint8_t cs_smem[];
+    uint32_t* packed = reinterpret_cast<uint32_t*>(cs_smem);                       // [8][16][33]: count << 20 | sum of q
+    TileSeg* stage = reinterpret_cast<TileSeg*>(cs_smem + 8 * CS_BINW * 4);
+    uint32_t* kmer = reinterpret_cast<uint32_t*>(stage + CS_STAGE);                // [1024][32]: one column per lane
     const int wid = threadIdx.x >> 5, lane = lane_id();
-    const int64_t c0 = (int64_t)blockIdx.x * CS_TILE;      // first cycle of this CTA
+    const int64_t t0 = (int64_t)blockIdx.x * CS_TILE;      // first byte of this tile, relative to the aligned segment start
     const int64_t g0 = (int64_t)blockIdx.y * CS_GROUP;
     const int64_t g1 = min(nseg, g0 + CS_GROUP);
-    for (int i = threadIdx.x; i < 1024; i += CS_THREADS) kmer[i] = 0;
-    for (int i = threadIdx.x; i < 8 * CS_TILE; i += CS_THREADS) (&packed[0][0])[i] = 0;
-    const int64_t cl = c0 + 16 * lane;                     // this lane's first cycle
-    const uint32_t pk_lane = shared_addr(&packed[0][0]) + (uint32_t)lane * 4u;
-    const uint32_t km_base = shared_addr(&kmer[0]);
-    const uint32_t km_sink = km_base + (1024u + (uint32_t)lane) * 4u;
-    bool any = false;
+    {
+        const int maxlen = segs[g0].len;                   // sorted: the group's longest segment
+        if (maxlen <= 0 || t0 >= (int64_t)maxlen + 15) return;
+    }
+    for (int i = threadIdx.x; i < 8 * CS_BINW; i += NT) packed[i] = 0;
+    if (DO_KMER) {
+        uint4* kz = reinterpret_cast<uint4*>(kmer);
+        for (int i = threadIdx.x; i < 1024 * 32 / 4; i += NT) kz[i] = make_uint4(0, 0, 0, 0);
+    }
+    const uint32_t pk_lane = shared_addr(packed) + (uint32_t)lane * 4u;
+    const uint32_t km_lane = shared_addr(kmer) + (uint32_t)lane * 4u;
+    const uint8_t* seq_lane = seqbuf + 16 * lane;
+    const uint8_t* qual_lane = qualbuf + 16 * lane;
     for (int64_t s0 = g0; s0 < g1; s0 += CS_STAGE) {
         __syncthreads();
-        if (threadIdx.x == 0) d_n = 0;
-        __syncthreads();
-        // stage the descriptors of the segments that reach this tile
-        for (int64_t s = s0 + threadIdx.x; s < min(g1, s0 + CS_STAGE); s += CS_THREADS) {
-            const StatSeg sg = segs[s];
-            if ((int64_t)sg.len > c0) {
-                const int k = atomicAdd(&d_n, 1);
-                d_off[k] = sg.off; d_len[k] = sg.len;
+        // stage the descriptors; the ones that can reach this tile are a prefix (sorted by length)
+        int n = 0;
+        for (int i0 = 0; i0 < CS_STAGE; i0 += NT) {
+            const int i = i0 + threadIdx.x;
+            bool reach = false;
+            if (i < CS_STAGE && s0 + i < g1) {
+                const SegD sg = segs[s0 + i];
+                TileSeg ts;
+                ts.sh = (int32_t)(sg.off & 15);
+                ts.a = sg.off - ts.sh + t0;
+                const int64_t lim = (int64_t)ts.sh + sg.len - t0;
+                ts.lim = lim > 0 ? (int32_t)lim : 0;
+                stage[i] = ts;
+                reach = sg.len > 0 && (int64_t)sg.len + 15 > t0;
             }
+            n += __syncthreads_count(reach);
         }
-        __syncthreads();
-        const int n = d_n;
-        if (n) any = true;
-        // software pipeline: the vectors of segment k+CS_WARPS are in flight while segment k is processed
-        Raw16 nrs, nrq;
-        nrs.x = nrs.y = nrq.x = nrq.y = make_uint4(0, 0, 0, 0);
+        if (n == 0) break;
+        // software pipeline: the vectors of segment k+(NT / 32) are in flight while segment k is processed
+        uint4 ns = make_uint4(0, 0, 0, 0), nq = ns;
         uint32_t nprev0 = 0;
-        unsigned nsh = 0;
-        int nlen = 0;
+        int nsh = 0, nlim = 0;
         auto fetch = [&](int k) {
-            const int64_t off = d_off[k];
-            nlen = d_len[k];
-            const uint8_t* sp = seqbuf + off + c0;
-            nsh = (unsigned)(reinterpret_cast<uintptr_t>(sp) & 15);   // same for the quality buffer (both 16-byte aligned bases)
-            if (cl < nlen) {
-                nrs = load16_raw(sp + 16 * lane);
-                nrq = load16_raw(qualbuf + off + c0 + 16 * lane);
+            const TileSeg ts = stage[k];
+            nsh = ts.sh; nlim = ts.lim;
+            ns = nq = make_uint4(0, 0, 0, 0);
+            if (16 * lane < ts.lim) {
+                ns = __ldg(reinterpret_cast<const uint4*>(seq_lane + ts.a));
+                nq = __ldg(reinterpret_cast<const uint4*>(qual_lane + ts.a));
             }
-            if (DO_KMER && lane == 0) nprev0 = c0 >= 4 ? load4_before(sp) : 0u;
+            if (DO_KMER && lane == 0) nprev0 = ts.a >= 4 ? __ldg(reinterpret_cast<const uint32_t*>(seqbuf + ts.a - 4)) : 0u;
         };
         if (wid < n) fetch(wid);
-        for (int k = wid; k < n; k += CS_WARPS) {
-            const Raw16 rs = nrs, rq = nrq;
-            const unsigned sh = nsh;
-            const int len = nlen;
+        for (int k = wid; k < n; k += (NT / 32)) {
+            const uint32_t sw[4] = {ns.x, ns.y, ns.z, ns.w};
+            uint32_t qm[4] = {nq.x, nq.y, nq.z, nq.w};
+            const int sh = nsh, lim = nlim;
             const uint32_t prev0 = nprev0;
-            if (k + CS_WARPS < n) fetch(k + CS_WARPS);
-            const bool active = cl < len;
-            uint32_t sw[4] = {0, 0, 0, 0}, qw[4] = {0, 0, 0, 0};
-            if (active) { assemble16(rs, sh, sw); assemble16(rq, sh, qw); }
-            // per word: validity nibble (A,C,G,T,U) and four 2-bit codes; the previous lane's last word supplies the
-            // four bases in front of this lane's vector (lane 0: the word loaded in front of the tile)
-            uint32_t vn[4] = {0, 0, 0, 0}, pc[4] = {0, 0, 0, 0}, pvn = 0, ppc = 0;
-            if (DO_KMER) {
+            if (k + (NT / 32) < n) fetch(k + (NT / 32));
+            if (lim <= 0) continue;                        // warp-uniform: the segment ends in front of this tile
+            // which of the lane's 16 bytes are cycles of the segment (vmask) and can end a 5-mer (kmask: cycle >= 4)
+            uint32_t cw[4] = {0x10101010u, 0x10101010u, 0x10101010u, 0x10101010u};
+            uint32_t kmask = 0xFFFFu;
+            if (lim < CS_TILE || t0 == 0) {                // warp-uniform: the segment starts or ends in this tile
+                const int cyc0 = (int)t0 + 16 * lane - sh;                          // cycle of byte 0, negative in front
+                const int lo = max(0, -cyc0), hi = min(16, max(0, lim - 16 * lane));
+                const uint32_t vmask = hi > lo ? ((0xFFFFu >> (16 - hi)) & (0xFFFFu << lo)) : 0u;
+                const int klo = min(16, max(0, 4 - cyc0));
+                kmask = vmask & (0xFFFFu << klo);
+                if (vmask != 0xFFFFu) {
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    vn[i] = active ? (valid_acgtu(sw[i]) * 0x10204080u) >> 28 : 0u;
-                    pc[i] = pack_codes(sw[i]);
+                    for (int i = 0; i < 4; i++) {
+                        const uint32_t bm = nibble_to_bytes((vmask >> (4 * i)) & 15u);
+                        qm[i] &= bm; cw[i] &= bm;
+                    }
                 }
-                pvn = __shfl_up_sync(0xffffffffu, vn[3], 1); ppc = __shfl_up_sync(0xffffffffu, pc[3], 1);
-                if (lane == 0) { pvn = (valid_acgtu(prev0) * 0x10204080u) >> 28; ppc = pack_codes(prev0); }
             }
-            if (!active) continue;
-            const int nvalid = (int)min((int64_t)16, (int64_t)len - cl);
-            // ---- per-(bin, cycle) counters: word = count << 20 | sum of quality chars ----
-            // shared byte address of packed[base & 7][t*32 + lane] = pk_lane + ((base & 7) << 11) + (t << 7)
-            auto count = [&](int t) {
-                const uint32_t w = sw[t >> 2];
-                const int j = t & 3;
-                const uint32_t binoff = j == 0 ? (w << 11) : j == 1 ? (w << 3) : j == 2 ? (w >> 5) : (w >> 13);
-                const uint32_t val = __byte_perm(qw[t >> 2], 0x00100000u, 0x7650 + j);   // q | 1 << 20
-                red_shared_add(pk_lane + (binoff & 0x3800u) + ((uint32_t)t << 7), val);
-            };
-            if (nvalid == 16) {
-#pragma unroll
-                for (int t = 0; t < 16; t++) count(t);
-            } else {
-#pragma unroll
-                for (int t = 0; t < 16; t++)
-                    if (t < nvalid) count(t);
+            // ---- per-(bin, cycle) counters ----
+            {
+                const uint32_t wm[4] = {sw[0] & 0x07070707u, sw[1] & 0x07070707u, sw[2] & 0x07070707u, sw[3] & 0x07070707u};
+                switch (sh) {
+                    case 0: count16<15>(wm, qm, cw, pk_lane); break;
+                    case 1: count16<14>(wm, qm, cw, pk_lane); break;
+                    case 2: count16<13>(wm, qm, cw, pk_lane); break;
+                    case 3: count16<12>(wm, qm, cw, pk_lane); break;
+                    case 4: count16<11>(wm, qm, cw, pk_lane); break;
+                    case 5: count16<10>(wm, qm, cw, pk_lane); break;
+                    case 6: count16<9>(wm, qm, cw, pk_lane); break;
+                    case 7: count16<8>(wm, qm, cw, pk_lane); break;
+                    case 8: count16<7>(wm, qm, cw, pk_lane); break;
+                    case 9: count16<6>(wm, qm, cw, pk_lane); break;
+                    case 10: count16<5>(wm, qm, cw, pk_lane); break;
+                    case 11: count16<4>(wm, qm, cw, pk_lane); break;
+                    case 12: count16<3>(wm, qm, cw, pk_lane); break;
+                    case 13: count16<2>(wm, qm, cw, pk_lane); break;
+                    case 14: count16<1>(wm, qm, cw, pk_lane); break;
+                    default: count16<0>(wm, qm, cw, pk_lane); break;
+                }
             }
             if (!DO_KMER) continue;
-            // ---- 5-mers ending in this lane's 16 cycles: all five bases in ACGTU ----
-            const uint32_t V20 = pvn | (vn[0] << 4) | (vn[1] << 8) | (vn[2] << 12) | (vn[3] << 16);
-            uint32_t ok = V20 & (V20 >> 1) & (V20 >> 2) & (V20 >> 3) & (V20 >> 4);   // bit t: bytes t-4..t all valid
-            if (nvalid < 16) ok &= (1u << nvalid) - 1u;
-            if (ok) {
-                // 20 codes, oldest first, 2 bits each: Phi = codes of bytes -4..11 (32 bits), Plo = bytes 4..15 low part
-                const uint32_t Phi = (ppc << 24) | (pc[0] << 16) | (pc[1] << 8) | pc[2];   // bytes -4..11
-                const uint32_t Plo = (pc[1] << 24) | (pc[2] << 16) | (pc[3] << 8);         // bytes 4..15, then 8 zero bits
+            // ---- 5-mers ending in this lane's 16 bytes: all five bases in ACGTU, end cycle in [4, len) ----
+            // per word: invalidity nibble and four 2-bit codes c' = (b >> 1) & 3 (A=0, C=1, T/U=2, G=3; the flush maps them
+            // to base2val's); the previous lane's last word supplies the four bases in front of this lane's vector
+            // (lane 0: the word loaded in front of the tile)
+            uint32_t in[4], pc[4];
 #pragma unroll
-                for (int t = 0; t < 16; t++) {
-                    // 5-mer ending at byte t = codes of bytes t-4..t
-                    const uint32_t idx = t <= 11 ? (Phi >> (2 * (11 - t))) & 0x3FFu : (Plo >> (2 * (15 - t) + 8)) & 0x3FFu;
-                    // invalid 5-mers go to a per-lane sink slot instead of branching around the reduction
-                    red_shared_add((ok >> t & 1u) ? km_base + idx * 4u : km_sink, 1u);
-                }
+            for (int i = 0; i < 4; i++) {
+                const uint32_t x1 = sw[i] >> 1;
+                in[i] = (invalid_acgtu(sw[i], x1) * 0x00204081u) >> 28;
+                pc[i] = ((x1 & 0x03030303u) * 0x40100401u) >> 24;
             }
+            uint32_t pin = __shfl_up_sync(0xffffffffu, in[3], 1), ppc = __shfl_up_sync(0xffffffffu, pc[3], 1);
+            if (lane == 0) {
+                const uint32_t x1 = prev0 >> 1;
+                pin = (invalid_acgtu(prev0, x1) * 0x00204081u) >> 28;
+                ppc = ((x1 & 0x03030303u) * 0x40100401u) >> 24;
+            }
+            const uint32_t I20 = mad_u32(in[3], 65536u, mad_u32(in[2], 4096u, mad_u32(in[1], 256u, mad_u32(in[0], 16u, pin))));
+            const uint32_t bad = I20 | (I20 >> 1) | (I20 >> 2) | (I20 >> 3) | (I20 >> 4);   // bit t: a byte of t-4..t is invalid
+            const uint32_t ok = ~bad & kmask;
+            // 20 codes, oldest first, 2 bits each: Phi = codes of bytes -4..11 (32 bits), Plo = bytes 4..15, then 8 zero bits
+            const uint32_t Phi = mad_u32(ppc, 1u << 24, mad_u32(pc[0], 1u << 16, mad_u32(pc[1], 256u, pc[2])));
+            const uint32_t Plo = mad_u32(pc[1], 1u << 24, mad_u32(pc[2], 1u << 16, pc[3] * 256u));
+            kmer1<0, 0>(Phi, ok, km_lane); kmer1<2, 1>(Phi, ok, km_lane); kmer1<4, 2>(Phi, ok, km_lane); kmer1<6, 3>(Phi, ok, km_lane);
+            kmer1<8, 4>(Phi, ok, km_lane); kmer1<10, 5>(Phi, ok, km_lane); kmer1<12, 6>(Phi, ok, km_lane); kmer1<14, 7>(Phi, ok, km_lane);
+            kmer1<16, 8>(Phi, ok, km_lane); kmer1<18, 9>(Phi, ok, km_lane); kmer1<20, 10>(Phi, ok, km_lane); kmer1<22, 11>(Phi, ok, km_lane);
+            kmer1<8, 12>(Plo, ok, km_lane); kmer1<10, 13>(Plo, ok, km_lane); kmer1<12, 14>(Plo, ok, km_lane); kmer1<14, 15>(Plo, ok, km_lane);
         }
+        if (n < CS_STAGE) break;     // the rest of the group is shorter still
     }
     __syncthreads();
-    if (!any) return;   // block-uniform: d_n was read after a barrier by every thread
     // flush: content[b][c] += count ; qual[b][c] += sumq - 33*count
     unsigned long long* content = stats;
     unsigned long long* qualsum = stats + 8 * C;
-    for (int i = threadIdx.x; i < 8 * CS_TILE; i += CS_THREADS) {
-        const int bin = i / CS_TILE, col = i % CS_TILE;
-        const uint32_t v = packed[bin][col];
+    for (int i = threadIdx.x; i < 8 * CS_BINW; i += NT) {
+        const uint32_t v = packed[i];
         if (v) {
-            const int j = col >> 5, ln = col & 31;
-            const int64_t c = c0 + 16 * ln + j;
+            const int bin = i / CS_BINW, p = i % CS_BINW;
+            const int64_t c = t0 - 15 + 16 * (p % CS_ROWW) + p / CS_ROWW;
             const long long cnt = v >> 20, sq = v & 0xFFFFFu;
             atomicAdd(&content[(int64_t)bin * C + c], (unsigned long long)cnt);
             atomicAdd(&qualsum[(int64_t)bin * C + c], (unsigned long long)(sq - 33 * cnt));
@@ -225,22 +272,89 @@ k_cycle_stats(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qu
     }
     if (DO_KMER) {
         unsigned long long* tail = stats + 16 * C;
-        for (int i = threadIdx.x; i < 1024; i += CS_THREADS)
-            if (kmer[i]) {
-                atomicAdd(&tail[FPL_STATS_KMER + i], (unsigned long long)kmer[i]);
-                if (kmer_also) atomicAdd(&kmer_also[i], (unsigned long long)kmer[i]);
+        for (int i = threadIdx.x; i < 1024; i += NT) {
+            uint32_t sum = 0;
+#pragma unroll 8
+            for (int l = 0; l < 32; l++) sum += kmer[i * 32 + ((l + threadIdx.x) & 31)];
+            if (sum) {
+                // table index: five c' pairs (b2, b1); base2val's code is (b1, b2): swap the bits of every pair
+                const int code = ((i & 0x155) << 1) | ((i >> 1) & 0x155);
+                atomicAdd(&tail[FPL_STATS_KMER + code], (unsigned long long)sum);
+                if (kmer_also) atomicAdd(&kmer_also[code], (unsigned long long)sum);
             }
+        }
     }
 }
 
-// kmer_to: where the 5-mer counts of this launch go besides `stats` (nullptr = nowhere else); do_kmer = false skips them
-void launch_cycle_stats(const uint8_t* seq, const uint8_t* qual, const StatSeg* segs, int64_t nseg, int64_t max_len,
-                        unsigned long long* stats, int64_t C, bool do_kmer, unsigned long long* kmer_also,
-                        cudaStream_t stream) {
-    if (nseg == 0 || max_len <= 0) return;
-    dim3 grid((unsigned)((max_len + CS_TILE - 1) / CS_TILE), (unsigned)((nseg + CS_GROUP - 1) / CS_GROUP));
-    if (do_kmer) k_cycle_stats<true><<<grid, CS_THREADS, 0, stream>>>(seq, qual, segs, nseg, stats, C, kmer_also);
-    else k_cycle_stats<false><<<grid, CS_THREADS, 0, stream>>>(seq, qual, segs, nseg, stats, C, nullptr);
+namespace {
+__global__ void k_cs_keys(const StatSeg* __restrict__ segs, int64_t n, uint32_t* __restrict__ keys, int32_t* __restrict__ vals) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    keys[i] = (uint32_t)max(segs[i].len, 0);
+    vals[i] = (int32_t)i;
+}
+__global__ void k_cs_gather(const StatSeg* __restrict__ segs, const uint32_t* __restrict__ keys, const int32_t* __restrict__ vals,
+                            int64_t n, SegD* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    SegD d;
+    d.off = segs[vals[i]].off; d.len = (int32_t)keys[i]; d.pad = 0;
+    out[i] = d;
+}
+}  // namespace
+
+void fpl_cycle_ws_free(CycleWs* ws) {
+    cudaFree(ws->tmp); cudaFree(ws->k_in); cudaFree(ws->k_out); cudaFree(ws->v_in); cudaFree(ws->v_out); cudaFree(ws->sorted);
+    *ws = CycleWs();
+}
+
+// kmer_also: where the 5-mer counts of this launch go besides `stats` (nullptr = nowhere else); do_kmer = false skips
+// them.  Returns 0, or -1 when the workspace cannot be allocated.
+int launch_cycle_stats(CycleWs* ws, const uint8_t* seq, const uint8_t* qual, const StatSeg* segs, int64_t nseg, int64_t max_len,
+                       unsigned long long* stats, int64_t C, bool do_kmer, unsigned long long* kmer_also, cudaStream_t stream) {
+    if (nseg == 0 || max_len <= 0) return 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(k_cycle_stats<true, CS_NT_KMER>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM_KMER) != cudaSuccess ||
+            cudaFuncSetAttribute(k_cycle_stats<false, CS_NT_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM_BASE) != cudaSuccess)
+            return -1;
+        attr_set = true;
+    }
+    int end_bit = 1;
+    while (end_bit < 31 && (max_len >> end_bit)) end_bit++;
+    size_t need = 0;
+    cub::DeviceRadixSort::SortPairsDescending(nullptr, need, ws->k_in, ws->k_out, ws->v_in, ws->v_out, (int)nseg, 0, end_bit, stream);
+    if (nseg > ws->cap || need > ws->tmp_bytes) {
+        cudaStreamSynchronize(stream);
+        const int64_t cap = nseg > ws->cap ? nseg : ws->cap;
+        void* tmp = ws->tmp; size_t tmp_bytes = ws->tmp_bytes;
+        if (nseg > ws->cap) {
+            cudaFree(ws->k_in); cudaFree(ws->k_out); cudaFree(ws->v_in); cudaFree(ws->v_out); cudaFree(ws->sorted);
+            ws->k_in = ws->k_out = nullptr; ws->v_in = ws->v_out = nullptr; ws->sorted = nullptr; ws->cap = 0;
+            if (cudaMalloc(&ws->k_in, 4 * cap) != cudaSuccess || cudaMalloc(&ws->k_out, 4 * cap) != cudaSuccess ||
+                cudaMalloc(&ws->v_in, 4 * cap) != cudaSuccess || cudaMalloc(&ws->v_out, 4 * cap) != cudaSuccess ||
+                cudaMalloc(&ws->sorted, sizeof(SegD) * cap) != cudaSuccess)
+                return -1;
+            ws->cap = cap;
+            // the temporary storage grows with the item count
+            cub::DeviceRadixSort::SortPairsDescending(nullptr, need, ws->k_in, ws->k_out, ws->v_in, ws->v_out, (int)cap, 0, 31, stream);
+        }
+        if (need > tmp_bytes) {
+            cudaFree(tmp); ws->tmp = nullptr; ws->tmp_bytes = 0;
+            if (cudaMalloc(&ws->tmp, need) != cudaSuccess) return -1;
+            ws->tmp_bytes = need;
+        }
+    }
+    const unsigned blocks = (unsigned)((nseg + 255) / 256);
+    k_cs_keys<<<blocks, 256, 0, stream>>>(segs, nseg, ws->k_in, ws->v_in);
+    size_t bytes = ws->tmp_bytes;
+    cub::DeviceRadixSort::SortPairsDescending(ws->tmp, bytes, ws->k_in, ws->k_out, ws->v_in, ws->v_out, (int)nseg, 0, end_bit, stream);
+    k_cs_gather<<<blocks, 256, 0, stream>>>(segs, ws->k_out, ws->v_out, nseg, static_cast<SegD*>(ws->sorted));
+    dim3 grid((unsigned)((max_len + 15 + CS_TILE - 1) / CS_TILE), (unsigned)((nseg + CS_GROUP - 1) / CS_GROUP));
+    const SegD* sorted = static_cast<const SegD*>(ws->sorted);
+    if (do_kmer) k_cycle_stats<true, CS_NT_KMER><<<grid, CS_NT_KMER, CS_SMEM_KMER, stream>>>(seq, qual, sorted, nseg, stats, C, kmer_also);
+    else k_cycle_stats<false, CS_NT_PLAIN><<<grid, CS_NT_PLAIN, CS_SMEM_BASE, stream>>>(seq, qual, sorted, nseg, stats, C, nullptr);
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
