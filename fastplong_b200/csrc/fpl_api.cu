@@ -93,6 +93,11 @@ struct fpl_ctx {
     std::vector<int32_t> h_lens;
     // tiling + measurement
     int64_t tile_bases = 0;
+    // fpl_process_host: the upload runs on its own stream, piece by piece, and the kernels of a piece start as soon
+    // as its bytes have arrived (copy/compute overlap inside one call)
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> piece_events;
+    int64_t piece_bytes = 16ll << 20;
     bool timing = false;
     float kernel_ms[K_NKERNELS];
     int64_t kernel_n[K_NKERNELS];
@@ -171,7 +176,10 @@ static void collect_times(fpl_ctx* c) {
 }
 
 // Runs every kernel over reads [0, n) of a device-resident batch whose lens are known on the host.
-static int run_batch(fpl_ctx* c, const DevBatch& full, const int32_t* h_lens, fpl_read_result* d_res_out, int64_t n_bytes) {
+// cuts/arrived (optional): the batch arrives in pieces — reads [cuts[j], cuts[j+1]) are on the device once event
+// arrived[j] has fired; the kernels then run piece by piece.
+static int run_batch(fpl_ctx* c, const DevBatch& full, const int32_t* h_lens, fpl_read_result* d_res_out, int64_t n_bytes,
+                     const std::vector<int64_t>* cuts = nullptr, const cudaEvent_t* arrived = nullptr) {
     const int64_t n = full.n_reads;
     CK(cudaSetDevice(c->device));
     collect_times(c);
@@ -189,12 +197,25 @@ static int run_batch(fpl_ctx* c, const DevBatch& full, const int32_t* h_lens, fp
     const bool ext = c->P.opt.mask_enabled || c->P.opt.break_enabled;   // variable number of output reads: one tile
     c->ext.n_segs = 0; c->ext.n_regs = 0;
     int64_t r0 = 0;
+    size_t piece = 0;
     while (r0 < n) {
         int64_t r1 = r0, bases = 0, tmax = 0;
-        while (r1 < n && (r1 == r0 || ext || bases + h_lens[r1] <= c->tile_bases)) {
-            bases += h_lens[r1];
-            if (h_lens[r1] > tmax) tmax = h_lens[r1];
-            r1++;
+        if (cuts) {
+            if (ext) {       // one tile: wait for everything
+                for (size_t j = 0; j + 1 < cuts->size(); j++) CK(cudaStreamWaitEvent(c->stream, arrived[j], 0));
+                r1 = n;
+            } else {
+                CK(cudaStreamWaitEvent(c->stream, arrived[piece], 0));
+                r1 = (*cuts)[piece + 1];
+                piece++;
+            }
+            for (int64_t i = r0; i < r1; i++) if (h_lens[i] > tmax) tmax = h_lens[i];
+        } else {
+            while (r1 < n && (r1 == r0 || ext || bases + h_lens[r1] <= c->tile_bases)) {
+                bases += h_lens[r1];
+                if (h_lens[r1] > tmax) tmax = h_lens[r1];
+                r1++;
+            }
         }
         DevBatch b = full;
         b.offsets = full.offsets + r0; b.lens = full.lens + r0; b.n_reads = r1 - r0;
@@ -362,6 +383,9 @@ int fpl_create(const fpl_options* opt, const fpl_adapters* ad, fpl_ctx** out) {
     // 0 (default) = no tiling: every kernel streams the whole batch from HBM (measured faster than L2-sized tiles,
     // whose launches are too small to fill the GPU: profiles/README.md)
     c->tile_bases = (tb && atoll(tb) > 0) ? atoll(tb) * 1000000ll : (1ll << 62);
+    // fpl_process_host uploads in pieces of this many MiB per buffer and overlaps them with the kernels (0 = one piece)
+    const char* pm = getenv("FPL_PIECE_MB");
+    if (pm) c->piece_bytes = atoll(pm) > 0 ? atoll(pm) << 20 : 0;
     for (int k = 0; k < K_NKERNELS; k++) { c->kernel_ms[k] = 0; c->kernel_n[k] = 0; }
     if (reserve_cycles(c, 1024)) { fpl_destroy(c); return -1; }
     CKC(cudaStreamSynchronize(c->stream));
@@ -379,6 +403,8 @@ void fpl_destroy(fpl_ctx* c) {
     cudaFree(c->d_adapters); cudaFree(c->d_alen); cudaFree(c->d_peq); cudaFree(c->d_peq16); cudaFree(c->d_acode);
     cudaFree(c->d_stats[0]); cudaFree(c->d_stats[1]); cudaFree(c->d_counters);
     fpl_cycle_ws_free(&c->cycle_ws);
+    for (auto e : c->piece_events) cudaEventDestroy(e);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     cudaFree(c->d_state); cudaFree(c->d_results); cudaFree(c->d_preseg); cudaFree(c->d_postseg);
     cudaFree(c->d_seq); cudaFree(c->d_qual); cudaFree(c->d_offsets); cudaFree(c->d_lens);
     fpl_ingest_free(&c->ingest);
@@ -420,8 +446,10 @@ int fpl_process_host(fpl_ctx* c, const fpl_batch* b, fpl_read_result* results) {
     if (n < 0 || b->n_bytes < 0) return fail("fpl_process_host: negative size");
     if (n > 0 && !results) return fail("fpl_process_host: results is null");
     // validate the slot layout on the host (cheap, O(reads))
+    bool monotonic = true;
     for (int64_t i = 0; i < n; i++) {
         const int64_t o = b->offsets[i];
+        if (i > 0 && o < b->offsets[i - 1] + b->lens[i - 1]) monotonic = false;
         if (o < 0 || (o & 15) || b->lens[i] < 0 || o + b->lens[i] > b->n_bytes)
             return fail("fpl_process_host: read %lld has a bad slot (offset %lld, len %d, n_bytes %lld; offsets must be multiples of 16)",
                         (long long)i, (long long)o, b->lens[i], (long long)b->n_bytes);
@@ -439,18 +467,42 @@ int fpl_process_host(fpl_ctx* c, const fpl_batch* b, fpl_read_result* results) {
         CK(cudaMalloc(&c->d_lens, sizeof(int32_t) * n));
         c->cap_idx = n;
     }
-    if (b->n_bytes) {
-        CK(cudaMemcpyAsync(c->d_seq, b->seq, b->n_bytes, cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemcpyAsync(c->d_qual, b->qual, b->n_bytes, cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemsetAsync(c->d_seq + b->n_bytes, 0, 64, c->stream));
-        CK(cudaMemsetAsync(c->d_qual + b->n_bytes, 0, 64, c->stream));
+    // pieces of about piece_bytes, cut at read boundaries (slots in increasing order; otherwise one piece)
+    std::vector<int64_t> cuts(1, 0);
+    if (monotonic && c->piece_bytes > 0) {
+        int64_t start = 0;
+        for (int64_t i = 1; i < n; i++)
+            if (b->offsets[i] - start >= c->piece_bytes) { cuts.push_back(i); start = b->offsets[i]; }
     }
+    cuts.push_back(n);
+    const size_t np = cuts.size() - 1;
+    if (!c->copy_stream) CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    while (c->piece_events.size() < np) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->piece_events.push_back(e);
+    }
+    // every call ends with a synchronize of the compute stream, so the device buffers are free to overwrite here
+    cudaStream_t cs = c->copy_stream;
     if (n) {
-        CK(cudaMemcpyAsync(c->d_offsets, b->offsets, sizeof(int64_t) * n, cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemcpyAsync(c->d_lens, b->lens, sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->d_offsets, b->offsets, sizeof(int64_t) * n, cudaMemcpyHostToDevice, cs));
+        CK(cudaMemcpyAsync(c->d_lens, b->lens, sizeof(int32_t) * n, cudaMemcpyHostToDevice, cs));
+    }
+    for (size_t j = 0; j < np; j++) {
+        const int64_t lo = j == 0 ? 0 : b->offsets[cuts[j]];
+        const int64_t hi = j + 1 == np ? b->n_bytes : b->offsets[cuts[j + 1]];
+        if (hi > lo) {
+            CK(cudaMemcpyAsync(c->d_seq + lo, b->seq + lo, hi - lo, cudaMemcpyHostToDevice, cs));
+            CK(cudaMemcpyAsync(c->d_qual + lo, b->qual + lo, hi - lo, cudaMemcpyHostToDevice, cs));
+        }
+        if (j + 1 == np) {
+            CK(cudaMemsetAsync(c->d_seq + b->n_bytes, 0, 64, cs));
+            CK(cudaMemsetAsync(c->d_qual + b->n_bytes, 0, 64, cs));
+        }
+        CK(cudaEventRecord(c->piece_events[j], cs));
     }
     DevBatch d = {c->d_seq, c->d_qual, c->d_offsets, c->d_lens, n};
-    if (run_batch(c, d, b->lens, nullptr, b->n_bytes)) return -1;
+    if (run_batch(c, d, b->lens, nullptr, b->n_bytes, &cuts, c->piece_events.data())) return -1;
     if (n) CK(cudaMemcpyAsync(results, c->d_results, sizeof(fpl_read_result) * n, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     collect_times(c);

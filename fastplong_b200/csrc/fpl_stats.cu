@@ -92,8 +92,9 @@ __device__ __forceinline__ uint32_t nibble_to_bytes(uint32_t n) { return ((n * 0
 // table word is [code][lane] (no bank conflicts); an invalid 5-mer adds 0 (no branch around the reduction).
 template <int SHL, int T>
 __device__ __forceinline__ void kmer1(uint32_t P, uint32_t ok, uint32_t km_lane) {
-    const uint32_t idx = (P << SHL) >> 22;
-    red_shared_add(mad_u32(idx, 128u, km_lane), (ok << (31 - T)) >> 31);
+    // left shifts as multiplies: they run on the IMAD pipe, the logic pipe is the busy one in this kernel
+    const uint32_t idx = (SHL ? mad_u32(P, 1u << SHL, 0u) : P) >> 22;
+    red_shared_add(mad_u32(idx, 128u, km_lane), mad_u32(ok, 1u << (31 - T), 0u) >> 31);
 }
 
 }  // namespace
