@@ -24,8 +24,12 @@
 #define CS_BINW (16 * CS_ROWW + 16)              // words per base bin: a multiple of 32, so the bank is the lane's whatever the bin
 #define CS_GROUP 4000                            // segments per CTA; packed counter: count <= 4095, sum of q < 2^20
 #define CS_STAGE 1000                            // descriptors staged in shared memory at a time
+#define CS_SLOT 1040                             // ring slot: 512 B sequence, 512 B quality, the 4 bytes in front of the tile (+pad)
+#define CS_DEPTH_KMER 1                          // segments in flight per warp (the 5-mer variant is bound by the logic pipe)
+#define CS_DEPTH_PLAIN 3
 #define CS_SMEM_BASE (8 * CS_BINW * 4 + CS_STAGE * 16)            // counters + staged descriptors
-#define CS_SMEM_KMER (CS_SMEM_BASE + 1024 * 32 * 4)               // + lane-private 5-mer tables
+#define CS_SMEM_PLAIN (CS_SMEM_BASE + (CS_NT_PLAIN / 32) * (CS_DEPTH_PLAIN + 1) * CS_SLOT)
+#define CS_SMEM_KMER (CS_SMEM_BASE + (CS_NT_KMER / 32) * (CS_DEPTH_KMER + 1) * CS_SLOT + 1024 * 32 * 4)   // + lane-private 5-mer tables
 
 namespace {
 
@@ -56,6 +60,26 @@ __device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c) 
     uint32_t d;
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
 }
 
 template <int IMM>
@@ -120,14 +144,15 @@ struct __align__(16) TileSeg {
 // sorted by length (so a group's segments end in the same few tiles and the CTAs beyond the longest one leave at once).
 // Every load is an aligned 16-byte vector: the misalignment of a segment (its address & 15, different for every
 // post-filter segment) moves the COLUMNS its bytes count into instead of the bytes (count16<S>).
-template <bool DO_KMER, int NT>
+template <bool DO_KMER, int NT, int DEPTH>
 __global__ void __launch_bounds__(NT, DO_KMER ? 1 : 2048 / NT / 2)
 k_cycle_stats(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qualbuf, const SegD* __restrict__ segs,
               int64_t nseg, unsigned long long* __restrict__ stats, int64_t C, unsigned long long* __restrict__ kmer_also) {
     extern __shared__ __align__(16) uint8_t cs_smem[];
     uint32_t* packed = reinterpret_cast<uint32_t*>(cs_smem);                       // [8][16][33]: count << 20 | sum of q
     TileSeg* stage = reinterpret_cast<TileSeg*>(cs_smem + 8 * CS_BINW * 4);
-    uint32_t* kmer = reinterpret_cast<uint32_t*>(stage + CS_STAGE);                // [1024][32]: one column per lane
+    uint8_t* ring = reinterpret_cast<uint8_t*>(stage + CS_STAGE);                  // [warps][DEPTH+1] slots of CS_SLOT bytes
+    uint32_t* kmer = reinterpret_cast<uint32_t*>(ring + (NT / 32) * (DEPTH + 1) * CS_SLOT);   // [1024][32]: one column per lane
     const int wid = threadIdx.x >> 5, lane = lane_id();
     const int64_t t0 = (int64_t)blockIdx.x * CS_TILE;      // first byte of this tile, relative to the aligned segment start
     const int64_t g0 = (int64_t)blockIdx.y * CS_GROUP;
@@ -145,6 +170,7 @@ k_cycle_stats(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qu
     const uint32_t km_lane = shared_addr(kmer) + (uint32_t)lane * 4u;
     const uint8_t* seq_lane = seqbuf + 16 * lane;
     const uint8_t* qual_lane = qualbuf + 16 * lane;
+    const uint32_t ring_lane = shared_addr(ring) + (uint32_t)wid * ((DEPTH + 1) * CS_SLOT) + (uint32_t)lane * 16u;
     for (int64_t s0 = g0; s0 < g1; s0 += CS_STAGE) {
         __syncthreads();
         // stage the descriptors; the ones that can reach this tile are a prefix (sorted by length)
@@ -165,27 +191,38 @@ k_cycle_stats(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qu
             n += __syncthreads_count(reach);
         }
         if (n == 0) break;
-        // software pipeline: the vectors of segment k+(NT / 32) are in flight while segment k is processed
-        uint4 ns = make_uint4(0, 0, 0, 0), nq = ns;
-        uint32_t nprev0 = 0;
-        int nsh = 0, nlim = 0;
-        auto fetch = [&](int k) {
+        // software pipeline: the vectors of the next DEPTH segments of this warp are in flight (cp.async into the warp's
+        // ring of DEPTH+1 slots: no registers held, every lane copies and later reads its own 16 bytes) while one is
+        // processed; a lane beyond the segment's end copies 0 bytes, which zero-fills its slot bytes
+        auto issue = [&](int k, int slot) {
             const TileSeg ts = stage[k];
-            nsh = ts.sh; nlim = ts.lim;
-            ns = nq = make_uint4(0, 0, 0, 0);
-            if (16 * lane < ts.lim) {
-                ns = __ldg(reinterpret_cast<const uint4*>(seq_lane + ts.a));
-                nq = __ldg(reinterpret_cast<const uint4*>(qual_lane + ts.a));
-            }
-            if (DO_KMER && lane == 0) nprev0 = ts.a >= 4 ? __ldg(reinterpret_cast<const uint32_t*>(seqbuf + ts.a - 4)) : 0u;
+            const bool act = 16 * lane < ts.lim;
+            const uint32_t dst = ring_lane + (uint32_t)slot * CS_SLOT;
+            cp_async16(dst, act ? seq_lane + ts.a : seqbuf, act ? 16 : 0);
+            cp_async16(dst + 512, act ? qual_lane + ts.a : qualbuf, act ? 16 : 0);
+            if (DO_KMER && lane == 0) cp_async4(dst + 1024 - 16 * lane, ts.a >= 4 ? seqbuf + ts.a - 4 : seqbuf, ts.a >= 4 ? 4 : 0);
         };
-        if (wid < n) fetch(wid);
+        int kk = wid;
+#pragma unroll
+        for (int d = 0; d < DEPTH; d++) {
+            if (kk < n) issue(kk, d);
+            cp_async_commit();
+            kk += NT / 32;
+        }
+        int slot = 0, fill = DEPTH;
         for (int k = wid; k < n; k += (NT / 32)) {
+            cp_async_wait<DEPTH - 1>();
+            const uint32_t src = ring_lane + (uint32_t)slot * CS_SLOT;
+            const uint4 ns = lds128(src), nq = lds128(src + 512);
+            const uint32_t prev0 = (DO_KMER && lane == 0) ? lds32(src + 1024) : 0u;
             const uint32_t sw[4] = {ns.x, ns.y, ns.z, ns.w};
             uint32_t qm[4] = {nq.x, nq.y, nq.z, nq.w};
-            const int sh = nsh, lim = nlim;
-            const uint32_t prev0 = nprev0;
-            if (k + (NT / 32) < n) fetch(k + (NT / 32));
+            const int sh = stage[k].sh, lim = stage[k].lim;
+            if (kk < n) issue(kk, fill);
+            cp_async_commit();
+            kk += NT / 32;
+            slot = slot == DEPTH ? 0 : slot + 1;
+            fill = fill == DEPTH ? 0 : fill + 1;
             if (lim <= 0) continue;                        // warp-uniform: the segment ends in front of this tile
             // which of the lane's 16 bytes are cycles of the segment (vmask) and can end a 5-mer (kmask: cycle >= 4)
             uint32_t cw[4] = {0x10101010u, 0x10101010u, 0x10101010u, 0x10101010u};
@@ -316,8 +353,8 @@ int launch_cycle_stats(CycleWs* ws, const uint8_t* seq, const uint8_t* qual, con
     if (nseg == 0 || max_len <= 0) return 0;
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(k_cycle_stats<true, CS_NT_KMER>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM_KMER) != cudaSuccess ||
-            cudaFuncSetAttribute(k_cycle_stats<false, CS_NT_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM_BASE) != cudaSuccess)
+        if (cudaFuncSetAttribute(k_cycle_stats<true, CS_NT_KMER, CS_DEPTH_KMER>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM_KMER) != cudaSuccess ||
+            cudaFuncSetAttribute(k_cycle_stats<false, CS_NT_PLAIN, CS_DEPTH_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM_PLAIN) != cudaSuccess)
             return -1;
         attr_set = true;
     }
@@ -353,8 +390,8 @@ int launch_cycle_stats(CycleWs* ws, const uint8_t* seq, const uint8_t* qual, con
     k_cs_gather<<<blocks, 256, 0, stream>>>(segs, ws->k_out, ws->v_out, nseg, static_cast<SegD*>(ws->sorted));
     dim3 grid((unsigned)((max_len + 15 + CS_TILE - 1) / CS_TILE), (unsigned)((nseg + CS_GROUP - 1) / CS_GROUP));
     const SegD* sorted = static_cast<const SegD*>(ws->sorted);
-    if (do_kmer) k_cycle_stats<true, CS_NT_KMER><<<grid, CS_NT_KMER, CS_SMEM_KMER, stream>>>(seq, qual, sorted, nseg, stats, C, kmer_also);
-    else k_cycle_stats<false, CS_NT_PLAIN><<<grid, CS_NT_PLAIN, CS_SMEM_BASE, stream>>>(seq, qual, sorted, nseg, stats, C, nullptr);
+    if (do_kmer) k_cycle_stats<true, CS_NT_KMER, CS_DEPTH_KMER><<<grid, CS_NT_KMER, CS_SMEM_KMER, stream>>>(seq, qual, sorted, nseg, stats, C, kmer_also);
+    else k_cycle_stats<false, CS_NT_PLAIN, CS_DEPTH_PLAIN><<<grid, CS_NT_PLAIN, CS_SMEM_PLAIN, stream>>>(seq, qual, sorted, nseg, stats, C, nullptr);
     return 0;
 }
 
@@ -431,19 +468,25 @@ __device__ __forceinline__ uint8_t hist_median(const uint32_t* h, int len, int l
 }
 
 // h[q] += delta for the bytes qp[0..n): 16-byte vector body, byte head/tail (delta = 1 or 0xFFFFFFFF)
+__device__ __forceinline__ void hist_vec(uint32_t hbase, const uint4& v, uint32_t delta) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) red_shared_add(hbase + (((w[k] >> (8 * j)) & 127u) << 2), delta);
+}
 __device__ __forceinline__ void hist_bytes(uint32_t hbase, const uint8_t* qp, int n, uint32_t delta, int lane) {
     const int head = min(n, (int)((16 - (reinterpret_cast<uintptr_t>(qp) & 15)) & 15));
     if (lane < head) red_shared_add(hbase + ((uint32_t)(qp[lane] & 127) << 2), delta);
     const int nvec = (n - head) >> 4;
     const uint4* vp = reinterpret_cast<const uint4*>(qp + head);
-    for (int i = lane; i < nvec; i += 32) {
-        const uint4 v = __ldg(vp + i);
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-#pragma unroll
-            for (int j = 0; j < 4; j++) red_shared_add(hbase + (((w[k] >> (8 * j)) & 127u) << 2), delta);
+    // four vectors per lane in flight: a warp alone keeps 2 KB of loads outstanding (the kernel is latency-bound otherwise)
+    int i = lane;
+    for (; i + 96 < nvec; i += 128) {
+        const uint4 v0 = __ldg(vp + i), v1 = __ldg(vp + i + 32), v2 = __ldg(vp + i + 64), v3 = __ldg(vp + i + 96);
+        hist_vec(hbase, v0, delta); hist_vec(hbase, v1, delta); hist_vec(hbase, v2, delta); hist_vec(hbase, v3, delta);
     }
+    for (; i < nvec; i += 32) hist_vec(hbase, __ldg(vp + i), delta);
     const int done = head + (nvec << 4);
     if (done + lane < n) red_shared_add(hbase + ((uint32_t)(qp[done + lane] & 127) << 2), delta);   // < 16 tail bytes
 }
