@@ -292,7 +292,7 @@ int fpl_create(const fpl_options* opt, const fpl_adapters* ad, fpl_ctx** out) {
     std::vector<uint8_t> h_ad((size_t)n * FPL_MAX_ADAPTER_LEN, 0);
     std::vector<int> h_alen(n, 0);
     std::vector<uint4> h_peq((size_t)n * 256, make_uint4(0, 0, 0, 0));
-    std::vector<uint32_t> h_peq16((size_t)n * 256, 0);
+    std::vector<uint32_t> h_peq16((size_t)n * 512, 0);   // [adapter][prefix | suffix][byte]
     std::vector<uint32_t> h_acode((size_t)n * 4, 0);
     for (int k = 0; k < n; k++) {
         const char* s = k == 0 ? ad->start : k == 1 ? ad->end : ad->fasta[k - 2];
@@ -323,8 +323,8 @@ int fpl_create(const fpl_options* opt, const fpl_adapters* ad, fpl_ctx** out) {
             uint8_t ch = (uint8_t)s[j];
             uint32_t* w = reinterpret_cast<uint32_t*>(&h_peq[(size_t)k * 256 + ch]);
             w[j >> 5] |= 1u << (j & 31);
-            if ((int)j < plen) h_peq16[(size_t)k * 256 + ch] |= 1u << j;                            // first plen chars
-            if ((int)j >= (int)len - plen) h_peq16[(size_t)k * 256 + ch] |= 1u << (16 + j - (len - plen));  // last plen chars
+            if ((int)j < plen) h_peq16[(size_t)k * 512 + ch] |= 1u << j;                            // first plen chars
+            if ((int)j >= (int)len - plen) h_peq16[(size_t)k * 512 + 256 + ch] |= 1u << (j - (len - plen));  // last plen chars
         }
     }
     memset(&c->P, 0, sizeof(c->P));

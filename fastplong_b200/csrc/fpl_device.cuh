@@ -14,7 +14,7 @@ struct DevParams {
     const uint8_t* adapters;  // [n][FPL_MAX_ADAPTER_LEN] adapter bytes
     const int* alen;          // [n]
     const uint4* peq;         // [n][256]: 128-bit match mask of the whole adapter for every byte value
-    const uint32_t* peq16;    // [n][256]: low 16 = mask of the first plen chars, high 16 = mask of the last plen chars
+    const uint32_t* peq16;    // [n][2][256]: [0] = match masks of the first plen chars, [1] = of the last plen chars
     const uint32_t* acode;    // [n][4]: 2-bit codes ((byte>>1)&3 at bit 2i) lo/hi + position mask lo/hi; mask == 0: not ACGT-only or > 32 bp
     short thr[FPL_MAX_ADAPTER_LEN + 1];  // thr(n) = (int)round(ed_max*n), tabulated on the host with libm round
 };

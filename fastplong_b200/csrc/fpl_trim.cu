@@ -62,26 +62,28 @@ __device__ __forceinline__ int ed_adapter(const uint8_t* text, int n, const uint
     return alen <= 32 ? myers32(text, n, peq, shift, m) : myers128(text, n, peq, shift, m);
 }
 
-// 16-bit pattern variant for the probe loops (:202-216, :273-286); eq16 = precomputed masks, already shifted.
-__device__ __forceinline__ int myers16(const uint8_t* text, int n, const uint32_t* peq16, bool suffix, int m) {
+// 16-bit pattern variant for the probe loops (:202-216, :273-286); peq = the 256 match masks of the probe pattern.
+// The score is m + (#columns whose top horizontal delta is +1) - (#columns where it is -1): the two counts are
+// accumulated in units of `top` and the left shifts are multiplies, which keeps the logic pipe to 8 ops per column.
+__device__ __forceinline__ int myers16(const uint8_t* text, int n, const uint32_t* peq, int m) {
     uint32_t VP = (1u << m) - 1u, VN = 0;
     const uint32_t top = 1u << (m - 1);
-    int score = m;
+    uint32_t accP = 0, accN = 0;
+#pragma unroll 4
     for (int i = 0; i < n; i++) {
-        uint32_t e = __ldg(&peq16[text[i]]);
-        uint32_t Eq = suffix ? (e >> 16) : (e & 0xFFFFu);
-        uint32_t Xv = Eq | VN;
-        uint32_t Xh = (((Eq & VP) + VP) ^ VP) | Eq;
+        const uint32_t Eq = __ldg(&peq[text[i]]);
+        const uint32_t Xv = Eq | VN;
+        const uint32_t Xh = (((Eq & VP) + VP) ^ VP) | Eq;
         uint32_t HP = VN | ~(Xh | VP);
         uint32_t HN = VP & Xh;
-        if (HP & top) score++;
-        else if (HN & top) score--;
-        HP = (HP << 1) | 1u;
-        HN = HN << 1;
+        accP += HP & top;
+        accN += HN & top;
+        asm("mad.lo.u32 %0, %1, 2, 1;" : "=r"(HP) : "r"(HP));
+        asm("mad.lo.u32 %0, %1, 2, 0;" : "=r"(HN) : "r"(HN));
         VP = HN | ~(Xv | HP);
         VN = HP & Xv;
     }
-    return score;
+    return m + (int)(accP >> (m - 1)) - (int)(accN >> (m - 1));
 }
 
 __device__ __forceinline__ int hamming(const uint8_t* r, const uint8_t* a, int alen) {
@@ -208,9 +210,9 @@ __device__ int trim_start(const DevParams& P, const uint8_t* seq, Win& w, int ai
     const int np = min(rlen - plen, FPL_WINDOW - plen);
     const int T16 = P.thr[plen];
     unsigned best = 0xFFFFFFFFu;
-    const uint32_t* t16 = P.peq16 + (size_t)aidx * 256;
+    const uint32_t* t16 = P.peq16 + (size_t)aidx * 512 + 256;   // last plen chars
     for (int p = lane; p < np; p += 32) {
-        int ed = myers16(rdata + p, plen, t16, true, plen);
+        int ed = myers16(rdata + p, plen, t16, plen);
         if (ed <= T16) best = min(best, ((unsigned)ed << 16) | (unsigned)p);
     }
     best = __reduce_min_sync(0xffffffffu, best);
@@ -248,9 +250,9 @@ __device__ int trim_end(const DevParams& P, const uint8_t* seq, Win& w, int aidx
     // all distances in parallel into scratch, then the (short) sequential selection.
     const int np = min(rlen - plen, FPL_WINDOW - plen);
     const int T16 = P.thr[plen];
-    const uint32_t* t16 = P.peq16 + (size_t)aidx * 256;
+    const uint32_t* t16 = P.peq16 + (size_t)aidx * 512;         // first plen chars
     for (int p = lane; p < np; p += 32) {
-        int ed = myers16(rdata + rlen - plen - p, plen, t16, false, plen);
+        int ed = myers16(rdata + rlen - plen - p, plen, t16, plen);
         scratch[p] = (uint8_t)(ed <= T16 ? ed : 255);
     }
     __syncwarp();
