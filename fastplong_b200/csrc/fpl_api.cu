@@ -228,7 +228,8 @@ static int run_batch(fpl_ctx* c, const DevBatch& full, const int32_t* h_lens, fp
         { Timed t(c, K_TRIM); launch_trim(c->P, b, st, res, c->d_counters, s); }
         { Timed t(c, K_CYCLE_PRE);
           if (launch_cycle_stats(&c->cycle_ws, full.seq, full.qual, pre, b.n_reads, tmax, c->d_stats[0], c->C, true,
-                                 ext ? nullptr : c->d_stats[1] + 16 * c->C + FPL_STATS_KMER, s)) return fail("out of device memory (cycle stats workspace)"); }
+                                 ext ? nullptr : c->d_stats[1] + 16 * c->C + FPL_STATS_KMER, s)) return fail("out of device memory (cycle stats workspace)");
+          c->launches += 2; }   // + k_cs_keys and k_cs_gather around the (library) radix sort
         {
             Timed t(c, K_SCAN);
             if (c->jit.fn) { if (fpl_jit_launch_scan(&c->jit, b, st, s)) return fail("launching k_scan_jit failed"); }
@@ -240,7 +241,8 @@ static int run_batch(fpl_ctx* c, const DevBatch& full, const int32_t* h_lens, fp
             { Timed t(c, K_COUNT); launch_count(res, b.n_reads, c->d_counters, true, s); }
             { Timed t(c, K_CYCLE_POST);
               if (launch_cycle_stats(&c->cycle_ws, full.seq, full.qual, post, 2 * b.n_reads, tmax, c->d_stats[1], c->C, false, nullptr, s))
-                  return fail("out of device memory (cycle stats workspace)"); }
+                  return fail("out of device memory (cycle stats workspace)");
+          c->launches += 2; }   // + k_cs_keys and k_cs_gather around the (library) radix sort
             { Timed t(c, K_KMER_FIX); launch_kmer_fix(b, res, c->d_stats[1] + 16 * c->C + FPL_STATS_KMER, s); }
             { Timed t(c, K_QUAL_PRE); launch_read_qual(b, c->d_stats[0], c->d_stats[1], c->C, res, false, s); }
         } else {
@@ -254,7 +256,8 @@ static int run_batch(fpl_ctx* c, const DevBatch& full, const int32_t* h_lens, fp
                 return fail("--mask/--break stage: %s", xerr);
             { Timed t(c, K_CYCLE_POST);
               if (launch_cycle_stats(&c->cycle_ws, fseq, full.qual, c->ext.d_stat, c->ext.n_segs, tmax, c->d_stats[1], c->C, true, nullptr, s))
-                  return fail("out of device memory (cycle stats workspace)"); }
+                  return fail("out of device memory (cycle stats workspace)");
+          c->launches += 2; }   // + k_cs_keys and k_cs_gather around the (library) radix sort
         }
         r0 = r1;
     }

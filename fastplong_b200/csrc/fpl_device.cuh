@@ -65,6 +65,34 @@ __device__ __forceinline__ int warp_incl_scan(int v) {
     return v;
 }
 
+// myers32 for a whole warp that wants ONE distance (n <= 32 text bytes): lane i fetches the match mask of text byte i,
+// so the two dependent loads per column happen once, side by side, instead of n times in a row; every lane then runs
+// the recurrence on shuffled masks and returns the same value.  Must be called by all 32 lanes.
+__device__ __forceinline__ int myers32_warp(const uint8_t* text, int n, const uint4* peq, int shift, int m) {
+    if (m == 0) return n;
+    if (n == 0) return m;
+    const uint32_t mask = m >= 32 ? 0xFFFFFFFFu : ((1u << m) - 1u);
+    const int lane = threadIdx.x & 31;
+    uint32_t mine = 0;
+    if (lane < n) mine = (__ldg(&peq[text[lane]].x) >> shift) & mask;
+    uint32_t VP = mask, VN = 0;
+    const uint32_t top = 1u << (m - 1);
+    int score = m;
+    for (int i = 0; i < n; i++) {
+        const uint32_t Eq = __shfl_sync(0xffffffffu, mine, i);
+        const uint32_t Xv = Eq | VN;
+        const uint32_t Xh = (((Eq & VP) + VP) ^ VP) | Eq;
+        uint32_t HP = VN | ~(Xh | VP);
+        uint32_t HN = VP & Xh;
+        score += (HP & top) ? 1 : ((HN & top) ? -1 : 0);
+        HP = (HP << 1) | 1u;
+        HN = HN << 1;
+        VP = HN | ~(Xv | HP);
+        VN = HP & Xv;
+    }
+    return score;
+}
+
 // Levenshtein distance (Myers/Hyyro bit-parallel, global), pattern = adapter bits [shift, shift+m) with
 // shift+m <= 32, text = n read bytes.  Exact, == edit_distance() of src/editdistance.cpp:100-126.
 __device__ __forceinline__ int myers32(const uint8_t* text, int n, const uint4* peq, int shift, int m) {

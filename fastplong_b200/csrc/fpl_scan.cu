@@ -258,7 +258,7 @@ k_final(const __grid_constant__ DevParams P, DevBatch b, const ReadState* __rest
                 if (s.best[k] != ~0ull) {
                     const int alen = P.alen[k];
                     const int p = (int)(s.best[k] & 0xFFFFFFFFu);
-                    const int ed = alen <= 32 ? myers32(seq + p, alen, P.peq + (size_t)k * 256, 0, alen)
+                    const int ed = alen <= 32 ? myers32_warp(seq + p, alen, P.peq + (size_t)k * 256, 0, alen)
                                              : myers128_f(seq + p, alen, P.peq + (size_t)k * 256, alen);
                     if (ed <= P.thr[alen]) pos[k] = p;
                 }

@@ -65,6 +65,8 @@ __device__ __forceinline__ int ed_adapter(const uint8_t* text, int n, const uint
 // 16-bit pattern variant for the probe loops (:202-216, :273-286); peq = the 256 match masks of the probe pattern.
 // The score is m + (#columns whose top horizontal delta is +1) - (#columns where it is -1): the two counts are
 // accumulated in units of `top` and the left shifts are multiplies, which keeps the logic pipe to 8 ops per column.
+// (A warp-wide early exit on the lower bound score_i - (n - i) was measured and lost: the vote and the score
+// reconstruction every four columns cost more than the columns they save.)
 __device__ __forceinline__ int myers16(const uint8_t* text, int n, const uint32_t* peq, int m) {
     uint32_t VP = (1u << m) - 1u, VN = 0;
     const uint32_t top = 1u << (m - 1);
