@@ -93,6 +93,36 @@ __device__ __forceinline__ int myers32_warp(const uint8_t* text, int n, const ui
     return score;
 }
 
+// Two distances at once, one per half-warp (lanes 0-15: problem 0, lanes 16-31: problem 1), each with n <= 32 text bytes
+// and an m <= 32 bit pattern; a half whose `on` is false idles through the same instructions.  Every lane returns its
+// own half's distance.  Must be called by all 32 lanes.
+__device__ __forceinline__ int myers32_halves(const uint8_t* text, int n, const uint4* peq, int m, bool on) {
+    const int lane = threadIdx.x & 31, hl = lane & 15, base = lane & 16;
+    const uint32_t mask = m >= 32 ? 0xFFFFFFFFu : ((1u << m) - 1u);
+    uint32_t e0 = 0, e1 = 0;            // match masks of text bytes hl and hl + 16
+    if (on && hl < n) e0 = __ldg(&peq[text[hl]].x) & mask;
+    if (on && hl + 16 < n) e1 = __ldg(&peq[text[hl + 16]].x) & mask;
+    const int nmax = max(__shfl_sync(0xffffffffu, on ? n : 0, 0), __shfl_sync(0xffffffffu, on ? n : 0, 16));
+    uint32_t VP = mask, VN = 0;
+    const uint32_t top = 1u << (m - 1);
+    int score = m;
+    for (int i = 0; i < nmax; i++) {
+        const uint32_t Eq = __shfl_sync(0xffffffffu, i < 16 ? e0 : e1, base + (i & 15));
+        if (i < n) {
+            const uint32_t Xv = Eq | VN;
+            const uint32_t Xh = (((Eq & VP) + VP) ^ VP) | Eq;
+            uint32_t HP = VN | ~(Xh | VP);
+            uint32_t HN = VP & Xh;
+            score += (HP & top) ? 1 : ((HN & top) ? -1 : 0);
+            HP = (HP << 1) | 1u;
+            HN = HN << 1;
+            VP = HN | ~(Xv | HP);
+            VN = HP & Xv;
+        }
+    }
+    return score;
+}
+
 // Levenshtein distance (Myers/Hyyro bit-parallel, global), pattern = adapter bits [shift, shift+m) with
 // shift+m <= 32, text = n read bytes.  Exact, == edit_distance() of src/editdistance.cpp:100-126.
 __device__ __forceinline__ int myers32(const uint8_t* text, int n, const uint4* peq, int shift, int m) {

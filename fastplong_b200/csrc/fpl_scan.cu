@@ -251,16 +251,28 @@ k_final(const __grid_constant__ DevParams P, DevBatch b, const ReadState* __rest
         bool split = false, seg0right = false;
         if (P.opt.adapter_enabled) {
             const int ext = P.opt.trimming_extension;
-            int pos[2];
+            int pos[2] = {-1, -1};
+            if (P.alen[0] <= 32 && P.alen[1] <= 32 && P.alen[0] > 0 && P.alen[1] > 0) {
+                // both verifications side by side: half-warp k checks the arg-min of adapter k
+                const int k = lane >> 4;
+                const bool on = s.best[k] != ~0ull;
+                const int alen = P.alen[k];
+                const int p = (int)(s.best[k] & 0xFFFFFFFFu);
+                const int ed = myers32_halves(seq + (on ? p : 0), alen, P.peq + (size_t)k * 256, alen, on);
+                const bool hit = on && ed <= P.thr[alen];
+                const unsigned hm = __ballot_sync(0xffffffffu, hit);
+                if (hm & 1u) pos[0] = (int)(s.best[0] & 0xFFFFFFFFu);
+                if (hm & 0x10000u) pos[1] = (int)(s.best[1] & 0xFFFFFFFFu);
+            } else {
 #pragma unroll
-            for (int k = 0; k < 2; k++) {
-                pos[k] = -1;
-                if (s.best[k] != ~0ull) {
-                    const int alen = P.alen[k];
-                    const int p = (int)(s.best[k] & 0xFFFFFFFFu);
-                    const int ed = alen <= 32 ? myers32_warp(seq + p, alen, P.peq + (size_t)k * 256, 0, alen)
-                                             : myers128_f(seq + p, alen, P.peq + (size_t)k * 256, alen);
-                    if (ed <= P.thr[alen]) pos[k] = p;
+                for (int k = 0; k < 2; k++) {
+                    if (s.best[k] != ~0ull) {
+                        const int alen = P.alen[k];
+                        const int p = (int)(s.best[k] & 0xFFFFFFFFu);
+                        const int ed = alen <= 32 ? myers32_warp(seq + p, alen, P.peq + (size_t)k * 256, 0, alen)
+                                                 : myers128_f(seq + p, alen, P.peq + (size_t)k * 256, alen);
+                        if (ed <= P.thr[alen]) pos[k] = p;
+                    }
                 }
             }
             int start = -1, glen = 0;
