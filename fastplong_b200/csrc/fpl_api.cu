@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <string>
 #include <vector>
 #include "fpl_device.cuh"
@@ -282,12 +283,24 @@ int fpl_create(const fpl_options* opt, const fpl_adapters* ad, fpl_ctx** out) {
         return fail("fpl_create: cut window size must be within 1..%d", FPL_MAX_WINDOW);
     const int n = 2 + (ad->n_fasta > 0 ? ad->n_fasta : 0);
     if (n > FPL_MAX_ADAPTERS) return fail("fpl_create: %d adapters exceed FPL_MAX_ADAPTERS=%d", n, FPL_MAX_ADAPTERS);
+    // FPL_TIMING=1: where the start-up time goes (stderr)
+    const bool tlog = getenv("FPL_TIMING") != nullptr;
+    auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
+    double t_last = now();
+    auto stamp = [&](const char* what) {
+        if (!tlog) return;
+        const double t = now();
+        fprintf(stderr, "[libfplgpu] fpl_create: %-28s %7.3f s\n", what, t - t_last);
+        t_last = t;
+    };
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
         return fail("fpl_create: no usable CUDA device (%s); libfplgpu has no CPU fallback", cudaGetErrorString(e));
     if (opt->device < 0 || opt->device >= ndev) return fail("fpl_create: device %d out of range (%d devices)", opt->device, ndev);
     CK(cudaSetDevice(opt->device));
+    CK(cudaFree(0));
+    stamp("driver + device context");
     fpl_ctx* c = new fpl_ctx();
     c->device = opt->device;
     c->n_adapters = n;
@@ -372,6 +385,7 @@ int fpl_create(const fpl_options* opt, const fpl_adapters* ad, fpl_ctx** out) {
     c->counter_words = FPL_COUNTER_WORDS(n);
     CKC(cudaMalloc(&c->d_counters, sizeof(unsigned long long) * c->counter_words));
     CKC(cudaMemset(c->d_counters, 0, sizeof(unsigned long long) * c->counter_words));
+    stamp("tables");
     // specialise the scan kernel on the adapters (NVRTC); FPL_NO_JIT=1 keeps the precompiled k_scan_fast
     if (c->plan.fast && getenv("FPL_NO_JIT") == nullptr) {
         char jerr[512] = "";
@@ -382,6 +396,7 @@ int fpl_create(const fpl_options* opt, const fpl_adapters* ad, fpl_ctx** out) {
             c->jit.fn = nullptr;
         }
     }
+    stamp("scan kernel specialisation");
     const char* tb = getenv("FPL_TILE_MBASES");
     // 0 (default) = no tiling: every kernel streams the whole batch from HBM (measured faster than L2-sized tiles,
     // whose launches are too small to fill the GPU: profiles/README.md)
@@ -392,6 +407,7 @@ int fpl_create(const fpl_options* opt, const fpl_adapters* ad, fpl_ctx** out) {
     for (int k = 0; k < K_NKERNELS; k++) { c->kernel_ms[k] = 0; c->kernel_n[k] = 0; }
     if (reserve_cycles(c, 1024)) { fpl_destroy(c); return -1; }
     CKC(cudaStreamSynchronize(c->stream));
+    stamp("accumulators");
 #undef CKC
     *out = c;
     return 0;

@@ -528,6 +528,33 @@ void SingleEndProcessor::processorTask(ThreadConfig* config) {
     if (mOptions->verbose) loginfo("thread " + to_string(config->getThreadId() + 1) + " finished");
 }
 
+static double nowSec();
+// The CUDA driver takes about 1.5 s to come up on an 8-GPU box.  Start it when the program is loaded, so that it
+// overlaps main()'s option parsing and evaluator pre-pass (reference code, src/main.cpp:255-285); process() waits for
+// it.  Only when the command line names an input file (not for --help / --version); FPL_NO_WARMUP=1 disables it.
+struct CudaWarmup {
+    std::thread th;
+    double t0;
+    CudaWarmup() : t0(nowSec()) {
+        if (getenv("FPL_NO_WARMUP")) return;
+        bool hasInput = false;
+        if (FILE* f = fopen("/proc/self/cmdline", "rb")) {
+            std::vector<char> buf(1 << 16);
+            const size_t n = fread(buf.data(), 1, buf.size() - 1, f);
+            fclose(f);
+            for (size_t i = 0; i < n;) {
+                const char* a = buf.data() + i;
+                if (!strcmp(a, "-i") || !strcmp(a, "--in") || !strncmp(a, "--in=", 5)) hasInput = true;
+                i += strlen(a) + 1;
+            }
+        }
+        if (hasInput) th = std::thread([] { cudaFree(0); });
+    }
+    void wait() { if (th.joinable()) th.join(); }
+    ~CudaWarmup() { wait(); }
+};
+static CudaWarmup g_warm;
+
 static double nowSec() {
     struct timespec ts;
     clock_gettime(CLOCK_MONOTONIC, &ts);
@@ -537,7 +564,10 @@ static double nowSec() {
 
 bool SingleEndProcessor::process() {
     const bool timing = getenv("FPL_TIMING") != nullptr;
-    double t_last = nowSec();
+    double t_last = g_warm.t0;
+    FPL_STAMP("program start -> process()");
+    g_warm.wait();
+    FPL_STAMP("wait for the CUDA driver");
     if (!mOptions->split.enabled) initOutput();
     const int T = mOptions->thread;
 
@@ -556,10 +586,21 @@ bool SingleEndProcessor::process() {
     ad.start = g_adapters[0].c_str(); ad.end = g_adapters[1].c_str();
     ad.n_fasta = (int)fasta.size(); ad.fasta = fasta.empty() ? NULL : fasta.data();
     g_workers.clear();
-    for (int t = 0; t < T; t++) {
-        g_workers.emplace_back(new GpuWorker());
-        fpl_options o = makeAbiOptions(mOptions, t % ndev);
-        check(fpl_create(&o, &ad, &g_workers[t]->ctx), "fpl_create");
+    for (int t = 0; t < T; t++) g_workers.emplace_back(new GpuWorker());
+    {
+        // the contexts are independent: create them side by side (the first one pays the driver start-up and the
+        // kernel specialisation, the others find both cached)
+        std::vector<int> rc(T, 0);
+        std::vector<std::string> msg(T);
+        std::vector<std::thread> mk;
+        for (int t = 0; t < T; t++) mk.emplace_back([&, t] {
+            fpl_options o = makeAbiOptions(mOptions, t % ndev);
+            rc[t] = fpl_create(&o, &ad, &g_workers[t]->ctx);
+            if (rc[t]) msg[t] = fpl_last_error();
+        });
+        for (auto& th : mk) th.join();
+        for (int t = 0; t < T; t++)
+            if (rc[t]) error_exit("fastplong_gpu: fpl_create: " + msg[t]);
     }
 
     FPL_STAMP("CUDA init + contexts + JIT");
@@ -758,5 +799,6 @@ bool SingleEndProcessor::process() {
     FPL_STAMP("final Stats released");
     if (!mOptions->split.enabled) closeOutput();
     FPL_STAMP("outputs closed");
+    if (timing) fprintf(stderr, "[fastplong_gpu] %-34s %8.3f s\n", "program start -> end of process()", nowSec() - g_warm.t0);
     return true;
 }

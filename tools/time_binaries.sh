@@ -20,6 +20,6 @@ echo -n "ref -w 16: "; { time oracle/_ref/fastplong_ref -i /dev/shm/c1.fq -o /de
 echo -n "gpu -w 4 device parse: "; { time build/fastplong_gpu -i /dev/shm/c1.fq -o /dev/shm/gpu.fq -s $S -w 4 -j /dev/shm/g.json -h /dev/shm/g.html >/dev/null 2>&1; } 2>&1
 done
 cmp /dev/shm/ref.fq /dev/shm/gpu.fq && echo "outputs identical"
-FPL_TIMING=1 build/fastplong_gpu -i /dev/shm/c1.fq -o /dev/shm/gpu.fq -s $S -w 4 -j /dev/shm/g.json -h /dev/shm/g.html 2>&1 | grep "fastplong_gpu\]"
+FPL_TIMING=1 build/fastplong_gpu -i /dev/shm/c1.fq -o /dev/shm/gpu.fq -s $S -w 4 -j /dev/shm/g.json -h /dev/shm/g.html 2>&1 | grep -E "fastplong_gpu\]|libfplgpu\]"
 echo -n "gpu -w 4 reference reader: "; { time FPL_HOST_PARSE=1 build/fastplong_gpu -i /dev/shm/c1.fq -o /dev/shm/gpu.fq -s $S -w 4 -j /dev/shm/g.json -h /dev/shm/g.html >/dev/null 2>&1; } 2>&1
 rm -f /dev/shm/c1.fq /dev/shm/ref.fq /dev/shm/gpu.fq
