@@ -65,32 +65,37 @@ __device__ __forceinline__ int warp_incl_scan(int v) {
     return v;
 }
 
-// myers32 for a whole warp that wants ONE distance (n <= 32 text bytes): lane i fetches the match mask of text byte i,
-// so the two dependent loads per column happen once, side by side, instead of n times in a row; every lane then runs
-// the recurrence on shuffled masks and returns the same value.  Must be called by all 32 lanes.
-__device__ __forceinline__ int myers32_warp(const uint8_t* text, int n, const uint4* peq, int shift, int m) {
-    if (m == 0) return n;
-    if (n == 0) return m;
-    const uint32_t mask = m >= 32 ? 0xFFFFFFFFu : ((1u << m) - 1u);
-    const int lane = threadIdx.x & 31;
-    uint32_t mine = 0;
-    if (lane < n) mine = (__ldg(&peq[text[lane]].x) >> shift) & mask;
-    uint32_t VP = mask, VN = 0;
-    const uint32_t top = 1u << (m - 1);
-    int score = m;
-    for (int i = 0; i < n; i++) {
-        const uint32_t Eq = __shfl_sync(0xffffffffu, mine, i);
+// Myers/Hyyro bit-parallel Levenshtein, global alignment, with the m-bit pattern held in the TOP m bits of the word:
+// the last row's horizontal deltas are then bit 31 of HP / HN (one shift each to count them) and the bits below the
+// pattern stay inert (VP = VN = 0, HP = all ones there; the +1 that enters row 0 comes in at bit 0 of the word and the
+// ones below the pattern carry it up).  Left shifts are multiplies (IMAD pipe).  9 logic-pipe ops per column.
+struct Myers32 {
+    uint32_t VP, VN, accP, accN;
+    __device__ __forceinline__ void init(int m) {
+        VP = m >= 32 ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> m);
+        VN = 0; accP = 0; accN = 0;
+    }
+    // Eq: match mask of this text byte, already in the top m bits
+    __device__ __forceinline__ void column(uint32_t Eq) {
         const uint32_t Xv = Eq | VN;
         const uint32_t Xh = (((Eq & VP) + VP) ^ VP) | Eq;
         uint32_t HP = VN | ~(Xh | VP);
         uint32_t HN = VP & Xh;
-        score += (HP & top) ? 1 : ((HN & top) ? -1 : 0);
-        HP = (HP << 1) | 1u;
-        HN = HN << 1;
+        accP += HP >> 31;
+        accN += HN >> 31;
+        asm("mad.lo.u32 %0, %1, 2, 1;" : "=r"(HP) : "r"(HP));
+        asm("mad.lo.u32 %0, %1, 2, 0;" : "=r"(HN) : "r"(HN));
         VP = HN | ~(Xv | HP);
         VN = HP & Xv;
     }
-    return score;
+    __device__ __forceinline__ int score(int m) const { return m + (int)accP - (int)accN; }
+};
+// table word -> top-aligned match mask of pattern bits [shift, shift + m)
+__device__ __forceinline__ uint32_t myers_eq_top(uint32_t w, int shift, int m) {
+    uint32_t e = w >> shift, d;
+    const uint32_t mul = m >= 32 ? 1u : (1u << (32 - m));
+    asm("mad.lo.u32 %0, %1, %2, 0;" : "=r"(d) : "r"(e), "r"(mul));
+    return d;
 }
 
 // Two distances at once, one per half-warp (lanes 0-15: problem 0, lanes 16-31: problem 1), each with n <= 32 text bytes
@@ -98,29 +103,32 @@ __device__ __forceinline__ int myers32_warp(const uint8_t* text, int n, const ui
 // own half's distance.  Must be called by all 32 lanes.
 __device__ __forceinline__ int myers32_halves(const uint8_t* text, int n, const uint4* peq, int m, bool on) {
     const int lane = threadIdx.x & 31, hl = lane & 15, base = lane & 16;
-    const uint32_t mask = m >= 32 ? 0xFFFFFFFFu : ((1u << m) - 1u);
     uint32_t e0 = 0, e1 = 0;            // match masks of text bytes hl and hl + 16
-    if (on && hl < n) e0 = __ldg(&peq[text[hl]].x) & mask;
-    if (on && hl + 16 < n) e1 = __ldg(&peq[text[hl + 16]].x) & mask;
+    if (on && hl < n) e0 = myers_eq_top(__ldg(&peq[text[hl]].x), 0, m);
+    if (on && hl + 16 < n) e1 = myers_eq_top(__ldg(&peq[text[hl + 16]].x), 0, m);
     const int nmax = max(__shfl_sync(0xffffffffu, on ? n : 0, 0), __shfl_sync(0xffffffffu, on ? n : 0, 16));
-    uint32_t VP = mask, VN = 0;
-    const uint32_t top = 1u << (m - 1);
-    int score = m;
+    Myers32 M;
+    M.init(m);
     for (int i = 0; i < nmax; i++) {
         const uint32_t Eq = __shfl_sync(0xffffffffu, i < 16 ? e0 : e1, base + (i & 15));
-        if (i < n) {
-            const uint32_t Xv = Eq | VN;
-            const uint32_t Xh = (((Eq & VP) + VP) ^ VP) | Eq;
-            uint32_t HP = VN | ~(Xh | VP);
-            uint32_t HN = VP & Xh;
-            score += (HP & top) ? 1 : ((HN & top) ? -1 : 0);
-            HP = (HP << 1) | 1u;
-            HN = HN << 1;
-            VP = HN | ~(Xv | HP);
-            VN = HP & Xv;
-        }
+        if (i < n) M.column(Eq);
     }
-    return score;
+    return M.score(m);
+}
+
+// myers32 for a whole warp that wants ONE distance (n <= 32 text bytes): lane i fetches the match mask of text byte i,
+// so the two dependent loads per column happen once, side by side, instead of n times in a row; every lane then runs
+// the recurrence on shuffled masks and returns the same value.  Must be called by all 32 lanes.
+__device__ __forceinline__ int myers32_warp(const uint8_t* text, int n, const uint4* peq, int shift, int m) {
+    if (m == 0) return n;
+    if (n == 0) return m;
+    const int lane = threadIdx.x & 31;
+    uint32_t mine = 0;
+    if (lane < n) mine = myers_eq_top(__ldg(&peq[text[lane]].x), shift, m);
+    Myers32 M;
+    M.init(m);
+    for (int i = 0; i < n; i++) M.column(__shfl_sync(0xffffffffu, mine, i));
+    return M.score(m);
 }
 
 // Levenshtein distance (Myers/Hyyro bit-parallel, global), pattern = adapter bits [shift, shift+m) with
@@ -128,21 +136,9 @@ __device__ __forceinline__ int myers32_halves(const uint8_t* text, int n, const 
 __device__ __forceinline__ int myers32(const uint8_t* text, int n, const uint4* peq, int shift, int m) {
     if (m == 0) return n;
     if (n == 0) return m;
-    const uint32_t mask = m >= 32 ? 0xFFFFFFFFu : ((1u << m) - 1u);
-    uint32_t VP = mask, VN = 0;
-    const uint32_t top = 1u << (m - 1);
-    int score = m;
-    for (int i = 0; i < n; i++) {
-        const uint32_t Eq = (__ldg(&peq[text[i]].x) >> shift) & mask;
-        const uint32_t Xv = Eq | VN;
-        const uint32_t Xh = (((Eq & VP) + VP) ^ VP) | Eq;
-        uint32_t HP = VN | ~(Xh | VP);
-        uint32_t HN = VP & Xh;
-        score += (HP & top) ? 1 : ((HN & top) ? -1 : 0);
-        HP = (HP << 1) | 1u;
-        HN = HN << 1;
-        VP = HN | ~(Xv | HP);
-        VN = HP & Xv;
-    }
-    return score;
+    Myers32 M;
+    M.init(m);
+#pragma unroll 4
+    for (int i = 0; i < n; i++) M.column(myers_eq_top(__ldg(&peq[text[i]].x), shift, m));
+    return M.score(m);
 }
