@@ -212,17 +212,39 @@ __device__ int pass_filter(const fpl_options& o, int rlen, const Counts& c) {
     return FPL_PASS_FILTER;
 }
 
+// Filter::passFilter's counts for one segment of a split read (warp-wide).  16-byte vector loads: the segment starts
+// anywhere, so the vectors are aligned down and the bytes outside [0, len) masked (sequence and quality buffers are
+// equally aligned, so one misalignment serves both).
 __device__ Counts recount(const fpl_options& o, const uint8_t* seq, const uint8_t* qual, int len) {
     Counts c = {0, 0, 0, 0};
     const int lane = lane_id();
     const bool doCounts = (o.qual_filter_enabled || o.length_filter_enabled);
+    const bool doCplx = o.complexity_enabled != 0;
     const int qq = (int)(signed char)o.qualified_qual;
-    for (int i = lane; i < len; i += 32) {
-        if (doCounts) {
-            int q = (int)(signed char)qual[i];
-            c.totalq += q - 33; c.lowq += q < qq; c.nn += seq[i] == 'N';
+    const int pre = (int)(reinterpret_cast<uintptr_t>(seq) & 15);
+    const uint4* sv = reinterpret_cast<const uint4*>(seq - pre);
+    const uint4* qv = reinterpret_cast<const uint4*>(qual - pre);
+    const int total = pre + len;
+    for (int v = lane; v * 16 < total; v += 32) {
+        const uint4 s4 = __ldg(sv + v), q4 = __ldg(qv + v);
+        const uint32_t sw[4] = {s4.x, s4.y, s4.z, s4.w}, qw[4] = {q4.x, q4.y, q4.z, q4.w};
+        // the byte after this vector, for the last adjacent pair
+        const int after = v * 16 + 16 - pre;
+        const uint32_t nextb = (doCplx && after < len) ? (uint32_t)seq[after] : 0u;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const int pos = v * 16 + j - pre;
+            if (pos < 0 || pos >= len) continue;
+            const uint32_t sb = (sw[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+            if (doCounts) {
+                const int q = (int)(signed char)((qw[j >> 2] >> (8 * (j & 3))) & 0xFFu);
+                c.totalq += q - 33; c.lowq += q < qq; c.nn += sb == 'N';
+            }
+            if (doCplx && pos < len - 1) {
+                const uint32_t nb = j < 15 ? (sw[(j + 1) >> 2] >> (8 * ((j + 1) & 3))) & 0xFFu : nextb;
+                c.diff += sb != nb;
+            }
         }
-        if (o.complexity_enabled && i < len - 1) c.diff += seq[i] != seq[i + 1];
     }
     c.lowq = __reduce_add_sync(0xffffffffu, c.lowq); c.nn = __reduce_add_sync(0xffffffffu, c.nn);
     c.totalq = __reduce_add_sync(0xffffffffu, c.totalq); c.diff = __reduce_add_sync(0xffffffffu, c.diff);
