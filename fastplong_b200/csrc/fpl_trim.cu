@@ -213,9 +213,13 @@ __device__ int trim_start(const DevParams& P, const uint8_t* seq, Win& w, int ai
     const int T16 = P.thr[plen];
     unsigned best = 0xFFFFFFFFu;
     const uint32_t* t16 = P.peq16 + (size_t)aidx * 512 + 256;   // last plen chars
-    for (int p = lane; p < np; p += 32) {
-        int ed = myers16(rdata + p, plen, t16, plen);
-        if (ed <= T16) best = min(best, ((unsigned)ed << 16) | (unsigned)p);
+    for (int p0 = 0; p0 < np; p0 += 32) {
+        const int p = p0 + lane;
+        if (p < np) {
+            const int ed = myers16(rdata + p, plen, t16, plen);
+            if (ed <= T16) best = min(best, ((unsigned)ed << 16) | (unsigned)p);
+        }
+        if (__any_sync(0xffffffffu, best < 0x10000u)) break;   // an exact hit: no later position can beat (0, p)
     }
     best = __reduce_min_sync(0xffffffffu, best);
     if (best != 0xFFFFFFFFu) {
@@ -248,23 +252,22 @@ __device__ int trim_end(const DevParams& P, const uint8_t* seq, Win& w, int aidx
         resize_(w, mpos);
         return rlen - mpos;
     }
-    // probe from the tail with the "last best, stop at the first worse hit" rule (:273-286):
-    // all distances in parallel into scratch, then the (short) sequential selection.
+    // probe from the tail with the "last best, stop at the first worse hit" rule (:273-286), 32 positions per step:
+    // the distances of a step in parallel, then the sequential rule in closed form — walk the hits in
+    // order, stop at the first hit whose distance exceeds the previous hit's, keep the hit before it.  The reference
+    // stops probing there and so do we: with an adapter near the end that is the first or second step.
     const int np = min(rlen - plen, FPL_WINDOW - plen);
     const int T16 = P.thr[plen];
     const uint32_t* t16 = P.peq16 + (size_t)aidx * 512;         // first plen chars
-    for (int p = lane; p < np; p += 32) {
-        int ed = myers16(rdata + rlen - plen - p, plen, t16, plen);
-        scratch[p] = (uint8_t)(ed <= T16 ? ed : 255);
-    }
-    __syncwarp();
-    // sequential rule of :273-286 in closed form: walk the hits in order, stop at the first hit whose
-    // distance exceeds the previous hit's, keep the hit before it; 32 positions per step.
     int pos = -1, carryE = -1, carryPos = -1;
     bool done = false;
     for (int c0 = 0; c0 < np && !done; c0 += 32) {
         const int p = c0 + lane;
-        const int e = p < np ? (int)scratch[p] : 255;
+        int e = 255;
+        if (p < np) {
+            const int ed = myers16(rdata + rlen - plen - p, plen, t16, plen);
+            e = ed <= T16 ? ed : 255;
+        }
         const bool hit = e != 255;
         const unsigned m = __ballot_sync(0xffffffffu, hit);
         const unsigned lower = m & ((1u << lane) - 1u);
