@@ -35,8 +35,8 @@ ALG_BYTES_PER_BASE = 2      # 1 sequence byte + 1 quality byte, each read once (
 ALG_BYTES_PER_READ = 64     # offset, length, result record
 HBM_FALLBACK_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
 # CPU arm: a sample large enough that the binary's fixed costs (start-up, adapter detection pre-pass, report writing)
-# do not dominate: 20k reads x 15 kb = 0.3 Gbases, a few seconds of reference CPU time per run with 16 workers
-REF_SAMPLE_READS = 20000
+# do not dominate: 40k reads x 15 kb = 0.6 Gbases, a few seconds of reference CPU time per run with 16 workers
+REF_SAMPLE_READS = 40000
 
 
 WORKLOADS = {
@@ -370,26 +370,41 @@ def reference_cpu_run(sample_reads, repeats):
         for _ in range(repeats):
             cmd = [binary, "-i", fq, "-o", fq + ".out", "-j", fq + ".json", "-h", fq + ".html", "-w", str(cores), "-V"]
             cmd += opt.cli_flags()
+            # -V makes the reference log "start to load data" (src/seprocessor.cpp:334) and "start to generate reports"
+            # (:105-106); its own timestamps have 1 s resolution, so the lines are stamped here as they arrive
             t0 = time.perf_counter()
-            r = subprocess.run(cmd, capture_output=True, text=True)
+            pr = subprocess.Popen(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, bufsize=1)
+            t_load = t_rep = None
+            tail = []
+            for ln in pr.stderr:
+                now = time.perf_counter()
+                tail.append(ln)
+                if t_load is None and "start to load data" in ln:
+                    t_load = now
+                elif "start to generate reports" in ln:
+                    t_rep = now
+            pr.wait()
             wall = time.perf_counter() - t0
-            if r.returncode != 0:
+            if pr.returncode != 0:
                 return {"value": None, "unit": "Gbases/s", "cores": cores, "kind": "reference",
-                        "sample": "fastplong_ref failed: " + r.stderr[-200:]}
-            # processing phase between the -V lines (src/seprocessor.cpp:334,105-106); 1 s resolution -> use wall
-            # minus nothing: report both
-            if best is None or wall < best:
-                best = wall
+                        "sample": "fastplong_ref failed: " + "".join(tail)[-200:]}
+            phase = (t_rep - t_load) if (t_load is not None and t_rep is not None and t_rep > t_load) else wall
+            if best is None or phase < best[0]:
+                best = (phase, wall)
     finally:
         for suffix in (".out", ".json", ".html"):
             try:
                 os.remove(fq + suffix)
             except OSError:
                 pass
-    return {"value": round(n_bases / best / 1e9, 5), "unit": "Gbases/s", "cores": cores, "kind": "reference",
-            "sample": f"{sample_reads} reads / {n_bases} bases of the same generator, fastplong_ref -w {cores} "
-                      f"whole-binary wall {best:.2f} s (plain FASTQ on tmpfs, incl. detection pre-pass and reports)",
-            "wall_s": round(best, 3), "bases": n_bases}
+    phase, wall = best
+    return {"value": round(n_bases / phase / 1e9, 5), "unit": "Gbases/s", "cores": cores, "kind": "reference",
+            "sample": f"{sample_reads} reads / {n_bases} bases of the same generator, fastplong_ref -w {cores}, plain FASTQ on "
+                      f"tmpfs; value = bases / processing phase ({phase:.2f} s between the -V lines 'start to load data' and "
+                      f"'start to generate reports': reader + workers + writer, the path itself); the whole binary took "
+                      f"{wall:.2f} s (adapter detection pre-pass, Stats allocation and JSON/HTML reports included)",
+            "phase_s": round(phase, 3), "wall_s": round(wall, 3), "whole_binary_gbases_s": round(n_bases / wall / 1e9, 5),
+            "bases": n_bases}
 
 
 def run_reference(args):
@@ -405,8 +420,8 @@ def run_reference(args):
         if base["value"] is None:
             print(json.dumps({"impl": "reference", "unavailable": base["sample"]}))
             return
-        walls.append(base["wall_s"])
-    ms = 1e3 * sum(walls) / len(walls)
+        walls.append(base["phase_s"])
+    ms = 1e3 * sum(walls) / len(walls)      # a step = the processing phase of one run over the sample
     value = base["bases"] / (ms * 1e-3) / 1e9
     cb = dict(base)
     cb["value"] = round(value, 5)
@@ -414,8 +429,9 @@ def run_reference(args):
             "value": round(value, 5), "unit": "Gbases/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
             "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": round(ms, 2), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "configs[1] shape, bounded sample: %d ONT reads mean 15 kb (0.3 Gbases) per step, auto-detected "
-                                   "adapters + --cut_front --cut_tail -W 10 (reference CPU build, host cores only)" % sample_reads},
+            "config": {"workload": "configs[1] shape, bounded sample: %d ONT reads mean 15 kb (%.1f Gbases) per step, auto-detected "
+                                   "adapters + --cut_front --cut_tail -W 10 (reference CPU build, host cores only; a step is timed "
+                                   "over the binary's processing phase)" % (sample_reads, base["bases"] / 1e9)},
             "cpu_baseline": cb,
             "e2e": {"value": round(value, 5), "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
