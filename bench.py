@@ -146,6 +146,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL writes its version banner (NCCL_DEBUG=VERSION on these boxes) to stdout by default; stdout carries the
+        # one JSON line, so send NCCL's log to stderr unless the caller chose a file
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     opt = workload_options(args.workload)
