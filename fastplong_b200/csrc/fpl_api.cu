@@ -1,6 +1,7 @@
 // C-ABI implementation of include/fplgpu.h: context management, device tables, batch tiling and kernel sequencing.
 // No CPU fallback anywhere: every entry point fails loudly when CUDA is unusable.
 #include <cuda_runtime.h>
+#include <limits.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -97,6 +98,8 @@ struct fpl_ctx {
     // fpl_process_host: the upload runs on its own stream, piece by piece, and the kernels of a piece start as soon
     // as its bytes have arrived (copy/compute overlap inside one call)
     cudaStream_t copy_stream = nullptr;
+    int* d_minmax = nullptr;            // fpl_process_device: min / max read length of the batch
+    int* h_minmax = nullptr;
     std::vector<cudaEvent_t> piece_events;
     int64_t piece_bytes = 16ll << 20;
     bool timing = false;
@@ -176,11 +179,25 @@ static void collect_times(fpl_ctx* c) {
     c->events.resize(keep);
 }
 
+// min and max of the read lengths (fpl_process_device)
+__global__ void k_lens_minmax(const int32_t* __restrict__ lens, int64_t n, int* __restrict__ out) {
+    int lo = INT_MAX, hi = INT_MIN;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int v = lens[i];
+        lo = min(lo, v); hi = max(hi, v);
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
+    if ((threadIdx.x & 31) == 0) { atomicMin(&out[0], lo); atomicMax(&out[1], hi); }
+}
+
 // Runs every kernel over reads [0, n) of a device-resident batch whose lens are known on the host.
 // cuts/arrived (optional): the batch arrives in pieces — reads [cuts[j], cuts[j+1]) are on the device once event
 // arrived[j] has fired; the kernels then run piece by piece.
+// h_lens may be null when the caller knows the longest read (known_max_len >= 0) and nothing below needs the individual
+// lengths (no tiling, no pieces): a device-resident batch then never waits for the host to walk a million lengths.
 static int run_batch(fpl_ctx* c, const DevBatch& full, const int32_t* h_lens, fpl_read_result* d_res_out, int64_t n_bytes,
-                     const std::vector<int64_t>* cuts = nullptr, const cudaEvent_t* arrived = nullptr) {
+                     const std::vector<int64_t>* cuts = nullptr, const cudaEvent_t* arrived = nullptr,
+                     int64_t known_max_len = -1) {
     const int64_t n = full.n_reads;
     CK(cudaSetDevice(c->device));
     collect_times(c);
@@ -189,9 +206,13 @@ static int run_batch(fpl_ctx* c, const DevBatch& full, const int32_t* h_lens, fp
     fpl_read_result* d_res = d_res_out ? d_res_out : c->d_results;
     c->last_results = d_res;
     int64_t max_len = 0;
-    for (int64_t i = 0; i < n; i++) {
-        if (h_lens[i] < 0) return fail("read %lld has a negative length", (long long)i);
-        if (h_lens[i] > max_len) max_len = h_lens[i];
+    if (h_lens) {
+        for (int64_t i = 0; i < n; i++) {
+            if (h_lens[i] < 0) return fail("read %lld has a negative length", (long long)i);
+            if (h_lens[i] > max_len) max_len = h_lens[i];
+        }
+    } else {
+        max_len = known_max_len;
     }
     if (reserve_cycles(c, max_len > 0 ? max_len : 1)) return -1;
     // tiles of reads whose payload stays L2-resident across the kernels that revisit it
@@ -211,6 +232,8 @@ static int run_batch(fpl_ctx* c, const DevBatch& full, const int32_t* h_lens, fp
                 piece++;
             }
             for (int64_t i = r0; i < r1; i++) if (h_lens[i] > tmax) tmax = h_lens[i];
+        } else if (!h_lens || ext || c->tile_bases >= (1ll << 61)) {
+            r1 = n; tmax = max_len;      // one tile
         } else {
             while (r1 < n && (r1 == r0 || ext || bases + h_lens[r1] <= c->tile_bases)) {
                 bases += h_lens[r1];
@@ -423,6 +446,7 @@ void fpl_destroy(fpl_ctx* c) {
     cudaFree(c->d_stats[0]); cudaFree(c->d_stats[1]); cudaFree(c->d_counters);
     fpl_cycle_ws_free(&c->cycle_ws);
     for (auto e : c->piece_events) cudaEventDestroy(e);
+    cudaFree(c->d_minmax); if (c->h_minmax) cudaFreeHost(c->h_minmax);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     cudaFree(c->d_state); cudaFree(c->d_results); cudaFree(c->d_preseg); cudaFree(c->d_postseg);
     cudaFree(c->d_seq); cudaFree(c->d_qual); cudaFree(c->d_offsets); cudaFree(c->d_lens);
@@ -438,13 +462,33 @@ int fpl_process_device(fpl_ctx* c, const fpl_batch* b, fpl_read_result* results_
     CK(cudaSetDevice(c->device));
     const int64_t n = b->n_reads;
     if (n < 0) return fail("fpl_process_device: negative n_reads");
-    c->h_lens.resize((size_t)n);
-    if (n) {
-        CK(cudaMemcpyAsync(c->h_lens.data(), b->lens, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
-    }
     DevBatch d = {b->seq, b->qual, b->offsets, b->lens, n};
-    return run_batch(c, d, c->h_lens.data(), results_dev, b->n_bytes);
+    if (c->tile_bases < (1ll << 61)) {       // read tiling was asked for: the tile boundaries need every length
+        c->h_lens.resize((size_t)n);
+        if (n) {
+            CK(cudaMemcpyAsync(c->h_lens.data(), b->lens, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+        }
+        return run_batch(c, d, c->h_lens.data(), results_dev, b->n_bytes);
+    }
+    // only the extremes of the lengths are needed on the host (Stats capacity, grid sizes): reduce them on the side
+    // stream, which does not wait for the kernels of the previous batch still running on the compute stream
+    if (!c->copy_stream) CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    if (!c->d_minmax) {
+        CK(cudaMalloc(&c->d_minmax, 2 * sizeof(int)));
+        CK(cudaMallocHost(&c->h_minmax, 2 * sizeof(int)));
+    }
+    c->h_minmax[0] = 0; c->h_minmax[1] = 0;
+    if (n) {
+        const int init[2] = {INT_MAX, INT_MIN};
+        CK(cudaMemcpyAsync(c->d_minmax, init, sizeof(init), cudaMemcpyHostToDevice, c->copy_stream));
+        const unsigned blocks = (unsigned)((n + 1023) / 1024 < 1184 ? (n + 1023) / 1024 : 1184);
+        k_lens_minmax<<<blocks, 256, 0, c->copy_stream>>>(b->lens, n, c->d_minmax);
+        CK(cudaMemcpyAsync(c->h_minmax, c->d_minmax, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->copy_stream));
+        CK(cudaStreamSynchronize(c->copy_stream));
+        if (c->h_minmax[0] < 0) return fail("fpl_process_device: a read has a negative length");
+    }
+    return run_batch(c, d, nullptr, results_dev, b->n_bytes, nullptr, nullptr, n ? c->h_minmax[1] : 0);
 }
 
 void* fpl_stream(fpl_ctx* c) { return c ? (void*)c->stream : nullptr; }

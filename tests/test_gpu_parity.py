@@ -146,3 +146,49 @@ def test_size_independent_properties_large():
     # idempotence of the accumulators: a second pass doubles every counter
     g.process(b)
     assert np.array_equal(g.stats(0, cyc), 2 * pre) and np.array_equal(g.counters(), 2 * cnt)
+
+
+def _device_batch(batch):
+    import torch
+    dev = torch.device("cuda:0")
+    pad = 256
+    seq = torch.zeros(batch.seq.size + pad, dtype=torch.uint8, device=dev)
+    qual = torch.zeros(batch.qual.size + pad, dtype=torch.uint8, device=dev)
+    seq[:batch.seq.size] = torch.from_numpy(batch.seq).to(dev)
+    qual[:batch.qual.size] = torch.from_numpy(batch.qual).to(dev)
+    offs = torch.from_numpy(batch.offsets.astype(np.int64)).to(dev)
+    lens = torch.from_numpy(batch.lens.astype(np.int32)).to(dev)
+    torch.cuda.synchronize()
+    return seq, qual, offs, lens
+
+
+@pytest.mark.parametrize("tiling", [None, "2"])
+def test_device_resident_entry_point(tiling, monkeypatch):
+    """fpl_process_device (what bench.py's `value` leg and a GPU-resident caller use): same records, Stats blocks and
+    counters as the oracle; with and without read tiling (without it the host only learns the longest read, from a
+    device-side reduction on the side stream)."""
+    if tiling:
+        monkeypatch.setenv("FPL_TILE_MBASES", tiling)
+    opt = cases.OPTION_SETS["cut_polyx_cplx"]
+    batch = cases.ont_batch(21, n=900, mean=4000, p_chimera=0.05, p_polya=0.05)
+    seq, qual, offs, lens = _device_batch(batch)
+    g, o = gpu_engine(opt), OracleEngine(opt)
+    for rep in range(2):      # back to back: the second call must not depend on the first one having drained
+        g.process_device(seq.data_ptr(), qual.data_ptr(), offs.data_ptr(), lens.data_ptr(), batch.n_reads, batch.seq.size)
+    g.sync()
+    res = g.fetch_results(batch.n_reads)
+    exp = o.process(batch)
+    o.process(batch)
+    compare_results(res, exp, "device")
+    cyc = int(batch.lens.max())
+    for w in (0, 1):
+        compare_stats(g.stats(w, cyc), o.stats(w, cyc), f"device/stats{w}")
+    compare_stats(g.counters(), o.counters(), "device/counters")
+    # empty batch, then a negative length
+    g.process_device(seq.data_ptr(), qual.data_ptr(), offs.data_ptr(), lens.data_ptr(), 0, 0)
+    import torch
+    bad = lens.clone()
+    bad[3] = -5
+    with pytest.raises(Exception):
+        g.process_device(seq.data_ptr(), qual.data_ptr(), offs.data_ptr(), bad.data_ptr(), batch.n_reads, batch.seq.size)
+    g.close()
