@@ -146,9 +146,6 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL writes its version banner (NCCL_DEBUG=VERSION on these boxes) to stdout by default; stdout carries the
-        # one JSON line, so send NCCL's log to stderr unless the caller chose a file
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     opt = workload_options(args.workload)
@@ -340,7 +337,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "roofline": roofline, "kernels": kern, "cpu_baseline": cpu_baseline,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -421,7 +418,7 @@ def run_reference(args):
     for _ in range(args.steps):
         base = reference_cpu_run(sample_reads, 1)
         if base["value"] is None:
-            print(json.dumps({"impl": "reference", "unavailable": base["sample"]}))
+            emit({"impl": "reference", "unavailable": base["sample"]})
             return
         walls.append(base["phase_s"])
     ms = 1e3 * sum(walls) / len(walls)      # a step = the processing phase of one run over the sample
@@ -438,10 +435,30 @@ def run_reference(args):
             "cpu_baseline": cb,
             "e2e": {"value": round(value, 5), "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
+
+
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly one JSON line.  Libraries write there too (NCCL prints its version banner with a plain
+    printf when NCCL_DEBUG=VERSION): keep a private handle on the real stdout for the line and point file descriptor 1
+    at stderr for everybody else."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
