@@ -15,6 +15,7 @@
 #include "fpl_device.cuh"
 #include "fpl_stats.h"
 
+#include <atomic>
 #include <cub/cub.cuh>
 
 #define CS_NT_KMER 1024                          // threads per CTA with the 5-mer tables (one CTA per SM: 145 KB of shared memory)
@@ -352,12 +353,16 @@ void fpl_cycle_ws_free(CycleWs* ws) {
 int launch_cycle_stats(CycleWs* ws, const uint8_t* seq, const uint8_t* qual, const StatSeg* segs, int64_t nseg, int64_t max_len,
                        unsigned long long* stats, int64_t C, bool do_kmer, unsigned long long* kmer_also, cudaStream_t stream) {
     if (nseg == 0 || max_len <= 0) return 0;
-    static bool attr_set = false;
-    if (!attr_set) {
+    // the opt-in to more than 48 KB of dynamic shared memory is a per-device function attribute
+    static std::atomic<unsigned long long> attr_set{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(attr_set.load() & bit)) {
         if (cudaFuncSetAttribute(k_cycle_stats<true, CS_NT_KMER, CS_DEPTH_KMER>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM_KMER) != cudaSuccess ||
             cudaFuncSetAttribute(k_cycle_stats<false, CS_NT_PLAIN, CS_DEPTH_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM_PLAIN) != cudaSuccess)
             return -1;
-        attr_set = true;
+        attr_set.fetch_or(bit);
     }
     int end_bit = 1;
     while (end_bit < 31 && (max_len >> end_bit)) end_bit++;
