@@ -36,7 +36,7 @@ ALG_BYTES_PER_READ = 64     # offset, length, result record
 HBM_FALLBACK_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
 # CPU arm: a sample large enough that the binary's fixed costs (start-up, adapter detection pre-pass, report writing)
 # do not dominate: 40k reads x 15 kb = 0.6 Gbases, a few seconds of reference CPU time per run with 16 workers
-REF_SAMPLE_READS = 40000
+REF_SAMPLE_READS = int(os.environ.get("FPL_BENCH_REF_READS", "40000"))   # the override exists for the CPU test of this arm
 
 
 WORKLOADS = {
