@@ -1,16 +1,18 @@
-// Stats::statRead (src/stats.cpp:265-375) as two kernels over a list of segments
+// Stats::statRead (src/stats.cpp:265-375) as kernels over a list of segments
 // (pre-filter Stats: every input read; post-filter Stats: every passing segment):
 //
-//  k_cycle_stats  column-tiled: a CTA owns a tile of 512 cycles x a group of up to 4000 segments; its warps take the
-//                 segments that reach the tile round-robin, one 16-byte vector of sequence and of quality per
-//                 lane.  The per-(base-bin, cycle) counters live in shared memory (column j*32+lane: conflict-free)
-//                 and are updated with shared-memory atomics; one 32-bit word packs (count << 20 | sum of raw
-//                 quality chars).  The tile is flushed once to the global int64 arrays mCycleBaseContents /
-//                 mCycleBaseQual.  Also counts the 5-mers (mKmer) with a SWAR fast path for all-ACGTU vectors.
+//  k_cycle_stats  column-tiled over the LENGTH-SORTED segment list: a CTA owns a 512-byte tile of the segments'
+//                 16-byte-aligned byte ranges x a group of up to 4000 segments; its warps take the group's segments
+//                 round-robin, one aligned 16-byte vector of sequence and of quality per lane (cp.async ring, several
+//                 segments in flight).  The per-(base-bin, cycle) counters live in shared memory, one 32-bit word =
+//                 (count << 20 | sum of raw quality chars), laid out so that the 32 lanes of a reduction hit 32 banks
+//                 whatever the segment's misalignment; the tile is flushed once to the global int64 arrays
+//                 mCycleBaseContents / mCycleBaseQual.  The 5-mer variant also fills lane-private 1024-bin tables
+//                 (mKmer) from 2-bit codes packed by multiplication, with an exact A/C/G/T/U test.
 //  k_read_qual    row-shaped: a warp owns a read, builds its quality histogram with shared-memory atomics
-//                 (16-byte vector loads), adds it to mBaseQualHistogram and derives the per-read median quality
-//                 (mMedianReadQualHistogram / mMedianReadQualBases / mReads / mLengthSum) for BOTH Stats objects:
-//                 a passing segment's histogram is the read's minus the removed ends.
+//                 (16-byte vector loads, four per lane in flight), adds it to mBaseQualHistogram and derives the
+//                 per-read median quality (mMedianReadQualHistogram / mMedianReadQualBases / mReads / mLengthSum)
+//                 for BOTH Stats objects: a passing segment's histogram is the read's minus the removed ends.
 //  k_kmer_fix     post-filter 5-mer table = pre-filter table - the 5-mers outside the passing segments.
 #include "fpl_device.cuh"
 #include "fpl_stats.h"
