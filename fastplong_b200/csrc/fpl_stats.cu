@@ -441,7 +441,9 @@ k_kmer_fix(DevBatch b, const fpl_read_result* __restrict__ res, unsigned long lo
                         red_shared_add(rem_base + (((c4 << 8) | (c3 << 6) | (c2 << 4) | (c1 << 2) | c0) << 2), 1u);
                 }
             }
-            if (k < nk) from = max(from, ke[k]);
+            // the next removed range starts behind this one and behind the segment; a passing segment shorter than
+            // four bases (only possible with --length_required < 5) ends in front of `to` and must not pull it back
+            if (k < nk) from = max(from, max(to, ke[k]));
         }
     }
     __syncthreads();

@@ -192,3 +192,13 @@ def test_device_resident_entry_point(tiling, monkeypatch):
     with pytest.raises(Exception):
         g.process_device(seq.data_ptr(), qual.data_ptr(), offs.data_ptr(), bad.data_ptr(), batch.n_reads, batch.seq.size)
     g.close()
+
+
+def test_passing_segments_shorter_than_a_5mer():
+    """--length_required 0 lets segments of 2-4 bases pass: the post-filter 5-mer table (pre minus removed) must not
+    subtract the bases behind such a segment twice (found by tools/fuzz_gpu_vs_oracle.py)."""
+    opt = Options(disable_adapter_trimming=True, cut_front=True, cut_tail=True, length_required=0, length_limit=500,
+                  low_complexity_filter=True, complexity_threshold=60)
+    check_against_oracle(opt, cases.adversarial_batch(825889), "short-segments")
+    reads = [(b"ACGTACGTACGTACGTACGT"[:n], bytes([33 + 30]) * n) for n in (1, 2, 3, 4, 5, 6, 9)] * 3
+    check_against_oracle(Options(disable_adapter_trimming=True, length_required=0), pack_reads(reads), "tiny-reads")
