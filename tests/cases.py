@@ -115,3 +115,48 @@ def blocky_quality_batch(seed, n=150):
             pos += bad + int(rng.integers(20, 900))
     from fastplong_b200 import PackedBatch
     return PackedBatch(b.seq, q, b.offsets, b.lens)
+
+
+# ---- randomised option sets x batches (tools/fuzz_*.py, test_*random*): the draw order is part of the contract, a
+# (seed, index) pair names the same case everywhere ----
+def random_option_kwargs(rng):
+    def rand_adapter(lo=6, hi=45):
+        return ''.join(rng.choice('ACGT') for _ in range(rng.randint(lo, hi)))
+    kw = {}
+    mode = rng.random()
+    if mode < 0.15: kw['disable_adapter_trimming'] = True
+    else:
+        if rng.random() < 0.8: kw['start_adapter'] = rng.choice([synth.ADAPTER_START, rand_adapter()])
+        if rng.random() < 0.8: kw['end_adapter'] = rng.choice([synth.ADAPTER_END, rand_adapter()])
+        if rng.random() < 0.2: kw['adapter_fasta'] = [rand_adapter(8, 40) for _ in range(rng.randint(1, 4))]
+        if rng.random() < 0.3: kw['distance_threshold'] = rng.choice([0.1, 0.2, 0.3, 0.4])
+        if rng.random() < 0.3: kw['trimming_extension'] = rng.choice([0, 3, 10, 25])
+    if rng.random() < 0.4: kw['cut_front'] = True
+    if rng.random() < 0.4: kw['cut_tail'] = True
+    if rng.random() < 0.4: kw['cut_window_size'] = rng.choice([1, 4, 10, 30]); kw['cut_mean_quality'] = rng.choice([10, 15, 20, 30])
+    if rng.random() < 0.3: kw['trim_front'] = rng.choice([0, 1, 5, 40])
+    if rng.random() < 0.3: kw['trim_tail'] = rng.choice([0, 1, 5, 40])
+    if rng.random() < 0.3: kw['trim_poly_x'] = True; kw['poly_x_min_len'] = rng.choice([5, 10, 20])
+    if rng.random() < 0.2: kw['disable_quality_filtering'] = True
+    if rng.random() < 0.3: kw['qualified_quality_phred'] = rng.choice([5, 15, 25])
+    if rng.random() < 0.3: kw['mean_qual'] = rng.choice([0, 8, 15])
+    if rng.random() < 0.3: kw['n_base_limit'] = rng.choice([0, 2, 50])
+    if rng.random() < 0.3: kw['n_percent_limit'] = rng.choice([1, 10, 50])
+    if rng.random() < 0.3: kw['length_required'] = rng.choice([0, 15, 100, 1000])
+    if rng.random() < 0.2: kw['length_limit'] = rng.choice([0, 500, 5000])
+    if rng.random() < 0.3: kw['low_complexity_filter'] = True; kw['complexity_threshold'] = rng.choice([10, 30, 60])
+    if rng.random() < 0.2: kw['mask'] = True; kw['mask_window_size'] = rng.choice([5, 10, 50]); kw['mask_mean_quality'] = rng.choice([8, 12, 20])
+    if rng.random() < 0.2: kw['break_reads'] = True; kw['break_window_size'] = rng.choice([10, 30, 100]); kw['break_mean_quality'] = rng.choice([8, 12, 20])
+    return kw
+
+
+def random_case(rng):
+    """-> (Options, batch, description)"""
+    kw = random_option_kwargs(rng)
+    opt = Options(**kw)
+    kind = rng.random()
+    seed = rng.randint(1, 10**6)
+    if kind < 0.4: batch = adversarial_batch(seed)
+    elif kind < 0.7: batch = blocky_quality_batch(seed, n=40)
+    else: batch = ont_batch(seed, n=40, mean=1500, p_chimera=0.1, p_polya=0.1)
+    return opt, batch, f"{kw} kind={kind:.3f} seed={seed}"

@@ -202,3 +202,25 @@ def test_passing_segments_shorter_than_a_5mer():
     check_against_oracle(opt, cases.adversarial_batch(825889), "short-segments")
     reads = [(b"ACGTACGTACGTACGTACGT"[:n], bytes([33 + 30]) * n) for n in (1, 2, 3, 4, 5, 6, 9)] * 3
     check_against_oracle(Options(disable_adapter_trimming=True, length_required=0), pack_reads(reads), "tiny-reads")
+
+
+def test_random_option_sets_gpu():
+    """Seeded random option sets x batches against the oracle (cases.random_case; tools/fuzz_gpu_vs_oracle.py runs the
+    same generator for longer): every record, both Stats blocks, counters, and the --mask/--break lists."""
+    import random
+    from oracle_lib import compare_lists
+    rng = random.Random(12)
+    for i in range(60):
+        opt, batch, what = cases.random_case(rng)
+        g, o = gpu_engine(opt), OracleEngine(opt)
+        try:
+            compare_results(g.process(batch), o.process(batch), what)
+            if opt.mask or opt.break_reads:
+                compare_lists(g.segments(), o.segments(), what + "/segments")
+                compare_lists(g.mask_regions(), o.mask_regions(), what + "/regions")
+            cyc = max(1, int(batch.lens.max()))
+            for w in (0, 1):
+                compare_stats(g.stats(w, cyc), o.stats(w, cyc), f"{what}/stats{w}")
+            compare_stats(g.counters(), o.counters(), what + "/counters")
+        finally:
+            g.close()

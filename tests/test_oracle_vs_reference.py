@@ -71,3 +71,21 @@ def test_mask_break(name, kind):
     for w in (0, 1):
         compare_stats(o.stats(w, cyc), r.stats(w, cyc), f"{what}/stats{w}")
     compare_stats(o.counters(), r.counters(), what + "/counters")
+
+
+@pytest.mark.parametrize("seed", [31, 32, 33])
+def test_random_option_sets(seed):
+    """Seeded random option sets x batches (cases.random_case; tools/fuzz_oracle_vs_reference.py runs the same for longer)."""
+    import random
+    rng = random.Random(seed)
+    for i in range(40):
+        opt, batch, what = cases.random_case(rng)
+        o, r = OracleEngine(opt), RefEngine(opt)
+        compare_results(o.process(batch), r.process(batch), f"{what}")
+        if opt.mask or opt.break_reads:
+            compare_lists(o.segments(), r.segments(), what + "/segments")
+            compare_lists(o.mask_regions(), r.mask_regions(), what + "/regions")
+        cyc = max(1, int(batch.lens.max()))
+        for w in (0, 1):
+            compare_stats(o.stats(w, cyc), r.stats(w, cyc), f"{what}/stats{w}")
+        compare_stats(o.counters(), r.counters(), what + "/counters")
