@@ -290,6 +290,7 @@ def run_ours(args):
                       "achieved_gbs": round(alg_bytes_step / (per_step_ms * 1e-3) / 1e9, 1) if per_step_ms > 0 else None}
     dom = max(kern, key=lambda k: kern[k]["ms_per_step"]) if kern else None
     traffic = None
+    secondary = None      # the integer-pipe roofline, reported where it binds (from the committed ncu capture)
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if dom and os.path.exists(tp):
         try:
@@ -297,8 +298,14 @@ def run_ours(args):
             if dom in tj:   # DRAM bytes per algorithmic byte from the committed ncu --set full capture
                 nl = max(1, kern[dom]["launches_per_step"])
                 traffic = tj[dom]["dram_bytes_per_alg_byte"] * alg_bytes_step / nl
+                if "alu_pipe_active_pct" in tj[dom]:
+                    secondary = {"bound": "integer logic pipe (LOP3/SHF/PRMT issue slots)",
+                                 "frac": round(tj[dom]["alu_pipe_active_pct"] / 100.0, 4),
+                                 "source": "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active, ncu --set full capture "
+                                           "summarised in profiles/r01_ncu_full_summary.txt (not measured live)"}
         except Exception:
             traffic = None
+            secondary = None
     roofline = None
     if dom:
         nl = max(1, kern[dom]["launches_per_step"])
@@ -306,7 +313,7 @@ def run_ours(args):
         roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                     "alg_bytes_per_launch": alg_bytes_step / nl, "avg_launch_ms": round(kern[dom]["ms_per_step"] / nl, 5),
-                    "launches_per_step": nl}
+                    "launches_per_step": nl, "secondary": secondary}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
