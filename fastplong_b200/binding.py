@@ -50,6 +50,12 @@ def load_library():
     lib.fpl_counter_words.restype = C.c_int64
     lib.fpl_counters_download.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     lib.fpl_counters_device_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+    lib.fpl_comm_unique_id.argtypes = [C.c_void_p]
+    lib.fpl_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    lib.fpl_comm_destroy.argtypes = [C.c_void_p]
+    lib.fpl_comm_size.argtypes = [C.c_void_p]
+    lib.fpl_comm_agree_cycles.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+    lib.fpl_allreduce_stats.argtypes = [C.c_void_p, C.c_int64]
     lib.fpl_reset.argtypes = [C.c_void_p]
     lib.fpl_last_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_float),
                                           C.POINTER(C.c_int64), C.c_int]
@@ -65,6 +71,7 @@ def load_library():
 EXPORTS = ["fpl_last_error", "fpl_abi_version", "fpl_create", "fpl_destroy", "fpl_process_host", "fpl_process_device", "fpl_process_fastq_host",
            "fpl_sync", "fpl_stream", "fpl_last_segments", "fpl_last_mask_regions", "fpl_fetch_results", "fpl_stats_cycles", "fpl_stats_reserve", "fpl_stats_download",
            "fpl_stats_device_ptr", "fpl_counter_words", "fpl_counters_download", "fpl_counters_device_ptr",
+           "fpl_comm_unique_id", "fpl_comm_init", "fpl_comm_destroy", "fpl_comm_size", "fpl_comm_agree_cycles", "fpl_allreduce_stats",
            "fpl_reset", "fpl_last_kernel_times", "fpl_launch_count", "fpl_set_timing"]
 
 
@@ -144,7 +151,6 @@ class Engine:
 
     def _list(self, fn, dtype):
         n = C.c_int64()
-        self._check(fn(self.h, None, 0, C.byref(n)) if False else 0)
         # ask for the count first (a call with cap 0 fails only when there are entries)
         fn(self.h, None, 0, C.byref(n))
         out = np.zeros(n.value, dtype=dtype)
@@ -199,6 +205,30 @@ class Engine:
 
     def reset(self):
         self._check(self.lib.fpl_reset(self.h))
+
+    # --- multi-GPU merge (one process per GPU): Stats::merge / FilterResult::merge as NCCL all-reduces ---
+    @staticmethod
+    def comm_unique_id():
+        """Rank 0: the FPL_COMM_ID_BYTES rendezvous id to hand to every rank."""
+        lib = load_library()
+        buf = (C.c_uint8 * abi.COMM_ID_BYTES)()
+        if lib.fpl_comm_unique_id(buf) != 0:
+            raise FplError(lib.fpl_last_error().decode())
+        return bytes(buf)
+
+    def comm_init(self, unique_id, rank, n_ranks):
+        buf = (C.c_uint8 * abi.COMM_ID_BYTES).from_buffer_copy(unique_id)
+        self._check(self.lib.fpl_comm_init(self.h, buf, int(rank), int(n_ranks)))
+
+    def agree_cycles(self):
+        n = C.c_int64()
+        self._check(self.lib.fpl_comm_agree_cycles(self.h, C.byref(n)))
+        return int(n.value)
+
+    def allreduce_stats(self, cycles=0):
+        """In-place sum over the ranks of both Stats blocks and the counters, on the context's stream (asynchronous).
+        cycles = 0: agree on the number of cycles first (synchronous)."""
+        self._check(self.lib.fpl_allreduce_stats(self.h, int(cycles)))
 
     # --- measurement ---
     def set_timing(self, on=True):

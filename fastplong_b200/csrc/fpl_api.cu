@@ -10,6 +10,8 @@
 #include <time.h>
 #include <string>
 #include <vector>
+#include <dlfcn.h>
+#include <nccl.h>
 #include "fpl_device.cuh"
 #include "fpl_scanplan.h"
 #include "fpl_stats.h"
@@ -106,6 +108,12 @@ struct fpl_ctx {
     float kernel_ms[K_NKERNELS];
     int64_t kernel_n[K_NKERNELS];
     int64_t launches = 0;
+    // multi-GPU merge (fpl_comm_init / fpl_allreduce_stats): one NCCL communicator per context
+    ncclComm_t comm = nullptr;
+    int comm_rank = 0, comm_size = 1;
+    int64_t used_cycles = 0;            // longest read accumulated since the last fpl_reset
+    long long* d_agree = nullptr;       // device word for the all-reduce(max) of the cycle count
+    long long* h_agree = nullptr;       // pinned
     struct Ev { int k; cudaEvent_t a, b; };
     std::vector<Ev> events;
     std::vector<cudaEvent_t> pool;
@@ -215,6 +223,7 @@ static int run_batch(fpl_ctx* c, const DevBatch& full, const int32_t* h_lens, fp
         max_len = known_max_len;
     }
     if (reserve_cycles(c, max_len > 0 ? max_len : 1)) return -1;
+    if (max_len > c->used_cycles) c->used_cycles = max_len;
     // tiles of reads whose payload stays L2-resident across the kernels that revisit it
     const bool ext = c->P.opt.mask_enabled || c->P.opt.break_enabled;   // variable number of output reads: one tile
     c->ext.n_segs = 0; c->ext.n_regs = 0;
@@ -447,6 +456,8 @@ void fpl_destroy(fpl_ctx* c) {
     fpl_cycle_ws_free(&c->cycle_ws);
     for (auto e : c->piece_events) cudaEventDestroy(e);
     cudaFree(c->d_minmax); if (c->h_minmax) cudaFreeHost(c->h_minmax);
+    fpl_comm_destroy(c);
+    cudaFree(c->d_agree); if (c->h_agree) cudaFreeHost(c->h_agree);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     cudaFree(c->d_state); cudaFree(c->d_results); cudaFree(c->d_preseg); cudaFree(c->d_postseg);
     cudaFree(c->d_seq); cudaFree(c->d_qual); cudaFree(c->d_offsets); cudaFree(c->d_lens);
@@ -693,6 +704,7 @@ int fpl_reset(fpl_ctx* c) {
     for (int w = 0; w < 2; w++)
         CK(cudaMemsetAsync(c->d_stats[w], 0, sizeof(unsigned long long) * FPL_STATS_WORDS(c->C), c->stream));
     CK(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * c->counter_words, c->stream));
+    c->used_cycles = 0;
     return 0;
 }
 
@@ -714,6 +726,129 @@ int fpl_set_timing(fpl_ctx* c, int enabled) {
     c->timing = enabled != 0;
     collect_times(c);
     for (int k = 0; k < K_NKERNELS; k++) { c->kernel_ms[k] = 0; c->kernel_n[k] = 0; }
+    return 0;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------------
+// Multi-GPU merge: the replacement of Stats::merge (src/stats.cpp:1013-1082) and FilterResult::merge
+// (src/filterresult.cpp:28-61) for one process per GPU.  NCCL is resolved at run time (dlopen of libnccl.so.2: inside
+// a torch process that is the copy torch already loaded), so the library stays loadable without it; the collectives
+// run on the context's own stream, after the kernels that fill the blocks, with no host synchronisation.
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+struct Nccl {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+    Nccl() {
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return;
+        GetUniqueId = (decltype(GetUniqueId))dlsym(h, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(h, "ncclCommInitRank");
+        CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
+        AllReduce = (decltype(AllReduce))dlsym(h, "ncclAllReduce");
+        GroupStart = (decltype(GroupStart))dlsym(h, "ncclGroupStart");
+        GroupEnd = (decltype(GroupEnd))dlsym(h, "ncclGroupEnd");
+        GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
+        ok = GetUniqueId && CommInitRank && CommDestroy && AllReduce && GroupStart && GroupEnd && GetErrorString;
+    }
+};
+Nccl& nccl() { static Nccl n; return n; }
+}  // namespace
+
+#define CKN(call)                                                                                        \
+    do {                                                                                                 \
+        ncclResult_t r_ = (call);                                                                        \
+        if (r_ != ncclSuccess) return fail("%s failed: %s", #call, nccl().GetErrorString(r_));          \
+    } while (0)
+
+static_assert(sizeof(ncclUniqueId) == FPL_COMM_ID_BYTES, "FPL_COMM_ID_BYTES must be sizeof(ncclUniqueId)");
+
+extern "C" {
+
+int fpl_comm_unique_id(uint8_t* id) {
+    g_err[0] = 0;
+    if (!id) return fail("fpl_comm_unique_id: null argument");
+    if (!nccl().ok) return fail("fpl_comm_unique_id: libnccl.so.2 is not loadable");
+    ncclUniqueId u;
+    CKN(nccl().GetUniqueId(&u));
+    memcpy(id, &u, sizeof(u));
+    return 0;
+}
+
+int fpl_comm_init(fpl_ctx* c, const uint8_t* id, int rank, int n_ranks) {
+    g_err[0] = 0;
+    if (!c || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail("fpl_comm_init: bad argument");
+    if (!nccl().ok) return fail("fpl_comm_init: libnccl.so.2 is not loadable");
+    if (c->comm) return fail("fpl_comm_init: the context already has a communicator");
+    CK(cudaSetDevice(c->device));
+    ncclUniqueId u;
+    memcpy(&u, id, sizeof(u));
+    CKN(nccl().CommInitRank(&c->comm, n_ranks, u, rank));
+    c->comm_rank = rank; c->comm_size = n_ranks;
+    if (!c->d_agree) {
+        CK(cudaMalloc(&c->d_agree, sizeof(long long)));
+        CK(cudaMallocHost(&c->h_agree, sizeof(long long)));
+    }
+    return 0;
+}
+
+int fpl_comm_destroy(fpl_ctx* c) {
+    if (!c || !c->comm) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    nccl().CommDestroy(c->comm);
+    c->comm = nullptr; c->comm_size = 1; c->comm_rank = 0;
+    return 0;
+}
+
+int fpl_comm_size(fpl_ctx* c) { return c ? c->comm_size : 0; }
+
+int fpl_comm_agree_cycles(fpl_ctx* c, int64_t* cycles) {
+    g_err[0] = 0;
+    if (!c || !c->comm) return fail("fpl_comm_agree_cycles: no communicator (fpl_comm_init first)");
+    CK(cudaSetDevice(c->device));
+    *c->h_agree = (long long)c->used_cycles;
+    CK(cudaMemcpyAsync(c->d_agree, c->h_agree, sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    CKN(nccl().AllReduce(c->d_agree, c->d_agree, 1, ncclInt64, ncclMax, c->comm, c->stream));
+    CK(cudaMemcpyAsync(c->h_agree, c->d_agree, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    const int64_t agreed = (int64_t)*c->h_agree;
+    if (reserve_cycles(c, agreed > 0 ? agreed : 1)) return -1;      // every rank now holds at least `agreed` columns
+    CK(cudaStreamSynchronize(c->stream));
+    if (cycles) *cycles = agreed;
+    return 0;
+}
+
+int fpl_allreduce_stats(fpl_ctx* c, int64_t cycles) {
+    g_err[0] = 0;
+    if (!c || !c->comm) return fail("fpl_allreduce_stats: no communicator (fpl_comm_init first)");
+    CK(cudaSetDevice(c->device));
+    if (cycles <= 0 && fpl_comm_agree_cycles(c, &cycles)) return -1;
+    if (cycles > c->C) return fail("fpl_allreduce_stats: %lld cycles exceed this rank's capacity %lld (fpl_stats_reserve first)",
+                                   (long long)cycles, (long long)c->C);
+    if (cycles < c->used_cycles) return fail("fpl_allreduce_stats: %lld cycles do not cover this rank's longest read (%lld)",
+                                             (long long)cycles, (long long)c->used_cycles);
+    // rows [b*C, b*C + cycles) of the 16 per-cycle arrays, then the tail; the row pointers depend on this rank's C, the
+    // counts do not, so ranks need not share a capacity.  One group = one fused launch.
+    CKN(nccl().GroupStart());
+    for (int w = 0; w < 2; w++) {
+        unsigned long long* blk = c->d_stats[w];
+        if (cycles > 0)
+            for (int b = 0; b < 16; b++)
+                CKN(nccl().AllReduce(blk + (int64_t)b * c->C, blk + (int64_t)b * c->C, (size_t)cycles, ncclInt64, ncclSum, c->comm, c->stream));
+        CKN(nccl().AllReduce(blk + 16 * c->C, blk + 16 * c->C, FPL_STATS_TAIL, ncclInt64, ncclSum, c->comm, c->stream));
+    }
+    CKN(nccl().AllReduce(c->d_counters, c->d_counters, (size_t)c->counter_words, ncclInt64, ncclSum, c->comm, c->stream));
+    CKN(nccl().GroupEnd());
     return 0;
 }
 

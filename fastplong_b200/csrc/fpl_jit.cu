@@ -9,11 +9,13 @@
 #include <string.h>
 #include <map>
 #include <mutex>
+#include <functional>
 #include <string>
 #include <vector>
 #include "fpl_device.cuh"
 #include "fpl_jit.h"
 #include "fpl_scan_jit_src.h"
+#include "fpl_scan_jit2_src.h"
 
 #include <dlfcn.h>
 
@@ -42,14 +44,86 @@ struct Driver {
     }
 };
 Driver& driver() { static Driver d; return d; }
+
+// ---- version 2: the match counter of one adapter as straight-line CUDA source ----
+// A streaming 3:2 compressor: every letter's match vector (one funnel shift of the letter's mask of this lane and of
+// its neighbour) is pushed at weight 1; as soon as a weight holds three vectors a full adder turns them into one
+// vector of that weight and a carry that is pushed at the next weight.  What is left at the end (at most two vectors
+// per weight) is rippled upwards.  Every full adder removes one vector, so an adapter of n letters costs about
+// n - log2(n) of them (25 for 30 letters) and at most three vectors per weight are ever live.
+std::string gen_counter(int which, const char* adapter) {
+    const int alen = (int)strlen(adapter);
+    int amax_bits = 0;
+    while ((1 << amax_bits) <= alen) amax_bits++;        // planes this adapter's count needs
+    std::string out = "__device__ __forceinline__ void count_matches_" + std::to_string(which) +
+                      "(const Masks& m, uint32_t (&c)[NPL]) {\n";
+    std::vector<std::vector<std::string>> buf(12);
+    int tmp = 0;
+    auto fresh = [&] { return std::string("t") + std::to_string(which) + "_" + std::to_string(tmp++); };
+    std::function<void(const std::string&, int)> push = [&](const std::string& v, int w) {
+        buf[w].push_back(v);
+        if (buf[w].size() == 3) {
+            const std::string sname = fresh(), cname = fresh();
+            out += "    FA(" + sname + ", " + cname + ", " + buf[w][0] + ", " + buf[w][1] + ", " + buf[w][2] + ")\n";
+            buf[w].clear();
+            buf[w].push_back(sname);
+            push(cname, w + 1);
+        }
+    };
+    for (int i = 0; i < alen; i++) {
+        const char L = adapter[i];
+        const int w = i >> 5, sh = i & 31;
+        const std::string base = std::string("m.") + L;
+        const std::string v = sh == 0 ? base + "[" + std::to_string(w) + "]"
+                                      : "FS(" + base + "[" + std::to_string(w) + "], " + base + "[" + std::to_string(w + 1) + "], " + std::to_string(sh) + ")";
+        const std::string name = fresh();
+        out += "    const uint32_t " + name + " = " + v + ";\n";
+        push(name, 0);
+    }
+    for (int w = 0; w < 11; w++) {
+        if (buf[w].size() == 2) {
+            const std::string sname = fresh(), cname = fresh();
+            out += "    HA(" + sname + ", " + cname + ", " + buf[w][0] + ", " + buf[w][1] + ")\n";
+            buf[w].clear();
+            buf[w].push_back(sname);
+            push(cname, w + 1);
+        }
+    }
+    out += "#pragma unroll\n    for (int b = 0; b < NPL; b++) c[b] = 0u;\n";
+    for (int w = 0; w < 11; w++)
+        if (!buf[w].empty()) out += "    if constexpr (" + std::to_string(w) + " < NPL) c[" + std::to_string(w) + "] = " + buf[w][0] + ";\n";
+    out += "}\n";
+    (void)amax_bits;
+    return out;
+}
+
+std::string scan_source_v2(const char* a0, const char* a1) {
+    std::string src = kScanJit2Source;
+    const std::string marker = "//@@COUNTERS@@";
+    const size_t at = src.find(marker);
+    src.replace(at, marker.size(), gen_counter(0, a0) + gen_counter(1, a1));
+    return src;
+}
 }  // namespace
+
+// development aid (tools/jit_check.py): the source text NVRTC would be given for these adapters
+extern "C" const char* fpl_jit_debug_source(const char* a0, const char* a1) {
+    static std::string keep;
+    keep = scan_source_v2(a0, a1);
+    return keep.c_str();
+}
 
 int fpl_jit_build_scan(int device, const char* a0, const char* a1, bool doAdapters, bool doCounts, bool doCplx, int qq,
                        FplJitKernel* out, char* err, size_t errlen) {
     out->fn = nullptr;
     std::string defs;
-    defs += std::string("#define FPL_A0 \"") + (doAdapters ? a0 : "") + "\"\n";
-    defs += std::string("#define FPL_A1 \"") + (doAdapters ? a1 : "") + "\"\n";
+    if (!doAdapters) { a0 = ""; a1 = ""; }
+    const bool v1 = getenv("FPL_JIT_V1") != nullptr;       // the round-1 kernel, kept for A/B measurements
+    defs += std::string("#define FPL_A0 \"") + a0 + "\"\n";
+    defs += std::string("#define FPL_A1 \"") + a1 + "\"\n";
+    defs += "#define FPL_ALEN0 " + std::to_string(strlen(a0)) + "\n";
+    defs += "#define FPL_ALEN1 " + std::to_string(strlen(a1)) + "\n";
+    defs += std::string("#define FPL_JIT_VERSION ") + (v1 ? "1" : "2") + "\n";
     defs += std::string("#define FPL_DO_ADAPTERS ") + (doAdapters ? "true" : "false") + "\n";
     defs += std::string("#define FPL_DO_COUNTS ") + (doCounts ? "true" : "false") + "\n";
     defs += std::string("#define FPL_DO_CPLX ") + (doCplx ? "true" : "false") + "\n";
@@ -61,7 +135,7 @@ int fpl_jit_build_scan(int device, const char* a0, const char* a1, bool doAdapte
     auto it = g_cache.find(key);
     if (it != g_cache.end()) { out->fn = (void*)it->second.fn; return 0; }
 
-    const std::string src = defs + kScanJitSource;
+    const std::string src = defs + (v1 ? std::string(kScanJitSource) : scan_source_v2(a0, a1));
     nvrtcProgram prog;
     if (nvrtcCreateProgram(&prog, src.c_str(), "fpl_scan_jit.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) {
         snprintf(err, errlen, "nvrtcCreateProgram failed");
@@ -105,7 +179,10 @@ int fpl_jit_launch_scan(const FplJitKernel* k, const DevBatch& b, ReadState* st,
     const uint8_t* qual = b.qual;
     const int64_t* offsets = b.offsets;
     int64_t n = b.n_reads;
-    void* args[] = {(void*)&seq, (void*)&qual, (void*)&offsets, (void*)&st, (void*)&n};
+    // `one` is the multiplier of the IMADs that must stay IMADs (an add the compiler cannot see through stays on the
+    // FMA pipe); version 1 ignores the extra argument
+    unsigned one = 1;
+    void* args[] = {(void*)&seq, (void*)&qual, (void*)&offsets, (void*)&st, (void*)&n, (void*)&one};
     // one CTA per read.  (Measured: persistent CTAs walking the reads round-robin are slower — 14.7 / 15.7 / 17.1 ms with
     // 32 / 16 / 8 CTAs per SM against 13.8 ms — the hardware scheduler balances the gamma-distributed read lengths better.)
     CUresult cr = driver().LaunchKernel((CUfunction)k->fn, (unsigned)b.n_reads, 1, 1, 128, 1, 1, 0, (CUstream)stream, args, nullptr);

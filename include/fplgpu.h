@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define FPL_ABI_VERSION 2
+#define FPL_ABI_VERSION 3
 
 /* Filter result codes — identical to src/common.h:43-50 (they index FilterResult::mFilterReadStats[32]). */
 enum {
@@ -299,6 +299,29 @@ int fpl_stats_device_ptr(fpl_ctx* ctx, int which, void** dptr, int64_t* n_words)
 int64_t fpl_counter_words(fpl_ctx* ctx);
 int fpl_counters_download(fpl_ctx* ctx, int64_t* out, int64_t n_words);
 int fpl_counters_device_ptr(fpl_ctx* ctx, void** dptr, int64_t* n_words);
+
+/*
+ * Multi-GPU merge, one process (or thread) per GPU — the replacement of Stats::merge (src/stats.cpp:1013-1082) and
+ * FilterResult::merge (src/filterresult.cpp:28-61), which SingleEndProcessor::process calls on the per-worker
+ * ThreadConfigs (src/seprocessor.cpp:108-121).  Reads shard by read, so this is the path's only exchange.
+ *   fpl_comm_unique_id   rank 0 creates the rendezvous id (ncclGetUniqueId) and hands its FPL_COMM_ID_BYTES bytes to
+ *                        the other ranks by whatever channel the host has (file, socket, torch.distributed broadcast);
+ *   fpl_comm_init        every rank joins (ncclCommInitRank, collective); one communicator per context;
+ *   fpl_comm_agree_cycles  all-reduce(max) of the longest read accumulated since fpl_reset; grows this rank's Stats
+ *                        capacity to it; synchronous (one int64 comes back to the host);
+ *   fpl_allreduce_stats  ncclAllReduce(sum, int64) of [0, cycles) of the 16 per-cycle rows, the tail and the counter
+ *                        block of both Stats objects + FilterResult, in place, as ONE group on the context's stream:
+ *                        stream-ordered behind the kernels, no host synchronisation.  cycles must be the same on every
+ *                        rank and cover every rank's longest read; cycles <= 0 = agree first (fpl_comm_agree_cycles).
+ * NCCL (libnccl.so.2) is resolved at run time; without it these calls fail loudly and nothing else is affected.
+ */
+#define FPL_COMM_ID_BYTES 128
+int fpl_comm_unique_id(uint8_t* id);
+int fpl_comm_init(fpl_ctx* ctx, const uint8_t* id, int rank, int n_ranks);
+int fpl_comm_destroy(fpl_ctx* ctx);
+int fpl_comm_size(fpl_ctx* ctx);
+int fpl_comm_agree_cycles(fpl_ctx* ctx, int64_t* cycles);
+int fpl_allreduce_stats(fpl_ctx* ctx, int64_t cycles);
 
 /* Zero all accumulators (a fresh ThreadConfig); stream-ordered, asynchronous. */
 int fpl_reset(fpl_ctx* ctx);
