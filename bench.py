@@ -3,9 +3,10 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-Workload (BASELINE.json configs[1]): 1M ONT-like reads, mean 15 kb, adapters as the reference's evaluator
-auto-detects them on this generator's reads, --cut_front --cut_tail -W 10, default Q/length filters, pre+post
-Stats.  A seeded host tile of 16,384 reads is replicated 64x in HBM (the full set is 30 GB of payload).
+Workload (BASELINE.json configs[1]): 1M DISTINCT ONT-like reads, mean 15 kb (32 GB of payload, generated on the
+device), adapters as the reference's evaluator auto-detects them on this generator's reads, --cut_front --cut_tail
+-W 10, default Q/length filters, pre+post Stats.  Before anything is timed the first reads of the input go through
+the GPU library and the CPU oracle and are compared word by word (`parity_checked`).
 One step = one pass of processSingleEnd over the whole per-GPU batch (+ the Stats/FilterResult all-reduce when N>1).
 `value` = device-resident throughput; `e2e` = the same metric through fpl_process_host with pinned HOST buffers
 (H2D of every byte + D2H of the per-read records inside the timed region).
@@ -27,8 +28,6 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-TILE_READS = 16384
-REPLICAS = 64
 MEAN_LEN = 15000
 SEED = 20260924
 ALG_BYTES_PER_BASE = 2      # 1 sequence byte + 1 quality byte, each read once
@@ -37,26 +36,43 @@ HBM_FALLBACK_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
 # CPU arm: a sample large enough that the binary's fixed costs (start-up, adapter detection pre-pass, report writing)
 # do not dominate: 40k reads x 15 kb = 0.6 Gbases, a few seconds of reference CPU time per run with 16 workers
 REF_SAMPLE_READS = int(os.environ.get("FPL_BENCH_REF_READS", "40000"))   # the override exists for the CPU test of this arm
+PARITY_BASES = 60_000_000   # the slice compared with the oracle outside the timed region (a few seconds of CPU)
+E2E_SUBMISSIONS = 64        # host submissions per step of the end-to-end leg
+E2E_HOST_CHUNKS = 4         # distinct pinned host chunks cycled through them
 
 
+# name: (reads per GPU, replicas, mean length, generator keywords, description)
 WORKLOADS = {
-    # name: (reads per tile, replicas, mean length, description)
-    "c2": (TILE_READS, REPLICAS, MEAN_LEN, "configs[1]: 1M ONT reads mean 15 kb, auto-detected adapters + --cut_front --cut_tail "
-                                           "-W 10, default filters, pre+post stats"),
-    "c3": (8192, 8, 20000, "configs[2] shape at 1/76 scale: 65k HiFi-like reads mean 20 kb, 64-entry adapter FASTA + polyX"),
-    "c5": (512, 8, 500000, "configs[4] shape: 4k ultra-long reads mean 500 kb, adapter trim only (-Q -L)"),
+    "c2": (1 << 20, 1, MEAN_LEN, {},
+           "configs[1]: 1M ONT reads mean 15 kb, auto-detected adapters + --cut_front --cut_tail -W 10, default filters, "
+           "pre+post stats"),
+    "c3": (625_000, 1, 20000, dict(q_mean=33.0, q_sd=6.0, q_clip=60, p_polya=0.05, p_planted=0.2),
+           "configs[2], one GPU's share of an 8-GPU run (5M / 8 = 625k PacBio-HiFi-like reads mean 20 kb; the whole set "
+           "is 200 GB and does not fit one GPU): --adapter_fasta 64-entry set + polyX trim"),
+    "c4": (2_500_000, 1, 10000, {},
+           "configs[3], one GPU's share (20M / 8 = 2.5M ONT reads mean 10 kb): full pipeline — adapters + Q filter + "
+           "length filter (--length_required 1000 --length_limit 60000) + low-complexity filter (-y) + pre/post stats"),
+    "c5-1k": (100_000, 1, 1000, dict(min_len=100), "configs[4]: 100k reads mean 1 kb, adapter trim only (-Q -L)"),
+    "c5-50k": (100_000, 1, 50000, {}, "configs[4]: 100k reads mean 50 kb, adapter trim only (-Q -L)"),
+    "c5-500k": (20_000, 1, 500000, {}, "configs[4] at 1/5 of the read count (20k reads mean 500 kb = 10 Gbases; 100k would be "
+                                       "100 GB of payload): adapter trim only (-Q -L)"),
 }
+
+
+def c3_fasta():
+    rng = np.random.default_rng(64)
+    return sorted("".join("ACGT"[i] for i in rng.integers(0, 4, size=int(rng.integers(20, 45)))) for _ in range(64))
 
 
 def workload_options(name="c2"):
     from fastplong_b200 import Options, synth
     if name == "c3":
-        import numpy as np
-        rng = np.random.default_rng(64)
-        fasta = ["".join("ACGT"[i] for i in rng.integers(0, 4, size=int(rng.integers(20, 45)))) for _ in range(64)]
-        return Options(start_adapter=synth.ADAPTER_START, end_adapter=synth.ADAPTER_END, adapter_fasta=sorted(fasta),
+        return Options(start_adapter=synth.ADAPTER_START, end_adapter=synth.ADAPTER_END, adapter_fasta=c3_fasta(),
                        trim_poly_x=True)
-    if name == "c5":
+    if name == "c4":
+        return Options(start_adapter=synth.ADAPTER_START, end_adapter=synth.ADAPTER_END, low_complexity_filter=True,
+                       length_required=1000, length_limit=60000)
+    if name.startswith("c5"):
         return Options(start_adapter=synth.ADAPTER_START, end_adapter=synth.ADAPTER_END, disable_quality_filtering=True,
                        disable_length_filtering=True)
     # -s/-e left at "auto" on the CLI; the strings below are what Evaluator::evalAdapterAndReadNum detects on this
@@ -129,11 +145,49 @@ def physical_device_index(local):
     return local
 
 
+def parity_check(opt, host_slice):
+    """One slice of the bench input through the GPU library and through the CPU oracle (the checker, outside every timed
+    region): per-read records, both Stats blocks and the counters, word by word.  Raises on the first difference."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from fastplong_b200.binding import Engine
+    from oracle_lib import OracleEngine, compare_results, compare_stats
+    gpu = Engine(opt)
+    res = gpu.process(host_slice)
+    orc = OracleEngine(opt)
+    ref = orc.process(host_slice)
+    compare_results(res, ref, "bench parity slice")
+    cyc = int(host_slice.lens.max())
+    for w in (0, 1):
+        compare_stats(gpu.stats(w, cyc), orc.stats(w, cyc), f"bench parity slice/stats{w}")
+    compare_stats(gpu.counters(), orc.counters(), "bench parity slice/counters")
+    gpu.close()
+    orc.close()
+    return {"reads": host_slice.n_reads, "bases": host_slice.n_bases,
+            "compared": "records field by field, pre and post Stats blocks and FilterResult counters word by word, GPU library vs "
+                        "the C oracle (oracle/fpl_oracle.c) on the first reads of this run's input, outside the timed region"}
+
+
+def h2d_peak_gbs(torch, dev):
+    """Pinned host -> device copy bandwidth of this box (the roofline of the end-to-end leg)."""
+    n = 1 << 30
+    h = torch.empty(n, dtype=torch.uint8).pin_memory()
+    d = torch.empty(n, dtype=torch.uint8, device=dev)
+    best = 0.0
+    for _ in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        d.copy_(h, non_blocking=True)
+        e1.record()
+        e1.synchronize()
+        best = max(best, n / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+    return best
+
+
 # ----------------------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from fastplong_b200 import synth
+    from fastplong_b200 import synth_fast
     from fastplong_b200.binding import Engine
 
     rank = int(os.environ.get("RANK", "0"))
@@ -150,60 +204,72 @@ def run_ours(args):
 
     opt = workload_options(args.workload)
     opt.device = local
-    wl_reads, wl_reps, mean_len, wl_desc = WORKLOADS[args.workload]
-    tile_reads = args.tile_reads or wl_reads
+    wl_reads, wl_reps, mean_len, gen_kw, wl_desc = WORKLOADS[args.workload]
+    tile_reads = args.reads or args.tile_reads or wl_reads
     replicas = args.replicas or wl_reps
-    # ---- synthetic workload: seeded host tile (per rank: independent shards, weak scaling) ----
-    t0 = time.time()
-    kw = {}
+    gen_kw = dict(gen_kw)
     if args.workload == "c3":
-        kw = dict(q_mean=33.0, q_sd=6.0, q_clip=60, p_polya=0.05, planted=opt.adapter_fasta[:4], p_planted=0.2)
-    tile = synth.ont_like(tile_reads, mean_len, SEED + rank, **kw)
+        gen_kw["planted"] = opt.adapter_fasta[:4]
+    # ---- synthetic workload: DISTINCT reads generated on the device (torch Philox streams; the per-read structure is
+    # drawn on the host).  Every rank draws the same read lengths and end pieces (equal work per GPU: weak scaling) and
+    # its own bases and qualities. ----
+    t0 = time.time()
+    plan = synth_fast.read_plan(tile_reads, mean_len, SEED, **{k: v for k, v in gen_kw.items() if k in
+                                                                ("p_polya", "planted", "p_planted", "min_len")})
+    tile = synth_fast.ont_like_device(tile_reads, mean_len, SEED + 1000 * rank, dev, plan=plan,
+                                      **{k: v for k, v in gen_kw.items() if k in ("q_mean", "q_sd", "q_clip")})
+    torch.cuda.synchronize()
     gen_s = time.time() - t0
     tile_bytes = tile.n_bytes - 256            # drop the tail pad: replicas are laid back to back (multiple of 128)
     n_reads = tile_reads * replicas
     n_bases = tile.n_bases * replicas
-    d_seq = torch.empty(tile_bytes * replicas + 256, dtype=torch.uint8, device=dev)
-    d_qual = torch.empty_like(d_seq)
-    h_seq = torch.from_numpy(tile.seq[:tile_bytes]).pin_memory()
-    h_qual = torch.from_numpy(tile.qual[:tile_bytes]).pin_memory()
-    t_seq = h_seq.to(dev, non_blocking=True)
-    t_qual = h_qual.to(dev, non_blocking=True)
-    for k in range(replicas):
-        d_seq[k * tile_bytes:(k + 1) * tile_bytes].copy_(t_seq)
-        d_qual[k * tile_bytes:(k + 1) * tile_bytes].copy_(t_qual)
-    d_seq[tile_bytes * replicas:].zero_()
-    d_qual[tile_bytes * replicas:].zero_()
-    offs = (torch.from_numpy(tile.offsets).to(dev)[None, :] +
-            (torch.arange(replicas, device=dev, dtype=torch.int64) * tile_bytes)[:, None]).reshape(-1).contiguous()
-    lens = torch.from_numpy(tile.lens).to(dev).repeat(replicas).contiguous()
-    del t_seq, t_qual
+    if replicas == 1:
+        d_seq, d_qual = tile.seq, tile.qual
+        offs = torch.from_numpy(tile.offsets).to(dev)
+        lens = torch.from_numpy(tile.lens).to(dev)
+    else:
+        d_seq = torch.empty(tile_bytes * replicas + 256, dtype=torch.uint8, device=dev)
+        d_qual = torch.empty_like(d_seq)
+        for k in range(replicas):
+            d_seq[k * tile_bytes:(k + 1) * tile_bytes].copy_(tile.seq[:tile_bytes])
+            d_qual[k * tile_bytes:(k + 1) * tile_bytes].copy_(tile.qual[:tile_bytes])
+        d_seq[tile_bytes * replicas:].zero_()
+        d_qual[tile_bytes * replicas:].zero_()
+        offs = (torch.from_numpy(tile.offsets).to(dev)[None, :] +
+                (torch.arange(replicas, device=dev, dtype=torch.int64) * tile_bytes)[:, None]).reshape(-1).contiguous()
+        lens = torch.from_numpy(tile.lens).to(dev).repeat(replicas).contiguous()
     torch.cuda.synchronize()
+
+    # ---- parity: the first reads of this very input, GPU library vs oracle, before anything is timed ----
+    parity = None
+    if not args.no_parity:
+        csum = np.cumsum(tile.lens.astype(np.int64))
+        n_par = int(min(tile_reads, max(16, np.searchsorted(csum, PARITY_BASES))))
+        parity = parity_check(opt, tile.to_host(0, n_par))
 
     eng = Engine(opt)
     ext = torch.cuda.ExternalStream(eng.stream_ptr, device=dev)
-    cur = torch.cuda.current_stream()
-
-    def merge_stats():
-        # the multi-GPU replacement of Stats::merge / FilterResult::merge: one NCCL all-reduce per block
-        cur.wait_stream(ext)
-        for blk in (eng.stats_device(0), eng.stats_device(1), eng.counters_device()):
-            dist.all_reduce(torch.as_tensor(blk, device=dev))
-        ext.wait_stream(cur)
-
+    merge_cycles = 0
     if world > 1:
-        # all ranks pad their Stats blocks to the same number of cycles before the first all-reduce
-        c = torch.tensor([int(tile.lens.max())], device=dev)
-        dist.all_reduce(c, op=dist.ReduceOp.MAX)
-        eng.reserve_cycles(int(c.item()))
+        # the C ABI's own communicator (ncclCommInitRank on rank 0's id); torch.distributed only carries the id
+        ident = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            ident = torch.frombuffer(bytearray(Engine.comm_unique_id()), dtype=torch.uint8).to(dev)
+        dist.broadcast(ident, 0)
+        eng.comm_init(bytes(ident.cpu().numpy().tobytes()), rank, world)
 
     def step():
         eng.reset()
         eng.process_device(d_seq.data_ptr(), d_qual.data_ptr(), offs.data_ptr(), lens.data_ptr(), n_reads,
                            d_seq.numel())
         if world > 1:
-            merge_stats()
+            # Stats::merge / FilterResult::merge: one NCCL group on the library's stream, behind the kernels
+            eng.allreduce_stats(merge_cycles)
 
+    if world > 1:
+        eng.reset()
+        eng.process_device(d_seq.data_ptr(), d_qual.data_ptr(), offs.data_ptr(), lens.data_ptr(), n_reads, d_seq.numel())
+        merge_cycles = eng.agree_cycles()      # once: every rank reduces the same [0, cycles) of every row
     for _ in range(max(args.warmup, 3)):
         step()
     eng.sync()
@@ -240,25 +306,33 @@ def run_ours(args):
     value = total_bases / (ms_per_step * 1e-3) / 1e9
 
     # ---- end to end through the C ABI with HOST buffers (pinned): H2D of the payload + D2H of the records ----
+    # the per-GPU batch arrives as E2E_SUBMISSIONS host submissions; E2E_HOST_CHUNKS distinct chunks of this run's
+    # input (1/64 of the reads each) are held in pinned memory and cycled
     from fastplong_b200 import PackedBatch
     from fastplong_b200.abi import RESULT_DTYPE
-    h_off = torch.from_numpy(tile.offsets).pin_memory()
-    h_len = torch.from_numpy(tile.lens).pin_memory()
-    h_res = torch.empty(tile_reads * RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
-    hb = PackedBatch(h_seq.numpy(), h_qual.numpy(), h_off.numpy(), h_len.numpy())
-    res_view = h_res.numpy().view(RESULT_DTYPE)
-    e2e_steps = max(1, min(args.steps, 3))
-
-    def e2e_step():
-        eng.reset()
-        for _ in range(replicas):          # the per-GPU batch arrives as `replicas` host submissions
-            eng.process(hb, out=res_view)
-        if world > 1:
-            merge_stats()
-            eng.sync()
-
-    e2e_value = None
+    e2e = None
     if not args.no_e2e:
+        per = max(1, tile_reads // E2E_SUBMISSIONS)
+        chunks = []
+        for k in range(min(E2E_HOST_CHUNKS, max(1, tile_reads // per))):
+            hb = tile.to_host(k * per, min(tile_reads, (k + 1) * per))
+            pinned = [torch.from_numpy(x).pin_memory() for x in (hb.seq, hb.qual, hb.offsets, hb.lens)]
+            res = torch.empty(hb.n_reads * RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+            chunks.append((PackedBatch(*[x.numpy() for x in pinned]), res.numpy().view(RESULT_DTYPE), pinned, res))
+        e2e_steps = max(1, min(args.steps, 3))
+        sub_bases = sum(chunks[k % len(chunks)][0].n_bases for k in range(E2E_SUBMISSIONS))
+        h2d = sum(2 * chunks[k % len(chunks)][0].n_bytes + 12 * chunks[k % len(chunks)][0].n_reads for k in range(E2E_SUBMISSIONS))
+        d2h = sum(chunks[k % len(chunks)][0].n_reads for k in range(E2E_SUBMISSIONS)) * RESULT_DTYPE.itemsize
+
+        def e2e_step():
+            eng.reset()
+            for k in range(E2E_SUBMISSIONS):
+                hb, out = chunks[k % len(chunks)][:2]
+                eng.process(hb, out=out)
+            if world > 1:
+                eng.allreduce_stats(merge_cycles)
+                eng.sync()
+
         e2e_step()
         torch.cuda.synchronize()
         if world > 1:
@@ -272,9 +346,17 @@ def run_ours(args):
             t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_s = float(t.item())
-        e2e_value = total_bases / e2e_s / 1e9
-    h2d = replicas * (2 * tile_bytes + tile_reads * 12)
-    d2h = replicas * tile_reads * RESULT_DTYPE.itemsize
+        pcie = h2d_peak_gbs(torch, dev) if world == 1 else None      # measured alone: with N ranks the links are shared
+        e2e = {"value": round(sub_bases * world / e2e_s / 1e9, 3), "unit": "Gbases/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+               "how": "fpl_process_host on pinned host buffers, %d submissions/step (%d distinct chunks of this run's reads, "
+                      "cycled); inside a call the upload runs in 16 MiB pieces on a copy stream and the kernels of a piece "
+                      "start when it has arrived" % (E2E_SUBMISSIONS, len(chunks)),
+               "achieved_pcie_gbs": round((h2d + d2h) / e2e_s / 1e9, 2)}
+        if pcie:
+            e2e["roofline"] = {"bound": "pcie h2d", "peak": round(pcie, 2), "unit": "GB/s",
+                               "frac": round((h2d + d2h) / e2e_s / 1e9 / pcie, 4),
+                               "peak_source": "measured here: 1 GiB pinned host -> device copy, best of 4, CUDA events"}
 
     # ---- roofline of the dominant kernel (largest share of the step's device time) ----
     peak, peak_src = peaks()
@@ -288,7 +370,8 @@ def run_ours(args):
         kern[name] = {"ms_per_step": round(per_step_ms, 4), "share": round(kms / tot_kernel_ms, 4),
                       "launches_per_step": cnt // args.steps,
                       "achieved_gbs": round(alg_bytes_step / (per_step_ms * 1e-3) / 1e9, 1) if per_step_ms > 0 else None}
-    dom = max(kern, key=lambda k: kern[k]["ms_per_step"]) if kern else None
+    ours = {k: v for k, v in kern.items() if not k.startswith("nccl")}
+    dom = max(ours, key=lambda k: ours[k]["ms_per_step"]) if ours else None
     traffic = None
     secondary = None      # the integer-pipe roofline, reported where it binds (from the committed ncu capture)
     tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -301,8 +384,8 @@ def run_ours(args):
                 if "alu_pipe_active_pct" in tj[dom]:
                     secondary = {"bound": "integer logic pipe (LOP3/SHF/PRMT issue slots)",
                                  "frac": round(tj[dom]["alu_pipe_active_pct"] / 100.0, 4),
-                                 "source": "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active, ncu --set full capture "
-                                           "summarised in profiles/r01_ncu_full_summary.txt (not measured live)"}
+                                 "fma_pipe_frac": round(tj[dom].get("fma_pipe_active_pct", 0) / 100.0, 4),
+                                 "source": tj[dom].get("source", "ncu --set full capture under profiles/ (not measured live)")}
         except Exception:
             traffic = None
             secondary = None
@@ -313,7 +396,14 @@ def run_ours(args):
         roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                     "alg_bytes_per_launch": alg_bytes_step / nl, "avg_launch_ms": round(kern[dom]["ms_per_step"] / nl, 5),
-                    "launches_per_step": nl, "secondary": secondary}
+                    "launches_per_step": nl, "secondary": secondary,
+                    "whole_path": {"achieved": round(alg_bytes_step / (ms_per_step * 1e-3) / 1e9, 1),
+                                   "frac": round(alg_bytes_step / (ms_per_step * 1e-3) / 1e9 / peak, 4),
+                                   "note": "one pass of algorithmic bytes over the whole step (the path makes several passes)"}}
+        if "k_scan" in kern and dom != "k_scan":
+            a = kern["k_scan"]["achieved_gbs"]
+            roofline["adapter_quality_kernel"] = {"kernel": "k_scan", "achieved": a, "frac": round(a / peak, 4),
+                                                  "avg_launch_ms": kern["k_scan"]["ms_per_step"]}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -331,17 +421,20 @@ def run_ours(args):
         "dtype": "u8", "data": "synthetic",
         "config": {"workload": wl_desc,
                    "reads_per_gpu": n_reads, "bases_per_gpu": n_bases, "mean_len": mean_len,
-                   "tile": f"{tile_reads} seeded reads x {replicas} replicas in HBM",
+                   "input": (f"{tile_reads} distinct reads generated on the device (fastplong_b200/synth_fast.py, seeded; torch "
+                             "Philox streams for bases and qualities)" +
+                             (f", replicated {replicas}x in HBM" if replicas > 1 else "")),
                    "adapters": "as auto-detected by the reference evaluator on this generator (30 bp start + revcomp end)",
                    "l2": "inputs (2 x %.1f GB) larger than L2; no flush needed" % (d_seq.numel() / 1e9),
-                   "parallelism": f"reads sharded over {world} GPU(s), NCCL all-reduce of Stats/FilterResult blocks"
+                   "parallelism": f"reads sharded over {world} GPU(s), equal bases per GPU; Stats/FilterResult merged by one NCCL "
+                                  "all-reduce group per step issued by the C ABI (fpl_allreduce_stats) on the library's stream"
                    if world > 1 else "single GPU", "read_tiling": (os.environ.get("FPL_TILE_MBASES") + " Mbases") if os.environ.get("FPL_TILE_MBASES") else "none (every kernel streams the whole batch)",
-                   "host_tile_gen_s": round(gen_s, 1)},
+                   "input_gen_s": round(gen_s, 1)},
+        "parity_checked": parity is not None, "parity": parity,
         "clocks": clocks,
-        "e2e": None if e2e_value is None else {"value": round(e2e_value, 3), "unit": "Gbases/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "how": "fpl_process_host on pinned host buffers, %d submissions/step; inside a call the upload runs in 16 MiB pieces "
-                       "on a copy stream and the kernels of a piece start when it has arrived" % replicas},
+        "e2e": e2e,
         "gpu_launches": int(launches),
+        "collective_ms": kern.get("nccl_allreduce(stats)", {}).get("ms_per_step") if world > 1 else None,
         "roofline": roofline, "kernels": kern, "cpu_baseline": cpu_baseline,
     }
     emit(line)
@@ -364,7 +457,8 @@ def reference_cpu_run(sample_reads, repeats):
     if fq in _SAMPLE_CACHE:
         n_bases = _SAMPLE_CACHE[fq]
     else:
-        batch = synth.ont_like(sample_reads, MEAN_LEN, SEED)
+        from fastplong_b200 import synth_fast
+        batch = synth_fast.ont_like_fast(sample_reads, MEAN_LEN, SEED)      # the generator of the GPU arm, on the CPU
         synth.to_fastq(batch, fq)
         n_bases = _SAMPLE_CACHE[fq] = batch.n_bases
         import atexit
@@ -472,9 +566,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS),
-                    help="c2 = BASELINE configs[1] (the bench line); c3/c5 = other BASELINE config shapes, informational")
-    ap.add_argument("--tile-reads", type=int, default=0)
-    ap.add_argument("--replicas", type=int, default=0)
+                    help="c2 = BASELINE configs[1] (the bench line); the others = the remaining BASELINE config shapes")
+    ap.add_argument("--reads", type=int, default=0, help="distinct reads per GPU (default: the workload's)")
+    ap.add_argument("--tile-reads", type=int, default=0, help="alias of --reads (profiling: a small tile ...)")
+    ap.add_argument("--replicas", type=int, default=0, help="... replicated this many times in HBM")
+    ap.add_argument("--no-parity", action="store_true", help="profiling aid: skip the oracle comparison of the first reads")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling aid: skip the end-to-end leg (keeps an ncu launch list short)")
     args = ap.parse_args()

@@ -117,6 +117,8 @@ class Engine:
     def process(self, batch, out=None):
         """Host batch (numpy / pinned buffers) -> per-read records (numpy structured array)."""
         res = out if out is not None else np.zeros(batch.n_reads, dtype=RESULT_DTYPE)
+        if res.shape[0] < batch.n_reads or res.dtype != RESULT_DTYPE:
+            raise FplError(f"process: `out` holds {res.shape[0]} records, the batch has {batch.n_reads} reads")
         b = batch.to_abi()
         self._check(self.lib.fpl_process_host(self.h, C.byref(b), res.ctypes.data))
         return res

@@ -53,10 +53,11 @@ static int fail(const char* fmt, ...) {
         if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-enum { K_PRESEG, K_CYCLE_PRE, K_QUAL_PRE, K_TRIM, K_SCAN, K_FINAL, K_COUNT, K_CYCLE_POST, K_QUAL_POST, K_KMER_FIX, K_NKERNELS };
+enum { K_PRESEG, K_CYCLE_PRE, K_QUAL_PRE, K_TRIM, K_SCAN, K_FINAL, K_COUNT, K_CYCLE_POST, K_QUAL_POST, K_KMER_FIX, K_ALLREDUCE, K_NKERNELS };
 static const char* const kKernelNames[K_NKERNELS] = {"k_make_preseg", "k_cycle_stats(pre)", "k_read_qual(pre+post)",
                                                      "k_trim", "k_scan", "k_final", "k_count",
-                                                     "k_cycle_stats(post)", "k_read_qual(post)", "k_kmer_fix"};
+                                                     "k_cycle_stats(post)", "k_read_qual(post)", "k_kmer_fix",
+                                                     "nccl_allreduce(stats)"};
 
 struct fpl_ctx {
     int device = 0;
@@ -164,12 +165,12 @@ static cudaEvent_t get_event(fpl_ctx* c) {
 }
 
 struct Timed {
-    fpl_ctx* c; int k; cudaEvent_t a = nullptr, b = nullptr;
-    Timed(fpl_ctx* c_, int k_) : c(c_), k(k_) {
+    fpl_ctx* c; int k; bool ours; cudaEvent_t a = nullptr, b = nullptr;
+    Timed(fpl_ctx* c_, int k_, bool ours_ = true) : c(c_), k(k_), ours(ours_) {   // ours = false: a library kernel (NCCL), timed but not counted
         if (c->timing) { a = get_event(c); b = get_event(c); cudaEventRecord(a, c->stream); }
     }
     ~Timed() {
-        c->launches++;
+        if (ours) c->launches++;
         if (c->timing) { cudaEventRecord(b, c->stream); c->events.push_back({k, a, b}); }
     }
 };
@@ -839,6 +840,7 @@ int fpl_allreduce_stats(fpl_ctx* c, int64_t cycles) {
                                              (long long)cycles, (long long)c->used_cycles);
     // rows [b*C, b*C + cycles) of the 16 per-cycle arrays, then the tail; the row pointers depend on this rank's C, the
     // counts do not, so ranks need not share a capacity.  One group = one fused launch.
+    Timed t(c, K_ALLREDUCE, false);
     CKN(nccl().GroupStart());
     for (int w = 0; w < 2; w++) {
         unsigned long long* blk = c->d_stats[w];

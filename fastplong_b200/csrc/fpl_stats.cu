@@ -112,6 +112,26 @@ __device__ __forceinline__ void count16(const uint32_t (&wm)[4], const uint32_t 
     count1<S, 12>(wm, qm, cw, pk); count1<S, 13>(wm, qm, cw, pk); count1<S, 14>(wm, qm, cw, pk); count1<S, 15>(wm, qm, cw, pk);
 }
 
+// The same for a vector whose 16 bytes all count (warp-uniform fast path): both operands of the reduction come from
+// the FMA pipe, which issues beside the logic pipe (tools/ubench_pipes.cu: LOP3 + IDP.4A together run at 0.94
+// warp-instructions per clock and sub-partition, LOP3 alone at 0.48).  wb: (base & 7) << 4 in every byte, so that
+// one dp4a with the weight 136 on byte J is bin * CS_BINW * 4 (+ the lane's base address); qm: quality chars.
+template <int S, int J>
+__device__ __forceinline__ void count1f(const uint32_t (&wb)[4], const uint32_t (&qm)[4], uint32_t pk_lane) {
+    constexpr int jj = J & 3, m = J + S;
+    static_assert(CS_BINW * 4 == 136 * 16, "dp4a weight of the bin stride");
+    const uint32_t addr = __dp4a(wb[J >> 2], 136u << (8 * jj), pk_lane);
+    const uint32_t val = __dp4a(qm[J >> 2], 1u << (8 * jj), 1u << 20);
+    red_shared_add_imm<4 * ((m & 15) * CS_ROWW + (m >> 4))>(addr, val);
+}
+template <int S>
+__device__ __forceinline__ void count16f(const uint32_t (&wb)[4], const uint32_t (&qm)[4], uint32_t pk) {
+    count1f<S, 0>(wb, qm, pk); count1f<S, 1>(wb, qm, pk); count1f<S, 2>(wb, qm, pk); count1f<S, 3>(wb, qm, pk);
+    count1f<S, 4>(wb, qm, pk); count1f<S, 5>(wb, qm, pk); count1f<S, 6>(wb, qm, pk); count1f<S, 7>(wb, qm, pk);
+    count1f<S, 8>(wb, qm, pk); count1f<S, 9>(wb, qm, pk); count1f<S, 10>(wb, qm, pk); count1f<S, 11>(wb, qm, pk);
+    count1f<S, 12>(wb, qm, pk); count1f<S, 13>(wb, qm, pk); count1f<S, 14>(wb, qm, pk); count1f<S, 15>(wb, qm, pk);
+}
+
 // 0xFF in byte k of the result iff bit k of the nibble n
 __device__ __forceinline__ uint32_t nibble_to_bytes(uint32_t n) { return ((n * 0x00204081u) & 0x01010101u) * 0xFFu; }
 
@@ -123,6 +143,25 @@ __device__ __forceinline__ void kmer1(uint32_t P, uint32_t ok, uint32_t km_lane)
     // shifts as mul.hi were measured too: IMAD.HI is slow on this part — 13.7 ms against 11.4 ms for the kernel.)
     const uint32_t idx = (SHL ? mad_u32(P, 1u << SHL, 0u) : P) >> 22;
     red_shared_add(mad_u32(idx, 128u, km_lane), mad_u32(ok, 1u << (31 - T), 0u) >> 31);
+}
+
+// the same when the 5-mer is known to count: the value is the immediate 1
+template <int SHL>
+__device__ __forceinline__ void kmer1f(uint32_t P, uint32_t km_lane) {
+    const uint32_t idx = (SHL ? mad_u32(P, 1u << SHL, 0u) : P) >> 22;
+    red_shared_add(mad_u32(idx, 128u, km_lane), 1u);
+}
+
+// Per 4 bytes of sequence: in7 = (nibble of "byte is not one of A, C, G, T, U") << 7, exact for any byte value, and
+// pc = four 2-bit codes c' = (b >> 1) & 3, oldest first.  g = b2 & ~b1 (set for T/U); with bit 7 and bits 2..1 masked
+// off, a valid byte is 0x41 (A, C, G) or, with g, 0x51 (T, U): d == 0.  d < 0x80, so d + 0x7f sets bit 7 iff d != 0 and
+// cannot carry into the next byte; the byte's own bit 7 is or-ed in by the same LOP3.  The two gathers are dp4a.
+__device__ __forceinline__ void encode4(uint32_t w, uint32_t one, uint32_t& nz, uint32_t& pc) {
+    const uint32_t x1 = w >> 1;
+    const uint32_t g = (x1 >> 1) & ~x1 & 0x01010101u;
+    const uint32_t d = ((w & 0x79797979u) | g) ^ 0x41414141u ^ mad_u32(g, 16u, 0u);
+    nz = (mad_u32(d, one, 0x7f7f7f7fu) | w) & 0x80808080u;
+    pc = __dp4a(x1 & 0x03030303u, 0x01041040u, 0u);
 }
 
 }  // namespace
@@ -151,7 +190,8 @@ struct __align__(16) TileSeg {
 template <bool DO_KMER, int NT, int DEPTH>
 __global__ void __launch_bounds__(NT, DO_KMER ? 1 : 2048 / NT / 2)
 k_cycle_stats(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qualbuf, const SegD* __restrict__ segs,
-              int64_t nseg, unsigned long long* __restrict__ stats, int64_t C, unsigned long long* __restrict__ kmer_also) {
+              int64_t nseg, unsigned long long* __restrict__ stats, int64_t C, unsigned long long* __restrict__ kmer_also,
+              uint32_t one) {
     extern __shared__ __align__(16) uint8_t cs_smem[];
     uint32_t* packed = reinterpret_cast<uint32_t*>(cs_smem);                       // [8][16][33]: count << 20 | sum of q
     TileSeg* stage = reinterpret_cast<TileSeg*>(cs_smem + 8 * CS_BINW * 4);
@@ -228,10 +268,34 @@ k_cycle_stats(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qu
             slot = slot == DEPTH ? 0 : slot + 1;
             fill = fill == DEPTH ? 0 : fill + 1;
             if (lim <= 0) continue;                        // warp-uniform: the segment ends in front of this tile
-            // which of the lane's 16 bytes are cycles of the segment (vmask) and can end a 5-mer (kmask: cycle >= 4)
-            uint32_t cw[4] = {0x10101010u, 0x10101010u, 0x10101010u, 0x10101010u};
+            const bool full = lim >= CS_TILE && t0 != 0;   // warp-uniform: every byte of every lane is a cycle >= 4
             uint32_t kmask = 0xFFFFu;
-            if (lim < CS_TILE || t0 == 0) {                // warp-uniform: the segment starts or ends in this tile
+            if (full) {
+                // ---- per-(bin, cycle) counters, all 16 bytes of every lane: address and value by dp4a ----
+                const uint32_t wb[4] = {mad_u32(sw[0], 16u, 0u) & 0x70707070u, mad_u32(sw[1], 16u, 0u) & 0x70707070u,
+                                        mad_u32(sw[2], 16u, 0u) & 0x70707070u, mad_u32(sw[3], 16u, 0u) & 0x70707070u};
+                switch (sh) {
+                    case 0: count16f<15>(wb, qm, pk_lane); break;
+                    case 1: count16f<14>(wb, qm, pk_lane); break;
+                    case 2: count16f<13>(wb, qm, pk_lane); break;
+                    case 3: count16f<12>(wb, qm, pk_lane); break;
+                    case 4: count16f<11>(wb, qm, pk_lane); break;
+                    case 5: count16f<10>(wb, qm, pk_lane); break;
+                    case 6: count16f<9>(wb, qm, pk_lane); break;
+                    case 7: count16f<8>(wb, qm, pk_lane); break;
+                    case 8: count16f<7>(wb, qm, pk_lane); break;
+                    case 9: count16f<6>(wb, qm, pk_lane); break;
+                    case 10: count16f<5>(wb, qm, pk_lane); break;
+                    case 11: count16f<4>(wb, qm, pk_lane); break;
+                    case 12: count16f<3>(wb, qm, pk_lane); break;
+                    case 13: count16f<2>(wb, qm, pk_lane); break;
+                    case 14: count16f<1>(wb, qm, pk_lane); break;
+                    default: count16f<0>(wb, qm, pk_lane); break;
+                }
+            } else {
+                // the segment starts or ends in this tile: which of the lane's 16 bytes are cycles of the segment (vmask)
+                // and can end a 5-mer (kmask: cycle >= 4)
+                uint32_t cw[4] = {0x10101010u, 0x10101010u, 0x10101010u, 0x10101010u};
                 const int cyc0 = (int)t0 + 16 * lane - sh;                          // cycle of byte 0, negative in front
                 const int lo = max(0, -cyc0), hi = min(16, max(0, lim - 16 * lane));
                 const uint32_t vmask = hi > lo ? ((0xFFFFu >> (16 - hi)) & (0xFFFFu << lo)) : 0u;
@@ -244,9 +308,6 @@ k_cycle_stats(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qu
                         qm[i] &= bm; cw[i] &= bm;
                     }
                 }
-            }
-            // ---- per-(bin, cycle) counters ----
-            {
                 const uint32_t wm[4] = {sw[0] & 0x07070707u, sw[1] & 0x07070707u, sw[2] & 0x07070707u, sw[3] & 0x07070707u};
                 switch (sh) {
                     case 0: count16<15>(wm, qm, cw, pk_lane); break;
@@ -269,32 +330,53 @@ k_cycle_stats(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qu
             }
             if (!DO_KMER) continue;
             // ---- 5-mers ending in this lane's 16 bytes: all five bases in ACGTU, end cycle in [4, len) ----
-            // per word: invalidity nibble and four 2-bit codes c' = (b >> 1) & 3 (A=0, C=1, T/U=2, G=3; the flush maps them
-            // to base2val's); the previous lane's last word supplies the four bases in front of this lane's vector
+            // per word: the "not ACGTU" flags and four 2-bit codes c' = (b >> 1) & 3 (A=0, C=1, T/U=2, G=3; the flush maps
+            // them to base2val's); the previous lane's last word supplies the four bases in front of this lane's vector
             // (lane 0: the word loaded in front of the tile)
-            uint32_t in[4], pc[4];
+            uint32_t nz[4], pc[4];
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const uint32_t x1 = sw[i] >> 1;
-                in[i] = (invalid_acgtu(sw[i], x1) * 0x00204081u) >> 28;
-                pc[i] = ((x1 & 0x03030303u) * 0x40100401u) >> 24;
-            }
-            uint32_t pin = __shfl_up_sync(0xffffffffu, in[3], 1), ppc = __shfl_up_sync(0xffffffffu, pc[3], 1);
+            for (int i = 0; i < 4; i++) encode4(sw[i], one, nz[i], pc[i]);
+            // flags << 7: bit 7+t = byte t-4 of the 20 bytes (previous four, then the lane's sixteen)
+            uint32_t pin7 = __shfl_up_sync(0xffffffffu, __dp4a(nz[3], 0x08040201u, 0u), 1), ppc = __shfl_up_sync(0xffffffffu, pc[3], 1);
             if (lane == 0) {
-                const uint32_t x1 = prev0 >> 1;
-                pin = (invalid_acgtu(prev0, x1) * 0x00204081u) >> 28;
-                ppc = ((x1 & 0x03030303u) * 0x40100401u) >> 24;
+                uint32_t pnz;
+                encode4(prev0, one, pnz, ppc);
+                pin7 = __dp4a(pnz, 0x08040201u, 0u);
             }
-            const uint32_t I20 = mad_u32(in[3], 65536u, mad_u32(in[2], 4096u, mad_u32(in[1], 256u, mad_u32(in[0], 16u, pin))));
-            const uint32_t bad = I20 | (I20 >> 1) | (I20 >> 2) | (I20 >> 3) | (I20 >> 4);   // bit t: a byte of t-4..t is invalid
-            const uint32_t ok = ~bad & kmask;
+            const uint32_t in01 = __dp4a(nz[0], 0x08040201u, __dp4a(nz[1], 0x80402010u, 0u));
+            const uint32_t in23 = __dp4a(nz[2], 0x08040201u, __dp4a(nz[3], 0x80402010u, 0u));
+            const uint32_t I27 = mad_u32(in23, 4096u, mad_u32(in01, 16u, pin7));     // 20 flags at bits 7..26
             // 20 codes, oldest first, 2 bits each: Phi = codes of bytes -4..11 (32 bits), Plo = bytes 4..15, then 8 zero bits
             const uint32_t Phi = mad_u32(ppc, 1u << 24, mad_u32(pc[0], 1u << 16, mad_u32(pc[1], 256u, pc[2])));
             const uint32_t Plo = mad_u32(pc[1], 1u << 24, mad_u32(pc[2], 1u << 16, pc[3] * 256u));
-            kmer1<0, 0>(Phi, ok, km_lane); kmer1<2, 1>(Phi, ok, km_lane); kmer1<4, 2>(Phi, ok, km_lane); kmer1<6, 3>(Phi, ok, km_lane);
-            kmer1<8, 4>(Phi, ok, km_lane); kmer1<10, 5>(Phi, ok, km_lane); kmer1<12, 6>(Phi, ok, km_lane); kmer1<14, 7>(Phi, ok, km_lane);
-            kmer1<16, 8>(Phi, ok, km_lane); kmer1<18, 9>(Phi, ok, km_lane); kmer1<20, 10>(Phi, ok, km_lane); kmer1<22, 11>(Phi, ok, km_lane);
-            kmer1<8, 12>(Plo, ok, km_lane); kmer1<10, 13>(Plo, ok, km_lane); kmer1<12, 14>(Plo, ok, km_lane); kmer1<14, 15>(Plo, ok, km_lane);
+            if (full) {
+                // every 5-mer is counted with the immediate 1 ...
+                kmer1f<0>(Phi, km_lane); kmer1f<2>(Phi, km_lane); kmer1f<4>(Phi, km_lane); kmer1f<6>(Phi, km_lane);
+                kmer1f<8>(Phi, km_lane); kmer1f<10>(Phi, km_lane); kmer1f<12>(Phi, km_lane); kmer1f<14>(Phi, km_lane);
+                kmer1f<16>(Phi, km_lane); kmer1f<18>(Phi, km_lane); kmer1f<20>(Phi, km_lane); kmer1f<22>(Phi, km_lane);
+                kmer1f<8>(Plo, km_lane); kmer1f<10>(Plo, km_lane); kmer1f<12>(Plo, km_lane); kmer1f<14>(Plo, km_lane);
+                // ... and the rare ones that contain a byte outside ACGTU are taken out again (an N costs its lane five
+                // extra reductions; nothing here runs for a vector of plain bases)
+                if (I27 & 0x07FFFF80u) {
+                    const uint32_t I20 = I27 >> 7;
+                    uint32_t bad = (I20 | (I20 >> 1) | (I20 >> 2) | (I20 >> 3) | (I20 >> 4)) & 0xFFFFu;   // bit t: a byte of t-4..t is invalid
+                    const unsigned long long Pall = ((unsigned long long)Phi << 8) | (Plo >> 8 & 0xFFu);   // 20 codes, the newest in bits 1..0
+                    while (bad) {
+                        const int t = __ffs(bad) - 1;
+                        bad &= bad - 1;
+                        const uint32_t idx = (uint32_t)(Pall >> (2 * (15 - t))) & 1023u;
+                        red_shared_add(km_lane + idx * 128u, 0xFFFFFFFFu);
+                    }
+                }
+            } else {
+                const uint32_t I20 = I27 >> 7;
+                const uint32_t bad = I20 | (I20 >> 1) | (I20 >> 2) | (I20 >> 3) | (I20 >> 4);   // bit t: a byte of t-4..t is invalid
+                const uint32_t ok = ~bad & kmask;
+                kmer1<0, 0>(Phi, ok, km_lane); kmer1<2, 1>(Phi, ok, km_lane); kmer1<4, 2>(Phi, ok, km_lane); kmer1<6, 3>(Phi, ok, km_lane);
+                kmer1<8, 4>(Phi, ok, km_lane); kmer1<10, 5>(Phi, ok, km_lane); kmer1<12, 6>(Phi, ok, km_lane); kmer1<14, 7>(Phi, ok, km_lane);
+                kmer1<16, 8>(Phi, ok, km_lane); kmer1<18, 9>(Phi, ok, km_lane); kmer1<20, 10>(Phi, ok, km_lane); kmer1<22, 11>(Phi, ok, km_lane);
+                kmer1<8, 12>(Plo, ok, km_lane); kmer1<10, 13>(Plo, ok, km_lane); kmer1<12, 14>(Plo, ok, km_lane); kmer1<14, 15>(Plo, ok, km_lane);
+            }
         }
         if (n < CS_STAGE) break;     // the rest of the group is shorter still
     }
@@ -398,8 +480,8 @@ int launch_cycle_stats(CycleWs* ws, const uint8_t* seq, const uint8_t* qual, con
     k_cs_gather<<<blocks, 256, 0, stream>>>(segs, ws->k_out, ws->v_out, nseg, static_cast<SegD*>(ws->sorted));
     dim3 grid((unsigned)((max_len + 15 + CS_TILE - 1) / CS_TILE), (unsigned)((nseg + CS_GROUP - 1) / CS_GROUP));
     const SegD* sorted = static_cast<const SegD*>(ws->sorted);
-    if (do_kmer) k_cycle_stats<true, CS_NT_KMER, CS_DEPTH_KMER><<<grid, CS_NT_KMER, CS_SMEM_KMER, stream>>>(seq, qual, sorted, nseg, stats, C, kmer_also);
-    else k_cycle_stats<false, CS_NT_PLAIN, CS_DEPTH_PLAIN><<<grid, CS_NT_PLAIN, CS_SMEM_PLAIN, stream>>>(seq, qual, sorted, nseg, stats, C, nullptr);
+    if (do_kmer) k_cycle_stats<true, CS_NT_KMER, CS_DEPTH_KMER><<<grid, CS_NT_KMER, CS_SMEM_KMER, stream>>>(seq, qual, sorted, nseg, stats, C, kmer_also, 1u);
+    else k_cycle_stats<false, CS_NT_PLAIN, CS_DEPTH_PLAIN><<<grid, CS_NT_PLAIN, CS_SMEM_PLAIN, stream>>>(seq, qual, sorted, nseg, stats, C, nullptr, 1u);
     return 0;
 }
 

@@ -301,6 +301,102 @@ __device__ int trim_end(const DevParams& P, const uint8_t* seq, Win& w, int aidx
     return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Pre-filter for trimByMultiSequences (src/adaptertrimmer.cpp:42-57) with many FASTA adapters (BASELINE configs[2]: 64).
+// For every adapter the reference runs trimBySequenceStart and trimBySequenceEnd: a Hamming search of the 200-base end
+// window plus one Levenshtein verification, then up to 184 sixteen-mer Levenshtein probes — and on a read without that
+// adapter all of it finds nothing.  "Finds nothing" is decided here for 32 (adapter, side) pairs at a time, one per lane,
+// by two approximate-matching passes of Myers' bit-vector algorithm in SEARCH mode over the window (text = the window,
+// free start): sg(e) = min over s of ED(window[s..e], pattern) is a lower bound of the distance of EVERY alignment the
+// exact code evaluates that ends at e — ED(read[p..p+alen), adapter) in searchAdapter, which also bounds the Hamming
+// distance from below, and ED(read[p..p+16), 16-mer) in the probe loops.  If sg never reaches thr(alen) for the whole
+// adapter nor thr(16) for the probe 16-mer, neither stage can return a hit and the pair is skipped; otherwise the exact
+// code runs as before.  The filter only ever says "maybe" too often, never "no" wrongly: results are unchanged.
+// ------------------------------------------------------------------------------------------------------------------
+#define PF_WIN FPL_WINDOW
+
+template <typename W>
+struct SearchMyers {                      // pattern in the low m bits; standard Myers/Hyyro search recurrence
+    W VP, VN, top;
+    int score, best;
+    __device__ __forceinline__ void init(int m) {
+        VP = m >= (int)(8 * sizeof(W)) ? ~(W)0 : (((W)1 << m) - 1);
+        VN = 0; top = (W)1 << (m - 1); score = m; best = m;
+    }
+    __device__ __forceinline__ void column(W Eq) {
+        const W Xv = Eq | VN;
+        const W Xh = (((Eq & VP) + VP) ^ VP) | Eq;
+        W HP = VN | ~(Xh | VP);
+        W HN = VP & Xh;
+        score += (HP & top) ? 1 : 0;
+        score -= (HN & top) ? 1 : 0;
+        HP <<= 1; HN <<= 1;                // search mode: the horizontal delta entering row 0 is 0
+        VP = HN | ~(Xv | HP);
+        VN = HP & Xv;
+        best = min(best, score);
+    }
+};
+
+// maybe-bits of the (adapter, side) items [first_item, 2 * (n_adapters - 2)) for the window w: item = 2 * (k - 2) + side.
+// head / tail: the warp's staging buffers (PF_WIN bytes each); bits: one bit per item.  All 32 lanes.
+template <typename W>
+__device__ void prefilter_round(const DevParams& P, const uint8_t* head, const uint8_t* tail, int hw, int base, int nitems,
+                                uint32_t* bits) {
+    const int lane = lane_id();
+    const int item = base + lane;
+    const bool active = item < nitems;
+    const int k = 2 + (active ? item : 0) / 2, side = item & 1;
+    const int alen = active ? P.alen[k] : 1;
+    const bool filterable = active && alen >= 1 && alen <= (int)(8 * sizeof(W));
+    const int plen = min(FPL_PATTERN_LEN, alen);
+    const uint4* peq = P.peq + (size_t)k * 256;
+    auto eq_of = [&](uint32_t ch) -> W {
+        const uint4 v = __ldg(&peq[ch]);
+        if (sizeof(W) == 8) return (W)(((unsigned long long)v.y << 32) | v.x);
+        return (W)v.x;
+    };
+    W eA = 0, eC = 0, eG = 0, eT = 0;
+    if (filterable) { eA = eq_of('A'); eC = eq_of('C'); eG = eq_of('G'); eT = eq_of('T'); }
+    // the probe pattern: the adapter's LAST plen chars on the start side, its FIRST plen chars on the end side
+    const int sh16 = side == 0 ? alen - plen : 0;
+    const uint32_t m16 = plen >= 32 ? 0xFFFFFFFFu : ((1u << plen) - 1u);
+    SearchMyers<W> F;
+    SearchMyers<uint32_t> Q;
+    F.init(max(alen, 1)); Q.init(max(plen, 1));
+    const uint8_t* text = side == 0 ? head : tail;
+    for (int j = 0; j < hw; j++) {
+        const uint32_t b = text[j];
+        const uint32_t code = (b >> 1) & 3u;                 // A 0, C 1, T 2, G 3 — for exact A/C/G/T bytes
+        W Eq;
+        if (is_acgt(b)) Eq = code == 0 ? eA : code == 1 ? eC : code == 2 ? eT : eG;
+        else Eq = filterable ? eq_of(b) : 0;                 // N, lower case, IUPAC: the table knows
+        F.column(Eq);
+        Q.column((uint32_t)(Eq >> sh16) & m16);
+    }
+    const bool maybe = active && (!filterable || F.best <= P.thr[alen] || Q.best <= P.thr[plen]);
+    const uint32_t mask = __ballot_sync(0xffffffffu, maybe);
+    if (lane == 0) bits[base >> 5] = mask;
+}
+
+__device__ void prefilter(const DevParams& P, const uint8_t* seq, const Win& w, int first_item, uint8_t* head, uint8_t* tail,
+                          uint32_t* bits) {
+    const int lane = lane_id();
+    const int nitems = 2 * (P.n_adapters - 2);
+    const int hw = min(w.len, PF_WIN);
+    __syncwarp();
+    for (int j = lane; j < hw; j += 32) { head[j] = seq[w.lo + j]; tail[j] = seq[w.lo + w.len - hw + j]; }
+    __syncwarp();
+    for (int base = first_item & ~31; base < nitems; base += 32) {
+        // one width per round: 64-bit vectors only if an adapter of this round needs them
+        const int it = base + lane;
+        const bool wide = __any_sync(0xffffffffu, it < nitems && P.alen[2 + (it < nitems ? it : 0) / 2] > 32);
+        if (wide) prefilter_round<unsigned long long>(P, head, tail, hw, base, nitems, bits);
+        else prefilter_round<uint32_t>(P, head, tail, hw, base, nitems, bits);
+    }
+    __syncwarp();
+}
+
 // first s in [s_lo, s_hi) whose w-wide quality window sum reaches `need`; s_hi if none (filter.cpp:171-181)
 __device__ int first_good_window_fwd(const uint8_t* qual, int s_lo, int s_hi, int w, int need) {
     const int lane = lane_id();
@@ -438,6 +534,8 @@ __global__ void __launch_bounds__(TRIM_WARPS * 32)
 k_trim(const __grid_constant__ DevParams P, DevBatch b, ReadState* __restrict__ st, fpl_read_result* __restrict__ res,
        unsigned long long* __restrict__ counters) {
     __shared__ __align__(16) uint8_t scratch_all[TRIM_WARPS][208];   // probe distances / packed window (36 words)
+    __shared__ __align__(16) uint8_t pf_win[TRIM_WARPS][2][PF_WIN + 8];     // many-adapter pre-filter: end windows ...
+    __shared__ uint32_t pf_bits[TRIM_WARPS][(2 * FPL_MAX_ADAPTERS + 31) / 32];   // ... and its maybe-bits
     const int wid = threadIdx.x >> 5, lane = lane_id();
     const int64_t r = (int64_t)blockIdx.x * TRIM_WARPS + wid;
     if (r >= b.n_reads) return;
@@ -461,9 +559,25 @@ k_trim(const __grid_constant__ DevParams P, DevBatch b, ReadState* __restrict__ 
     if (alive && P.opt.adapter_enabled) {
         if (P.alen[0] > 0) trimmed += trim_start(P, seq, w, 0, ev, scratch);
         if (P.alen[1] > 0) trimmed += trim_end(P, seq, w, 1, ev, scratch);
-        for (int k = 2; k < P.n_adapters; k++) {
-            trimmed += trim_start(P, seq, w, k, ev, scratch);
-            trimmed += trim_end(P, seq, w, k, ev, scratch);
+        if (P.n_adapters > 2) {
+            // FASTA adapters in order, each on the read as the previous ones left it; pairs the pre-filter rules out are
+            // skipped, and a trim (which moves the end windows) re-filters what is still to come
+            uint32_t* bits = pf_bits[wid];
+            const bool use_pf = P.n_adapters > 4 && w.len >= FPL_PATTERN_LEN;
+            if (use_pf) prefilter(P, seq, w, 0, pf_win[wid][0], pf_win[wid][1], bits);
+            for (int k = 2; k < P.n_adapters; k++) {
+                const int i0 = 2 * (k - 2);
+                if (!use_pf || (bits[i0 >> 5] >> (i0 & 31) & 1u)) {
+                    const int t = trim_start(P, seq, w, k, ev, scratch);
+                    trimmed += t;
+                    if (t && use_pf) prefilter(P, seq, w, i0 + 1, pf_win[wid][0], pf_win[wid][1], bits);
+                }
+                if (!use_pf || (bits[(i0 + 1) >> 5] >> ((i0 + 1) & 31) & 1u)) {
+                    const int t = trim_end(P, seq, w, k, ev, scratch);
+                    trimmed += t;
+                    if (t && use_pf && k + 1 < P.n_adapters) prefilter(P, seq, w, i0 + 2, pf_win[wid][0], pf_win[wid][1], bits);
+                }
+            }
         }
     }
     if (lane == 0) {

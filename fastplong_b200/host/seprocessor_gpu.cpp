@@ -325,11 +325,38 @@ size_t recordBoundary(const uint8_t* buf, size_t n) {
     return 0;
 }
 
+// The device parser takes the strict layout only (LF line ends, four lines per record); everything else the reference
+// accepts — CR or CRLF line ends, blank or stray lines between records, a truncated last record
+// (FastqReader::getLine / read, src/fastqreader.cpp:219-347) — goes through the reference's own reader.  This looks at
+// the head and the tail of the file so that such a file is routed there before any work is done; a deviation in the
+// middle of a file is caught later (the raw-text run is then abandoned and restarted, see process()).
+bool looksStrict(const std::string& path) {
+    FILE* fp = fopen(path.c_str(), "rb");
+    if (!fp) return false;
+    const size_t kHead = 1u << 20, kTail = 1u << 16;
+    std::vector<unsigned char> buf(kHead);
+    size_t n = fread(buf.data(), 1, kHead, fp);
+    bool ok = true;
+    if (n > 0 && buf[0] != '@') ok = false;
+    if (memchr(buf.data(), '\r', n)) ok = false;
+    for (size_t i = 1; ok && i < n; i++)
+        if (buf[i] == '\n' && buf[i - 1] == '\n') ok = false;                  // a blank line
+    if (ok && n == kHead && fseek(fp, -(long)kTail, SEEK_END) == 0) {
+        n = fread(buf.data(), 1, kTail, fp);
+        if (memchr(buf.data(), '\r', n)) ok = false;
+        for (size_t i = 1; ok && i < n; i++)
+            if (buf[i] == '\n' && buf[i - 1] == '\n') ok = false;
+    }
+    fclose(fp);
+    return ok;
+}
+
 bool rawTextEligible(Options* o) {
     if (getenv("FPL_HOST_PARSE")) return false;
     if (o->inputFromSTDIN || o->in == "/dev/stdin" || ends_with(o->in, ".gz")) return false;
     if (o->readsToProcess > 0 || o->split.enabled) return false;
-    return true;
+    if (o->outputToSTDOUT) return false;      // an abandoned raw-text run cannot take back what it wrote to a pipe
+    return looksStrict(o->in);
 }
 
 }  // namespace
@@ -637,7 +664,7 @@ bool SingleEndProcessor::process() {
             cur->n = 0;
             long k = 0;
             bool eof = false;
-            while (!eof) {
+            while (!eof && !notStrict) {
                 if (cur->cap - cur->n < kChunk) growChunk(cur, cur->cap * 2);
                 const size_t got = fread(cur->p + cur->n, 1, kChunk, fp);
                 cur->n += got;
@@ -668,6 +695,18 @@ bool SingleEndProcessor::process() {
             std::vector<fpl_fastq_record> recs;
             std::vector<fpl_read_result> res;
             while (TextChunk* c = queues[t].pop()) {
+                // abandoned run: every chunk dealt out still hands the writers one (empty) string, because WriterThread::output
+                // walks the worker lists strictly round-robin (src/writerthread.cpp:37-48) and would wait for a gap for ever
+                auto skipChunk = [&] {
+                    if (left) left->input(t, new string());
+                    if (failedW) failedW->input(t, new string());
+                    freeList.push(c);
+                };
+                if (notStrict) { skipChunk(); continue; }
+                // writer back-pressure (the reference's reader waits the same way, src/seprocessor.cpp:391-395): at most
+                // a couple of finished chunks per worker wait for the single writer thread (which also compresses)
+                while (left && left->bufferLength() > 2L * T && !notStrict) usleep(1000);
+                while (failedW && failedW->bufferLength() > 2L * T && !notStrict) usleep(1000);
                 // four newlines per record: count them to size the record tables
                 size_t nl = 0;
                 for (const uint8_t* q = c->p, *e = c->p + c->n; (q = (const uint8_t*)memchr(q, '\n', (size_t)(e - q))) != nullptr; q++) nl++;
@@ -677,7 +716,7 @@ bool SingleEndProcessor::process() {
                 const int rc = fpl_process_fastq_host(w.ctx, c->p, (int64_t)c->n, c->last ? 1 : 0, recs.data(), res.data(),
                                                       (int64_t)cap, &n, &used);
                 if (rc < 0) check(rc, "fpl_process_fastq_host");
-                if (rc == 1 || (size_t)used != c->n) { notStrict = 1; n = 0; }
+                if (rc == 1 || (size_t)used != c->n) { notStrict = 1; skipChunk(); continue; }
                 string* outstr = new string();
                 string* failedOut = new string();
                 const char* text = (const char*)c->p;
@@ -714,12 +753,37 @@ bool SingleEndProcessor::process() {
             cudaFreeHost(c->p);
             delete c;
         }
-        if (notStrict)
-            error_exit("fastplong_gpu: the input is not in the strict 4-line FASTQ layout the device parser handles "
-                       "(CR line ends, blank lines or a malformed record); rerun with FPL_HOST_PARSE=1 to use the reference reader");
-        if (mLeftWriter) mLeftWriter->setInputCompleted();
-        if (mFailedWriter) mFailedWriter->setInputCompleted();
-    } else {
+        if (notStrict) {
+            // Somewhere inside the file the text left the strict layout (a CR, a blank line, a malformed or truncated
+            // record).  What the reference does with such input depends on its reader's own buffer logic, so the whole
+            // file goes through that reader: take back everything this run produced — stop the writers, truncate the
+            // outputs, zero the accumulators on the devices and on the host — and start over.
+            if (mOptions->verbose) loginfo("the input is not in the strict FASTQ layout: restarting with the reference reader");
+            if (mLeftWriter) mLeftWriter->setInputCompleted();
+            if (mFailedWriter) mFailedWriter->setInputCompleted();
+            if (leftWriter) leftWriter->join();
+            if (failedWriter) failedWriter->join();
+            leftWriter.reset(); failedWriter.reset();
+            closeOutput();
+            initOutput();                                   // reopens (truncates) --out / --failed_out
+            if (mLeftWriter) leftWriter.reset(new std::thread(std::bind(&SingleEndProcessor::writerTask, this, mLeftWriter)));
+            if (mFailedWriter) failedWriter.reset(new std::thread(std::bind(&SingleEndProcessor::writerTask, this, mFailedWriter)));
+            for (int t = 0; t < T; t++) {
+                check(fpl_reset(g_workers[t]->ctx), "fpl_reset");
+                check(fpl_sync(g_workers[t]->ctx), "fpl_sync");
+                delete configs[t];
+                configs[t] = new ThreadConfig(mOptions, t, false);
+                configs[t]->setInputList(mInputLists[t]);
+                initConfig(configs[t]);
+            }
+            rawText = false;
+        }
+        if (rawText) {
+            if (mLeftWriter) mLeftWriter->setInputCompleted();
+            if (mFailedWriter) mFailedWriter->setInputCompleted();
+        }
+    }
+    if (!rawText) {
         std::thread reader(std::bind(&SingleEndProcessor::readerTask, this));
         std::vector<std::thread> workers;
         for (int t = 0; t < T; t++) workers.emplace_back(std::bind(&SingleEndProcessor::processorTask, this, configs[t]));

@@ -44,8 +44,15 @@ class PackedBatch:
         return self.seq[o:o + n].tobytes(), self.qual[o:o + n].tobytes()
 
     def slice(self, lo, hi):
-        """Reads [lo, hi) sharing the same buffers (offsets stay absolute)."""
-        return PackedBatch(self.seq, self.qual, self.offsets[lo:hi].copy(), self.lens[lo:hi].copy())
+        """Reads [lo, hi) as views of the same buffers, offsets rebased to the slice's first byte: a rank that
+        uploads its shard moves its own bytes only (slots are contiguous and in increasing order)."""
+        if hi <= lo:
+            return PackedBatch(self.seq[:TAIL_PAD], self.qual[:TAIL_PAD], self.offsets[:0].copy(), self.lens[:0].copy())
+        b0 = int(self.offsets[lo])
+        b1 = int(self.offsets[hi]) if hi < self.n_reads else self.n_bytes - TAIL_PAD
+        b1 = max(b1, int(self.offsets[hi - 1]) + int(self.lens[hi - 1]))
+        return PackedBatch(self.seq[b0:b1 + TAIL_PAD], self.qual[b0:b1 + TAIL_PAD], self.offsets[lo:hi] - b0,
+                           self.lens[lo:hi].copy())
 
 
 def slot_offsets(lens, align=SLOT_ALIGN):

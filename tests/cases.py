@@ -13,6 +13,15 @@ FASTA5 = [  # a 5-entry adapter "FASTA" in std::map header order, incl. a 72-bp 
     "ACTTGCCTGTCGCTCTATCTTC",
 ]
 
+def fasta64():
+    """BASELINE.json configs[2]: a 64-entry adapter FASTA of random 20-44-mers in std::map (sorted header) order —
+    the same set bench.py --workload c3 uses."""
+    rng = np.random.default_rng(64)
+    return sorted("".join("ACGT"[i] for i in rng.integers(0, 4, size=int(rng.integers(20, 45)))) for _ in range(64))
+
+
+FASTA64 = fasta64()
+
 OPTION_SETS = {
     "default_se": Options(start_adapter=S),
     "cut_polyx_cplx": Options(start_adapter=S, end_adapter=E, cut_front=True, cut_tail=True, cut_window_size=10,
@@ -22,6 +31,7 @@ OPTION_SETS = {
     "loose_ed": Options(start_adapter=S, distance_threshold=0.3, trimming_extension=4, cut_tail=True,
                         cut_tail_window_size=1, cut_tail_mean_quality=25),
     "fasta5": Options(start_adapter=S, adapter_fasta=FASTA5, trim_poly_x=True, poly_x_min_len=8),
+    "fasta64_polyx": Options(start_adapter=S, end_adapter=E, adapter_fasta=FASTA64, trim_poly_x=True),
     "literal_auto": Options(start_adapter="auto", end_adapter="auto", cut_front=True, cut_front_window_size=7,
                             cut_front_mean_quality=15),
     "no_adapter_no_filters": Options(disable_adapter_trimming=True, disable_quality_filtering=True,
@@ -75,6 +85,12 @@ def planted_fasta_reads(seed, n=120):
         q = (np.rint(rng.normal(20, 8, size=L)).clip(1, 50).astype(np.uint8) + 33).tobytes()
         out.append((bytes(s), q))
     return out
+
+
+def hifi_fasta64_batch(seed, n=200, mean=2500):
+    """configs[2]-shaped reads: HiFi-like qualities, poly-A/T tails, entries of FASTA64 planted in front of the reads."""
+    return synth.ont_like(n, mean, seed, q_mean=33.0, q_sd=6.0, q_clip=60, p_polya=0.1, planted=FASTA64[:6] + FASTA64[40:43],
+                          p_planted=0.4, p_chimera=0.03)
 
 
 def adversarial_batch(seed):

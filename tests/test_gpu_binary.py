@@ -59,7 +59,7 @@ def test_gpu_binary_matches_golden_reference_run(name, tmp_path):
 @pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/fastplong_ref not built")
 @pytest.mark.parametrize("parse", ["device", "host"])
 @pytest.mark.parametrize("name,threads", [("default_se", 1), ("cut_polyx_cplx", 4), ("fasta5", 3), ("literal_auto", 2),
-                                          ("trims_limits", 3), ("end_only_wide_window", 8)])
+                                          ("trims_limits", 3), ("end_only_wide_window", 8), ("fasta64_polyx", 5)])
 def test_gpu_binary_matches_reference_binary(name, threads, parse, tmp_path):
     """Fresh input, both binaries side by side (config-1 shape: ONT-like reads, known 30 bp adapters), with the FASTQ
     parsed on the device (default for plain files) and by the reference's FastqReader (FPL_HOST_PARSE=1)."""
@@ -147,6 +147,47 @@ def test_config1_full_size_bit_exact(tmp_path):
         f"config1 {batch.n_reads} reads {batch.n_bases} bases ref_w16_s {t1 - t0:.3f} gpu_w4_device_parse_s {t2 - t1:.3f} "
         f"gpu_w4_host_parse_s {t3 - t2:.3f}\n") \
         if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else None
+    assert got["out_md5"] == ref["out_md5"]
+    assert got["failed_md5"] == ref["failed_md5"]
+    assert got["json_text_md5"] == ref["json_text_md5"]
+
+
+def _mutate_fastq(src, dst, kind):
+    """Inputs the reference accepts but the device parser does not (FastqReader::getLine / read, src/fastqreader.cpp:219-347)."""
+    data = open(src, "rb").read()
+    if kind == "crlf":
+        data = data.replace(b"\n", b"\r\n")
+    elif kind == "blank_line_mid":                     # beyond the pre-scanned head, far from the tail: found mid-run -> restart
+        at = data.index(b"\n@read", len(data) // 2) + 1
+        data = data[:at] + b"\n" + data[at:]
+    elif kind == "cr_mid":
+        at = data.index(b"\n+\n", len(data) // 2)
+        data = data[:at] + b"\r" + data[at:]
+    elif kind == "blank_line_eof":
+        data = data + b"\n"
+    elif kind == "truncated_last_record":
+        data = data[:data.rindex(b"\n+\n") + 3]         # the last record loses its quality line
+    elif kind == "stray_line_between_records":
+        at = data.index(b"\n@read", len(data) // 2) + 1
+        data = data[:at] + b"this line is skipped by the reference\n" + data[at:]
+    open(dst, "wb").write(data)
+
+
+@needs_bin
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/fastplong_ref not built")
+@pytest.mark.parametrize("kind", ["crlf", "blank_line_mid", "cr_mid", "blank_line_eof", "truncated_last_record",
+                                  "stray_line_between_records"])
+def test_gpu_binary_non_strict_fastq_like_reference(kind, tmp_path):
+    """Drop-in robustness: whatever the reference's reader makes of a non-strict FASTQ, the GPU binary makes the same of
+    it (routed to the reference reader up front, or the raw-text run abandoned and restarted) — never a late abort with
+    partial outputs."""
+    opt = cases.OPTION_SETS["cut_polyx_cplx"]
+    batch = synth.ont_like(900, 4000, 77, p_chimera=0.03)
+    plain, fq = str(tmp_path / "plain.fq"), str(tmp_path / "in.fq")
+    synth.to_fastq(batch, plain)
+    _mutate_fastq(plain, fq, kind)
+    ref = run(REF_BIN, opt, fq, str(tmp_path), "ref", 3)
+    got = run(GPU_BIN, opt, fq, str(tmp_path), "gpu", 3)
     assert got["out_md5"] == ref["out_md5"]
     assert got["failed_md5"] == ref["failed_md5"]
     assert got["json_text_md5"] == ref["json_text_md5"]

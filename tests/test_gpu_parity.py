@@ -54,6 +54,13 @@ def test_ont_like_vs_oracle(name):
                          cases.ont_batch(91, n=400, mean=3000, p_chimera=0.05, p_polya=0.05), name + "/ont")
 
 
+@pytest.mark.parametrize("seed", [5, 6])
+def test_config3_shape_fasta64_vs_oracle(seed):
+    """BASELINE configs[2]: HiFi-like reads, 64-entry adapter FASTA (trimByMultiSequences over all 64 in map order) +
+    polyX trim, entries planted at the read starts."""
+    check_against_oracle(cases.OPTION_SETS["fasta64_polyx"], cases.hifi_fasta64_batch(seed), f"fasta64/hifi{seed}")
+
+
 @pytest.mark.parametrize("n", sorted(cases.LONG_ADAPTERS))
 def test_long_adapters_vs_oracle(n):
     """-s/-e adapters of 31..128 bp: every halo-word / counter-plane class of k_scan_jit and k_scan_fast."""
