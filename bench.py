@@ -429,7 +429,10 @@ def run_ours(args):
                    "parallelism": f"reads sharded over {world} GPU(s), equal bases per GPU; Stats/FilterResult merged by one NCCL "
                                   "all-reduce group per step issued by the C ABI (fpl_allreduce_stats) on the library's stream"
                    if world > 1 else "single GPU", "read_tiling": (os.environ.get("FPL_TILE_MBASES") + " Mbases") if os.environ.get("FPL_TILE_MBASES") else "none (every kernel streams the whole batch)",
-                   "input_gen_s": round(gen_s, 1)},
+                   "input_gen_s": round(gen_s, 1),
+                   "variants": {"k_scan_jit": "v1 (round 1)" if os.environ.get("FPL_JIT_V1") else "v2",
+                                "k_cycle_stats_staging": "1-D TMA (cp.async.bulk + mbarrier)" if os.environ.get("FPL_CS_TMA", "0") not in ("", "0")
+                                else "cp.async (LDGSTS) ring"}},
         "parity_checked": parity is not None, "parity": parity,
         "clocks": clocks,
         "e2e": e2e,

@@ -2,9 +2,9 @@
 import ctypes as C
 import numpy as np
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 COMM_ID_BYTES = 128        # FPL_COMM_ID_BYTES == sizeof(ncclUniqueId)
-MAX_ADAPTER_LEN = 128
+MAX_ADAPTER_LEN = 1024
 MAX_ADAPTERS = 1024
 INLINE_EVENTS = 4
 

@@ -74,6 +74,7 @@ struct fpl_ctx {
     uint4* d_peq = nullptr;
     uint32_t* d_peq16 = nullptr;
     uint32_t* d_acode = nullptr;
+    unsigned long long* d_peq_long = nullptr;
     // accumulators
     int64_t C = 0;
     unsigned long long* d_stats[2] = {nullptr, nullptr};
@@ -343,6 +344,14 @@ int fpl_create(const fpl_options* opt, const fpl_adapters* ad, fpl_ctx** out) {
     std::vector<uint4> h_peq((size_t)n * 256, make_uint4(0, 0, 0, 0));
     std::vector<uint32_t> h_peq16((size_t)n * 512, 0);   // [adapter][prefix | suffix][byte]
     std::vector<uint32_t> h_acode((size_t)n * 4, 0);
+    size_t maxlen = 0;
+    for (int k = 0; k < n; k++) {
+        const char* s = k == 0 ? ad->start : k == 1 ? ad->end : ad->fasta[k - 2];
+        if (s && strlen(s) > maxlen) maxlen = strlen(s);
+    }
+    // adapters longer than 128 bp: multi-word match masks for myers_long (the 128-bit table below stays as it is)
+    const int peq_words = maxlen > 128 ? (int)((maxlen + 63) / 64) + 1 : 0;
+    std::vector<unsigned long long> h_peq_long((size_t)n * 256 * peq_words, 0ull);
     for (int k = 0; k < n; k++) {
         const char* s = k == 0 ? ad->start : k == 1 ? ad->end : ad->fasta[k - 2];
         if (!s) s = "";
@@ -371,13 +380,15 @@ int fpl_create(const fpl_options* opt, const fpl_adapters* ad, fpl_ctx** out) {
         for (size_t j = 0; j < len; j++) {
             uint8_t ch = (uint8_t)s[j];
             uint32_t* w = reinterpret_cast<uint32_t*>(&h_peq[(size_t)k * 256 + ch]);
-            w[j >> 5] |= 1u << (j & 31);
+            if (j < 128) w[j >> 5] |= 1u << (j & 31);
+            if (peq_words) h_peq_long[((size_t)k * 256 + ch) * peq_words + (j >> 6)] |= 1ull << (j & 63);
             if ((int)j < plen) h_peq16[(size_t)k * 512 + ch] |= 1u << j;                            // first plen chars
             if ((int)j >= (int)len - plen) h_peq16[(size_t)k * 512 + 256 + ch] |= 1u << (j - (len - plen));  // last plen chars
         }
     }
     memset(&c->P, 0, sizeof(c->P));
     c->P.opt = *opt;
+    c->P.one = 1u;
     c->P.n_adapters = n;
     // plan for the bit-sliced middle-adapter scan (k_scan_fast); anything it cannot express uses k_scan
     memset(&c->plan, 0, sizeof(c->plan));
@@ -387,7 +398,7 @@ int fpl_create(const fpl_options* opt, const fpl_adapters* ad, fpl_ctx** out) {
         for (int k = 0; k < 2 && fast && opt->adapter_enabled; k++) {
             const char* s = k == 0 ? ad->start : ad->end;
             const int len = h_alen[k];
-            if (len < 1) { fast = false; break; }
+            if (len < 1 || len > 128) { fast = false; break; }   // bit-sliced counters: up to 8 planes, 4 halo words
             if (len > maxa) maxa = len;
             for (int i = 0; i < len; i++) {
                 const char ch = s[i];
@@ -414,6 +425,11 @@ int fpl_create(const fpl_options* opt, const fpl_adapters* ad, fpl_ctx** out) {
     CKC(cudaMemcpy(c->d_alen, h_alen.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
     CKC(cudaMemcpy(c->d_peq, h_peq.data(), sizeof(uint4) * h_peq.size(), cudaMemcpyHostToDevice));
     CKC(cudaMemcpy(c->d_peq16, h_peq16.data(), sizeof(uint32_t) * h_peq16.size(), cudaMemcpyHostToDevice));
+    if (peq_words) {
+        CKC(cudaMalloc(&c->d_peq_long, sizeof(unsigned long long) * h_peq_long.size()));
+        CKC(cudaMemcpy(c->d_peq_long, h_peq_long.data(), sizeof(unsigned long long) * h_peq_long.size(), cudaMemcpyHostToDevice));
+    }
+    c->P.peq_long = c->d_peq_long; c->P.peq_words = peq_words;
     c->P.adapters = c->d_adapters; c->P.alen = c->d_alen; c->P.peq = c->d_peq; c->P.peq16 = c->d_peq16; c->P.acode = c->d_acode;
     c->counter_words = FPL_COUNTER_WORDS(n);
     CKC(cudaMalloc(&c->d_counters, sizeof(unsigned long long) * c->counter_words));
@@ -452,7 +468,7 @@ void fpl_destroy(fpl_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     collect_times(c);
     for (auto e : c->pool) cudaEventDestroy(e);
-    cudaFree(c->d_adapters); cudaFree(c->d_alen); cudaFree(c->d_peq); cudaFree(c->d_peq16); cudaFree(c->d_acode);
+    cudaFree(c->d_adapters); cudaFree(c->d_alen); cudaFree(c->d_peq); cudaFree(c->d_peq16); cudaFree(c->d_acode); cudaFree(c->d_peq_long);
     cudaFree(c->d_stats[0]); cudaFree(c->d_stats[1]); cudaFree(c->d_counters);
     fpl_cycle_ws_free(&c->cycle_ws);
     for (auto e : c->piece_events) cudaEventDestroy(e);

@@ -17,6 +17,9 @@ struct DevParams {
     const uint32_t* peq16;    // [n][2][256]: [0] = match masks of the first plen chars, [1] = of the last plen chars
     const uint32_t* acode;    // [n][4]: 2-bit codes ((byte>>1)&3 at bit 2i) lo/hi + position mask lo/hi; mask == 0: not ACGT-only or > 32 bp
     short thr[FPL_MAX_ADAPTER_LEN + 1];  // thr(n) = (int)round(ed_max*n), tabulated on the host with libm round
+    const unsigned long long* peq_long;  // [n][256][peq_words]: match masks of adapters longer than 128 bp (else nullptr)
+    int peq_words;            // 64-bit words per mask in peq_long
+    uint32_t one;             // 1: the multiplier of the IMADs that must stay on the FMA pipe (an add the compiler cannot fold)
 };
 
 // Device view of a packed batch.
@@ -142,3 +145,48 @@ __device__ __forceinline__ int myers32(const uint8_t* text, int n, const uint4* 
     for (int i = 0; i < n; i++) M.column(myers_eq_top(__ldg(&peq[text[i]].x), shift, m));
     return M.score(m);
 }
+
+// Levenshtein distance for adapters longer than 128 bp: Myers/Hyyro in 64-bit blocks with the horizontal delta carried
+// from block to block (global distance: +1 enters the first block in every column).  Pattern = adapter bits
+// [shift, shift + m), m <= FPL_MAX_ADAPTER_LEN; exact, == edit_distance() of src/editdistance.cpp:100-126 (which switches
+// to its own multi-block form at 64 bp and to a plain DP beyond 640).  One call per lane; rare, not tuned.
+static __device__ __noinline__ int myers_long(const uint8_t* text, int n, const unsigned long long* peq, int words, int shift, int m) {
+    if (m == 0) return n;
+    if (n == 0) return m;
+    constexpr int MAXB = FPL_MAX_ADAPTER_LEN / 64;
+    unsigned long long VP[MAXB], VN[MAXB];
+    const int nb = (m + 63) >> 6;
+    const int lastbits = m - 64 * (nb - 1);
+    for (int b = 0; b < nb; b++) { VP[b] = ~0ull; VN[b] = 0; }
+    if (lastbits < 64) VP[nb - 1] = (1ull << lastbits) - 1;
+    const unsigned long long lasttop = 1ull << (lastbits - 1);
+    const int w0 = shift >> 6, sh = shift & 63;
+    int score = m;
+    for (int i = 0; i < n; i++) {
+        const unsigned long long* e = peq + (size_t)text[i] * words;
+        int hin = 1;
+        for (int b = 0; b < nb; b++) {
+            unsigned long long Eq = __ldg(&e[w0 + b]) >> sh;
+            if (sh && w0 + b + 1 < words) Eq |= __ldg(&e[w0 + b + 1]) << (64 - sh);
+            const bool last = b == nb - 1;
+            if (last && lastbits < 64) Eq &= (1ull << lastbits) - 1;
+            const unsigned long long Pv = VP[b], Mv = VN[b];
+            const unsigned long long Xv = Eq | Mv;
+            if (hin < 0) Eq |= 1ull;
+            const unsigned long long Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+            unsigned long long Ph = Mv | ~(Xh | Pv);
+            unsigned long long Mh = Pv & Xh;
+            const unsigned long long top = last ? lasttop : (1ull << 63);
+            const int hout = (Ph & top) ? 1 : (Mh & top) ? -1 : 0;
+            Ph <<= 1; Mh <<= 1;
+            if (hin < 0) Mh |= 1ull; else if (hin > 0) Ph |= 1ull;
+            VP[b] = Mh | ~(Xv | Ph);
+            VN[b] = Ph & Xv;
+            if (last && lastbits < 64) { VP[b] &= (1ull << lastbits) - 1; VN[b] &= (1ull << lastbits) - 1; }
+            hin = hout;
+        }
+        score += hin;
+    }
+    return score;
+}
+

@@ -107,7 +107,8 @@ k_scan(const __grid_constant__ DevParams P, DevBatch b, ReadState* __restrict__ 
                     const int np = which ? np1 : np0;
                     if (pbase >= np) continue;
                     const uint8_t* ad = which ? a1 : a0;
-                    uint32_t acc = 0;  // four byte-wide mismatch counters (alen <= 128 < 256)
+                    uint32_t acc = 0;  // four byte-wide mismatch counters, emptied into cnt[] before they can overflow
+                    uint32_t cnt[4] = {0, 0, 0, 0};
                     uint32_t wlo = w32[g], whi = w32[g + 1];
                     int wi = g + 1;
                     for (int i = 0; i < alen; i++) {
@@ -116,12 +117,19 @@ k_scan(const __grid_constant__ DevParams P, DevBatch b, ReadState* __restrict__ 
                         uint32_t a4 = (uint32_t)__ldg(&ad[i]) * 0x01010101u;
                         acc += nz_bytes(x ^ a4);
                         if (sh == 3) { wlo = whi; whi = w32[++wi]; }
+                        if ((i & 127) == 127) {
+#pragma unroll
+                            for (int k = 0; k < 4; k++) cnt[k] += (acc >> (8 * k)) & 0xFFu;
+                            acc = 0;
+                        }
                     }
+#pragma unroll
+                    for (int k = 0; k < 4; k++) cnt[k] += (acc >> (8 * k)) & 0xFFu;
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
                         const int p = pbase + k;
                         if (p < np) {
-                            unsigned long long key = ((unsigned long long)((acc >> (8 * k)) & 0xFFu) << 32) | (unsigned)p;
+                            unsigned long long key = ((unsigned long long)cnt[k] << 32) | (unsigned)p;
                             if (which) best1 = key < best1 ? key : best1;
                             else best0 = key < best0 ? key : best0;
                         }
@@ -212,28 +220,58 @@ __device__ int pass_filter(const fpl_options& o, int rlen, const Counts& c) {
     return FPL_PASS_FILTER;
 }
 
-// Filter::passFilter's counts for one segment of a split read (warp-wide).  16-byte vector loads: the segment starts
-// anywhere, so the vectors are aligned down and the bytes outside [0, len) masked (sequence and quality buffers are
-// equally aligned, so one misalignment serves both).
-__device__ Counts recount(const fpl_options& o, const uint8_t* seq, const uint8_t* qual, int len) {
+// Filter::passFilter's counts for a byte range of a split read (warp-wide): #(q < qualified), #N, sum(q - 33) over
+// [0, len) and #(seq[i] != seq[i+1]) over i in [0, len - 1).  16-byte vector loads: the range starts anywhere, so the
+// vectors are aligned down (sequence and quality buffers are equally aligned, one misalignment serves both).  A vector
+// whose 16 bytes and 16 adjacent pairs all lie inside the range takes the word-wise path — the quality counts as in
+// k_scan_jit (x = q + (128 - qualified) by IMAD; the unsigned and the signed dp4a sums of x differ by 256 per q >=
+// qualified), N and the unequal neighbours by zero-byte tests — the two ragged ends go byte by byte.
+__device__ __forceinline__ uint32_t zero_bytes80(uint32_t d) {     // 0x80 in every byte of d that is zero
+    return ~(((d & 0x7f7f7f7fu) + 0x7f7f7f7fu) | d) & 0x80808080u;
+}
+
+__device__ Counts count_range(const fpl_options& o, uint32_t one, const uint8_t* seq, const uint8_t* qual, int len) {
     Counts c = {0, 0, 0, 0};
     const int lane = lane_id();
     const bool doCounts = (o.qual_filter_enabled || o.length_filter_enabled);
     const bool doCplx = o.complexity_enabled != 0;
     const int qq = (int)(signed char)o.qualified_qual;
+    const uint32_t KQ = (uint32_t)(128 - (o.qualified_qual & 0x7f));
     const int pre = (int)(reinterpret_cast<uintptr_t>(seq) & 15);
     const uint4* sv = reinterpret_cast<const uint4*>(seq - pre);
     const uint4* qv = reinterpret_cast<const uint4*>(qual - pre);
     const int total = pre + len;
+    uint32_t accU = 0; int accS = 0, nfast = 0;
     for (int v = lane; v * 16 < total; v += 32) {
         const uint4 s4 = __ldg(sv + v), q4 = __ldg(qv + v);
         const uint32_t sw[4] = {s4.x, s4.y, s4.z, s4.w}, qw[4] = {q4.x, q4.y, q4.z, q4.w};
+        const int first = v * 16 - pre, after = first + 16;
         // the byte after this vector, for the last adjacent pair
-        const int after = v * 16 + 16 - pre;
         const uint32_t nextb = (doCplx && after < len) ? (uint32_t)seq[after] : 0u;
+        if (first >= 0 && after <= len - 1) {
+            if (doCounts) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    uint32_t x;
+                    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(x) : "r"(qw[k]), "r"(one), "r"(KQ * 0x01010101u));
+                    accU = __dp4a(x, 0x01010101u, accU);
+                    accS = __dp4a((int)x, 0x01010101, accS);
+                    c.nn += __popc(zero_bytes80(sw[k] ^ 0x4E4E4E4Eu));
+                }
+                nfast += 16;
+            }
+            if (doCplx) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t w2 = k < 3 ? sw[k + 1] : nextb;
+                    c.diff += 4 - __popc(zero_bytes80(sw[k] ^ __funnelshift_r(sw[k], w2, 8)));
+                }
+            }
+            continue;
+        }
 #pragma unroll
         for (int j = 0; j < 16; j++) {
-            const int pos = v * 16 + j - pre;
+            const int pos = first + j;
             if (pos < 0 || pos >= len) continue;
             const uint32_t sb = (sw[j >> 2] >> (8 * (j & 3))) & 0xFFu;
             if (doCounts) {
@@ -246,6 +284,9 @@ __device__ Counts recount(const fpl_options& o, const uint8_t* seq, const uint8_
             }
         }
     }
+    // fast vectors: #(q >= qualified) = (accU - accS) / 256, sum(q) = accU - KQ * n
+    c.lowq += nfast - (int)((accU - (uint32_t)accS) >> 8);
+    c.totalq += (int)accU - (int)(KQ + 33u) * nfast;
     c.lowq = __reduce_add_sync(0xffffffffu, c.lowq); c.nn = __reduce_add_sync(0xffffffffu, c.nn);
     c.totalq = __reduce_add_sync(0xffffffffu, c.totalq); c.diff = __reduce_add_sync(0xffffffffu, c.diff);
     return c;
@@ -271,6 +312,7 @@ k_final(const __grid_constant__ DevParams P, DevBatch b, const ReadState* __rest
         const int L = s.len;
         int nseg = 0, segLo[2] = {0, 0}, segLen[2] = {0, 0};
         bool split = false, seg0right = false;
+        int gapLo = 0, gapLen = 0;                       // the gap Read::breakByGap cuts out: [gapLo, gapLo + gapLen)
         if (P.opt.adapter_enabled) {
             const int ext = P.opt.trimming_extension;
             int pos[2] = {-1, -1};
@@ -292,7 +334,8 @@ k_final(const __grid_constant__ DevParams P, DevBatch b, const ReadState* __rest
                         const int alen = P.alen[k];
                         const int p = (int)(s.best[k] & 0xFFFFFFFFu);
                         const int ed = alen <= 32 ? myers32_warp(seq + p, alen, P.peq + (size_t)k * 256, 0, alen)
-                                                 : myers128_f(seq + p, alen, P.peq + (size_t)k * 256, alen);
+                                     : alen <= 128 ? myers128_f(seq + p, alen, P.peq + (size_t)k * 256, alen)
+                                                   : myers_long(seq + p, alen, P.peq_long + (size_t)k * 256 * P.peq_words, P.peq_words, 0, alen);
                         if (ed <= P.thr[alen]) pos[k] = p;
                     }
                 }
@@ -311,6 +354,7 @@ k_final(const __grid_constant__ DevParams P, DevBatch b, const ReadState* __rest
                 start = max(0, ep - ext); glen = en - start; split = true;
             }
             if (split) {
+                gapLo = start; gapLen = glen;
                 const int len1 = start, len2 = L - start - glen;
                 if (len1 > 0) { segLo[nseg] = 0; segLen[nseg] = len1; nseg++; }
                 if (len2 > 0) { segLo[nseg] = start + glen; segLen[nseg] = len2; nseg++; }
@@ -319,11 +363,31 @@ k_final(const __grid_constant__ DevParams P, DevBatch b, const ReadState* __rest
         } else { segLo[0] = 0; segLen[0] = L; nseg = 1; }
 
         int code[2] = {0, 0};
-        for (int k = 0; k < nseg; k++) {
-            Counts c;
-            if (split) c = recount(P.opt, seq + segLo[k], qual + segLo[k], segLen[k]);
-            else { c.lowq = s.lowq; c.nn = s.nn; c.totalq = s.totalq; c.diff = s.diff; }
-            code[k] = pass_filter(P.opt, segLen[k], c);
+        if (split && nseg > 0) {
+            // Read::breakByGap left [0, start) and [start + glen, L).  The scan counted the whole window; count the gap and
+            // the SHORTER side here and take the longer side by subtraction (a split 500-kb read costs its short side).
+            const int lenA = max(gapLo, 0);                                       // left side [0, lenA)
+            const int loB = gapLo + gapLen;                                        // right side [loB, L)
+            const int lenB = max(L - loB, 0);
+            const Counts tot = {s.lowq, s.nn, s.totalq, s.diff};
+            const Counts g = count_range(P.opt, P.one, seq + gapLo, qual + gapLo, gapLen);
+            const bool countA = lenA <= lenB;
+            const Counts sh = countA ? count_range(P.opt, P.one, seq, qual, lenA) : count_range(P.opt, P.one, seq + loB, qual + loB, lenB);
+            // adjacent pairs that straddle a boundary belong to no part
+            const int x1 = (lenA > 0 && gapLen > 0) ? (seq[gapLo - 1] != seq[gapLo]) : 0;
+            const int x2 = (lenB > 0 && gapLen > 0) ? (seq[loB - 1] != seq[loB]) : 0;
+            Counts lg;
+            lg.lowq = tot.lowq - g.lowq - sh.lowq; lg.nn = tot.nn - g.nn - sh.nn; lg.totalq = tot.totalq - g.totalq - sh.totalq;
+            lg.diff = P.opt.complexity_enabled ? tot.diff - g.diff - sh.diff - x1 - x2 : 0;
+            const Counts cA = countA ? sh : lg, cB = countA ? lg : sh;
+            if (nseg == 2) { code[0] = pass_filter(P.opt, segLen[0], cA); code[1] = pass_filter(P.opt, segLen[1], cB); }
+            else code[0] = pass_filter(P.opt, segLen[0], seg0right ? cB : cA);
+        } else {
+            for (int k = 0; k < nseg; k++) {
+                Counts c;
+                c.lowq = s.lowq; c.nn = s.nn; c.totalq = s.totalq; c.diff = s.diff;
+                code[k] = pass_filter(P.opt, segLen[k], c);
+            }
         }
         if (lane == 0) {
             uint32_t flags = out->flags;

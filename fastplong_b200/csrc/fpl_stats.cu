@@ -18,6 +18,7 @@
 #include "fpl_stats.h"
 
 #include <atomic>
+#include <stdlib.h>
 #include <cub/cub.cuh>
 
 #define CS_NT_KMER 1024                          // threads per CTA with the 5-mer tables (one CTA per SM: 145 KB of shared memory)
@@ -31,8 +32,9 @@
 #define CS_DEPTH_KMER 1                          // segments in flight per warp (the 5-mer variant is bound by the logic pipe)
 #define CS_DEPTH_PLAIN 3
 #define CS_SMEM_BASE (8 * CS_BINW * 4 + CS_STAGE * 16)            // counters + staged descriptors
-#define CS_SMEM_PLAIN (CS_SMEM_BASE + (CS_NT_PLAIN / 32) * (CS_DEPTH_PLAIN + 1) * CS_SLOT)
-#define CS_SMEM_KMER (CS_SMEM_BASE + (CS_NT_KMER / 32) * (CS_DEPTH_KMER + 1) * CS_SLOT + 1024 * 32 * 4)   // + lane-private 5-mer tables
+#define CS_MBAR_BYTES(NT, DEPTH) (((NT) / 32) * ((DEPTH) + 1) * 8)          // one mbarrier per ring slot (TMA staging)
+#define CS_SMEM_PLAIN (CS_SMEM_BASE + (CS_NT_PLAIN / 32) * (CS_DEPTH_PLAIN + 1) * CS_SLOT + CS_MBAR_BYTES(CS_NT_PLAIN, CS_DEPTH_PLAIN))
+#define CS_SMEM_KMER (CS_SMEM_BASE + (CS_NT_KMER / 32) * (CS_DEPTH_KMER + 1) * CS_SLOT + 1024 * 32 * 4 + CS_MBAR_BYTES(CS_NT_KMER, CS_DEPTH_KMER))   // + lane-private 5-mer tables
 
 namespace {
 
@@ -83,6 +85,29 @@ __device__ __forceinline__ uint32_t lds32(uint32_t a) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
     return v;
+}
+
+// ---- 1-D TMA (cp.async.bulk) staging: one lane copies a whole 512-byte tile row, completion on an mbarrier ----
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
 template <int IMM>
@@ -187,7 +212,9 @@ struct __align__(16) TileSeg {
 // sorted by length (so a group's segments end in the same few tiles and the CTAs beyond the longest one leave at once).
 // Every load is an aligned 16-byte vector: the misalignment of a segment (its address & 15, different for every
 // post-filter segment) moves the COLUMNS its bytes count into instead of the bytes (count16<S>).
-template <bool DO_KMER, int NT, int DEPTH>
+// TMA = true: the tile rows are staged by 1-D bulk copies (cp.async.bulk + mbarrier) issued by one lane per warp instead
+// of 32 lanes' cp.async — the variant FPL_CS_TMA=1 selects; both are measured in profiles/README.md.
+template <bool DO_KMER, int NT, int DEPTH, bool TMA>
 __global__ void __launch_bounds__(NT, DO_KMER ? 1 : 2048 / NT / 2)
 k_cycle_stats(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qualbuf, const SegD* __restrict__ segs,
               int64_t nseg, unsigned long long* __restrict__ stats, int64_t C, unsigned long long* __restrict__ kmer_also,
@@ -197,6 +224,7 @@ k_cycle_stats(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qu
     TileSeg* stage = reinterpret_cast<TileSeg*>(cs_smem + 8 * CS_BINW * 4);
     uint8_t* ring = reinterpret_cast<uint8_t*>(stage + CS_STAGE);                  // [warps][DEPTH+1] slots of CS_SLOT bytes
     uint32_t* kmer = reinterpret_cast<uint32_t*>(ring + (NT / 32) * (DEPTH + 1) * CS_SLOT);   // [1024][32]: one column per lane
+    uint8_t* mbars = reinterpret_cast<uint8_t*>(kmer) + (DO_KMER ? 1024 * 32 * 4 : 0);       // [warps][DEPTH+1] mbarriers (TMA)
     const int wid = threadIdx.x >> 5, lane = lane_id();
     const int64_t t0 = (int64_t)blockIdx.x * CS_TILE;      // first byte of this tile, relative to the aligned segment start
     const int64_t g0 = (int64_t)blockIdx.y * CS_GROUP;
@@ -215,6 +243,14 @@ k_cycle_stats(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qu
     const uint8_t* seq_lane = seqbuf + 16 * lane;
     const uint8_t* qual_lane = qualbuf + 16 * lane;
     const uint32_t ring_lane = shared_addr(ring) + (uint32_t)wid * ((DEPTH + 1) * CS_SLOT) + (uint32_t)lane * 16u;
+    const uint32_t ring_warp = ring_lane - (uint32_t)lane * 16u;
+    const uint32_t bar_warp = shared_addr(mbars) + (uint32_t)wid * ((DEPTH + 1) * 8);
+    uint32_t phase = 0;                                   // TMA: the parity each slot's mbarrier completes next (bit per slot)
+    if (TMA) {
+        if (lane == 0)
+            for (int d = 0; d <= DEPTH; d++) mbar_init(bar_warp + 8u * d, 1u);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     for (int64_t s0 = g0; s0 < g1; s0 += CS_STAGE) {
         __syncthreads();
         // stage the descriptors; the ones that can reach this tile are a prefix (sorted by length)
@@ -240,6 +276,21 @@ k_cycle_stats(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qu
         // processed; a lane beyond the segment's end copies 0 bytes, which zero-fills its slot bytes
         auto issue = [&](int k, int slot) {
             const TileSeg ts = stage[k];
+            if (TMA) {
+                // one lane: up to 512 bytes of sequence, the same of quality and (5-mers) the 16 bytes in front of the
+                // tile; a tile the segment does not fill is copied up to its last vector, the rest of the slot keeps
+                // stale bytes that the edge path masks
+                __syncwarp();                              // every lane is done reading the slot that is refilled
+                if (lane == 0) {
+                    const uint32_t dst = ring_warp + (uint32_t)slot * CS_SLOT, bar = bar_warp + 8u * slot;
+                    const uint32_t bytes = ts.lim > 0 ? (uint32_t)min(CS_TILE, (ts.lim + 15) & ~15) : 0u;
+                    const uint32_t pb = (DO_KMER && t0 != 0 && bytes) ? 16u : 0u;
+                    mbar_expect_tx(bar, 2u * bytes + pb);
+                    if (bytes) { bulk_g2s(dst, seqbuf + ts.a, bytes, bar); bulk_g2s(dst + 512u, qualbuf + ts.a, bytes, bar); }
+                    if (pb) bulk_g2s(dst + 1024u, seqbuf + ts.a - 16, 16u, bar);
+                }
+                return;
+            }
             const bool act = 16 * lane < ts.lim;
             const uint32_t dst = ring_lane + (uint32_t)slot * CS_SLOT;
             cp_async16(dst, act ? seq_lane + ts.a : seqbuf, act ? 16 : 0);
@@ -250,20 +301,21 @@ k_cycle_stats(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qu
 #pragma unroll
         for (int d = 0; d < DEPTH; d++) {
             if (kk < n) issue(kk, d);
-            cp_async_commit();
+            if (!TMA) cp_async_commit();
             kk += NT / 32;
         }
         int slot = 0, fill = DEPTH;
         for (int k = wid; k < n; k += (NT / 32)) {
-            cp_async_wait<DEPTH - 1>();
+            if (TMA) { mbar_wait(bar_warp + 8u * slot, (phase >> slot) & 1u); phase ^= 1u << slot; }
+            else cp_async_wait<DEPTH - 1>();
             const uint32_t src = ring_lane + (uint32_t)slot * CS_SLOT;
             const uint4 ns = lds128(src), nq = lds128(src + 512);
-            const uint32_t prev0 = (DO_KMER && lane == 0) ? lds32(src + 1024) : 0u;
+            const uint32_t prev0 = (DO_KMER && lane == 0) ? lds32(src + 1024 + (TMA ? 12 : 0)) : 0u;
             const uint32_t sw[4] = {ns.x, ns.y, ns.z, ns.w};
             uint32_t qm[4] = {nq.x, nq.y, nq.z, nq.w};
             const int sh = stage[k].sh, lim = stage[k].lim;
             if (kk < n) issue(kk, fill);
-            cp_async_commit();
+            if (!TMA) cp_async_commit();
             kk += NT / 32;
             slot = slot == DEPTH ? 0 : slot + 1;
             fill = fill == DEPTH ? 0 : fill + 1;
@@ -443,8 +495,10 @@ int launch_cycle_stats(CycleWs* ws, const uint8_t* seq, const uint8_t* qual, con
     cudaGetDevice(&dev);
     const unsigned long long bit = 1ull << (dev & 63);
     if (!(attr_set.load() & bit)) {
-        if (cudaFuncSetAttribute(k_cycle_stats<true, CS_NT_KMER, CS_DEPTH_KMER>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM_KMER) != cudaSuccess ||
-            cudaFuncSetAttribute(k_cycle_stats<false, CS_NT_PLAIN, CS_DEPTH_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM_PLAIN) != cudaSuccess)
+        if (cudaFuncSetAttribute(k_cycle_stats<true, CS_NT_KMER, CS_DEPTH_KMER, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM_KMER) != cudaSuccess ||
+            cudaFuncSetAttribute(k_cycle_stats<false, CS_NT_PLAIN, CS_DEPTH_PLAIN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM_PLAIN) != cudaSuccess ||
+            cudaFuncSetAttribute(k_cycle_stats<true, CS_NT_KMER, CS_DEPTH_KMER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM_KMER) != cudaSuccess ||
+            cudaFuncSetAttribute(k_cycle_stats<false, CS_NT_PLAIN, CS_DEPTH_PLAIN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM_PLAIN) != cudaSuccess)
             return -1;
         attr_set.fetch_or(bit);
     }
@@ -480,8 +534,14 @@ int launch_cycle_stats(CycleWs* ws, const uint8_t* seq, const uint8_t* qual, con
     k_cs_gather<<<blocks, 256, 0, stream>>>(segs, ws->k_out, ws->v_out, nseg, static_cast<SegD*>(ws->sorted));
     dim3 grid((unsigned)((max_len + 15 + CS_TILE - 1) / CS_TILE), (unsigned)((nseg + CS_GROUP - 1) / CS_GROUP));
     const SegD* sorted = static_cast<const SegD*>(ws->sorted);
-    if (do_kmer) k_cycle_stats<true, CS_NT_KMER, CS_DEPTH_KMER><<<grid, CS_NT_KMER, CS_SMEM_KMER, stream>>>(seq, qual, sorted, nseg, stats, C, kmer_also, 1u);
-    else k_cycle_stats<false, CS_NT_PLAIN, CS_DEPTH_PLAIN><<<grid, CS_NT_PLAIN, CS_SMEM_PLAIN, stream>>>(seq, qual, sorted, nseg, stats, C, nullptr, 1u);
+    static const bool tma = getenv("FPL_CS_TMA") != nullptr && atoi(getenv("FPL_CS_TMA")) != 0;
+    if (tma) {
+        if (do_kmer) k_cycle_stats<true, CS_NT_KMER, CS_DEPTH_KMER, true><<<grid, CS_NT_KMER, CS_SMEM_KMER, stream>>>(seq, qual, sorted, nseg, stats, C, kmer_also, 1u);
+        else k_cycle_stats<false, CS_NT_PLAIN, CS_DEPTH_PLAIN, true><<<grid, CS_NT_PLAIN, CS_SMEM_PLAIN, stream>>>(seq, qual, sorted, nseg, stats, C, nullptr, 1u);
+    } else {
+        if (do_kmer) k_cycle_stats<true, CS_NT_KMER, CS_DEPTH_KMER, false><<<grid, CS_NT_KMER, CS_SMEM_KMER, stream>>>(seq, qual, sorted, nseg, stats, C, kmer_also, 1u);
+        else k_cycle_stats<false, CS_NT_PLAIN, CS_DEPTH_PLAIN, false><<<grid, CS_NT_PLAIN, CS_SMEM_PLAIN, stream>>>(seq, qual, sorted, nseg, stats, C, nullptr, 1u);
+    }
     return 0;
 }
 

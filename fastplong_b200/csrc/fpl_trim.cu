@@ -58,8 +58,11 @@ __device__ int myers128(const uint8_t* text, int n, const uint4* peq, int shift,
     return score;
 }
 
-__device__ __forceinline__ int ed_adapter(const uint8_t* text, int n, const uint4* peq, int shift, int m, int alen) {
-    return alen <= 32 ? myers32(text, n, peq, shift, m) : myers128(text, n, peq, shift, m);
+__device__ __forceinline__ int ed_adapter(const DevParams& P, int aidx, const uint8_t* text, int n, int shift, int m, int alen) {
+    const uint4* peq = P.peq + (size_t)aidx * 256;
+    if (alen <= 32) return myers32(text, n, peq, shift, m);
+    if (alen <= 128) return myers128(text, n, peq, shift, m);
+    return myers_long(text, n, P.peq_long + (size_t)aidx * 256 * P.peq_words, P.peq_words, shift, m);
 }
 
 // 16-bit pattern variant for the probe loops (:202-216, :273-286); peq = the 256 match masks of the probe pattern.
@@ -164,8 +167,67 @@ __device__ int search_window(const DevParams& P, const uint8_t* rdata, int rlen,
     if (best == 0xFFFFFFFFu) return -1;
     unsigned key = best & 0xFFFFu;
     int pos = p0 + (int)(left ? (0xFFFFu - key) : key);
-    int ed = ed_adapter(rdata + pos, alen, P.peq + (size_t)aidx * 256, 0, alen, alen);
+    int ed = ed_adapter(P, aidx, rdata + pos, alen, 0, alen, alen);
     return ed <= T ? pos : -1;
+}
+
+template <typename W>
+struct SearchMyers {                      // pattern in the low m bits; standard Myers/Hyyro search recurrence
+    W VP, VN, top;
+    int score, best;
+    __device__ __forceinline__ void init(int m) {
+        VP = m >= (int)(8 * sizeof(W)) ? ~(W)0 : (((W)1 << m) - 1);
+        VN = 0; top = (W)1 << (m - 1); score = m; best = m;
+    }
+    __device__ __forceinline__ void column(W Eq) {
+        const W Xv = Eq | VN;
+        const W Xh = (((Eq & VP) + VP) ^ VP) | Eq;
+        W HP = VN | ~(Xh | VP);
+        W HN = VP & Xh;
+        score += (HP & top) ? 1 : 0;
+        score -= (HN & top) ? 1 : 0;
+        HP <<= 1; HN <<= 1;                // search mode: the horizontal delta entering row 0 is 0
+        VP = HN | ~(Xv | HP);
+        VN = HP & Xv;
+        best = min(best, score);
+    }
+};
+
+
+// The probe loops (src/adaptertrimmer.cpp:202-216, 273-286) take the Levenshtein distance of up to 184 sixteen-mers of
+// the end window to the adapter's 16-mer and use only those within thr(16).  Which positions CAN be within it is decided
+// first, by one search-mode pass per lane over its ~6 positions (+ 15 columns of run-in): sg(e), the best distance of any
+// window substring ending at e, bounds ED(window[e-15..e], 16-mer) from below.  Only those candidates get the exact
+// distance; the rest could never have been hits, so the loops' results are unchanged.
+// Start side: probe p is rdata[p .. p+plen); end side: probe p is rdata[rlen-plen-p .. rlen-p).
+// Returns the number of candidates, their positions (ascending) in list[].  All 32 lanes.
+__device__ int probe_candidates(const uint8_t* rdata, int rlen, int np, int plen, const uint32_t* t16, int T16, bool endside,
+                                uint8_t* list) {
+    const int lane = lane_id();
+    if (np <= 0) return 0;
+    const int CH = (np + 31) >> 5;
+    const int p0 = lane * CH, p1 = min(np, p0 + CH);
+    uint32_t cb = 0;
+    if (p0 < np) {
+        // text columns in read order; ends e of this lane's probes: start side e = p + plen - 1, end side e = rlen - 1 - p
+        const int e_lo = endside ? rlen - p1 : p0 + plen - 1;
+        const int e_hi = endside ? rlen - 1 - p0 : p1 - 1 + plen - 1;
+        SearchMyers<uint32_t> Q;
+        Q.init(plen);
+        for (int j = e_lo - (plen - 1); j <= e_hi; j++) {
+            Q.column(__ldg(&t16[rdata[j]]));
+            if (j >= e_lo && Q.score <= T16) cb |= 1u << ((endside ? rlen - 1 - j : j - (plen - 1)) - p0);
+        }
+    }
+    // compact the candidate positions, ascending, into list[]
+    const int cnt = __popc(cb);
+    const int before = warp_incl_scan(cnt) - cnt;
+    const int total = __shfl_sync(0xffffffffu, before + cnt, 31);
+    __syncwarp();
+    int k = before;
+    for (uint32_t m = cb; m; m &= m - 1) list[k++] = (uint8_t)(p0 + __ffs(m) - 1);
+    __syncwarp();
+    return total;
 }
 
 struct Win { int lo, len; };
@@ -213,19 +275,19 @@ __device__ int trim_start(const DevParams& P, const uint8_t* seq, Win& w, int ai
     const int T16 = P.thr[plen];
     unsigned best = 0xFFFFFFFFu;
     const uint32_t* t16 = P.peq16 + (size_t)aidx * 512 + 256;   // last plen chars
-    for (int p0 = 0; p0 < np; p0 += 32) {
-        const int p = p0 + lane;
-        if (p < np) {
+    const int ncand = probe_candidates(rdata, rlen, np, plen, t16, T16, false, scratch);
+    for (int c0 = 0; c0 < ncand; c0 += 32) {
+        if (c0 + lane < ncand) {
+            const int p = scratch[c0 + lane];
             const int ed = myers16(rdata + p, plen, t16, plen);
             if (ed <= T16) best = min(best, ((unsigned)ed << 16) | (unsigned)p);
         }
-        if (__any_sync(0xffffffffu, best < 0x10000u)) break;   // an exact hit: no later position can beat (0, p)
     }
     best = __reduce_min_sync(0xffffffffu, best);
     if (best != 0xFFFFFFFFu) {
         int pos = (int)(best & 0xFFFFu);
         int cmplen = min(pos + plen, alen);
-        int ed = ed_adapter(rdata + pos + plen - cmplen, cmplen, P.peq + (size_t)aidx * 256, alen - cmplen, cmplen, alen);
+        int ed = ed_adapter(P, aidx, rdata + pos + plen - cmplen, cmplen, alen - cmplen, cmplen, alen);
         if (ed <= P.thr[cmplen]) {
             pos = min(pos + ext, rlen - alen);
             ev.add(aidx, 0, cmplen);
@@ -261,10 +323,12 @@ __device__ int trim_end(const DevParams& P, const uint8_t* seq, Win& w, int aidx
     const uint32_t* t16 = P.peq16 + (size_t)aidx * 512;         // first plen chars
     int pos = -1, carryE = -1, carryPos = -1;
     bool done = false;
-    for (int c0 = 0; c0 < np && !done; c0 += 32) {
-        const int p = c0 + lane;
+    const int ncand = probe_candidates(rdata, rlen, np, plen, t16, T16, true, scratch);
+    for (int c0 = 0; c0 < ncand && !done; c0 += 32) {
+        const bool have = c0 + lane < ncand;
+        const int p = have ? scratch[c0 + lane] : 0;
         int e = 255;
-        if (p < np) {
+        if (have) {
             const int ed = myers16(rdata + rlen - plen - p, plen, t16, plen);
             e = ed <= T16 ? ed : 255;
         }
@@ -278,19 +342,19 @@ __device__ int trim_end(const DevParams& P, const uint8_t* seq, Win& w, int aidx
         if (bm) {
             const int bl = __ffs(bm) - 1;
             const unsigned lowerb = m & ((1u << bl) - 1u);
-            pos = lowerb ? c0 + 31 - __clz(lowerb) : carryPos;
+            pos = lowerb ? scratch[c0 + 31 - __clz(lowerb)] : carryPos;
             done = true;
         } else if (m) {
             const int last = 31 - __clz(m);
             carryE = __shfl_sync(0xffffffffu, e, last);
-            carryPos = c0 + last;
+            carryPos = scratch[c0 + last];
         }
     }
     if (!done) pos = carryPos;
     __syncwarp();
     if (pos > 0) {
         int cmplen = min(pos + plen, alen);
-        int ed = ed_adapter(rdata + rlen - plen - pos, cmplen, P.peq + (size_t)aidx * 256, 0, cmplen, alen);
+        int ed = ed_adapter(P, aidx, rdata + rlen - plen - pos, cmplen, 0, cmplen, alen);
         if (ed <= P.thr[cmplen]) {
             pos = min(pos + ext, rlen - plen);
             ev.add(aidx, 1, cmplen);
@@ -315,28 +379,6 @@ __device__ int trim_end(const DevParams& P, const uint8_t* seq, Win& w, int aidx
 // code runs as before.  The filter only ever says "maybe" too often, never "no" wrongly: results are unchanged.
 // ------------------------------------------------------------------------------------------------------------------
 #define PF_WIN FPL_WINDOW
-
-template <typename W>
-struct SearchMyers {                      // pattern in the low m bits; standard Myers/Hyyro search recurrence
-    W VP, VN, top;
-    int score, best;
-    __device__ __forceinline__ void init(int m) {
-        VP = m >= (int)(8 * sizeof(W)) ? ~(W)0 : (((W)1 << m) - 1);
-        VN = 0; top = (W)1 << (m - 1); score = m; best = m;
-    }
-    __device__ __forceinline__ void column(W Eq) {
-        const W Xv = Eq | VN;
-        const W Xh = (((Eq & VP) + VP) ^ VP) | Eq;
-        W HP = VN | ~(Xh | VP);
-        W HN = VP & Xh;
-        score += (HP & top) ? 1 : 0;
-        score -= (HN & top) ? 1 : 0;
-        HP <<= 1; HN <<= 1;                // search mode: the horizontal delta entering row 0 is 0
-        VP = HN | ~(Xv | HP);
-        VN = HP & Xv;
-        best = min(best, score);
-    }
-};
 
 // maybe-bits of the (adapter, side) items [first_item, 2 * (n_adapters - 2)) for the window w: item = 2 * (k - 2) + side.
 // head / tail: the warp's staging buffers (PF_WIN bytes each); bits: one bit per item.  All 32 lanes.

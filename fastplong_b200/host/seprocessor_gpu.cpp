@@ -771,7 +771,8 @@ bool SingleEndProcessor::process() {
             for (int t = 0; t < T; t++) {
                 check(fpl_reset(g_workers[t]->ctx), "fpl_reset");
                 check(fpl_sync(g_workers[t]->ctx), "fpl_sync");
-                delete configs[t];
+                delete configs[t];                          // (frees its input list as well: ThreadConfig::cleanup)
+                mInputLists[t] = new SingleProducerSingleConsumerList<ReadPack*>();
                 configs[t] = new ThreadConfig(mOptions, t, false);
                 configs[t]->setInputList(mInputLists[t]);
                 initConfig(configs[t]);

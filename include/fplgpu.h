@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define FPL_ABI_VERSION 3
+#define FPL_ABI_VERSION 4
 
 /* Filter result codes — identical to src/common.h:43-50 (they index FilterResult::mFilterReadStats[32]). */
 enum {
@@ -38,7 +38,8 @@ enum {
 };
 
 /* Limits of this implementation (the reference has none; exceeding them is a loud error, not a fallback). */
-#define FPL_MAX_ADAPTER_LEN 128  /* longest adapter (start/end/FASTA entry) accepted by fpl_create */
+#define FPL_MAX_ADAPTER_LEN 1024 /* longest adapter (start/end/FASTA entry) accepted by fpl_create; adapters of up to
+                                    128 bp take the register-resident bit-vector paths, longer ones a multi-word one */
 #define FPL_MAX_ADAPTERS 1024    /* start + end + FASTA entries */
 #define FPL_MAX_WINDOW 1000      /* cut_front/cut_tail window size, reference range 1..1000 (src/options.cpp) */
 #define FPL_INLINE_EVENTS 4

@@ -49,8 +49,9 @@ def _rand_adapter(n, seed):
     return "".join("ACGT"[i] for i in rng.integers(0, 4, size=n))
 
 
-# -s/-e adapters of every word-count class of the scan kernels (halo 1..4 words, 5..8 counter planes)
-LONG_ADAPTERS = {n: (_rand_adapter(n, 100 + n), _rand_adapter(max(4, n - 3), 200 + n)) for n in (31, 32, 33, 45, 64, 65, 96, 97, 127, 128)}
+# -s/-e adapters of every word-count class of the scan kernels (halo 1..4 words, 5..8 counter planes) and, beyond 128 bp,
+# of the multi-word paths (generic k_scan, myers_long); 641 is where the reference's own edit_distance changes method
+LONG_ADAPTERS = {n: (_rand_adapter(n, 100 + n), _rand_adapter(max(4, n - 3), 200 + n)) for n in (31, 32, 33, 45, 64, 65, 96, 97, 127, 128, 129, 200, 300, 641, 1024)}
 for _n, (_s, _e) in LONG_ADAPTERS.items():
     OPTION_SETS[f"long_adapter_{_n}"] = Options(start_adapter=_s, end_adapter=_e, low_complexity_filter=(_n % 2 == 0))
 
