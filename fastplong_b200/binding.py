@@ -56,6 +56,8 @@ def load_library():
     lib.fpl_comm_size.argtypes = [C.c_void_p]
     lib.fpl_comm_agree_cycles.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
     lib.fpl_allreduce_stats.argtypes = [C.c_void_p, C.c_int64]
+    lib.fpl_eval_adapter_kmers.argtypes = [C.c_int, C.POINTER(FplBatch), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                           C.POINTER(C.c_int64)]
     lib.fpl_reset.argtypes = [C.c_void_p]
     lib.fpl_last_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_float),
                                           C.POINTER(C.c_int64), C.c_int]
@@ -72,7 +74,7 @@ EXPORTS = ["fpl_last_error", "fpl_abi_version", "fpl_create", "fpl_destroy", "fp
            "fpl_sync", "fpl_stream", "fpl_last_segments", "fpl_last_mask_regions", "fpl_fetch_results", "fpl_stats_cycles", "fpl_stats_reserve", "fpl_stats_download",
            "fpl_stats_device_ptr", "fpl_counter_words", "fpl_counters_download", "fpl_counters_device_ptr",
            "fpl_comm_unique_id", "fpl_comm_init", "fpl_comm_destroy", "fpl_comm_size", "fpl_comm_agree_cycles", "fpl_allreduce_stats",
-           "fpl_reset", "fpl_last_kernel_times", "fpl_launch_count", "fpl_set_timing"]
+           "fpl_eval_adapter_kmers", "fpl_reset", "fpl_last_kernel_times", "fpl_launch_count", "fpl_set_timing"]
 
 
 class _DeviceArray:
@@ -247,6 +249,20 @@ class Engine:
     @property
     def launch_count(self):
         return int(self.lib.fpl_launch_count(self.h))
+
+
+def eval_adapter_kmers(batch, side, shift_tail=1, device=0):
+    """Device half of Evaluator::evalAdapterAndReadNum: (counts uint32[1<<20], position_acc uint64[1<<20], total)."""
+    lib = load_library()
+    counts = np.zeros(1 << 20, dtype=np.uint32)
+    acc = np.zeros(1 << 20, dtype=np.uint64)
+    total = C.c_int64()
+    b = batch.to_abi()
+    rc = lib.fpl_eval_adapter_kmers(int(device), C.byref(b), int(shift_tail), int(side), counts.ctypes.data, acc.ctypes.data,
+                                    C.byref(total))
+    if rc != 0:
+        raise FplError(f"fpl_eval_adapter_kmers failed ({rc})")
+    return counts, acc, int(total.value)
 
 
 def relayout_stats(raw, cap, cycles):

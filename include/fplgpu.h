@@ -324,6 +324,20 @@ int fpl_comm_size(fpl_ctx* ctx);
 int fpl_comm_agree_cycles(fpl_ctx* ctx, int64_t* cycles);
 int fpl_allreduce_stats(fpl_ctx* ctx, int64_t cycles);
 
+/*
+ * SURVEY §8f row 4 — the counting half of Evaluator::evalAdapterAndReadNum (src/evaluator.cpp:105-265), context-free
+ * because it runs before the adapters (and so the context) exist: over the reads of a HOST batch (the caller passes what
+ * the reference would load: the first <= 64 Ki reads / 512 Mbases of the input) count the ten-mers of the first
+ * (side 0: pos in [0, min(len - 10 - shift_tail, 127)]) or last (side 1: pos in [max(0, len - 10 - shift_tail - 128),
+ * len - 10 - shift_tail]) positions: counts[key]++, position_acc[key] += pos (side 0) or len - pos (side 1),
+ * *total = valid ten-mers seen; key = Evaluator::seq2int's packing (A 0, T/U 1, C 2, G 3, first base most significant;
+ * a window holding any other byte is skipped).  counts and position_acc have 1 << 20 entries.  shift_tail is the
+ * reference's max(1, opt.trim.tail).  Picking the top key and extending it (getTopKey / extendKeyToAdapter) is O(4^10)
+ * table work and stays with the host (fastplong_b200/evaluator.py).  Returns 0, or < 0 on a CUDA error.
+ */
+int fpl_eval_adapter_kmers(int device, const fpl_batch* host_batch, int32_t shift_tail, int32_t side, uint32_t* counts,
+                           uint64_t* position_acc, int64_t* total);
+
 /* Zero all accumulators (a fresh ThreadConfig); stream-ordered, asynchronous. */
 int fpl_reset(fpl_ctx* ctx);
 

@@ -187,3 +187,29 @@ def compare_stats(a, b, what="stats"):
         bad = np.nonzero(a != b)[0]
         raise AssertionError(f"{what}: {len(bad)} words differ, first at {int(bad[0])}: "
                              f"{int(a[bad[0]])} vs {int(b[bad[0]])}")
+
+
+def kmer10_tables(batch, side, shift_tail=1):
+    """TEST INFRASTRUCTURE: the ten-mer tables of Evaluator::evalAdapterAndReadNum (src/evaluator.cpp:176-191,219-234)
+    in plain numpy — the checker of fpl_eval_adapter_kmers and the table source of the CPU tests of evaluator.py."""
+    code = np.full(256, -1, dtype=np.int64)
+    for ch, v in ((b"A", 0), (b"T", 1), (b"U", 1), (b"C", 2), (b"G", 3)):
+        code[ch[0]] = v
+    counts = np.zeros(1 << 20, dtype=np.uint32)
+    acc = np.zeros(1 << 20, dtype=np.uint64)
+    total = 0
+    for i in range(batch.n_reads):
+        o, n = int(batch.offsets[i]), int(batch.lens[i])
+        last = n - 10 - shift_tail
+        p0, p1 = (0, min(last, 127)) if side == 0 else (max(0, last - 128), last)
+        if p1 < p0:
+            continue
+        c = code[batch.seq[o + p0:o + p1 + 10]]
+        win = np.lib.stride_tricks.sliding_window_view(c, 10)
+        ok = (win >= 0).all(axis=1)
+        keys = (win * (4 ** np.arange(9, -1, -1))).sum(axis=1)[ok]
+        pos = np.arange(p0, p1 + 1)[ok]
+        np.add.at(counts, keys, 1)
+        np.add.at(acc, keys, (pos if side == 0 else n - pos).astype(np.uint64))
+        total += int(ok.sum())
+    return counts, acc, total
