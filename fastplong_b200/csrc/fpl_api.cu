@@ -32,7 +32,7 @@ void launch_scan_fast(const DevParams&, const ScanPlan&, const DevBatch&, ReadSt
 void launch_final(const DevParams&, const DevBatch&, const ReadState*, fpl_read_result*, StatSeg*, cudaStream_t);
 void launch_count(const fpl_read_result*, int64_t, unsigned long long*, bool, cudaStream_t);
 int launch_cycle_stats(CycleWs*, const uint8_t*, const uint8_t*, const StatSeg*, int64_t, int64_t, unsigned long long*, int64_t,
-                        bool, unsigned long long*, cudaStream_t);
+                        bool, unsigned long long*, bool, cudaStream_t);
 void launch_kmer_fix(const DevBatch&, const fpl_read_result*, unsigned long long*, cudaStream_t);
 void launch_read_qual(const DevBatch&, unsigned long long*, unsigned long long*, int64_t, fpl_read_result*, bool, cudaStream_t);
 void launch_make_preseg(const DevBatch&, StatSeg*, cudaStream_t);
@@ -68,6 +68,7 @@ struct fpl_ctx {
     FplIngest ingest;   // device-side FASTQ parsing state
     FplExt ext;         // --mask / --break state (variable number of output reads)
     int64_t last_bytes = 0;
+    bool slots16 = false;               // this batch's read offsets are multiples of 16 (checked: host batches, device ingest)
     int n_adapters = 0;
     uint8_t* d_adapters = nullptr;
     int* d_alen = nullptr;
@@ -190,14 +191,17 @@ static void collect_times(fpl_ctx* c) {
 }
 
 // min and max of the read lengths (fpl_process_device)
-__global__ void k_lens_minmax(const int32_t* __restrict__ lens, int64_t n, int* __restrict__ out) {
+// ... and the OR of the low four bits of the slot offsets (out[2]): 0 <=> every read starts on a 16-byte boundary
+__global__ void k_lens_minmax(const int32_t* __restrict__ lens, const int64_t* __restrict__ offsets, int64_t n, int* __restrict__ out) {
     int lo = INT_MAX, hi = INT_MIN;
+    unsigned mis = 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int v = lens[i];
         lo = min(lo, v); hi = max(hi, v);
+        mis |= (unsigned)offsets[i] & 15u;
     }
-    lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
-    if ((threadIdx.x & 31) == 0) { atomicMin(&out[0], lo); atomicMax(&out[1], hi); }
+    lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi); mis = __reduce_or_sync(0xffffffffu, mis);
+    if ((threadIdx.x & 31) == 0) { atomicMin(&out[0], lo); atomicMax(&out[1], hi); if (mis) atomicOr(&out[2], (int)mis); }
 }
 
 // Runs every kernel over reads [0, n) of a device-resident batch whose lens are known on the host.
@@ -263,7 +267,7 @@ static int run_batch(fpl_ctx* c, const DevBatch& full, const int32_t* h_lens, fp
         { Timed t(c, K_TRIM); launch_trim(c->P, b, st, res, c->d_counters, s); }
         { Timed t(c, K_CYCLE_PRE);
           if (launch_cycle_stats(&c->cycle_ws, full.seq, full.qual, pre, b.n_reads, tmax, c->d_stats[0], c->C, true,
-                                 ext ? nullptr : c->d_stats[1] + 16 * c->C + FPL_STATS_KMER, s)) return fail("out of device memory (cycle stats workspace)");
+                                 ext ? nullptr : c->d_stats[1] + 16 * c->C + FPL_STATS_KMER, c->slots16, s)) return fail("out of device memory (cycle stats workspace)");
           c->launches += 2; }   // + k_cs_keys and k_cs_gather around the (library) radix sort
         {
             Timed t(c, K_SCAN);
@@ -275,7 +279,7 @@ static int run_batch(fpl_ctx* c, const DevBatch& full, const int32_t* h_lens, fp
         if (!ext) {
             { Timed t(c, K_COUNT); launch_count(res, b.n_reads, c->d_counters, true, s); }
             { Timed t(c, K_CYCLE_POST);
-              if (launch_cycle_stats(&c->cycle_ws, full.seq, full.qual, post, 2 * b.n_reads, tmax, c->d_stats[1], c->C, false, nullptr, s))
+              if (launch_cycle_stats(&c->cycle_ws, full.seq, full.qual, post, 2 * b.n_reads, tmax, c->d_stats[1], c->C, false, nullptr, false, s))
                   return fail("out of device memory (cycle stats workspace)");
           c->launches += 2; }   // + k_cs_keys and k_cs_gather around the (library) radix sort
             { Timed t(c, K_KMER_FIX); launch_kmer_fix(b, res, c->d_stats[1] + 16 * c->C + FPL_STATS_KMER, s); }
@@ -290,7 +294,7 @@ static int run_batch(fpl_ctx* c, const DevBatch& full, const int32_t* h_lens, fp
             if (fpl_ext_run(&c->ext, c->P, b, n_bytes, res, c->d_counters, c->d_stats[1], c->C, &fseq, s, xerr, sizeof(xerr)))
                 return fail("--mask/--break stage: %s", xerr);
             { Timed t(c, K_CYCLE_POST);
-              if (launch_cycle_stats(&c->cycle_ws, fseq, full.qual, c->ext.d_stat, c->ext.n_segs, tmax, c->d_stats[1], c->C, true, nullptr, s))
+              if (launch_cycle_stats(&c->cycle_ws, fseq, full.qual, c->ext.d_stat, c->ext.n_segs, tmax, c->d_stats[1], c->C, true, nullptr, false, s))
                   return fail("out of device memory (cycle stats workspace)");
           c->launches += 2; }   // + k_cs_keys and k_cs_gather around the (library) radix sort
         }
@@ -497,25 +501,27 @@ int fpl_process_device(fpl_ctx* c, const fpl_batch* b, fpl_read_result* results_
             CK(cudaMemcpyAsync(c->h_lens.data(), b->lens, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
             CK(cudaStreamSynchronize(c->stream));
         }
+        c->slots16 = false;     // offsets not inspected on this path: the per-segment alignment dispatch handles anything
         return run_batch(c, d, c->h_lens.data(), results_dev, b->n_bytes);
     }
     // only the extremes of the lengths are needed on the host (Stats capacity, grid sizes): reduce them on the side
     // stream, which does not wait for the kernels of the previous batch still running on the compute stream
     if (!c->copy_stream) CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     if (!c->d_minmax) {
-        CK(cudaMalloc(&c->d_minmax, 2 * sizeof(int)));
-        CK(cudaMallocHost(&c->h_minmax, 2 * sizeof(int)));
+        CK(cudaMalloc(&c->d_minmax, 4 * sizeof(int)));
+        CK(cudaMallocHost(&c->h_minmax, 4 * sizeof(int)));
     }
-    c->h_minmax[0] = 0; c->h_minmax[1] = 0;
+    c->h_minmax[0] = 0; c->h_minmax[1] = 0; c->h_minmax[2] = 0;
     if (n) {
-        const int init[2] = {INT_MAX, INT_MIN};
+        const int init[3] = {INT_MAX, INT_MIN, 0};
         CK(cudaMemcpyAsync(c->d_minmax, init, sizeof(init), cudaMemcpyHostToDevice, c->copy_stream));
         const unsigned blocks = (unsigned)((n + 1023) / 1024 < 1184 ? (n + 1023) / 1024 : 1184);
-        k_lens_minmax<<<blocks, 256, 0, c->copy_stream>>>(b->lens, n, c->d_minmax);
-        CK(cudaMemcpyAsync(c->h_minmax, c->d_minmax, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->copy_stream));
+        k_lens_minmax<<<blocks, 256, 0, c->copy_stream>>>(b->lens, b->offsets, n, c->d_minmax);
+        CK(cudaMemcpyAsync(c->h_minmax, c->d_minmax, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->copy_stream));
         CK(cudaStreamSynchronize(c->copy_stream));
         if (c->h_minmax[0] < 0) return fail("fpl_process_device: a read has a negative length");
     }
+    c->slots16 = c->h_minmax[2] == 0;
     return run_batch(c, d, nullptr, results_dev, b->n_bytes, nullptr, nullptr, n ? c->h_minmax[1] : 0);
 }
 
@@ -593,6 +599,7 @@ int fpl_process_host(fpl_ctx* c, const fpl_batch* b, fpl_read_result* results) {
         CK(cudaEventRecord(c->piece_events[j], cs));
     }
     DevBatch d = {c->d_seq, c->d_qual, c->d_offsets, c->d_lens, n};
+    c->slots16 = true;          // checked above: every offset is a multiple of 16
     if (run_batch(c, d, b->lens, nullptr, b->n_bytes, &cuts, c->piece_events.data())) return -1;
     if (n) CK(cudaMemcpyAsync(results, c->d_results, sizeof(fpl_read_result) * n, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -632,6 +639,7 @@ int fpl_process_fastq_host(fpl_ctx* c, const uint8_t* text, int64_t n_bytes, int
     CK(cudaMemcpyAsync(records, g.d_rec, sizeof(fpl_fastq_record) * nrec, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     DevBatch d = {c->d_seq, c->d_qual, g.d_offsets, g.d_lens, nrec};
+    c->slots16 = false;         // the device packer's slots are aligned, but nothing here depends on it
     if (run_batch(c, d, c->h_lens.data(), nullptr, g.packed_bytes)) return -1;
     CK(cudaMemcpyAsync(results, c->d_results, sizeof(fpl_read_result) * nrec, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));

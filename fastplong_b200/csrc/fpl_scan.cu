@@ -235,6 +235,7 @@ __device__ Counts count_range(const fpl_options& o, uint32_t one, const uint8_t*
     const int lane = lane_id();
     const bool doCounts = (o.qual_filter_enabled || o.length_filter_enabled);
     const bool doCplx = o.complexity_enabled != 0;
+    if (!doCounts && !doCplx) return c;                    // no filter reads these counts: touch nothing
     const int qq = (int)(signed char)o.qualified_qual;
     const uint32_t KQ = (uint32_t)(128 - (o.qualified_qual & 0x7f));
     const int pre = (int)(reinterpret_cast<uintptr_t>(seq) & 15);
@@ -364,22 +365,27 @@ k_final(const __grid_constant__ DevParams P, DevBatch b, const ReadState* __rest
 
         int code[2] = {0, 0};
         if (split && nseg > 0) {
-            // Read::breakByGap left [0, start) and [start + glen, L).  The scan counted the whole window; count the gap and
-            // the SHORTER side here and take the longer side by subtraction (a split 500-kb read costs its short side).
+            // Read::breakByGap left [0, start) and [start + glen, L); the filter counts of the two sides come from the
+            // scan's counts of the whole window minus what is counted here.
             const int lenA = max(gapLo, 0);                                       // left side [0, lenA)
             const int loB = gapLo + gapLen;                                        // right side [loB, L)
             const int lenB = max(L - loB, 0);
             const Counts tot = {s.lowq, s.nn, s.totalq, s.diff};
-            const Counts g = count_range(P.opt, P.one, seq + gapLo, qual + gapLo, gapLen);
-            const bool countA = lenA <= lenB;
-            const Counts sh = countA ? count_range(P.opt, P.one, seq, qual, lenA) : count_range(P.opt, P.one, seq + loB, qual + loB, lenB);
+            // the window is [A | gap | B] and the scan counted all of it: count the two SMALLEST parts here and take the
+            // largest by subtraction (two far-apart adapter hits of an ultra-long read make the gap the big part)
             // adjacent pairs that straddle a boundary belong to no part
             const int x1 = (lenA > 0 && gapLen > 0) ? (seq[gapLo - 1] != seq[gapLo]) : 0;
             const int x2 = (lenB > 0 && gapLen > 0) ? (seq[loB - 1] != seq[loB]) : 0;
-            Counts lg;
-            lg.lowq = tot.lowq - g.lowq - sh.lowq; lg.nn = tot.nn - g.nn - sh.nn; lg.totalq = tot.totalq - g.totalq - sh.totalq;
-            lg.diff = P.opt.complexity_enabled ? tot.diff - g.diff - sh.diff - x1 - x2 : 0;
-            const Counts cA = countA ? sh : lg, cB = countA ? lg : sh;
+            const int biggest = (lenA >= lenB && lenA >= gapLen) ? 0 : (lenB >= gapLen ? 2 : 1);      // 0 A, 1 gap, 2 B
+            const Counts zero = {0, 0, 0, 0};
+            Counts cA = biggest == 0 ? zero : count_range(P.opt, P.one, seq, qual, lenA);
+            Counts cG = biggest == 1 ? zero : count_range(P.opt, P.one, seq + gapLo, qual + gapLo, gapLen);
+            Counts cB = biggest == 2 ? zero : count_range(P.opt, P.one, seq + loB, qual + loB, lenB);
+            Counts rest;
+            rest.lowq = tot.lowq - cA.lowq - cG.lowq - cB.lowq; rest.nn = tot.nn - cA.nn - cG.nn - cB.nn;
+            rest.totalq = tot.totalq - cA.totalq - cG.totalq - cB.totalq;
+            rest.diff = P.opt.complexity_enabled ? tot.diff - cA.diff - cG.diff - cB.diff - x1 - x2 : 0;
+            if (biggest == 0) cA = rest; else if (biggest == 2) cB = rest;
             if (nseg == 2) { code[0] = pass_filter(P.opt, segLen[0], cA); code[1] = pass_filter(P.opt, segLen[1], cB); }
             else code[0] = pass_filter(P.opt, segLen[0], seg0right ? cB : cA);
         } else {

@@ -170,6 +170,15 @@ __device__ __forceinline__ void kmer1(uint32_t P, uint32_t ok, uint32_t km_lane)
     red_shared_add(mad_u32(idx, 128u, km_lane), mad_u32(ok, 1u << (31 - T), 0u) >> 31);
 }
 
+// the same with the reduction predicated on the 5-mer's validity bit (no value arithmetic): for the vectors of a full
+// tile in which some lane holds a byte outside ACGTU
+template <int SHL, int T>
+__device__ __forceinline__ void kmer1p(uint32_t P, uint32_t ok, uint32_t km_lane) {
+    const uint32_t idx = (SHL ? mad_u32(P, 1u << SHL, 0u) : P) >> 22;
+    asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %1, 0;\n@p red.shared.add.u32 [%0], 1;\n}\n"
+                 ::"r"(mad_u32(idx, 128u, km_lane)), "r"(ok & (1u << T)) : "memory");
+}
+
 // the same when the 5-mer is known to count: the value is the immediate 1
 template <int SHL>
 __device__ __forceinline__ void kmer1f(uint32_t P, uint32_t km_lane) {
@@ -218,7 +227,7 @@ template <bool DO_KMER, int NT, int DEPTH, bool TMA>
 __global__ void __launch_bounds__(NT, DO_KMER ? 1 : 2048 / NT / 2)
 k_cycle_stats(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qualbuf, const SegD* __restrict__ segs,
               int64_t nseg, unsigned long long* __restrict__ stats, int64_t C, unsigned long long* __restrict__ kmer_also,
-              uint32_t one) {
+              uint32_t one, int aligned) {
     extern __shared__ __align__(16) uint8_t cs_smem[];
     uint32_t* packed = reinterpret_cast<uint32_t*>(cs_smem);                       // [8][16][33]: count << 20 | sum of q
     TileSeg* stage = reinterpret_cast<TileSeg*>(cs_smem + 8 * CS_BINW * 4);
@@ -317,8 +326,9 @@ k_cycle_stats(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qu
             if (kk < n) issue(kk, fill);
             if (!TMA) cp_async_commit();
             kk += NT / 32;
-            slot = slot == DEPTH ? 0 : slot + 1;
-            fill = fill == DEPTH ? 0 : fill + 1;
+            static_assert(((DEPTH + 1) & DEPTH) == 0, "ring slots: a power of two");
+            slot = (slot + 1) & DEPTH;
+            fill = (fill + 1) & DEPTH;
             if (lim <= 0) continue;                        // warp-uniform: the segment ends in front of this tile
             const bool full = lim >= CS_TILE && t0 != 0;   // warp-uniform: every byte of every lane is a cycle >= 4
             uint32_t kmask = 0xFFFFu;
@@ -326,7 +336,9 @@ k_cycle_stats(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qu
                 // ---- per-(bin, cycle) counters, all 16 bytes of every lane: address and value by dp4a ----
                 const uint32_t wb[4] = {mad_u32(sw[0], 16u, 0u) & 0x70707070u, mad_u32(sw[1], 16u, 0u) & 0x70707070u,
                                         mad_u32(sw[2], 16u, 0u) & 0x70707070u, mad_u32(sw[3], 16u, 0u) & 0x70707070u};
-                switch (sh) {
+                // aligned: every segment starts on a 16-byte boundary (the pre-filter pass: whole reads in their slots)
+                if (aligned) count16f<15>(wb, qm, pk_lane);
+                else switch (sh) {
                     case 0: count16f<15>(wb, qm, pk_lane); break;
                     case 1: count16f<14>(wb, qm, pk_lane); break;
                     case 2: count16f<13>(wb, qm, pk_lane); break;
@@ -401,25 +413,20 @@ k_cycle_stats(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qu
             // 20 codes, oldest first, 2 bits each: Phi = codes of bytes -4..11 (32 bits), Plo = bytes 4..15, then 8 zero bits
             const uint32_t Phi = mad_u32(ppc, 1u << 24, mad_u32(pc[0], 1u << 16, mad_u32(pc[1], 256u, pc[2])));
             const uint32_t Plo = mad_u32(pc[1], 1u << 24, mad_u32(pc[2], 1u << 16, pc[3] * 256u));
-            if (full) {
-                // every 5-mer is counted with the immediate 1 ...
+            if (full && !__any_sync(0xffffffffu, (I27 & 0x07FFFF80u) != 0u)) {
+                // plain bases everywhere in the warp's 512 bytes: every 5-mer is counted with the immediate 1
                 kmer1f<0>(Phi, km_lane); kmer1f<2>(Phi, km_lane); kmer1f<4>(Phi, km_lane); kmer1f<6>(Phi, km_lane);
                 kmer1f<8>(Phi, km_lane); kmer1f<10>(Phi, km_lane); kmer1f<12>(Phi, km_lane); kmer1f<14>(Phi, km_lane);
                 kmer1f<16>(Phi, km_lane); kmer1f<18>(Phi, km_lane); kmer1f<20>(Phi, km_lane); kmer1f<22>(Phi, km_lane);
                 kmer1f<8>(Plo, km_lane); kmer1f<10>(Plo, km_lane); kmer1f<12>(Plo, km_lane); kmer1f<14>(Plo, km_lane);
-                // ... and the rare ones that contain a byte outside ACGTU are taken out again (an N costs its lane five
-                // extra reductions; nothing here runs for a vector of plain bases)
-                if (I27 & 0x07FFFF80u) {
-                    const uint32_t I20 = I27 >> 7;
-                    uint32_t bad = (I20 | (I20 >> 1) | (I20 >> 2) | (I20 >> 3) | (I20 >> 4)) & 0xFFFFu;   // bit t: a byte of t-4..t is invalid
-                    const unsigned long long Pall = ((unsigned long long)Phi << 8) | (Plo >> 8 & 0xFFu);   // 20 codes, the newest in bits 1..0
-                    while (bad) {
-                        const int t = __ffs(bad) - 1;
-                        bad &= bad - 1;
-                        const uint32_t idx = (uint32_t)(Pall >> (2 * (15 - t))) & 1023u;
-                        red_shared_add(km_lane + idx * 128u, 0xFFFFFFFFu);
-                    }
-                }
+            } else if (full) {
+                // some lane holds an N (or another byte outside ACGTU): the reductions are predicated on the validity bits
+                const uint32_t I20 = I27 >> 7;
+                const uint32_t ok = ~(I20 | (I20 >> 1) | (I20 >> 2) | (I20 >> 3) | (I20 >> 4));   // bit t: bytes t-4..t all valid
+                kmer1p<0, 0>(Phi, ok, km_lane); kmer1p<2, 1>(Phi, ok, km_lane); kmer1p<4, 2>(Phi, ok, km_lane); kmer1p<6, 3>(Phi, ok, km_lane);
+                kmer1p<8, 4>(Phi, ok, km_lane); kmer1p<10, 5>(Phi, ok, km_lane); kmer1p<12, 6>(Phi, ok, km_lane); kmer1p<14, 7>(Phi, ok, km_lane);
+                kmer1p<16, 8>(Phi, ok, km_lane); kmer1p<18, 9>(Phi, ok, km_lane); kmer1p<20, 10>(Phi, ok, km_lane); kmer1p<22, 11>(Phi, ok, km_lane);
+                kmer1p<8, 12>(Plo, ok, km_lane); kmer1p<10, 13>(Plo, ok, km_lane); kmer1p<12, 14>(Plo, ok, km_lane); kmer1p<14, 15>(Plo, ok, km_lane);
             } else {
                 const uint32_t I20 = I27 >> 7;
                 const uint32_t bad = I20 | (I20 >> 1) | (I20 >> 2) | (I20 >> 3) | (I20 >> 4);   // bit t: a byte of t-4..t is invalid
@@ -487,7 +494,8 @@ void fpl_cycle_ws_free(CycleWs* ws) {
 // kmer_also: where the 5-mer counts of this launch go besides `stats` (nullptr = nowhere else); do_kmer = false skips
 // them.  Returns 0, or -1 when the workspace cannot be allocated.
 int launch_cycle_stats(CycleWs* ws, const uint8_t* seq, const uint8_t* qual, const StatSeg* segs, int64_t nseg, int64_t max_len,
-                       unsigned long long* stats, int64_t C, bool do_kmer, unsigned long long* kmer_also, cudaStream_t stream) {
+                       unsigned long long* stats, int64_t C, bool do_kmer, unsigned long long* kmer_also, bool aligned,
+                       cudaStream_t stream) {
     if (nseg == 0 || max_len <= 0) return 0;
     // the opt-in to more than 48 KB of dynamic shared memory is a per-device function attribute
     static std::atomic<unsigned long long> attr_set{0};
@@ -536,11 +544,11 @@ int launch_cycle_stats(CycleWs* ws, const uint8_t* seq, const uint8_t* qual, con
     const SegD* sorted = static_cast<const SegD*>(ws->sorted);
     static const bool tma = getenv("FPL_CS_TMA") != nullptr && atoi(getenv("FPL_CS_TMA")) != 0;
     if (tma) {
-        if (do_kmer) k_cycle_stats<true, CS_NT_KMER, CS_DEPTH_KMER, true><<<grid, CS_NT_KMER, CS_SMEM_KMER, stream>>>(seq, qual, sorted, nseg, stats, C, kmer_also, 1u);
-        else k_cycle_stats<false, CS_NT_PLAIN, CS_DEPTH_PLAIN, true><<<grid, CS_NT_PLAIN, CS_SMEM_PLAIN, stream>>>(seq, qual, sorted, nseg, stats, C, nullptr, 1u);
+        if (do_kmer) k_cycle_stats<true, CS_NT_KMER, CS_DEPTH_KMER, true><<<grid, CS_NT_KMER, CS_SMEM_KMER, stream>>>(seq, qual, sorted, nseg, stats, C, kmer_also, 1u, aligned ? 1 : 0);
+        else k_cycle_stats<false, CS_NT_PLAIN, CS_DEPTH_PLAIN, true><<<grid, CS_NT_PLAIN, CS_SMEM_PLAIN, stream>>>(seq, qual, sorted, nseg, stats, C, nullptr, 1u, aligned ? 1 : 0);
     } else {
-        if (do_kmer) k_cycle_stats<true, CS_NT_KMER, CS_DEPTH_KMER, false><<<grid, CS_NT_KMER, CS_SMEM_KMER, stream>>>(seq, qual, sorted, nseg, stats, C, kmer_also, 1u);
-        else k_cycle_stats<false, CS_NT_PLAIN, CS_DEPTH_PLAIN, false><<<grid, CS_NT_PLAIN, CS_SMEM_PLAIN, stream>>>(seq, qual, sorted, nseg, stats, C, nullptr, 1u);
+        if (do_kmer) k_cycle_stats<true, CS_NT_KMER, CS_DEPTH_KMER, false><<<grid, CS_NT_KMER, CS_SMEM_KMER, stream>>>(seq, qual, sorted, nseg, stats, C, kmer_also, 1u, aligned ? 1 : 0);
+        else k_cycle_stats<false, CS_NT_PLAIN, CS_DEPTH_PLAIN, false><<<grid, CS_NT_PLAIN, CS_SMEM_PLAIN, stream>>>(seq, qual, sorted, nseg, stats, C, nullptr, 1u, aligned ? 1 : 0);
     }
     return 0;
 }
@@ -552,10 +560,41 @@ int launch_cycle_stats(CycleWs* ws, const uint8_t* seq, const uint8_t* qual, con
 // given, src/stats.cpp:309-311).  The removed ranges are short for almost every read.
 // ------------------------------------------------------------------------------------------------------------------
 #define KF_WARPS 8
+#define KF_LONG 2048          // a removed range longer than this is shared by the block's warps
+#define KF_LIST 16
+
+namespace {
+// the 5-mers ending at e in [from, to) of one read, strided over `nlanes` lanes (lane id `me`): rem[code]++
+__device__ __forceinline__ void kmer_remove_range(const uint8_t* seq, int from, int to, int me, int nlanes, uint32_t rem_base) {
+    // four positions per lane in flight: the loads of one round are independent, a lone warp walking a long range is
+    // bound by their latency otherwise
+    for (int e0 = from + me; e0 < to; e0 += 4 * nlanes) {
+        uint32_t c[4][5];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int e = e0 + u * nlanes;
+#pragma unroll
+            for (int i = 0; i < 5; i++) c[u][i] = e < to ? (uint32_t)seq[e - 4 + i] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t c4 = kmer_code(c[u][0]), c3 = kmer_code(c[u][1]), c2 = kmer_code(c[u][2]), c1 = kmer_code(c[u][3]),
+                           c0 = kmer_code(c[u][4]);
+            if (e0 + u * nlanes < to && ((c4 | c3 | c2 | c1 | c0) & 8u) == 0u)
+                red_shared_add(rem_base + (((c4 << 8) | (c3 << 6) | (c2 << 4) | (c1 << 2) | c0) << 2), 1u);
+        }
+    }
+}
+}  // namespace
+
 __global__ void __launch_bounds__(KF_WARPS * 32)
 k_kmer_fix(DevBatch b, const fpl_read_result* __restrict__ res, unsigned long long* __restrict__ post_kmer) {
     __shared__ uint32_t rem[1024];
+    __shared__ int n_long;
+    __shared__ long long long_off[KF_LIST];
+    __shared__ int long_from[KF_LIST], long_to[KF_LIST];
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) rem[i] = 0;
+    if (threadIdx.x == 0) n_long = 0;
     __syncthreads();
     const int wid = threadIdx.x >> 5, lane = lane_id();
     const uint32_t rem_base = shared_addr(&rem[0]);
@@ -574,20 +613,29 @@ k_kmer_fix(DevBatch b, const fpl_read_result* __restrict__ res, unsigned long lo
         int from = 4;
         for (int k = 0; k <= nk; k++) {
             const int to = k < nk ? min(ks[k], L) : L;
-            for (int e0 = from; e0 < to; e0 += 32) {
-                const int e = e0 + lane;
-                if (e < to) {
-                    const uint32_t c4 = kmer_code(seq[e - 4]), c3 = kmer_code(seq[e - 3]), c2 = kmer_code(seq[e - 2]),
-                                   c1 = kmer_code(seq[e - 1]), c0 = kmer_code(seq[e]);
-                    if (((c4 | c3 | c2 | c1 | c0) & 8u) == 0u)
-                        red_shared_add(rem_base + (((c4 << 8) | (c3 << 6) | (c2 << 4) | (c1 << 2) | c0) << 2), 1u);
+            if (to - from > KF_LONG) {
+                // a failed long read, or the gap between two far-apart adapter hits of an ultra-long read: the block's
+                // warps share it after the loop (a lone warp would walk it at the latency of its loads)
+                int slot = -1;
+                if (lane == 0) slot = atomicAdd(&n_long, 1);
+                slot = __shfl_sync(0xffffffffu, slot, 0);
+                if (slot < KF_LIST) {
+                    if (lane == 0) { long_off[slot] = b.offsets[r]; long_from[slot] = from; long_to[slot] = to; }
+                } else {
+                    kmer_remove_range(seq, from, to, lane, 32, rem_base);
                 }
+            } else {
+                kmer_remove_range(seq, from, to, lane, 32, rem_base);
             }
             // the next removed range starts behind this one and behind the segment; a passing segment shorter than
             // four bases (only possible with --length_required < 5) ends in front of `to` and must not pull it back
             if (k < nk) from = max(from, max(to, ke[k]));
         }
     }
+    __syncthreads();
+    const int nl = min(n_long, KF_LIST);
+    for (int i = 0; i < nl; i++)
+        kmer_remove_range(b.seq + long_off[i], long_from[i], long_to[i], threadIdx.x, KF_WARPS * 32, rem_base);
     __syncthreads();
     for (int i = threadIdx.x; i < 1024; i += blockDim.x)
         if (rem[i]) atomicAdd(&post_kmer[i], 0ull - (unsigned long long)rem[i]);
@@ -623,58 +671,57 @@ __device__ __forceinline__ uint8_t hist_median(const uint32_t* h, int len, int l
 __device__ __forceinline__ void hist_vec(uint32_t hbase, const uint4& v, uint32_t delta) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int k = 0; k < 4; k++)
+    for (int k = 0; k < 4; k++) {
+        // bin address = hbase + 4 * (byte & 127): one dp4a per byte (weight 4 on that byte) on the FMA pipe, after one
+        // LOP3 per word that keeps the bytes inside the 128-bin table
+        const uint32_t m = w[k] & 0x7f7f7f7fu;
 #pragma unroll
-        for (int j = 0; j < 4; j++) red_shared_add(hbase + (((w[k] >> (8 * j)) & 127u) << 2), delta);
+        for (int j = 0; j < 4; j++) red_shared_add(__dp4a(m, 4u << (8 * j), hbase), delta);
+    }
 }
-__device__ __forceinline__ void hist_bytes(uint32_t hbase, const uint8_t* qp, int n, uint32_t delta, int lane) {
+// h[q] += delta for the bytes qp[0..n) (delta = 1 or 0xFFFFFFFF): 16-byte vector body, byte head/tail; the work is
+// strided over `nth` threads, this one being `me` (a warp: lane / 32; a whole block: threadIdx.x / blockDim.x)
+__device__ __forceinline__ void hist_bytes(uint32_t hbase, const uint8_t* qp, int n, uint32_t delta, int me, int nth) {
     const int head = min(n, (int)((16 - (reinterpret_cast<uintptr_t>(qp) & 15)) & 15));
-    if (lane < head) red_shared_add(hbase + ((uint32_t)(qp[lane] & 127) << 2), delta);
+    if (me < head) red_shared_add(hbase + ((uint32_t)(qp[me] & 127) << 2), delta);
     const int nvec = (n - head) >> 4;
     const uint4* vp = reinterpret_cast<const uint4*>(qp + head);
-    // four vectors per lane in flight: a warp alone keeps 2 KB of loads outstanding (the kernel is latency-bound otherwise)
-    int i = lane;
-    for (; i + 96 < nvec; i += 128) {
-        const uint4 v0 = __ldg(vp + i), v1 = __ldg(vp + i + 32), v2 = __ldg(vp + i + 64), v3 = __ldg(vp + i + 96);
+    // four vectors per thread in flight: a warp alone keeps 2 KB of loads outstanding (the kernel is latency-bound otherwise)
+    int i = me;
+    for (; i + 3 * nth < nvec; i += 4 * nth) {
+        const uint4 v0 = __ldg(vp + i), v1 = __ldg(vp + i + nth), v2 = __ldg(vp + i + 2 * nth), v3 = __ldg(vp + i + 3 * nth);
         hist_vec(hbase, v0, delta); hist_vec(hbase, v1, delta); hist_vec(hbase, v2, delta); hist_vec(hbase, v3, delta);
     }
-    for (; i < nvec; i += 32) hist_vec(hbase, __ldg(vp + i), delta);
+    for (; i < nvec; i += nth) hist_vec(hbase, __ldg(vp + i), delta);
     const int done = head + (nvec << 4);
-    if (done + lane < n) red_shared_add(hbase + ((uint32_t)(qp[done + lane] & 127) << 2), delta);   // < 16 tail bytes
+    if (me < 16 && done + me < n) red_shared_add(hbase + ((uint32_t)(qp[done + me] & 127) << 2), delta);   // < 16 tail bytes
 }
-}  // namespace
 
-// Shared-memory atomics are the fast way to histogram on this part (tools/ubench_hist.cu: a 128-bin table updated
-// with atomicAdd by 8 warps streams quality bytes at HBM speed, 4x faster than lane-private read-modify-write).
-//
-// One warp per input read: the histogram of the whole read gives the pre-filter median and mBaseQualHistogram; the
-// histogram of each passing segment is derived from it by subtracting the (short) removed ends — or counted directly
-// when the segment is the smaller part — and gives the post-filter median and histogram.  One pass over the
-// quality bytes serves both Stats objects.
-__global__ void __launch_bounds__(RQ_WARPS * 32)
-k_read_qual(DevBatch b, unsigned long long* __restrict__ stats_pre, unsigned long long* __restrict__ stats_post, int64_t C,
-            fpl_read_result* __restrict__ res, bool pre_only) {
-    __shared__ uint32_t hist[RQ_WARPS][2][128];        // per warp: [0] whole read, [1] current segment
-    __shared__ uint32_t block_hist[2][128];            // this block's reads -> one flush per Stats block
-    __shared__ unsigned long long block_misc[2][2];    // reads, length sum
-    const int wid = threadIdx.x >> 5, lane = lane_id();
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) (&block_hist[0][0])[i] = 0;
-    if (threadIdx.x < 4) (&block_misc[0][0])[threadIdx.x] = 0;
-    __syncthreads();
-    unsigned long long* tail[2] = {stats_pre + 16 * C, stats_post + 16 * C};
-    uint32_t* hfull = hist[wid][0];
-    uint32_t* hseg = hist[wid][1];
+// One read: the histogram of the whole read gives the pre-filter median and mBaseQualHistogram; the histogram of each
+// passing segment is derived from it by subtracting the (short) removed ends — or counted directly when the segment is
+// the smaller part — and gives the post-filter median and histogram.  One pass over the quality bytes serves both Stats
+// objects.  COOP = false: one warp owns the read.  COOP = true: the whole block does (an ultra-long read streamed by
+// one warp is bound by the latency of that warp's loads); every thread of the block calls it for the same read, the
+// histograms are warp 0's, warp 0 does the medians.
+template <bool COOP>
+__device__ __forceinline__ void read_qual_one(const DevBatch& b, int64_t r, uint32_t* hfull, uint32_t* hseg, uint32_t (*block_hist)[128],
+                                              unsigned long long (*block_misc)[2], unsigned long long* const* tail,
+                                              fpl_read_result* __restrict__ res, bool pre_only) {
+    const int lane = lane_id(), wid = threadIdx.x >> 5;
+    const int me = COOP ? (int)threadIdx.x : lane, nth = COOP ? (int)blockDim.x : 32;
+    auto sync = [] { if (COOP) __syncthreads(); else __syncwarp(); };
+    const bool lead = !COOP || wid == 0;                 // the warp that owns the medians and the flushes
     const uint32_t hfull_s = shared_addr(hfull), hseg_s = shared_addr(hseg);
-    const int64_t nwarps = (int64_t)gridDim.x * RQ_WARPS;
-    for (int64_t r = (int64_t)blockIdx.x * RQ_WARPS + wid; r < b.n_reads; r += nwarps) {
-        const uint8_t* qp = b.qual + b.offsets[r];
-        const int L = b.lens[r];
-        fpl_read_result* o = &res[r];
-        for (int i = lane; i < 128; i += 32) hfull[i] = 0;
-        __syncwarp();
-        hist_bytes(hfull_s, qp, L, 1u, lane);
-        __syncwarp();
-        uint32_t own[4];
+    const uint8_t* qp = b.qual + b.offsets[r];
+    const int L = b.lens[r];
+    fpl_read_result* o = &res[r];
+    sync();
+    for (int i = me; i < 128; i += nth) hfull[i] = 0;
+    sync();
+    hist_bytes(hfull_s, qp, L, 1u, me, nth);
+    sync();
+    uint32_t own[4];
+    if (lead) {
         const uint8_t med = hist_median(hfull, L, lane, own);
 #pragma unroll
         for (int k = 0; k < 4; k++)
@@ -688,22 +735,24 @@ k_read_qual(DevBatch b, unsigned long long* __restrict__ stats_pre, unsigned lon
             }
             o->pre_median_qual = med;
         }
-        const int nseg = pre_only ? 0 : o->n_segments;   // --mask/--break: the post-filter part is k_ext_seg_qual's
-        for (int k = 0; k < nseg; k++) {
-            if (o->seg_result[k] != FPL_PASS_FILTER) continue;      // warp-uniform
-            const int a = o->seg_lo[k], n = o->seg_len[k];
-            __syncwarp();
-            if (L - n <= n) {            // copy the read's histogram and take the removed ends out
-                for (int i = lane; i < 128; i += 32) hseg[i] = hfull[i];
-                __syncwarp();
-                hist_bytes(hseg_s, qp, a, 0xFFFFFFFFu, lane);
-                hist_bytes(hseg_s, qp + a + n, L - a - n, 0xFFFFFFFFu, lane);
-            } else {
-                for (int i = lane; i < 128; i += 32) hseg[i] = 0;
-                __syncwarp();
-                hist_bytes(hseg_s, qp + a, n, 1u, lane);
-            }
-            __syncwarp();
+    }
+    const int nseg = pre_only ? 0 : o->n_segments;   // --mask/--break: the post-filter part is k_ext_seg_qual's
+    for (int k = 0; k < nseg; k++) {
+        if (o->seg_result[k] != FPL_PASS_FILTER) continue;      // uniform
+        const int a = o->seg_lo[k], n = o->seg_len[k];
+        sync();
+        if (L - n <= n) {            // copy the read's histogram and take the removed ends out
+            for (int i = me; i < 128; i += nth) hseg[i] = hfull[i];
+            sync();
+            hist_bytes(hseg_s, qp, a, 0xFFFFFFFFu, me, nth);
+            hist_bytes(hseg_s, qp + a + n, L - a - n, 0xFFFFFFFFu, me, nth);
+        } else {
+            for (int i = me; i < 128; i += nth) hseg[i] = 0;
+            sync();
+            hist_bytes(hseg_s, qp + a, n, 1u, me, nth);
+        }
+        sync();
+        if (lead) {
             const uint8_t smed = hist_median(hseg, n, lane, own);
 #pragma unroll
             for (int j = 0; j < 4; j++)
@@ -718,8 +767,44 @@ k_read_qual(DevBatch b, unsigned long long* __restrict__ stats_pre, unsigned lon
                 o->seg_median_qual[k] = smed;
             }
         }
-        __syncwarp();
     }
+    sync();
+}
+}  // namespace
+
+#define RQ_LONG (96 * 1024)      // reads longer than this are streamed by the whole block
+#define RQ_LIST 24
+
+// Shared-memory atomics are the fast way to histogram on this part (tools/ubench_hist.cu: a 128-bin table updated
+// with atomicAdd by 8 warps streams quality bytes at HBM speed, 4x faster than lane-private read-modify-write).
+__global__ void __launch_bounds__(RQ_WARPS * 32)
+k_read_qual(DevBatch b, unsigned long long* __restrict__ stats_pre, unsigned long long* __restrict__ stats_post, int64_t C,
+            fpl_read_result* __restrict__ res, bool pre_only) {
+    __shared__ uint32_t hist[RQ_WARPS][2][128];        // per warp: [0] whole read, [1] current segment
+    __shared__ uint32_t block_hist[2][128];            // this block's reads -> one flush per Stats block
+    __shared__ unsigned long long block_misc[2][2];    // reads, length sum
+    __shared__ int n_long;
+    __shared__ long long long_read[RQ_LIST];
+    const int wid = threadIdx.x >> 5, lane = lane_id();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) (&block_hist[0][0])[i] = 0;
+    if (threadIdx.x < 4) (&block_misc[0][0])[threadIdx.x] = 0;
+    if (threadIdx.x == 0) n_long = 0;
+    __syncthreads();
+    unsigned long long* tail[2] = {stats_pre + 16 * C, stats_post + 16 * C};
+    const int64_t nwarps = (int64_t)gridDim.x * RQ_WARPS;
+    for (int64_t r = (int64_t)blockIdx.x * RQ_WARPS + wid; r < b.n_reads; r += nwarps) {
+        if (b.lens[r] > RQ_LONG) {
+            int slot = -1;
+            if (lane == 0) slot = atomicAdd(&n_long, 1);
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+            if (slot < RQ_LIST) { if (lane == 0) long_read[slot] = r; continue; }
+        }
+        read_qual_one<false>(b, r, hist[wid][0], hist[wid][1], block_hist, block_misc, tail, res, pre_only);
+    }
+    __syncthreads();
+    const int nl = min(n_long, RQ_LIST);
+    for (int i = 0; i < nl; i++)
+        read_qual_one<true>(b, long_read[i], hist[0][0], hist[0][1], block_hist, block_misc, tail, res, pre_only);
     __syncthreads();
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
         const int which = i >> 7, bin = i & 127;
