@@ -60,7 +60,9 @@ __device__ int myers128(const uint8_t* text, int n, const uint4* peq, int shift,
 
 __device__ __forceinline__ int ed_adapter(const DevParams& P, int aidx, const uint8_t* text, int n, int shift, int m, int alen) {
     const uint4* peq = P.peq + (size_t)aidx * 256;
-    if (alen <= 32) return myers32(text, n, peq, shift, m);
+    // every lane wants the same distance: for <= 32 text bytes lane i looks up the match mask of byte i once and the
+    // recurrence runs on shuffled masks (no dependent loads inside the column loop)
+    if (alen <= 32) return n <= 32 ? myers32_warp(text, n, peq, shift, m) : myers32(text, n, peq, shift, m);
     if (alen <= 128) return myers128(text, n, peq, shift, m);
     return myers_long(text, n, P.peq_long + (size_t)aidx * 256 * P.peq_words, P.peq_words, shift, m);
 }
