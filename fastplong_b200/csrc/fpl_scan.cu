@@ -377,14 +377,19 @@ k_final(const __grid_constant__ DevParams P, DevBatch b, const ReadState* __rest
             const int x1 = (lenA > 0 && gapLen > 0) ? (seq[gapLo - 1] != seq[gapLo]) : 0;
             const int x2 = (lenB > 0 && gapLen > 0) ? (seq[loB - 1] != seq[loB]) : 0;
             const int biggest = (lenA >= lenB && lenA >= gapLen) ? 0 : (lenB >= gapLen ? 2 : 1);      // 0 A, 1 gap, 2 B
-            const Counts zero = {0, 0, 0, 0};
-            Counts cA = biggest == 0 ? zero : count_range(P.opt, P.one, seq, qual, lenA);
-            Counts cG = biggest == 1 ? zero : count_range(P.opt, P.one, seq + gapLo, qual + gapLo, gapLen);
-            Counts cB = biggest == 2 ? zero : count_range(P.opt, P.one, seq + loB, qual + loB, lenB);
-            Counts rest;
-            rest.lowq = tot.lowq - cA.lowq - cG.lowq - cB.lowq; rest.nn = tot.nn - cA.nn - cG.nn - cB.nn;
-            rest.totalq = tot.totalq - cA.totalq - cG.totalq - cB.totalq;
-            rest.diff = P.opt.complexity_enabled ? tot.diff - cA.diff - cG.diff - cB.diff - x1 - x2 : 0;
+            const int partLo[3] = {0, gapLo, loB}, partLen[3] = {lenA, gapLen, lenB};
+            Counts part[3] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
+            Counts rest = tot;
+            rest.diff = P.opt.complexity_enabled ? tot.diff - x1 - x2 : 0;
+#pragma unroll 1
+            for (int k = 0; k < 3; k++) {
+                if (k == biggest) continue;
+                const Counts c = count_range(P.opt, P.one, seq + partLo[k], qual + partLo[k], partLen[k]);
+                part[k] = c;
+                rest.lowq -= c.lowq; rest.nn -= c.nn; rest.totalq -= c.totalq;
+                if (P.opt.complexity_enabled) rest.diff -= c.diff;
+            }
+            Counts cA = part[0], cB = part[2];
             if (biggest == 0) cA = rest; else if (biggest == 2) cB = rest;
             if (nseg == 2) { code[0] = pass_filter(P.opt, segLen[0], cA); code[1] = pass_filter(P.opt, segLen[1], cB); }
             else code[0] = pass_filter(P.opt, segLen[0], seg0right ? cB : cA);

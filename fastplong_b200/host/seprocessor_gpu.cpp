@@ -15,6 +15,7 @@
 //   * at the end the device-accumulated Stats blocks and the adapter event table are added into each worker's
 //     Stats / FilterResult objects so that Stats::merge, summarize and the reporters run unchanged.
 // No per-base decision is taken on the host.
+#include <algorithm>
 #include <condition_variable>
 #include <cstdio>
 #include <cstring>
@@ -421,6 +422,11 @@ void SingleEndProcessor::readerTask() {
     const int T = mOptions->thread;
     long total = 0, reported = 0;
     bool stop = false;
+    // Back-pressure by BYTES, not packs (the reference bounds packs because it works pack by pack; a GPU worker gathers
+    // kBatchBases before it submits): the reader stays at most about three batches per worker — capped at 1.5 Gbases in
+    // all — ahead of what the workers have taken, and the writer's backlog is held to the same number of packs.
+    long packBasesSum = 0;
+    const long aheadBases = std::min<long>(3L * kBatchBases * T, 1536L << 20);
     while (!stop) {
         ReadPack* pack = new ReadPack;
         pack->data = new Read*[PACK_SIZE];
@@ -434,16 +440,18 @@ void SingleEndProcessor::readerTask() {
         }
         // the reference always emits a final (possibly empty) pack when the input ends on a pack boundary
         if (pack->count == 0 && !stop) { delete[] pack->data; delete pack; continue; }
+        for (int i = 0; i < pack->count; i++) packBasesSum += (long)pack->data[i]->mSeq->length();
         mInputLists[mPackReadCounter % T]->produce(pack);
         mPackReadCounter++;
         if (mOptions->verbose && total >= reported + 1000000) {
             reported = total;
             loginfo("loaded " + to_string(reported / 1000000) + "M reads");
         }
-        // back-pressure: do not run further ahead of the workers than they can hold
-        while (!stop && (long)mPackReadCounter - mPackProcessedCounter > 4L * PACK_IN_MEM_LIMIT * T) usleep(200);
+        const long avgPack = std::max<long>(1, packBasesSum / (long)mPackReadCounter);
+        const long aheadPacks = std::max<long>(2L * T, aheadBases / avgPack);
+        while (!stop && (long)mPackReadCounter - mPackProcessedCounter > aheadPacks) usleep(200);
         if (mLeftWriter)
-            while (!stop && mLeftWriter->bufferLength() > 4L * PACK_IN_MEM_LIMIT * T) usleep(1000);
+            while (!stop && mLeftWriter->bufferLength() > aheadPacks) usleep(1000);
     }
     for (int t = 0; t < T; t++) mInputLists[t]->setProducerFinished();
     mReaderFinished = true;
@@ -465,9 +473,9 @@ bool SingleEndProcessor::processSingleEnd(ReadPack* pack, ThreadConfig* config) 
             nreads++;
             nbytes += (p->data[i]->mSeq->length() + kSlotAlign - 1) / kSlotAlign * kSlotAlign;
         }
-    // first use sizes the pinned buffers for a full batch, so that later batches do not re-pin memory
-    w.seq.reserve(nbytes + 256, (size_t)kBatchBases + (8u << 20)); w.qual.reserve(nbytes + 256, (size_t)kBatchBases + (8u << 20));
-    w.offsets.reserve(nreads + 1, 1u << 16); w.lens.reserve(nreads + 1, 1u << 16); w.results.reserve(nreads + 1, 1u << 16);
+    // pinned buffers grow to what the batches need (doubling: a small input pins little, a large one re-pins a few times)
+    w.seq.reserve(nbytes + 256, 1u << 20); w.qual.reserve(nbytes + 256, 1u << 20);
+    w.offsets.reserve(nreads + 1, 1u << 12); w.lens.reserve(nreads + 1, 1u << 12); w.results.reserve(nreads + 1, 1u << 12);
     size_t k = 0, off = 0;
     for (ReadPack* p : w.packs)
         for (int i = 0; i < p->count; i++) {
