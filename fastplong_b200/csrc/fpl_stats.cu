@@ -565,25 +565,35 @@ int launch_cycle_stats(CycleWs* ws, const uint8_t* seq, const uint8_t* qual, con
 
 namespace {
 // the 5-mers ending at e in [from, to) of one read, strided over `nlanes` lanes (lane id `me`): rem[code]++
+__device__ __forceinline__ void kmer_remove_one(const uint8_t* seq, int e, uint32_t rem_base) {
+    const uint32_t c4 = kmer_code(seq[e - 4]), c3 = kmer_code(seq[e - 3]), c2 = kmer_code(seq[e - 2]),
+                   c1 = kmer_code(seq[e - 1]), c0 = kmer_code(seq[e]);
+    if (((c4 | c3 | c2 | c1 | c0) & 8u) == 0u)
+        red_shared_add(rem_base + (((c4 << 8) | (c3 << 6) | (c2 << 4) | (c1 << 2) | c0) << 2), 1u);
+}
 __device__ __forceinline__ void kmer_remove_range(const uint8_t* seq, int from, int to, int me, int nlanes, uint32_t rem_base) {
-    // four positions per lane in flight: the loads of one round are independent, a lone warp walking a long range is
-    // bound by their latency otherwise
-    for (int e0 = from + me; e0 < to; e0 += 4 * nlanes) {
+    if (to - from <= 4 * nlanes) {            // the usual case: a trimmed end or a short gap
+        for (int e = from + me; e < to; e += nlanes) kmer_remove_one(seq, e, rem_base);
+        return;
+    }
+    // a long range: four positions per lane in flight (the loads of one round are independent; a lone warp walking a
+    // long range is bound by their latency otherwise)
+    int e0 = from + me;
+    for (; e0 + 3 * nlanes < to; e0 += 4 * nlanes) {
         uint32_t c[4][5];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int e = e0 + u * nlanes;
+        for (int u = 0; u < 4; u++)
 #pragma unroll
-            for (int i = 0; i < 5; i++) c[u][i] = e < to ? (uint32_t)seq[e - 4 + i] : 0u;
-        }
+            for (int i = 0; i < 5; i++) c[u][i] = (uint32_t)seq[e0 + u * nlanes - 4 + i];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             const uint32_t c4 = kmer_code(c[u][0]), c3 = kmer_code(c[u][1]), c2 = kmer_code(c[u][2]), c1 = kmer_code(c[u][3]),
                            c0 = kmer_code(c[u][4]);
-            if (e0 + u * nlanes < to && ((c4 | c3 | c2 | c1 | c0) & 8u) == 0u)
+            if (((c4 | c3 | c2 | c1 | c0) & 8u) == 0u)
                 red_shared_add(rem_base + (((c4 << 8) | (c3 << 6) | (c2 << 4) | (c1 << 2) | c0) << 2), 1u);
         }
     }
+    for (; e0 < to; e0 += nlanes) kmer_remove_one(seq, e0, rem_base);
 }
 }  // namespace
 
