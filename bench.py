@@ -317,6 +317,13 @@ def run_ours(args):
     ktimes = eng.kernel_times()
     eng.set_timing(False)
     if world > 1:
+        # every rank's clocks and step time: the value is the max over ranks, so a GPU that ran slower (power cap under an
+        # 8-GPU load) shows here
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, {"rank": rank, "ms_per_step": round(ms / args.steps, 3), "sm_mhz": clocks["sm_mhz"],
+                                          "reasons": clocks["reasons"]})
+        clocks = dict(clocks, all_ranks=per_rank, min_sm_mhz=min((p["sm_mhz"] or 0) for p in per_rank),
+                      reasons=sorted(set(r for p in per_rank for r in p["reasons"])))
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())

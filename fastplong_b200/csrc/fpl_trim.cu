@@ -214,11 +214,22 @@ __device__ int probe_candidates(const uint8_t* rdata, int rlen, int np, int plen
         // text columns in read order; ends e of this lane's probes: start side e = p + plen - 1, end side e = rlen - 1 - p
         const int e_lo = endside ? rlen - p1 : p0 + plen - 1;
         const int e_hi = endside ? rlen - 1 - p0 : p1 - 1 + plen - 1;
+        // the match masks of the four bases stay in registers; anything else asks the table (rare)
+        const uint32_t eA = __ldg(&t16['A']), eC = __ldg(&t16['C']), eG = __ldg(&t16['G']), eT = __ldg(&t16['T']);
         SearchMyers<uint32_t> Q;
         Q.init(plen);
-        for (int j = e_lo - (plen - 1); j <= e_hi; j++) {
-            Q.column(__ldg(&t16[rdata[j]]));
-            if (j >= e_lo && Q.score <= T16) cb |= 1u << ((endside ? rlen - 1 - j : j - (plen - 1)) - p0);
+        const int j0 = e_lo - (plen - 1);
+        // at most plen - 1 + CH <= 21 columns; unrolled by four so that the byte loads of a group issue together
+#pragma unroll 4
+        for (int c = 0; c < FPL_PATTERN_LEN - 1 + 6; c++) {
+            const int j = j0 + c;
+            if (j <= e_hi) {
+                const uint32_t b = rdata[j];
+                const uint32_t code = (b >> 1) & 3u;             // A 0, C 1, T 2, G 3 for exact A/C/G/T bytes
+                const uint32_t Eq = is_acgt(b) ? (code == 0 ? eA : code == 1 ? eC : code == 2 ? eT : eG) : __ldg(&t16[b]);
+                Q.column(Eq);
+                if (j >= e_lo && Q.score <= T16) cb |= 1u << ((endside ? rlen - 1 - j : j - (plen - 1)) - p0);
+            }
         }
     }
     // compact the candidate positions, ascending, into list[]
@@ -574,7 +585,7 @@ __device__ void trim_polyx(const DevParams& P, const uint8_t* data, Win& w, fpl_
 
 #define TRIM_WARPS 4
 
-__global__ void __launch_bounds__(TRIM_WARPS * 32)
+__global__ void __launch_bounds__(TRIM_WARPS * 32, 8)
 k_trim(const __grid_constant__ DevParams P, DevBatch b, ReadState* __restrict__ st, fpl_read_result* __restrict__ res,
        unsigned long long* __restrict__ counters) {
     __shared__ __align__(16) uint8_t scratch_all[TRIM_WARPS][208];   // probe distances / packed window (36 words)
