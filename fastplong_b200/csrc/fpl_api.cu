@@ -76,6 +76,7 @@ struct fpl_ctx {
     uint32_t* d_peq16 = nullptr;
     uint32_t* d_acode = nullptr;
     unsigned long long* d_peq_long = nullptr;
+    int* d_pf_order = nullptr;
     // accumulators
     int64_t C = 0;
     unsigned long long* d_stats[2] = {nullptr, nullptr};
@@ -264,7 +265,8 @@ static int run_batch(fpl_ctx* c, const DevBatch& full, const int32_t* h_lens, fp
         StatSeg* post = c->d_postseg + 2 * r0;
         cudaStream_t s = c->stream;
         { Timed t(c, K_PRESEG); launch_make_preseg(b, pre, s); }
-        { Timed t(c, K_TRIM); launch_trim(c->P, b, st, res, c->d_counters, s); }
+        { Timed t(c, K_TRIM); launch_trim(c->P, b, st, res, c->d_counters, s);
+          if (c->P.opt.adapter_enabled && c->n_adapters > 2) c->launches++; }   // + k_trim_fasta
         { Timed t(c, K_CYCLE_PRE);
           if (launch_cycle_stats(&c->cycle_ws, full.seq, full.qual, pre, b.n_reads, tmax, c->d_stats[0], c->C, true,
                                  ext ? nullptr : c->d_stats[1] + 16 * c->C + FPL_STATS_KMER, c->slots16, s)) return fail("out of device memory (cycle stats workspace)");
@@ -434,6 +436,19 @@ int fpl_create(const fpl_options* opt, const fpl_adapters* ad, fpl_ctx** out) {
         CKC(cudaMemcpy(c->d_peq_long, h_peq_long.data(), sizeof(unsigned long long) * h_peq_long.size(), cudaMemcpyHostToDevice));
     }
     c->P.peq_long = c->d_peq_long; c->P.peq_words = peq_words;
+    if (n > 2) {
+        // k_trim's many-adapter pre-filter works on 32 (adapter, side) pairs at a time and uses 64-bit bit-vectors for a
+        // round as soon as one of its adapters is longer than 32 bp: group the adapters by width class
+        std::vector<int> order;
+        for (int cls = 0; cls < 3; cls++)
+            for (int k = 2; k < n; k++) {
+                const int kc = h_alen[k] <= 32 ? 0 : h_alen[k] <= 64 ? 1 : 2;
+                if (kc == cls) order.push_back(k);
+            }
+        CKC(cudaMalloc(&c->d_pf_order, sizeof(int) * order.size()));
+        CKC(cudaMemcpy(c->d_pf_order, order.data(), sizeof(int) * order.size(), cudaMemcpyHostToDevice));
+    }
+    c->P.pf_order = c->d_pf_order;
     c->P.adapters = c->d_adapters; c->P.alen = c->d_alen; c->P.peq = c->d_peq; c->P.peq16 = c->d_peq16; c->P.acode = c->d_acode;
     c->counter_words = FPL_COUNTER_WORDS(n);
     CKC(cudaMalloc(&c->d_counters, sizeof(unsigned long long) * c->counter_words));
@@ -472,7 +487,7 @@ void fpl_destroy(fpl_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     collect_times(c);
     for (auto e : c->pool) cudaEventDestroy(e);
-    cudaFree(c->d_adapters); cudaFree(c->d_alen); cudaFree(c->d_peq); cudaFree(c->d_peq16); cudaFree(c->d_acode); cudaFree(c->d_peq_long);
+    cudaFree(c->d_adapters); cudaFree(c->d_alen); cudaFree(c->d_peq); cudaFree(c->d_peq16); cudaFree(c->d_acode); cudaFree(c->d_peq_long); cudaFree(c->d_pf_order);
     cudaFree(c->d_stats[0]); cudaFree(c->d_stats[1]); cudaFree(c->d_counters);
     fpl_cycle_ws_free(&c->cycle_ws);
     for (auto e : c->piece_events) cudaEventDestroy(e);

@@ -17,6 +17,7 @@ struct DevParams {
     const uint32_t* peq16;    // [n][2][256]: [0] = match masks of the first plen chars, [1] = of the last plen chars
     const uint32_t* acode;    // [n][4]: 2-bit codes ((byte>>1)&3 at bit 2i) lo/hi + position mask lo/hi; mask == 0: not ACGT-only or > 32 bp
     short thr[FPL_MAX_ADAPTER_LEN + 1];  // thr(n) = (int)round(ed_max*n), tabulated on the host with libm round
+    const int* pf_order;      // [n - 2]: the FASTA adapters' indices sorted by pre-filter width class (<= 32 bp, <= 64 bp, longer)
     const unsigned long long* peq_long;  // [n][256][peq_words]: match masks of adapters longer than 128 bp (else nullptr)
     int peq_words;            // 64-bit words per mask in peq_long
     uint32_t one;             // 1: the multiplier of the IMADs that must stay on the FMA pipe (an add the compiler cannot fold)

@@ -214,22 +214,13 @@ __device__ int probe_candidates(const uint8_t* rdata, int rlen, int np, int plen
         // text columns in read order; ends e of this lane's probes: start side e = p + plen - 1, end side e = rlen - 1 - p
         const int e_lo = endside ? rlen - p1 : p0 + plen - 1;
         const int e_hi = endside ? rlen - 1 - p0 : p1 - 1 + plen - 1;
-        // the match masks of the four bases stay in registers; anything else asks the table (rare)
-        const uint32_t eA = __ldg(&t16['A']), eC = __ldg(&t16['C']), eG = __ldg(&t16['G']), eT = __ldg(&t16['T']);
+        // (measured: keeping the four bases' masks in registers and unrolling the columns costs 24 registers and loses —
+        //  7.7 vs 6.6 ms for config 2's k_trim; the two dependent L1 loads per column stay)
         SearchMyers<uint32_t> Q;
         Q.init(plen);
-        const int j0 = e_lo - (plen - 1);
-        // at most plen - 1 + CH <= 21 columns; unrolled by four so that the byte loads of a group issue together
-#pragma unroll 4
-        for (int c = 0; c < FPL_PATTERN_LEN - 1 + 6; c++) {
-            const int j = j0 + c;
-            if (j <= e_hi) {
-                const uint32_t b = rdata[j];
-                const uint32_t code = (b >> 1) & 3u;             // A 0, C 1, T 2, G 3 for exact A/C/G/T bytes
-                const uint32_t Eq = is_acgt(b) ? (code == 0 ? eA : code == 1 ? eC : code == 2 ? eT : eG) : __ldg(&t16[b]);
-                Q.column(Eq);
-                if (j >= e_lo && Q.score <= T16) cb |= 1u << ((endside ? rlen - 1 - j : j - (plen - 1)) - p0);
-            }
+        for (int j = e_lo - (plen - 1); j <= e_hi; j++) {
+            Q.column(__ldg(&t16[rdata[j]]));
+            if (j >= e_lo && Q.score <= T16) cb |= 1u << ((endside ? rlen - 1 - j : j - (plen - 1)) - p0);
         }
     }
     // compact the candidate positions, ascending, into list[]
@@ -393,15 +384,16 @@ __device__ int trim_end(const DevParams& P, const uint8_t* seq, Win& w, int aidx
 // ------------------------------------------------------------------------------------------------------------------
 #define PF_WIN FPL_WINDOW
 
-// maybe-bits of the (adapter, side) items [first_item, 2 * (n_adapters - 2)) for the window w: item = 2 * (k - 2) + side.
-// head / tail: the warp's staging buffers (PF_WIN bytes each); bits: one bit per item.  All 32 lanes.
+// maybe-bits of the (adapter, side) pairs of all FASTA adapters for the window w: bit 2 * (k - 2) + side.  The pairs are
+// walked in P.pf_order (adapters grouped by width class), 32 per round, one per lane.
+// head / tail: the warp's staging buffers (PF_WIN bytes each); bits: one bit per pair (zeroed by the caller).  All 32 lanes.
 template <typename W>
 __device__ void prefilter_round(const DevParams& P, const uint8_t* head, const uint8_t* tail, int hw, int base, int nitems,
                                 uint32_t* bits) {
     const int lane = lane_id();
     const int item = base + lane;
     const bool active = item < nitems;
-    const int k = 2 + (active ? item : 0) / 2, side = item & 1;
+    const int k = active ? __ldg(&P.pf_order[item >> 1]) : 2, side = item & 1;
     const int alen = active ? P.alen[k] : 1;
     const bool filterable = active && alen >= 1 && alen <= (int)(8 * sizeof(W));
     const int plen = min(FPL_PATTERN_LEN, alen);
@@ -430,22 +422,24 @@ __device__ void prefilter_round(const DevParams& P, const uint8_t* head, const u
         Q.column((uint32_t)(Eq >> sh16) & m16);
     }
     const bool maybe = active && (!filterable || F.best <= P.thr[alen] || Q.best <= P.thr[plen]);
-    const uint32_t mask = __ballot_sync(0xffffffffu, maybe);
-    if (lane == 0) bits[base >> 5] = mask;
+    if (maybe) {
+        const int bit = 2 * (k - 2) + side;
+        atomicOr(&bits[bit >> 5], 1u << (bit & 31));
+    }
 }
 
-__device__ void prefilter(const DevParams& P, const uint8_t* seq, const Win& w, int first_item, uint8_t* head, uint8_t* tail,
-                          uint32_t* bits) {
+__device__ void prefilter(const DevParams& P, const uint8_t* seq, const Win& w, uint8_t* head, uint8_t* tail, uint32_t* bits) {
     const int lane = lane_id();
     const int nitems = 2 * (P.n_adapters - 2);
     const int hw = min(w.len, PF_WIN);
     __syncwarp();
     for (int j = lane; j < hw; j += 32) { head[j] = seq[w.lo + j]; tail[j] = seq[w.lo + w.len - hw + j]; }
+    for (int i = lane; i * 32 < nitems; i += 32) bits[i] = 0;
     __syncwarp();
-    for (int base = first_item & ~31; base < nitems; base += 32) {
-        // one width per round: 64-bit vectors only if an adapter of this round needs them
+    for (int base = 0; base < nitems; base += 32) {
+        // one width per round: 64-bit vectors only if an adapter of this round needs them (the order groups them)
         const int it = base + lane;
-        const bool wide = __any_sync(0xffffffffu, it < nitems && P.alen[2 + (it < nitems ? it : 0) / 2] > 32);
+        const bool wide = __any_sync(0xffffffffu, it < nitems && P.alen[__ldg(&P.pf_order[(it < nitems ? it : 0) >> 1])] > 32);
         if (wide) prefilter_round<unsigned long long>(P, head, tail, hw, base, nitems, bits);
         else prefilter_round<uint32_t>(P, head, tail, hw, base, nitems, bits);
     }
@@ -585,12 +579,11 @@ __device__ void trim_polyx(const DevParams& P, const uint8_t* data, Win& w, fpl_
 
 #define TRIM_WARPS 4
 
-__global__ void __launch_bounds__(TRIM_WARPS * 32, 8)
+// The end-local stages for -s / -e: trimAndCut, trimPolyX, trimBySequenceStart(-s), trimBySequenceEnd(-e).
+__global__ void __launch_bounds__(TRIM_WARPS * 32)
 k_trim(const __grid_constant__ DevParams P, DevBatch b, ReadState* __restrict__ st, fpl_read_result* __restrict__ res,
        unsigned long long* __restrict__ counters) {
-    __shared__ __align__(16) uint8_t scratch_all[TRIM_WARPS][208];   // probe distances / packed window (36 words)
-    __shared__ __align__(16) uint8_t pf_win[TRIM_WARPS][2][PF_WIN + 8];     // many-adapter pre-filter: end windows ...
-    __shared__ uint32_t pf_bits[TRIM_WARPS][(2 * FPL_MAX_ADAPTERS + 31) / 32];   // ... and its maybe-bits
+    __shared__ __align__(16) uint8_t scratch_all[TRIM_WARPS][208];   // probe candidates / packed window (36 words)
     const int wid = threadIdx.x >> 5, lane = lane_id();
     const int64_t r = (int64_t)blockIdx.x * TRIM_WARPS + wid;
     if (r >= b.n_reads) return;
@@ -614,26 +607,6 @@ k_trim(const __grid_constant__ DevParams P, DevBatch b, ReadState* __restrict__ 
     if (alive && P.opt.adapter_enabled) {
         if (P.alen[0] > 0) trimmed += trim_start(P, seq, w, 0, ev, scratch);
         if (P.alen[1] > 0) trimmed += trim_end(P, seq, w, 1, ev, scratch);
-        if (P.n_adapters > 2) {
-            // FASTA adapters in order, each on the read as the previous ones left it; pairs the pre-filter rules out are
-            // skipped, and a trim (which moves the end windows) re-filters what is still to come
-            uint32_t* bits = pf_bits[wid];
-            const bool use_pf = P.n_adapters > 4 && w.len >= FPL_PATTERN_LEN;
-            if (use_pf) prefilter(P, seq, w, 0, pf_win[wid][0], pf_win[wid][1], bits);
-            for (int k = 2; k < P.n_adapters; k++) {
-                const int i0 = 2 * (k - 2);
-                if (!use_pf || (bits[i0 >> 5] >> (i0 & 31) & 1u)) {
-                    const int t = trim_start(P, seq, w, k, ev, scratch);
-                    trimmed += t;
-                    if (t && use_pf) prefilter(P, seq, w, i0 + 1, pf_win[wid][0], pf_win[wid][1], bits);
-                }
-                if (!use_pf || (bits[(i0 + 1) >> 5] >> ((i0 + 1) & 31) & 1u)) {
-                    const int t = trim_end(P, seq, w, k, ev, scratch);
-                    trimmed += t;
-                    if (t && use_pf && k + 1 < P.n_adapters) prefilter(P, seq, w, i0 + 2, pf_win[wid][0], pf_win[wid][1], bits);
-                }
-            }
-        }
     }
     if (lane == 0) {
         ReadState s;
@@ -649,9 +622,59 @@ k_trim(const __grid_constant__ DevParams P, DevBatch b, ReadState* __restrict__ 
     }
 }
 
+// trimByMultiSequences (src/adaptertrimmer.cpp:42-57): the FASTA adapters in order, each on the read as the previous
+// ones left it — a kernel of its own (launched only with --adapter_fasta) so that its 64-bit pre-filter does not set the
+// register budget of the two-adapter path above.  Continues from the window, the event count and the trimmed-base count
+// k_trim left in the read's state and record.
+__global__ void __launch_bounds__(TRIM_WARPS * 32)
+k_trim_fasta(const __grid_constant__ DevParams P, DevBatch b, ReadState* __restrict__ st, fpl_read_result* __restrict__ res,
+             unsigned long long* __restrict__ counters) {
+    __shared__ __align__(16) uint8_t scratch_all[TRIM_WARPS][208];
+    __shared__ __align__(16) uint8_t pf_win[TRIM_WARPS][2][PF_WIN + 8];     // many-adapter pre-filter: end windows ...
+    __shared__ uint32_t pf_bits[TRIM_WARPS][(2 * FPL_MAX_ADAPTERS + 31) / 32];   // ... and its maybe-bits
+    const int wid = threadIdx.x >> 5, lane = lane_id();
+    const int64_t r = (int64_t)blockIdx.x * TRIM_WARPS + wid;
+    if (r >= b.n_reads) return;
+    if (!st[r].alive) return;
+    uint8_t* scratch = scratch_all[wid];
+    const uint8_t* seq = b.seq + b.offsets[r];
+    fpl_read_result* out = &res[r];
+    Win w;
+    w.lo = st[r].lo; w.len = st[r].len;
+    int trimmed = out->adapter_trimmed_bases;
+    EventSink ev{out, counters + FPL_CNT_FIXED, (int)out->n_events};
+    __syncwarp();
+    // pairs the pre-filter rules out are skipped, and a trim (which moves the end windows) re-filters what is still to come
+    uint32_t* bits = pf_bits[wid];
+    const bool use_pf = P.n_adapters > 4 && w.len >= FPL_PATTERN_LEN;
+    if (use_pf) prefilter(P, seq, w, pf_win[wid][0], pf_win[wid][1], bits);
+    for (int k = 2; k < P.n_adapters; k++) {
+        const int i0 = 2 * (k - 2);
+        if (!use_pf || (bits[i0 >> 5] >> (i0 & 31) & 1u)) {
+            const int t = trim_start(P, seq, w, k, ev, scratch);
+            trimmed += t;
+            if (t && use_pf) prefilter(P, seq, w, pf_win[wid][0], pf_win[wid][1], bits);
+        }
+        if (!use_pf || (bits[(i0 + 1) >> 5] >> ((i0 + 1) & 31) & 1u)) {
+            const int t = trim_end(P, seq, w, k, ev, scratch);
+            trimmed += t;
+            if (t && use_pf && k + 1 < P.n_adapters) prefilter(P, seq, w, pf_win[wid][0], pf_win[wid][1], bits);
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        st[r].lo = w.lo; st[r].len = w.len;
+        out->trim_lo = w.lo; out->trim_len = w.len;
+        out->n_events = (uint16_t)ev.n;
+        out->adapter_trimmed_bases = trimmed;
+    }
+}
+
 void launch_trim(const DevParams& P, const DevBatch& b, ReadState* st, fpl_read_result* res,
                  unsigned long long* counters, cudaStream_t stream) {
     if (b.n_reads == 0) return;
     unsigned grid = (unsigned)((b.n_reads + TRIM_WARPS - 1) / TRIM_WARPS);
     k_trim<<<grid, TRIM_WARPS * 32, 0, stream>>>(P, b, st, res, counters);
+    if (P.opt.adapter_enabled && P.n_adapters > 2)
+        k_trim_fasta<<<grid, TRIM_WARPS * 32, 0, stream>>>(P, b, st, res, counters);
 }

@@ -177,3 +177,45 @@ def random_case(rng):
     elif kind < 0.7: batch = blocky_quality_batch(seed, n=40)
     else: batch = ont_batch(seed, n=40, mean=1500, p_chimera=0.1, p_polya=0.1)
     return opt, batch, f"{kw} kind={kind:.3f} seed={seed}"
+
+
+# ---- two more randomised families for tools/fuzz_gpu_vs_oracle.py (own draw order; random_case above is untouched) ----
+def random_case_many_adapters(rng):
+    """6-40 FASTA adapters of 8-70 bp (all three pre-filter widths: <= 32, <= 64, unfiltered), some planted at the read
+    ends: the many-adapter pre-filter of k_trim and its re-filtering after a trim."""
+    def rand_adapter(lo, hi):
+        return ''.join(rng.choice('ACGT') for _ in range(rng.randint(lo, hi)))
+    fasta = sorted(rand_adapter(8, rng.choice([20, 32, 44, 70])) for _ in range(rng.randint(6, 40)))
+    kw = dict(adapter_fasta=fasta)
+    if rng.random() < 0.7: kw['start_adapter'] = rng.choice([synth.ADAPTER_START, rand_adapter(6, 45)])
+    if rng.random() < 0.7: kw['end_adapter'] = rng.choice([synth.ADAPTER_END, rand_adapter(6, 45)])
+    if rng.random() < 0.3: kw['distance_threshold'] = rng.choice([0.1, 0.2, 0.3, 0.4])
+    if rng.random() < 0.3: kw['trimming_extension'] = rng.choice([0, 3, 10, 25])
+    if rng.random() < 0.3: kw['trim_poly_x'] = True
+    if rng.random() < 0.3: kw['cut_front'] = True; kw['cut_tail'] = True
+    seed = rng.randint(1, 10**6)
+    planted = [fasta[rng.randrange(len(fasta))] for _ in range(rng.randint(1, 5))]
+    batch = synth.ont_like(60, 1200, seed, planted=planted, p_planted=0.5, p_chimera=0.05, p_polya=0.1,
+                           q_mean=rng.choice([17.0, 33.0]))
+    return Options(**kw), batch, f"many {len(fasta)} adapters {kw.keys()} seed={seed}"
+
+
+def random_case_long_reads(rng):
+    """A few very long reads (up to ~400 kb) with chimeric inserts and every filter combination: the block-cooperative
+    quality histogram (> 96 kb), the shared long ranges of k_kmer_fix, k_final's part counting, long Stats blocks."""
+    kw = {}
+    if rng.random() < 0.85:
+        kw['start_adapter'] = synth.ADAPTER_START; kw['end_adapter'] = synth.ADAPTER_END
+    else:
+        kw['disable_adapter_trimming'] = True
+    if rng.random() < 0.3: kw['disable_quality_filtering'] = True
+    if rng.random() < 0.3: kw['disable_length_filtering'] = True
+    if rng.random() < 0.4: kw['low_complexity_filter'] = True; kw['complexity_threshold'] = rng.choice([10, 30, 60])
+    if rng.random() < 0.3: kw['qualified_quality_phred'] = rng.choice([5, 15, 25])
+    if rng.random() < 0.3: kw['unqualified_percent_limit'] = rng.choice([10, 30, 60])
+    if rng.random() < 0.3: kw['length_limit'] = rng.choice([0, 50000, 200000])
+    if rng.random() < 0.3: kw['cut_front'] = True; kw['cut_tail'] = True
+    if rng.random() < 0.3: kw['distance_threshold'] = rng.choice([0.25, 0.35, 0.45])     # loose: spurious middle hits, big gaps
+    seed = rng.randint(1, 10**6)
+    batch = synth.ont_like(rng.randint(3, 8), rng.choice([60000, 150000]), seed, p_chimera=0.6, q_mean=rng.choice([12.0, 18.0, 30.0]))
+    return Options(**kw), batch, f"long {kw} seed={seed}"

@@ -1,6 +1,7 @@
 """Development aid (run under gpurun): random option sets x seeded batches (tests/cases.py:random_case), GPU library vs
 the oracle — every record, both Stats blocks, the counters and the --mask/--break lists.
-usage: python tools/fuzz_gpu_vs_oracle.py <seed> <seconds>"""
+usage: python tools/fuzz_gpu_vs_oracle.py <seed> <seconds> [mixed|many|long]
+  mixed (default): cases.random_case; many: 6-40 FASTA adapters (k_trim's pre-filter); long: reads of 60-400 kb"""
 import os
 import random
 import sys
@@ -15,10 +16,12 @@ from fastplong_b200.binding import Engine
 
 rng = random.Random(int(sys.argv[1]) if len(sys.argv) > 1 else 1)
 budget = float(sys.argv[2]) if len(sys.argv) > 2 else 120
+FAMILY = {"mixed": cases.random_case, "many": cases.random_case_many_adapters,
+          "long": cases.random_case_long_reads}[sys.argv[3] if len(sys.argv) > 3 else "mixed"]
 t0 = time.time()
 n = bad = 0
 while time.time() - t0 < budget:
-    opt, batch, what = cases.random_case(rng)
+    opt, batch, what = FAMILY(rng)
     r = None
     try:
         o, r = OracleEngine(opt), Engine(opt)
