@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 #include <dlfcn.h>
@@ -395,6 +396,13 @@ int fpl_create(const fpl_options* opt, const fpl_adapters* ad, fpl_ctx** out) {
     memset(&c->P, 0, sizeof(c->P));
     c->P.opt = *opt;
     c->P.one = 1u;
+    {
+        auto cls = [](int a) { return a <= 32 ? 0 : a <= 64 ? 1 : 2; };
+        c->P.small_adapters = std::max(cls(h_alen[0]), cls(h_alen[1]));
+        int fc = 0;
+        for (int k = 2; k < n; k++) fc = std::max(fc, cls(h_alen[k]));
+        c->P.fasta_class = fc;
+    }
     c->P.n_adapters = n;
     // plan for the bit-sliced middle-adapter scan (k_scan_fast); anything it cannot express uses k_scan
     memset(&c->plan, 0, sizeof(c->plan));

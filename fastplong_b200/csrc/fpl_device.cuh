@@ -20,6 +20,8 @@ struct DevParams {
     const int* pf_order;      // [n - 2]: the FASTA adapters' indices sorted by pre-filter width class (<= 32 bp, <= 64 bp, longer)
     const unsigned long long* peq_long;  // [n][256][peq_words]: match masks of adapters longer than 128 bp (else nullptr)
     int peq_words;            // 64-bit words per mask in peq_long
+    int small_adapters;       // size class of -s / -e: 0 both <= 32 bp, 1 both <= 64 bp, 2 any (k_trim<CLS>)
+    int fasta_class;          // the same for the FASTA adapters (k_trim_fasta<CLS>)
     uint32_t one;             // 1: the multiplier of the IMADs that must stay on the FMA pipe (an add the compiler cannot fold)
 };
 

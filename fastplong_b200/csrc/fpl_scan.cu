@@ -297,6 +297,10 @@ __device__ Counts count_range(const fpl_options& o, uint32_t one, const uint8_t*
 
 #define FINAL_WARPS 4
 
+// CLS: size class of -s / -e (DevParams::small_adapters): 0 = both <= 32 bp — the kernel is then compiled without the
+// 128-bit and multi-word Myers forms and their local arrays, which would otherwise set its register budget and occupancy
+// (it is bound by the latency of its dependent loads)
+template <int CLS>
 __global__ void __launch_bounds__(FINAL_WARPS * 32)
 k_final(const __grid_constant__ DevParams P, DevBatch b, const ReadState* __restrict__ st,
         fpl_read_result* __restrict__ res, StatSeg* __restrict__ postseg) {
@@ -317,7 +321,7 @@ k_final(const __grid_constant__ DevParams P, DevBatch b, const ReadState* __rest
         if (P.opt.adapter_enabled) {
             const int ext = P.opt.trimming_extension;
             int pos[2] = {-1, -1};
-            if (P.alen[0] <= 32 && P.alen[1] <= 32 && P.alen[0] > 0 && P.alen[1] > 0) {
+            if (CLS == 0 && P.alen[0] > 0 && P.alen[1] > 0) {
                 // both verifications side by side: half-warp k checks the arg-min of adapter k
                 const int k = lane >> 4;
                 const bool on = s.best[k] != ~0ull;
@@ -334,9 +338,10 @@ k_final(const __grid_constant__ DevParams P, DevBatch b, const ReadState* __rest
                     if (s.best[k] != ~0ull) {
                         const int alen = P.alen[k];
                         const int p = (int)(s.best[k] & 0xFFFFFFFFu);
-                        const int ed = alen <= 32 ? myers32_warp(seq + p, alen, P.peq + (size_t)k * 256, 0, alen)
-                                     : alen <= 128 ? myers128_f(seq + p, alen, P.peq + (size_t)k * 256, alen)
-                                                   : myers_long(seq + p, alen, P.peq_long + (size_t)k * 256 * P.peq_words, P.peq_words, 0, alen);
+                        int ed;
+                        if (CLS == 0 || alen <= 32) ed = myers32_warp(seq + p, alen, P.peq + (size_t)k * 256, 0, alen);
+                        else if (alen <= 128) ed = myers128_f(seq + p, alen, P.peq + (size_t)k * 256, alen);
+                        else ed = myers_long(seq + p, alen, P.peq_long + (size_t)k * 256 * P.peq_words, P.peq_words, 0, alen);
                         if (ed <= P.thr[alen]) pos[k] = p;
                     }
                 }
@@ -423,7 +428,8 @@ void launch_final(const DevParams& P, const DevBatch& b, const ReadState* st, fp
                   cudaStream_t stream) {
     if (b.n_reads == 0) return;
     unsigned grid = (unsigned)((b.n_reads + FINAL_WARPS - 1) / FINAL_WARPS);
-    k_final<<<grid, FINAL_WARPS * 32, 0, stream>>>(P, b, st, res, postseg);
+    if (P.small_adapters == 0) k_final<0><<<grid, FINAL_WARPS * 32, 0, stream>>>(P, b, st, res, postseg);
+    else k_final<2><<<grid, FINAL_WARPS * 32, 0, stream>>>(P, b, st, res, postseg);
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -58,8 +58,41 @@ __device__ int myers128(const uint8_t* text, int n, const uint4* peq, int shift,
     return score;
 }
 
+// Levenshtein distance for adapters of 33..64 bp: one 64-bit word (the same recurrence as myers128 without its high half)
+__device__ int myers64(const uint8_t* text, int n, const uint4* peq, int shift, int m) {
+    if (m == 0) return n;
+    if (n == 0) return m;
+    unsigned long long VP = m >= 64 ? ~0ull : ((1ull << m) - 1), VN = 0;
+    const unsigned long long top = 1ull << (m - 1), mask = VP;
+    int score = m;
+    for (int i = 0; i < n; i++) {
+        const uint4 v = __ldg(&peq[text[i]]);
+        unsigned long long lo = ((unsigned long long)v.y << 32) | v.x, hi = ((unsigned long long)v.w << 32) | v.z;
+        unsigned long long Eq = shift == 0 ? lo : shift >= 64 ? (hi >> (shift - 64)) : ((lo >> shift) | (hi << (64 - shift)));
+        Eq &= mask;
+        const unsigned long long Xv = Eq | VN;
+        const unsigned long long Xh = (((Eq & VP) + VP) ^ VP) | Eq;
+        unsigned long long HP = VN | ~(Xh | VP);
+        unsigned long long HN = VP & Xh;
+        if (HP & top) score++;
+        else if (HN & top) score--;
+        HP = (HP << 1) | 1ull; HN <<= 1;
+        VP = HN | ~(Xv | HP);
+        VN = HP & Xv;
+    }
+    return score;
+}
+
+// CLS: the size class of the adapters a kernel handles (decided at fpl_create): 0 = all <= 32 bp, 1 = all <= 64 bp, 2 = any.
+// A kernel is compiled without the forms its class never needs, which would otherwise set its register budget.
+template <int CLS>
 __device__ __forceinline__ int ed_adapter(const DevParams& P, int aidx, const uint8_t* text, int n, int shift, int m, int alen) {
     const uint4* peq = P.peq + (size_t)aidx * 256;
+    if (CLS == 0) return n <= 32 ? myers32_warp(text, n, peq, shift, m) : myers32(text, n, peq, shift, m);
+    if (CLS == 1) {
+        if (alen <= 32) return n <= 32 ? myers32_warp(text, n, peq, shift, m) : myers32(text, n, peq, shift, m);
+        return myers64(text, n, peq, shift, m);
+    }
     // every lane wants the same distance: for <= 32 text bytes lane i looks up the match mask of byte i once and the
     // recurrence runs on shuffled masks (no dependent loads inside the column loop)
     if (alen <= 32) return n <= 32 ? myers32_warp(text, n, peq, shift, m) : myers32(text, n, peq, shift, m);
@@ -105,6 +138,7 @@ __device__ __forceinline__ bool is_acgt(uint32_t b) {   // exact: A 0x41, C 0x43
     return (b >> 5) == 2u && ((0x0010008Au >> (b & 31u)) & 1u);
 }
 
+template <int CLS>
 __device__ int search_window(const DevParams& P, const uint8_t* rdata, int rlen, int aidx, int searchStart,
                              int searchLen, bool left, uint32_t* pk) {
     const int lane = lane_id();
@@ -169,7 +203,7 @@ __device__ int search_window(const DevParams& P, const uint8_t* rdata, int rlen,
     if (best == 0xFFFFFFFFu) return -1;
     unsigned key = best & 0xFFFFu;
     int pos = p0 + (int)(left ? (0xFFFFu - key) : key);
-    int ed = ed_adapter(P, aidx, rdata + pos, alen, 0, alen, alen);
+    int ed = ed_adapter<CLS>(P, aidx, rdata + pos, alen, 0, alen, alen);
     return ed <= T ? pos : -1;
 }
 
@@ -260,6 +294,7 @@ struct EventSink {
 };
 
 // AdapterTrimmer::trimBySequenceStart (src/adaptertrimmer.cpp:168-236)
+template <int CLS>
 __device__ int trim_start(const DevParams& P, const uint8_t* seq, Win& w, int aidx, EventSink& ev, uint8_t* scratch) {
     const int lane = lane_id();
     const int alen = P.alen[aidx], ext = P.opt.trimming_extension;
@@ -267,7 +302,7 @@ __device__ int trim_start(const DevParams& P, const uint8_t* seq, Win& w, int ai
     const int rlen = w.len;
     if (rlen < FPL_PATTERN_LEN) return 0;
     const int plen = min(FPL_PATTERN_LEN, alen);
-    int mpos = search_window(P, rdata, rlen, aidx, 0, FPL_WINDOW, false, reinterpret_cast<uint32_t*>(scratch));
+    int mpos = search_window<CLS>(P, rdata, rlen, aidx, 0, FPL_WINDOW, false, reinterpret_cast<uint32_t*>(scratch));
     if (mpos >= 0) {
         mpos = min(mpos + ext, rlen - alen);
         ev.add(aidx, 0, alen);
@@ -291,7 +326,7 @@ __device__ int trim_start(const DevParams& P, const uint8_t* seq, Win& w, int ai
     if (best != 0xFFFFFFFFu) {
         int pos = (int)(best & 0xFFFFu);
         int cmplen = min(pos + plen, alen);
-        int ed = ed_adapter(P, aidx, rdata + pos + plen - cmplen, cmplen, alen - cmplen, cmplen, alen);
+        int ed = ed_adapter<CLS>(P, aidx, rdata + pos + plen - cmplen, cmplen, alen - cmplen, cmplen, alen);
         if (ed <= P.thr[cmplen]) {
             pos = min(pos + ext, rlen - alen);
             ev.add(aidx, 0, cmplen);
@@ -303,6 +338,7 @@ __device__ int trim_start(const DevParams& P, const uint8_t* seq, Win& w, int ai
 }
 
 // AdapterTrimmer::trimBySequenceEnd (src/adaptertrimmer.cpp:238-302)
+template <int CLS>
 __device__ int trim_end(const DevParams& P, const uint8_t* seq, Win& w, int aidx, EventSink& ev, uint8_t* scratch) {
     const int lane = lane_id();
     const int alen = P.alen[aidx], ext = P.opt.trimming_extension;
@@ -311,7 +347,7 @@ __device__ int trim_end(const DevParams& P, const uint8_t* seq, Win& w, int aidx
     if (rlen < FPL_PATTERN_LEN) return 0;
     const int plen = min(FPL_PATTERN_LEN, alen);
     const int searchStart = max(0, rlen - FPL_WINDOW);
-    int mpos = search_window(P, rdata, rlen, aidx, searchStart, FPL_WINDOW, true, reinterpret_cast<uint32_t*>(scratch));
+    int mpos = search_window<CLS>(P, rdata, rlen, aidx, searchStart, FPL_WINDOW, true, reinterpret_cast<uint32_t*>(scratch));
     if (mpos >= 0) {
         mpos = max(0, mpos - ext);
         ev.add(aidx, 1, alen);
@@ -358,7 +394,7 @@ __device__ int trim_end(const DevParams& P, const uint8_t* seq, Win& w, int aidx
     __syncwarp();
     if (pos > 0) {
         int cmplen = min(pos + plen, alen);
-        int ed = ed_adapter(P, aidx, rdata + rlen - plen - pos, cmplen, 0, cmplen, alen);
+        int ed = ed_adapter<CLS>(P, aidx, rdata + rlen - plen - pos, cmplen, 0, cmplen, alen);
         if (ed <= P.thr[cmplen]) {
             pos = min(pos + ext, rlen - plen);
             ev.add(aidx, 1, cmplen);
@@ -428,6 +464,7 @@ __device__ void prefilter_round(const DevParams& P, const uint8_t* head, const u
     }
 }
 
+template <int CLS>
 __device__ void prefilter(const DevParams& P, const uint8_t* seq, const Win& w, uint8_t* head, uint8_t* tail, uint32_t* bits) {
     const int lane = lane_id();
     const int nitems = 2 * (P.n_adapters - 2);
@@ -440,7 +477,7 @@ __device__ void prefilter(const DevParams& P, const uint8_t* seq, const Win& w, 
         // one width per round: 64-bit vectors only if an adapter of this round needs them (the order groups them)
         const int it = base + lane;
         const bool wide = __any_sync(0xffffffffu, it < nitems && P.alen[__ldg(&P.pf_order[(it < nitems ? it : 0) >> 1])] > 32);
-        if (wide) prefilter_round<unsigned long long>(P, head, tail, hw, base, nitems, bits);
+        if (CLS > 0 && wide) prefilter_round<unsigned long long>(P, head, tail, hw, base, nitems, bits);
         else prefilter_round<uint32_t>(P, head, tail, hw, base, nitems, bits);
     }
     __syncwarp();
@@ -580,6 +617,7 @@ __device__ void trim_polyx(const DevParams& P, const uint8_t* data, Win& w, fpl_
 #define TRIM_WARPS 4
 
 // The end-local stages for -s / -e: trimAndCut, trimPolyX, trimBySequenceStart(-s), trimBySequenceEnd(-e).
+template <int CLS>
 __global__ void __launch_bounds__(TRIM_WARPS * 32)
 k_trim(const __grid_constant__ DevParams P, DevBatch b, ReadState* __restrict__ st, fpl_read_result* __restrict__ res,
        unsigned long long* __restrict__ counters) {
@@ -605,8 +643,8 @@ k_trim(const __grid_constant__ DevParams P, DevBatch b, ReadState* __restrict__ 
     int trimmed = 0;
     EventSink ev{out, counters + FPL_CNT_FIXED, 0};
     if (alive && P.opt.adapter_enabled) {
-        if (P.alen[0] > 0) trimmed += trim_start(P, seq, w, 0, ev, scratch);
-        if (P.alen[1] > 0) trimmed += trim_end(P, seq, w, 1, ev, scratch);
+        if (P.alen[0] > 0) trimmed += trim_start<CLS>(P, seq, w, 0, ev, scratch);
+        if (P.alen[1] > 0) trimmed += trim_end<CLS>(P, seq, w, 1, ev, scratch);
     }
     if (lane == 0) {
         ReadState s;
@@ -626,6 +664,7 @@ k_trim(const __grid_constant__ DevParams P, DevBatch b, ReadState* __restrict__ 
 // ones left it — a kernel of its own (launched only with --adapter_fasta) so that its 64-bit pre-filter does not set the
 // register budget of the two-adapter path above.  Continues from the window, the event count and the trimmed-base count
 // k_trim left in the read's state and record.
+template <int CLS>
 __global__ void __launch_bounds__(TRIM_WARPS * 32)
 k_trim_fasta(const __grid_constant__ DevParams P, DevBatch b, ReadState* __restrict__ st, fpl_read_result* __restrict__ res,
              unsigned long long* __restrict__ counters) {
@@ -647,18 +686,18 @@ k_trim_fasta(const __grid_constant__ DevParams P, DevBatch b, ReadState* __restr
     // pairs the pre-filter rules out are skipped, and a trim (which moves the end windows) re-filters what is still to come
     uint32_t* bits = pf_bits[wid];
     const bool use_pf = P.n_adapters > 4 && w.len >= FPL_PATTERN_LEN;
-    if (use_pf) prefilter(P, seq, w, pf_win[wid][0], pf_win[wid][1], bits);
+    if (use_pf) prefilter<CLS>(P, seq, w, pf_win[wid][0], pf_win[wid][1], bits);
     for (int k = 2; k < P.n_adapters; k++) {
         const int i0 = 2 * (k - 2);
         if (!use_pf || (bits[i0 >> 5] >> (i0 & 31) & 1u)) {
-            const int t = trim_start(P, seq, w, k, ev, scratch);
+            const int t = trim_start<CLS>(P, seq, w, k, ev, scratch);
             trimmed += t;
-            if (t && use_pf) prefilter(P, seq, w, pf_win[wid][0], pf_win[wid][1], bits);
+            if (t && use_pf) prefilter<CLS>(P, seq, w, pf_win[wid][0], pf_win[wid][1], bits);
         }
         if (!use_pf || (bits[(i0 + 1) >> 5] >> ((i0 + 1) & 31) & 1u)) {
-            const int t = trim_end(P, seq, w, k, ev, scratch);
+            const int t = trim_end<CLS>(P, seq, w, k, ev, scratch);
             trimmed += t;
-            if (t && use_pf && k + 1 < P.n_adapters) prefilter(P, seq, w, pf_win[wid][0], pf_win[wid][1], bits);
+            if (t && use_pf && k + 1 < P.n_adapters) prefilter<CLS>(P, seq, w, pf_win[wid][0], pf_win[wid][1], bits);
         }
     }
     __syncwarp();
@@ -674,7 +713,12 @@ void launch_trim(const DevParams& P, const DevBatch& b, ReadState* st, fpl_read_
                  unsigned long long* counters, cudaStream_t stream) {
     if (b.n_reads == 0) return;
     unsigned grid = (unsigned)((b.n_reads + TRIM_WARPS - 1) / TRIM_WARPS);
-    k_trim<<<grid, TRIM_WARPS * 32, 0, stream>>>(P, b, st, res, counters);
-    if (P.opt.adapter_enabled && P.n_adapters > 2)
-        k_trim_fasta<<<grid, TRIM_WARPS * 32, 0, stream>>>(P, b, st, res, counters);
+    if (P.small_adapters == 0) k_trim<0><<<grid, TRIM_WARPS * 32, 0, stream>>>(P, b, st, res, counters);
+    else if (P.small_adapters == 1) k_trim<1><<<grid, TRIM_WARPS * 32, 0, stream>>>(P, b, st, res, counters);
+    else k_trim<2><<<grid, TRIM_WARPS * 32, 0, stream>>>(P, b, st, res, counters);
+    if (P.opt.adapter_enabled && P.n_adapters > 2) {
+        if (P.fasta_class == 0) k_trim_fasta<0><<<grid, TRIM_WARPS * 32, 0, stream>>>(P, b, st, res, counters);
+        else if (P.fasta_class == 1) k_trim_fasta<1><<<grid, TRIM_WARPS * 32, 0, stream>>>(P, b, st, res, counters);
+        else k_trim_fasta<2><<<grid, TRIM_WARPS * 32, 0, stream>>>(P, b, st, res, counters);
+    }
 }
