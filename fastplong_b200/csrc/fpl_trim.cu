@@ -294,15 +294,18 @@ struct EventSink {
 };
 
 // AdapterTrimmer::trimBySequenceStart (src/adaptertrimmer.cpp:168-236)
+// tryWindow / tryProbes: false when the caller's pre-filter has proved that stage cannot hit (the stage then returns what
+// it would have returned: nothing found)
 template <int CLS>
-__device__ int trim_start(const DevParams& P, const uint8_t* seq, Win& w, int aidx, EventSink& ev, uint8_t* scratch) {
+__device__ int trim_start(const DevParams& P, const uint8_t* seq, Win& w, int aidx, EventSink& ev, uint8_t* scratch,
+                          bool tryWindow = true, bool tryProbes = true) {
     const int lane = lane_id();
     const int alen = P.alen[aidx], ext = P.opt.trimming_extension;
     const uint8_t* rdata = seq + w.lo;
     const int rlen = w.len;
     if (rlen < FPL_PATTERN_LEN) return 0;
     const int plen = min(FPL_PATTERN_LEN, alen);
-    int mpos = search_window<CLS>(P, rdata, rlen, aidx, 0, FPL_WINDOW, false, reinterpret_cast<uint32_t*>(scratch));
+    int mpos = tryWindow ? search_window<CLS>(P, rdata, rlen, aidx, 0, FPL_WINDOW, false, reinterpret_cast<uint32_t*>(scratch)) : -1;
     if (mpos >= 0) {
         mpos = min(mpos + ext, rlen - alen);
         ev.add(aidx, 0, alen);
@@ -314,6 +317,7 @@ __device__ int trim_start(const DevParams& P, const uint8_t* seq, Win& w, int ai
     const int T16 = P.thr[plen];
     unsigned best = 0xFFFFFFFFu;
     const uint32_t* t16 = P.peq16 + (size_t)aidx * 512 + 256;   // last plen chars
+    if (!tryProbes) return 0;
     const int ncand = probe_candidates(rdata, rlen, np, plen, t16, T16, false, scratch);
     for (int c0 = 0; c0 < ncand; c0 += 32) {
         if (c0 + lane < ncand) {
@@ -339,7 +343,8 @@ __device__ int trim_start(const DevParams& P, const uint8_t* seq, Win& w, int ai
 
 // AdapterTrimmer::trimBySequenceEnd (src/adaptertrimmer.cpp:238-302)
 template <int CLS>
-__device__ int trim_end(const DevParams& P, const uint8_t* seq, Win& w, int aidx, EventSink& ev, uint8_t* scratch) {
+__device__ int trim_end(const DevParams& P, const uint8_t* seq, Win& w, int aidx, EventSink& ev, uint8_t* scratch,
+                        bool tryWindow = true, bool tryProbes = true) {
     const int lane = lane_id();
     const int alen = P.alen[aidx], ext = P.opt.trimming_extension;
     const uint8_t* rdata = seq + w.lo;
@@ -347,7 +352,7 @@ __device__ int trim_end(const DevParams& P, const uint8_t* seq, Win& w, int aidx
     if (rlen < FPL_PATTERN_LEN) return 0;
     const int plen = min(FPL_PATTERN_LEN, alen);
     const int searchStart = max(0, rlen - FPL_WINDOW);
-    int mpos = search_window<CLS>(P, rdata, rlen, aidx, searchStart, FPL_WINDOW, true, reinterpret_cast<uint32_t*>(scratch));
+    int mpos = tryWindow ? search_window<CLS>(P, rdata, rlen, aidx, searchStart, FPL_WINDOW, true, reinterpret_cast<uint32_t*>(scratch)) : -1;
     if (mpos >= 0) {
         mpos = max(0, mpos - ext);
         ev.add(aidx, 1, alen);
@@ -363,6 +368,7 @@ __device__ int trim_end(const DevParams& P, const uint8_t* seq, Win& w, int aidx
     const uint32_t* t16 = P.peq16 + (size_t)aidx * 512;         // first plen chars
     int pos = -1, carryE = -1, carryPos = -1;
     bool done = false;
+    if (!tryProbes) return 0;
     const int ncand = probe_candidates(rdata, rlen, np, plen, t16, T16, true, scratch);
     for (int c0 = 0; c0 < ncand && !done; c0 += 32) {
         const bool have = c0 + lane < ncand;
@@ -419,6 +425,7 @@ __device__ int trim_end(const DevParams& P, const uint8_t* seq, Win& w, int aidx
 // code runs as before.  The filter only ever says "maybe" too often, never "no" wrongly: results are unchanged.
 // ------------------------------------------------------------------------------------------------------------------
 #define PF_WIN FPL_WINDOW
+#define PF_WORDS ((2 * FPL_MAX_ADAPTERS + 31) / 32)
 
 // maybe-bits of the (adapter, side) pairs of all FASTA adapters for the window w: bit 2 * (k - 2) + side.  The pairs are
 // walked in P.pf_order (adapters grouped by width class), 32 per round, one per lane.
@@ -457,11 +464,12 @@ __device__ void prefilter_round(const DevParams& P, const uint8_t* head, const u
         F.column(Eq);
         Q.column((uint32_t)(Eq >> sh16) & m16);
     }
-    const bool maybe = active && (!filterable || F.best <= P.thr[alen] || Q.best <= P.thr[plen]);
-    if (maybe) {
-        const int bit = 2 * (k - 2) + side;
-        atomicOr(&bits[bit >> 5], 1u << (bit & 31));
-    }
+    // bitsF: the window stage (Hamming search + verification) can hit; bitsQ: a probe can
+    const bool mF = active && (!filterable || F.best <= P.thr[alen]);
+    const bool mQ = active && (!filterable || Q.best <= P.thr[plen]);
+    const int bit = 2 * (k - 2) + side;
+    if (mF) atomicOr(&bits[bit >> 5], 1u << (bit & 31));
+    if (mQ) atomicOr(&bits[PF_WORDS + (bit >> 5)], 1u << (bit & 31));
 }
 
 template <int CLS>
@@ -471,7 +479,7 @@ __device__ void prefilter(const DevParams& P, const uint8_t* seq, const Win& w, 
     const int hw = min(w.len, PF_WIN);
     __syncwarp();
     for (int j = lane; j < hw; j += 32) { head[j] = seq[w.lo + j]; tail[j] = seq[w.lo + w.len - hw + j]; }
-    for (int i = lane; i * 32 < nitems; i += 32) bits[i] = 0;
+    for (int i = lane; i * 32 < nitems; i += 32) { bits[i] = 0; bits[PF_WORDS + i] = 0; }
     __syncwarp();
     for (int base = 0; base < nitems; base += 32) {
         // one width per round: 64-bit vectors only if an adapter of this round needs them (the order groups them)
@@ -670,7 +678,7 @@ k_trim_fasta(const __grid_constant__ DevParams P, DevBatch b, ReadState* __restr
              unsigned long long* __restrict__ counters) {
     __shared__ __align__(16) uint8_t scratch_all[TRIM_WARPS][208];
     __shared__ __align__(16) uint8_t pf_win[TRIM_WARPS][2][PF_WIN + 8];     // many-adapter pre-filter: end windows ...
-    __shared__ uint32_t pf_bits[TRIM_WARPS][(2 * FPL_MAX_ADAPTERS + 31) / 32];   // ... and its maybe-bits
+    __shared__ uint32_t pf_bits[TRIM_WARPS][2 * PF_WORDS];   // ... and its maybe-bits: [window stage | probe stage]
     const int wid = threadIdx.x >> 5, lane = lane_id();
     const int64_t r = (int64_t)blockIdx.x * TRIM_WARPS + wid;
     if (r >= b.n_reads) return;
@@ -688,14 +696,16 @@ k_trim_fasta(const __grid_constant__ DevParams P, DevBatch b, ReadState* __restr
     const bool use_pf = P.n_adapters > 4 && w.len >= FPL_PATTERN_LEN;
     if (use_pf) prefilter<CLS>(P, seq, w, pf_win[wid][0], pf_win[wid][1], bits);
     for (int k = 2; k < P.n_adapters; k++) {
-        const int i0 = 2 * (k - 2);
-        if (!use_pf || (bits[i0 >> 5] >> (i0 & 31) & 1u)) {
-            const int t = trim_start<CLS>(P, seq, w, k, ev, scratch);
+        const int i0 = 2 * (k - 2), i1 = i0 + 1;
+        const bool f0 = !use_pf || (bits[i0 >> 5] >> (i0 & 31) & 1u), q0 = !use_pf || (bits[PF_WORDS + (i0 >> 5)] >> (i0 & 31) & 1u);
+        if (f0 || q0) {
+            const int t = trim_start<CLS>(P, seq, w, k, ev, scratch, f0, q0);
             trimmed += t;
             if (t && use_pf) prefilter<CLS>(P, seq, w, pf_win[wid][0], pf_win[wid][1], bits);
         }
-        if (!use_pf || (bits[(i0 + 1) >> 5] >> ((i0 + 1) & 31) & 1u)) {
-            const int t = trim_end<CLS>(P, seq, w, k, ev, scratch);
+        const bool f1 = !use_pf || (bits[i1 >> 5] >> (i1 & 31) & 1u), q1 = !use_pf || (bits[PF_WORDS + (i1 >> 5)] >> (i1 & 31) & 1u);
+        if (f1 || q1) {
+            const int t = trim_end<CLS>(P, seq, w, k, ev, scratch, f1, q1);
             trimmed += t;
             if (t && use_pf && k + 1 < P.n_adapters) prefilter<CLS>(P, seq, w, pf_win[wid][0], pf_win[wid][1], bits);
         }
