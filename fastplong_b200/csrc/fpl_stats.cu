@@ -48,14 +48,6 @@ __device__ __forceinline__ uint32_t kmer_code(uint32_t b) {
     return v;
 }
 
-// 0x80 in every byte of w that is NOT one of A, C, G, T, U (exact, any byte value).  With g = b2 & ~b1 (set for
-// T/U: 0x54/0x55), the valid bytes are exactly those with ((b & 0xF9) | g) == 0x41 ^ (g << 4).
-__device__ __forceinline__ uint32_t invalid_acgtu(uint32_t w, uint32_t x1) {
-    const uint32_t g = (w >> 2) & ~x1 & 0x01010101u;
-    const uint32_t d = ((w & 0xF9F9F9F9u) | g) ^ 0x41414141u ^ (g * 16u);
-    return (((d & 0x7f7f7f7fu) + 0x7f7f7f7fu) | d) & 0x80808080u;
-}
-
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {   // PTX semantics: selector bit 3 = sign fill
     uint32_t d;
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));

@@ -1,6 +1,9 @@
 """The index arithmetic of k_cycle_stats' shared-memory counters (fastplong_b200/csrc/fpl_stats.cu), checked on the CPU:
 the (lane, byte) -> word mapping is injective per bin, free of bank conflicts for every misalignment, and the flush maps
-every word back to the cycle the byte came from."""
+every word back to the cycle the byte came from.  (This checks the arithmetic the kernel's constants encode; that the
+hardware sees the resulting address pattern as conflict-free — 0 conflicts, 1 wavefront per reduction — is measured by
+tools/ubench_red.cu, profiles/r02k_ubench_red_ncu.csv.  The conflict wavefronts ncu reports inside the kernel come from the
+reductions sharing the data pipe with the cp.async ring fills and other warps' loads)"""
 import re
 import os
 
