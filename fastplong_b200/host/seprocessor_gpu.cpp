@@ -601,15 +601,19 @@ bool SingleEndProcessor::process() {
     const bool timing = getenv("FPL_TIMING") != nullptr;
     double t_last = g_warm.t0;
     FPL_STAMP("program start -> process()");
+    // opening --out truncates whatever the path held before (about 1 s for a multi-GB file on tmpfs): do it while the
+    // driver is still starting
+    if (!mOptions->split.enabled) initOutput();
+    FPL_STAMP("writers (initOutput)");
     g_warm.wait();
     FPL_STAMP("wait for the CUDA driver");
-    if (!mOptions->split.enabled) initOutput();
     const int T = mOptions->thread;
 
     // one GPU context per worker thread; workers are spread over the visible devices
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         error_exit("fastplong_gpu: no CUDA device available (this build has no CPU fallback for the hot path)");
+    FPL_STAMP("cudaGetDeviceCount");
     g_adapters.clear();
     g_adapters.push_back(mOptions->adapter.sequenceStart);
     g_adapters.push_back(mOptions->adapter.sequenceEnd);
@@ -666,6 +670,9 @@ bool SingleEndProcessor::process() {
         WriterThread* failedW = mFailedWriter;
         Options* opt = mOptions;
         std::atomic<int> notStrict(0);
+        // finished chunks the writer may hold before the workers wait (FPL_WRITER_BACKLOG: chunks per worker, default 2)
+        const long backlog = (getenv("FPL_WRITER_BACKLOG") ? std::max(1L, atol(getenv("FPL_WRITER_BACKLOG"))) : 2L) * T;
+        std::atomic<long> delivered(0);                         // chunks handed to the writers so far (all workers)
         if (mOptions->verbose) loginfo("start to load data");
         std::thread reader([&] {
             TextChunk* cur = freeList.pop();
@@ -702,19 +709,28 @@ bool SingleEndProcessor::process() {
             FilterResult* fr = config->getFilterResult();
             std::vector<fpl_fastq_record> recs;
             std::vector<fpl_read_result> res;
+            long mine = 0;
             while (TextChunk* c = queues[t].pop()) {
+                const long k = (mine++) * T + t;                // this chunk's place in the writer's round-robin walk
+                auto deliver = [&](string* l, string* f) {
+                    delivered++;                                // counted first: `written` below never under-counts
+                    if (left) left->input(t, l); else delete l;
+                    if (failedW) failedW->input(t, f); else delete f;
+                };
                 // abandoned run: every chunk dealt out still hands the writers one (empty) string, because WriterThread::output
                 // walks the worker lists strictly round-robin (src/writerthread.cpp:37-48) and would wait for a gap for ever
                 auto skipChunk = [&] {
-                    if (left) left->input(t, new string());
-                    if (failedW) failedW->input(t, new string());
+                    deliver(new string(), new string());
                     freeList.push(c);
                 };
                 if (notStrict) { skipChunk(); continue; }
-                // writer back-pressure (the reference's reader waits the same way, src/seprocessor.cpp:391-395): at most
-                // a couple of finished chunks per worker wait for the single writer thread (which also compresses)
-                while (left && left->bufferLength() > 2L * T && !notStrict) usleep(1000);
-                while (failedW && failedW->bufferLength() > 2L * T && !notStrict) usleep(1000);
+                // writer back-pressure (the reference's reader waits the same way, src/seprocessor.cpp:391-395): chunk k
+                // starts only once the single writer thread (which also compresses) is within `backlog` chunks of it.
+                // The writer takes chunks in order of k, so the worker holding the chunk it needs next (k == written)
+                // never waits: no cycle between the workers' waits and the writer's.
+                auto written = [&](WriterThread* w) { return delivered.load() - (long)w->bufferLength(); };
+                while (left && k - written(left) > backlog && !notStrict) usleep(200);
+                while (failedW && k - written(failedW) > backlog && !notStrict) usleep(200);
                 // four newlines per record: count them to size the record tables
                 size_t nl = 0;
                 for (const uint8_t* q = c->p, *e = c->p + c->n; (q = (const uint8_t*)memchr(q, '\n', (size_t)(e - q))) != nullptr; q++) nl++;
@@ -741,10 +757,7 @@ bool SingleEndProcessor::process() {
                     const fpl_region* rg = ext.regsOf(i, nregs);
                     scatterRead(v, res[i], sg, rg, nregs, config, failedW != NULL, *outstr, *failedOut, scratch);
                 }
-                if (left) { left->input(t, outstr); outstr = NULL; }
-                if (failedW) { failedW->input(t, failedOut); failedOut = NULL; }
-                delete outstr;
-                delete failedOut;
+                deliver(outstr, failedOut);
                 freeList.push(c);
             }
             (void)opt;
