@@ -36,6 +36,8 @@ def load_library():
     lib.fpl_sync.argtypes = [C.c_void_p]
     lib.fpl_process_fastq_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
                                            C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.fpl_emit_fastq_host.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p, C.c_int64,
+                                        C.POINTER(C.c_int64)]
     lib.fpl_stream.argtypes = [C.c_void_p]
     lib.fpl_stream.restype = C.c_void_p
     lib.fpl_fetch_results.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
@@ -70,7 +72,7 @@ def load_library():
     return lib
 
 
-EXPORTS = ["fpl_last_error", "fpl_abi_version", "fpl_create", "fpl_destroy", "fpl_process_host", "fpl_process_device", "fpl_process_fastq_host",
+EXPORTS = ["fpl_last_error", "fpl_abi_version", "fpl_create", "fpl_destroy", "fpl_process_host", "fpl_process_device", "fpl_process_fastq_host", "fpl_emit_fastq_host",
            "fpl_sync", "fpl_stream", "fpl_last_segments", "fpl_last_mask_regions", "fpl_fetch_results", "fpl_stats_cycles", "fpl_stats_reserve", "fpl_stats_download",
            "fpl_stats_device_ptr", "fpl_counter_words", "fpl_counters_download", "fpl_counters_device_ptr",
            "fpl_comm_unique_id", "fpl_comm_init", "fpl_comm_destroy", "fpl_comm_size", "fpl_comm_agree_cycles", "fpl_allreduce_stats",
@@ -140,6 +142,20 @@ class Engine:
             return None
         self._check(rc)
         return recs[:n.value], res[:n.value], used.value
+
+    def emit_fastq(self, want_failed=True):
+        """The --out / --failed_out text of the chunk the last process_fastq() call processed, assembled on the device
+        (fpl_emit_fastq_host): (out_bytes, failed_bytes).  First call sizes, second call copies."""
+        n_out, n_failed = C.c_int64(), C.c_int64()
+        rc = self.lib.fpl_emit_fastq_host(self.h, int(want_failed), None, 0, C.byref(n_out), None, 0, C.byref(n_failed))
+        if rc < 0:
+            self._check(rc)
+        out = np.empty(n_out.value, dtype=np.uint8)
+        failed = np.empty(n_failed.value, dtype=np.uint8)
+        self._check(self.lib.fpl_emit_fastq_host(self.h, int(want_failed), out.ctypes.data if out.size else None, out.size,
+                                                 C.byref(n_out), failed.ctypes.data if failed.size else None, failed.size,
+                                                 C.byref(n_failed)))
+        return out.tobytes(), failed.tobytes()
 
     def process_device(self, seq_ptr, qual_ptr, offsets_ptr, lens_ptr, n_reads, n_bytes, results_ptr=None):
         b = FplBatch(seq_ptr, qual_ptr, offsets_ptr, lens_ptr, n_reads, n_bytes)

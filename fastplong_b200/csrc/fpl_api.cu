@@ -19,6 +19,7 @@
 #include "fpl_jit.h"
 #include "fpl_ingest.h"
 #include "fpl_ext.h"
+#include "fpl_emit.h"
 
 static_assert(sizeof(fpl_options) == 144, "fpl_options ABI size");
 static_assert(sizeof(fpl_segment) == 20 && sizeof(fpl_region) == 12, "segment / region ABI size");
@@ -68,6 +69,9 @@ struct fpl_ctx {
     FplJitKernel jit;   // specialised scan kernel (NVRTC), fn == nullptr if not used
     FplIngest ingest;   // device-side FASTQ parsing state
     FplExt ext;         // --mask / --break state (variable number of output reads)
+    FplEmit emit;       // device-side output text of the last fpl_process_fastq_host chunk (fpl_emit_fastq_host)
+    bool emit_valid = false;            // the last call was a successful fpl_process_fastq_host: chunk + records + results in HBM
+    int64_t emit_n = 0;
     int64_t last_bytes = 0;
     bool slots16 = false;               // this batch's read offsets are multiples of 16 (checked: host batches, device ingest)
     int n_adapters = 0;
@@ -217,6 +221,7 @@ static int run_batch(fpl_ctx* c, const DevBatch& full, const int32_t* h_lens, fp
     const int64_t n = full.n_reads;
     CK(cudaSetDevice(c->device));
     collect_times(c);
+    c->emit_valid = false; c->emit.built = false;
     c->last_n = n;
     if (ensure_reads(c, n)) return -1;
     fpl_read_result* d_res = d_res_out ? d_res_out : c->d_results;
@@ -507,6 +512,7 @@ void fpl_destroy(fpl_ctx* c) {
     cudaFree(c->d_seq); cudaFree(c->d_qual); cudaFree(c->d_offsets); cudaFree(c->d_lens);
     fpl_ingest_free(&c->ingest);
     fpl_ext_free(&c->ext);
+    fpl_emit_free(&c->emit);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -642,7 +648,8 @@ int fpl_process_fastq_host(fpl_ctx* c, const uint8_t* text, int64_t n_bytes, int
     if (rc < 0) return fail("fpl_process_fastq_host: %s", err);
     if (rc > 0) return 1;
     *n_records = nrec;
-    if (nrec == 0) return 0;
+    c->emit_valid = false; c->emit.built = false;
+    if (nrec == 0) { c->emit_valid = true; c->emit_n = 0; return 0; }
     if (nrec > max_records) return 1;
     if (!records || !results) return fail("fpl_process_fastq_host: records/results is null");
     FplIngest& g = c->ingest;
@@ -667,6 +674,38 @@ int fpl_process_fastq_host(fpl_ctx* c, const uint8_t* text, int64_t n_bytes, int
     CK(cudaMemcpyAsync(results, c->d_results, sizeof(fpl_read_result) * nrec, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     collect_times(c);
+    c->emit_valid = true; c->emit_n = nrec;
+    return 0;
+}
+
+int fpl_emit_fastq_host(fpl_ctx* c, int want_failed, uint8_t* out, int64_t out_cap, int64_t* out_bytes, uint8_t* failed,
+                        int64_t failed_cap, int64_t* failed_bytes) {
+    g_err[0] = 0;
+    if (!c || !out_bytes || !failed_bytes) return fail("fpl_emit_fastq_host: null argument");
+    *out_bytes = *failed_bytes = 0;
+    if (!c->emit_valid)
+        return fail("fpl_emit_fastq_host: the last call on this context was not a successful fpl_process_fastq_host");
+    CK(cudaSetDevice(c->device));
+    FplEmit& e = c->emit;
+    if (!e.built || e.with_failed != (want_failed != 0)) {
+        const bool ext = c->P.opt.mask_enabled || c->P.opt.break_enabled;
+        EmitSource src;
+        src.text = c->ingest.d_text; src.rec = c->ingest.d_rec; src.res = c->last_results; src.n_reads = c->emit_n;
+        src.segs = ext ? c->ext.d_segs : nullptr;
+        src.seg_off = ext ? c->ext.d_off : nullptr;
+        src.mseq = (c->P.opt.mask_enabled && c->ext.n_segs > 0) ? c->ext.d_mseq : nullptr;   // fpl_ext_run made the masked copy
+        src.offsets = c->ingest.d_offsets;
+        char err[256] = "";
+        if (fpl_emit_build(&e, src, want_failed != 0, c->stream, err, sizeof(err))) return fail("fpl_emit_fastq_host: %s", err);
+        if (c->emit_n) c->launches += 2;
+    }
+    *out_bytes = e.out_bytes;
+    *failed_bytes = e.failed_bytes;
+    if (e.out_bytes > out_cap || e.failed_bytes > failed_cap) return 1;     // the text stays built: call again with room
+    if ((e.out_bytes && !out) || (e.failed_bytes && !failed)) return fail("fpl_emit_fastq_host: null output buffer");
+    if (e.out_bytes) CK(cudaMemcpyAsync(out, e.d_out, (size_t)e.out_bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (e.failed_bytes) CK(cudaMemcpyAsync(failed, e.d_failed, (size_t)e.failed_bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     return 0;
 }
 

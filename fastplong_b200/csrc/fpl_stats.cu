@@ -28,7 +28,7 @@
 #define CS_BINW (16 * CS_ROWW + 16)              // words per base bin: a multiple of 32, so the bank is the lane's whatever the bin
 #define CS_GROUP 4000                            // segments per CTA; packed counter: count <= 4095, sum of q < 2^20
 #define CS_STAGE 1000                            // descriptors staged in shared memory at a time
-#define CS_SLOT 1040                             // ring slot: 512 B sequence, 512 B quality, the 4 bytes in front of the tile (+pad)
+#define CS_SLOT 1040                             // ring slot: 16 B in front of the tile (its last 4 are used), 512 B sequence, 512 B quality
 #define CS_DEPTH_KMER 1                          // segments in flight per warp (the 5-mer variant is bound by the logic pipe)
 #define CS_DEPTH_PLAIN 3
 #define CS_SMEM_BASE (8 * CS_BINW * 4 + CS_STAGE * 16)            // counters + staged descriptors
@@ -133,42 +133,38 @@ __device__ __forceinline__ void count16(const uint32_t (&wm)[4], const uint32_t 
 // the FMA pipe, which issues beside the logic pipe (tools/ubench_pipes.cu: LOP3 + IDP.4A together run at 0.94
 // warp-instructions per clock and sub-partition, LOP3 alone at 0.48).  wb: (base & 7) << 4 in every byte, so that
 // one dp4a with the weight 136 on byte J is bin * CS_BINW * 4 (+ the lane's base address); qm: quality chars.
+// wa[j] = 136 << 8j and wv[j] = 1 << 8j arrive as run-time values (uniform registers for the whole loop): as literals
+// the compiler re-materialises the eight of them with UMOVs in front of every vector.
 template <int S, int J>
-__device__ __forceinline__ void count1f(const uint32_t (&wb)[4], const uint32_t (&qm)[4], uint32_t pk_lane) {
+__device__ __forceinline__ void count1f(const uint32_t (&wb)[4], const uint32_t (&qm)[4], uint32_t pk_lane,
+                                        const uint32_t (&wa)[4], const uint32_t (&wv)[4]) {
     constexpr int jj = J & 3, m = J + S;
     static_assert(CS_BINW * 4 == 136 * 16, "dp4a weight of the bin stride");
-    const uint32_t addr = __dp4a(wb[J >> 2], 136u << (8 * jj), pk_lane);
-    const uint32_t val = __dp4a(qm[J >> 2], 1u << (8 * jj), 1u << 20);
+    const uint32_t addr = __dp4a(wb[J >> 2], wa[jj], pk_lane);
+    const uint32_t val = __dp4a(qm[J >> 2], wv[jj], 1u << 20);
     red_shared_add_imm<4 * ((m & 15) * CS_ROWW + (m >> 4))>(addr, val);
 }
 template <int S>
-__device__ __forceinline__ void count16f(const uint32_t (&wb)[4], const uint32_t (&qm)[4], uint32_t pk) {
-    count1f<S, 0>(wb, qm, pk); count1f<S, 1>(wb, qm, pk); count1f<S, 2>(wb, qm, pk); count1f<S, 3>(wb, qm, pk);
-    count1f<S, 4>(wb, qm, pk); count1f<S, 5>(wb, qm, pk); count1f<S, 6>(wb, qm, pk); count1f<S, 7>(wb, qm, pk);
-    count1f<S, 8>(wb, qm, pk); count1f<S, 9>(wb, qm, pk); count1f<S, 10>(wb, qm, pk); count1f<S, 11>(wb, qm, pk);
-    count1f<S, 12>(wb, qm, pk); count1f<S, 13>(wb, qm, pk); count1f<S, 14>(wb, qm, pk); count1f<S, 15>(wb, qm, pk);
+__device__ __forceinline__ void count16f(const uint32_t (&wb)[4], const uint32_t (&qm)[4], uint32_t pk, const uint32_t (&wa)[4],
+                                         const uint32_t (&wv)[4]) {
+    count1f<S, 0>(wb, qm, pk, wa, wv); count1f<S, 1>(wb, qm, pk, wa, wv); count1f<S, 2>(wb, qm, pk, wa, wv); count1f<S, 3>(wb, qm, pk, wa, wv);
+    count1f<S, 4>(wb, qm, pk, wa, wv); count1f<S, 5>(wb, qm, pk, wa, wv); count1f<S, 6>(wb, qm, pk, wa, wv); count1f<S, 7>(wb, qm, pk, wa, wv);
+    count1f<S, 8>(wb, qm, pk, wa, wv); count1f<S, 9>(wb, qm, pk, wa, wv); count1f<S, 10>(wb, qm, pk, wa, wv); count1f<S, 11>(wb, qm, pk, wa, wv);
+    count1f<S, 12>(wb, qm, pk, wa, wv); count1f<S, 13>(wb, qm, pk, wa, wv); count1f<S, 14>(wb, qm, pk, wa, wv); count1f<S, 15>(wb, qm, pk, wa, wv);
 }
 
 // 0xFF in byte k of the result iff bit k of the nibble n
 __device__ __forceinline__ uint32_t nibble_to_bytes(uint32_t n) { return ((n * 0x00204081u) & 0x01010101u) * 0xFFu; }
 
-// 5-mer ending at byte T of the lane's vector.  P: 2-bit codes, oldest first, the 5-mer's in bits [22+2*SH .. 32); the
-// table word is [code][lane] (no bank conflicts); an invalid 5-mer adds 0 (no branch around the reduction).
+// 5-mer ending at byte T of the lane's vector.  P: 2-bit codes, oldest first, the 5-mer's in bits [22-SHL .. 32-SHL); the
+// table word is [code][lane] (no bank conflicts); an invalid 5-mer adds 0 (no branch around the reduction — a reduction
+// predicated on the validity bit is compiled into BSSY / BRA / BSYNC around it: four instructions instead of two).
+// Left shifts as multiplies: they run on the IMAD pipe.  (Right shifts as mul.hi were measured too: IMAD.HI is slow on
+// this part — 13.7 ms against 11.4 ms for the kernel; mask + shift-and-add compiles to the same four instructions.)
 template <int SHL, int T>
 __device__ __forceinline__ void kmer1(uint32_t P, uint32_t ok, uint32_t km_lane) {
-    // left shifts as multiplies: they run on the IMAD pipe, the logic pipe is the busy one in this kernel.  (The right
-    // shifts as mul.hi were measured too: IMAD.HI is slow on this part — 13.7 ms against 11.4 ms for the kernel.)
     const uint32_t idx = (SHL ? mad_u32(P, 1u << SHL, 0u) : P) >> 22;
-    red_shared_add(mad_u32(idx, 128u, km_lane), mad_u32(ok, 1u << (31 - T), 0u) >> 31);
-}
-
-// the same with the reduction predicated on the 5-mer's validity bit (no value arithmetic): for the vectors of a full
-// tile in which some lane holds a byte outside ACGTU
-template <int SHL, int T>
-__device__ __forceinline__ void kmer1p(uint32_t P, uint32_t ok, uint32_t km_lane) {
-    const uint32_t idx = (SHL ? mad_u32(P, 1u << SHL, 0u) : P) >> 22;
-    asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %1, 0;\n@p red.shared.add.u32 [%0], 1;\n}\n"
-                 ::"r"(mad_u32(idx, 128u, km_lane)), "r"(ok & (1u << T)) : "memory");
+    red_shared_add(mad_u32(idx, 128u, km_lane), (ok >> T) & 1u);
 }
 
 // the same when the 5-mer is known to count: the value is the immediate 1
@@ -243,9 +239,13 @@ k_cycle_stats(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qu
     const uint32_t km_lane = shared_addr(kmer) + (uint32_t)lane * 4u;
     const uint8_t* seq_lane = seqbuf + 16 * lane;
     const uint8_t* qual_lane = qualbuf + 16 * lane;
-    const uint32_t ring_lane = shared_addr(ring) + (uint32_t)wid * ((DEPTH + 1) * CS_SLOT) + (uint32_t)lane * 16u;
-    const uint32_t ring_warp = ring_lane - (uint32_t)lane * 16u;
+    // a slot: [16 bytes in front of the tile][512 bytes of sequence][512 bytes of quality]; the word in front of a lane's
+    // vector — the previous lane's last word, for lane 0 the front bytes — is at the same offset for every lane
+    const uint32_t ring_warp = shared_addr(ring) + (uint32_t)wid * ((DEPTH + 1) * CS_SLOT);
+    const uint32_t ring_lane = ring_warp + 16u + (uint32_t)lane * 16u;
     const uint32_t bar_warp = shared_addr(mbars) + (uint32_t)wid * ((DEPTH + 1) * 8);
+    const uint32_t wa[4] = {136u * one, (136u << 8) * one, (136u << 16) * one, (136u << 24) * one};   // one == 1
+    const uint32_t wv[4] = {one, one << 8, one << 16, one << 24};
     uint32_t phase = 0;                                   // TMA: the parity each slot's mbarrier completes next (bit per slot)
     if (TMA) {
         if (lane == 0)
@@ -287,16 +287,19 @@ k_cycle_stats(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qu
                     const uint32_t bytes = ts.lim > 0 ? (uint32_t)min(CS_TILE, (ts.lim + 15) & ~15) : 0u;
                     const uint32_t pb = (DO_KMER && t0 != 0 && bytes) ? 16u : 0u;
                     mbar_expect_tx(bar, 2u * bytes + pb);
-                    if (bytes) { bulk_g2s(dst, seqbuf + ts.a, bytes, bar); bulk_g2s(dst + 512u, qualbuf + ts.a, bytes, bar); }
-                    if (pb) bulk_g2s(dst + 1024u, seqbuf + ts.a - 16, 16u, bar);
+                    if (bytes) { bulk_g2s(dst + 16u, seqbuf + ts.a, bytes, bar); bulk_g2s(dst + 528u, qualbuf + ts.a, bytes, bar); }
+                    if (pb) bulk_g2s(dst, seqbuf + ts.a - 16, 16u, bar);
                 }
                 return;
             }
             const bool act = 16 * lane < ts.lim;
             const uint32_t dst = ring_lane + (uint32_t)slot * CS_SLOT;
-            cp_async16(dst, act ? seq_lane + ts.a : seqbuf, act ? 16 : 0);
-            cp_async16(dst + 512, act ? qual_lane + ts.a : qualbuf, act ? 16 : 0);
-            if (DO_KMER && lane == 0) cp_async4(dst + 1024 - 16 * lane, ts.a >= 4 ? seqbuf + ts.a - 4 : seqbuf, ts.a >= 4 ? 4 : 0);
+            const int64_t la = ts.a + (act ? 16 * lane : 0);     // an inactive lane copies 0 bytes (zero fill); the address stays valid
+            cp_async16(dst, seqbuf + la, act ? 16 : 0);
+            cp_async16(dst + 512, qualbuf + la, act ? 16 : 0);
+            // the four bases in front of the tile (lane 0's 5-mers): not needed in the first tile, where no 5-mer ends in
+            // front of cycle 4; behind it a >= 512 - 15
+            if (DO_KMER && lane == 0 && t0 != 0) cp_async4(dst - 4, seqbuf + ts.a - 4, 4);
         };
         int kk = wid;
 #pragma unroll
@@ -311,7 +314,7 @@ k_cycle_stats(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qu
             else cp_async_wait<DEPTH - 1>();
             const uint32_t src = ring_lane + (uint32_t)slot * CS_SLOT;
             const uint4 ns = lds128(src), nq = lds128(src + 512);
-            const uint32_t prev0 = (DO_KMER && lane == 0) ? lds32(src + 1024 + (TMA ? 12 : 0)) : 0u;
+            const uint32_t pw = DO_KMER ? lds32(src - 4) : 0u;     // the four bases in front of this lane's vector
             const uint32_t sw[4] = {ns.x, ns.y, ns.z, ns.w};
             uint32_t qm[4] = {nq.x, nq.y, nq.z, nq.w};
             const int sh = stage[k].sh, lim = stage[k].lim;
@@ -329,24 +332,24 @@ k_cycle_stats(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qu
                 const uint32_t wb[4] = {mad_u32(sw[0], 16u, 0u) & 0x70707070u, mad_u32(sw[1], 16u, 0u) & 0x70707070u,
                                         mad_u32(sw[2], 16u, 0u) & 0x70707070u, mad_u32(sw[3], 16u, 0u) & 0x70707070u};
                 // aligned: every segment starts on a 16-byte boundary (the pre-filter pass: whole reads in their slots)
-                if (aligned) count16f<15>(wb, qm, pk_lane);
+                if (aligned) count16f<15>(wb, qm, pk_lane, wa, wv);
                 else switch (sh) {
-                    case 0: count16f<15>(wb, qm, pk_lane); break;
-                    case 1: count16f<14>(wb, qm, pk_lane); break;
-                    case 2: count16f<13>(wb, qm, pk_lane); break;
-                    case 3: count16f<12>(wb, qm, pk_lane); break;
-                    case 4: count16f<11>(wb, qm, pk_lane); break;
-                    case 5: count16f<10>(wb, qm, pk_lane); break;
-                    case 6: count16f<9>(wb, qm, pk_lane); break;
-                    case 7: count16f<8>(wb, qm, pk_lane); break;
-                    case 8: count16f<7>(wb, qm, pk_lane); break;
-                    case 9: count16f<6>(wb, qm, pk_lane); break;
-                    case 10: count16f<5>(wb, qm, pk_lane); break;
-                    case 11: count16f<4>(wb, qm, pk_lane); break;
-                    case 12: count16f<3>(wb, qm, pk_lane); break;
-                    case 13: count16f<2>(wb, qm, pk_lane); break;
-                    case 14: count16f<1>(wb, qm, pk_lane); break;
-                    default: count16f<0>(wb, qm, pk_lane); break;
+                    case 0: count16f<15>(wb, qm, pk_lane, wa, wv); break;
+                    case 1: count16f<14>(wb, qm, pk_lane, wa, wv); break;
+                    case 2: count16f<13>(wb, qm, pk_lane, wa, wv); break;
+                    case 3: count16f<12>(wb, qm, pk_lane, wa, wv); break;
+                    case 4: count16f<11>(wb, qm, pk_lane, wa, wv); break;
+                    case 5: count16f<10>(wb, qm, pk_lane, wa, wv); break;
+                    case 6: count16f<9>(wb, qm, pk_lane, wa, wv); break;
+                    case 7: count16f<8>(wb, qm, pk_lane, wa, wv); break;
+                    case 8: count16f<7>(wb, qm, pk_lane, wa, wv); break;
+                    case 9: count16f<6>(wb, qm, pk_lane, wa, wv); break;
+                    case 10: count16f<5>(wb, qm, pk_lane, wa, wv); break;
+                    case 11: count16f<4>(wb, qm, pk_lane, wa, wv); break;
+                    case 12: count16f<3>(wb, qm, pk_lane, wa, wv); break;
+                    case 13: count16f<2>(wb, qm, pk_lane, wa, wv); break;
+                    case 14: count16f<1>(wb, qm, pk_lane, wa, wv); break;
+                    default: count16f<0>(wb, qm, pk_lane, wa, wv); break;
                 }
             } else {
                 // the segment starts or ends in this tile: which of the lane's 16 bytes are cycles of the segment (vmask)
@@ -387,18 +390,14 @@ k_cycle_stats(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qu
             if (!DO_KMER) continue;
             // ---- 5-mers ending in this lane's 16 bytes: all five bases in ACGTU, end cycle in [4, len) ----
             // per word: the "not ACGTU" flags and four 2-bit codes c' = (b >> 1) & 3 (A=0, C=1, T/U=2, G=3; the flush maps
-            // them to base2val's); the previous lane's last word supplies the four bases in front of this lane's vector
-            // (lane 0: the word loaded in front of the tile)
-            uint32_t nz[4], pc[4];
+            // them to base2val's); the word in front of the lane's vector (pw) supplies the four bases before it — every
+            // lane encodes its own copy: cheaper than two shuffles plus a lane-0 branch around a fifth encode
+            uint32_t nz[4], pc[4], pnz, ppc;
 #pragma unroll
             for (int i = 0; i < 4; i++) encode4(sw[i], one, nz[i], pc[i]);
+            encode4(pw, one, pnz, ppc);
             // flags << 7: bit 7+t = byte t-4 of the 20 bytes (previous four, then the lane's sixteen)
-            uint32_t pin7 = __shfl_up_sync(0xffffffffu, __dp4a(nz[3], 0x08040201u, 0u), 1), ppc = __shfl_up_sync(0xffffffffu, pc[3], 1);
-            if (lane == 0) {
-                uint32_t pnz;
-                encode4(prev0, one, pnz, ppc);
-                pin7 = __dp4a(pnz, 0x08040201u, 0u);
-            }
+            const uint32_t pin7 = __dp4a(pnz, 0x08040201u, 0u);
             const uint32_t in01 = __dp4a(nz[0], 0x08040201u, __dp4a(nz[1], 0x80402010u, 0u));
             const uint32_t in23 = __dp4a(nz[2], 0x08040201u, __dp4a(nz[3], 0x80402010u, 0u));
             const uint32_t I27 = mad_u32(in23, 4096u, mad_u32(in01, 16u, pin7));     // 20 flags at bits 7..26
@@ -412,13 +411,14 @@ k_cycle_stats(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qu
                 kmer1f<16>(Phi, km_lane); kmer1f<18>(Phi, km_lane); kmer1f<20>(Phi, km_lane); kmer1f<22>(Phi, km_lane);
                 kmer1f<8>(Plo, km_lane); kmer1f<10>(Plo, km_lane); kmer1f<12>(Plo, km_lane); kmer1f<14>(Plo, km_lane);
             } else if (full) {
-                // some lane holds an N (or another byte outside ACGTU): the reductions are predicated on the validity bits
+                // some lane holds an N (or another byte outside ACGTU): the reductions add the validity bit (a predicated
+                // reduction is compiled into a branch around it: four instructions per 5-mer instead of two)
                 const uint32_t I20 = I27 >> 7;
                 const uint32_t ok = ~(I20 | (I20 >> 1) | (I20 >> 2) | (I20 >> 3) | (I20 >> 4));   // bit t: bytes t-4..t all valid
-                kmer1p<0, 0>(Phi, ok, km_lane); kmer1p<2, 1>(Phi, ok, km_lane); kmer1p<4, 2>(Phi, ok, km_lane); kmer1p<6, 3>(Phi, ok, km_lane);
-                kmer1p<8, 4>(Phi, ok, km_lane); kmer1p<10, 5>(Phi, ok, km_lane); kmer1p<12, 6>(Phi, ok, km_lane); kmer1p<14, 7>(Phi, ok, km_lane);
-                kmer1p<16, 8>(Phi, ok, km_lane); kmer1p<18, 9>(Phi, ok, km_lane); kmer1p<20, 10>(Phi, ok, km_lane); kmer1p<22, 11>(Phi, ok, km_lane);
-                kmer1p<8, 12>(Plo, ok, km_lane); kmer1p<10, 13>(Plo, ok, km_lane); kmer1p<12, 14>(Plo, ok, km_lane); kmer1p<14, 15>(Plo, ok, km_lane);
+                kmer1<0, 0>(Phi, ok, km_lane); kmer1<2, 1>(Phi, ok, km_lane); kmer1<4, 2>(Phi, ok, km_lane); kmer1<6, 3>(Phi, ok, km_lane);
+                kmer1<8, 4>(Phi, ok, km_lane); kmer1<10, 5>(Phi, ok, km_lane); kmer1<12, 6>(Phi, ok, km_lane); kmer1<14, 7>(Phi, ok, km_lane);
+                kmer1<16, 8>(Phi, ok, km_lane); kmer1<18, 9>(Phi, ok, km_lane); kmer1<20, 10>(Phi, ok, km_lane); kmer1<22, 11>(Phi, ok, km_lane);
+                kmer1<8, 12>(Plo, ok, km_lane); kmer1<10, 13>(Plo, ok, km_lane); kmer1<12, 14>(Plo, ok, km_lane); kmer1<14, 15>(Plo, ok, km_lane);
             } else {
                 const uint32_t I20 = I27 >> 7;
                 const uint32_t bad = I20 | (I20 >> 1) | (I20 >> 2) | (I20 >> 3) | (I20 >> 4);   // bit t: a byte of t-4..t is invalid

@@ -167,7 +167,8 @@ void appendView(std::string& out, const ReadView& v, const char* seq, const std:
 // FilterResult / Stats side effects), driven by the device's record.  segs/regs: this read's entries of the
 // --mask/--break lists (nullptr in the plain mode, where the record's inline segments are used).
 bool scatterRead(const ReadView& v, const fpl_read_result& rr, const fpl_segment* segs, const fpl_region* regs, int nregs,
-                 ThreadConfig* config, bool haveFailedWriter, std::string& outstr, std::string& failedOut, std::string& scratch) {
+                 ThreadConfig* config, bool haveFailedWriter, std::string& outstr, std::string& failedOut, std::string& scratch,
+                 bool text = true) {      // text == false: the output text comes from fpl_emit_fastq_host, only the side effects here
     Stats* pre = config->getPreStats1();
     Stats* post = config->getPostStats1();
     FilterResult* fr = config->getFilterResult();
@@ -178,7 +179,7 @@ bool scatterRead(const ReadView& v, const fpl_read_result& rr, const fpl_segment
     if (rr.flags & FPL_FLAG_POLYX) fr->addPolyXTrimmed(rr.polyx_base, rr.polyx_len);
     if (rr.adapter_trimmed_bases > 0) fr->addReadTrimmed(rr.adapter_trimmed_bases);
     const char* mseq = v.seq;          // masked view of the bases (Read::maskRegionWithN), only materialised if needed
-    if (nregs > 0) {
+    if (nregs > 0 && text) {
         scratch.assign(v.seq, (size_t)L);
         for (int k = 0; k < nregs; k++) memset(&scratch[regs[k].lo], 'N', (size_t)regs[k].len);
         mseq = scratch.data();
@@ -197,14 +198,14 @@ bool scatterRead(const ReadView& v, const fpl_read_result& rr, const fpl_segment
         config->addFilterResult(code, 1);
         if (code == PASS_FILTER) {
             std::string prefix;          // "r<k>-" (Read::breakByRegions) goes in front of the breakByGap tag
-            if (bidx) prefix = "r" + std::to_string(bidx) + "-";
-            if (side) prefix += side == 2 ? "split-by-adapter-right-" : "split-by-adapter-left-";
-            appendView(outstr, v, mseq, prefix, NULL, lo, ln);
+            if (bidx && text) prefix = "r" + std::to_string(bidx) + "-";
+            if (side && text) prefix += side == 2 ? "split-by-adapter-right-" : "split-by-adapter-left-";
+            if (text) appendView(outstr, v, mseq, prefix, NULL, lo, ln);
             passed = true;
             post->mLengthVec.push_back(ln);
             post->mNeedCalcLength = true;
             if (ln > 0) post->mQualLength[(char)median].push_back(ln);
-        } else if (haveFailedWriter && rr.n_segments == 1) {
+        } else if (haveFailedWriter && rr.n_segments == 1 && text) {
             // the reference prints or1, trimmed in place — and masked in place only if the output read IS r1 (:278-280)
             appendView(failedOut, v, isR1 ? mseq : v.seq, std::string(), FAILED_TYPES[code], rr.trim_lo, rr.trim_len);
         }
@@ -660,7 +661,8 @@ bool SingleEndProcessor::process() {
     bool rawText = rawTextEligible(mOptions);
     if (rawText) {
         // ---- raw-text path: chunk reader -> T workers (device ingest + processSingleEnd + output assembly) ----
-        const size_t kChunk = 32u << 20;
+        // 32 MB of text per chunk (FPL_CHUNK_KB: smaller chunks, for tests of the chunk plumbing on small inputs)
+        const size_t kChunk = getenv("FPL_CHUNK_KB") ? (size_t)std::max(1L, atol(getenv("FPL_CHUNK_KB"))) << 10 : (size_t)32 << 20;
         std::vector<ChunkQueue> queues(T);
         ChunkQueue freeList;
         for (int i = 0; i < T + 2; i++) freeList.push(newChunk(kChunk + (8u << 20)));
@@ -673,6 +675,7 @@ bool SingleEndProcessor::process() {
         // finished chunks the writer may hold before the workers wait (FPL_WRITER_BACKLOG: chunks per worker, default 2)
         const long backlog = (getenv("FPL_WRITER_BACKLOG") ? std::max(1L, atol(getenv("FPL_WRITER_BACKLOG"))) : 2L) * T;
         std::atomic<long> delivered(0);                         // chunks handed to the writers so far (all workers)
+        const bool deviceEmit = getenv("FPL_DEVICE_EMIT") != nullptr;
         if (mOptions->verbose) loginfo("start to load data");
         std::thread reader([&] {
             TextChunk* cur = freeList.pop();
@@ -744,7 +747,22 @@ bool SingleEndProcessor::process() {
                 string* outstr = new string();
                 string* failedOut = new string();
                 const char* text = (const char*)c->p;
-                outstr->reserve(c->n);
+                // FPL_DEVICE_EMIT=1: the two output strings are assembled on the device from the chunk it still holds
+                // (fpl_emit_fastq_host: first call builds and reports the sizes, second call copies); the loop below then
+                // only applies the per-read side effects
+                if (deviceEmit && n > 0) {
+                    int64_t nOut = 0, nFailed = 0;
+                    int erc = fpl_emit_fastq_host(w.ctx, failedW != NULL, NULL, 0, &nOut, NULL, 0, &nFailed);
+                    if (erc < 0) check(erc, "fpl_emit_fastq_host");
+                    outstr->resize((size_t)nOut);
+                    failedOut->resize((size_t)nFailed);
+                    if (nOut + nFailed > 0)
+                        check(fpl_emit_fastq_host(w.ctx, failedW != NULL, nOut ? (uint8_t*)&(*outstr)[0] : NULL, nOut, &nOut,
+                                                  nFailed ? (uint8_t*)&(*failedOut)[0] : NULL, nFailed, &nFailed),
+                              "fpl_emit_fastq_host");
+                } else {
+                    outstr->reserve(c->n);
+                }
                 ExtLists ext;
                 ext.fetch(w.ctx, n > 0 && (opt->mask.enabled || opt->breakOpt.enabled));
                 std::string scratch;
@@ -755,7 +773,7 @@ bool SingleEndProcessor::process() {
                     int nregs = 0;
                     const fpl_segment* sg = ext.segsOf(res[i].n_segments);
                     const fpl_region* rg = ext.regsOf(i, nregs);
-                    scatterRead(v, res[i], sg, rg, nregs, config, failedW != NULL, *outstr, *failedOut, scratch);
+                    scatterRead(v, res[i], sg, rg, nregs, config, failedW != NULL, *outstr, *failedOut, scratch, !deviceEmit);
                 }
                 deliver(outstr, failedOut);
                 freeList.push(c);

@@ -12,11 +12,18 @@ import numpy as np
 from . import abi
 
 
+def _plus_line(strand, i):
+    return strand[i] if isinstance(strand, (list, tuple)) else strand
+
+
 def emit_fastq(batch, names, results, strand=b"+"):
-    """Returns (out_bytes, failed_bytes) exactly as the writer threads receive them (pack order == read order)."""
+    """Returns (out_bytes, failed_bytes) exactly as the writer threads receive them (pack order == read order).
+    `strand`: the '+' line of every read, or a list with one per read (it is kept verbatim, src/read.cpp:119-143)."""
     out, failed = [], []
     seq, qual = batch.seq, batch.qual
+    plus = strand
     for i in range(batch.n_reads):
+        strand = _plus_line(plus, i)
         r = results[i]
         o = int(batch.offsets[i])
         nseg = int(r["n_segments"])
@@ -48,7 +55,9 @@ def emit_fastq_ext(batch, names, results, segments, regions, strand=b"+"):
     for rg in regions:
         reg_by_read.setdefault(int(rg["read"]), []).append((int(rg["lo"]), int(rg["len"])))
     ptr = 0
+    plus = strand
     for i in range(batch.n_reads):
+        strand = _plus_line(plus, i)
         r = results[i]
         o, L = int(batch.offsets[i]), int(batch.lens[i])
         n = int(r["n_segments"])

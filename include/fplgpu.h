@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define FPL_ABI_VERSION 4
+#define FPL_ABI_VERSION 5
 
 /* Filter result codes — identical to src/common.h:43-50 (they index FilterResult::mFilterReadStats[32]). */
 enum {
@@ -276,6 +276,24 @@ typedef struct fpl_fastq_record {
 int fpl_process_fastq_host(fpl_ctx* ctx, const uint8_t* text, int64_t n_bytes, int is_last_chunk,
                            fpl_fastq_record* records, fpl_read_result* results, int64_t max_records,
                            int64_t* n_records, int64_t* bytes_consumed);
+
+/*
+ * SURVEY §8f row 2, device half: Read::appendToString / appendToStringWithTag (src/read.cpp:119-173) as the per-pack loop
+ * of processSingleEnd applies them (src/seprocessor.cpp:264-288), for the chunk the LAST call on this context — a
+ * successful fpl_process_fastq_host — has just processed.  The chunk, its record table and the results are still in
+ * device memory; this call compacts them into the text the two writer threads receive and copies it to host memory:
+ *   out     every passing output read, in input order: name line (with the "r<k>-" / "split-by-adapter-left-/right-"
+ *           tags of Read::breakByRegions / breakByGap after the '@'), the window of the bases (masked with --mask), the
+ *           '+' line as it was, the window of the qualities
+ *   failed  (want_failed != 0, i.e. --failed_out is open) every read whose only output read failed a filter: r1 after
+ *           the trims, name + ' ' + FAILED_TYPES[code] (src/common.h:55-64)
+ * *out_bytes / *failed_bytes are always set.  Returns 0 on success; 1 if a buffer is too small — nothing was copied, the
+ * text stays built on the device and a second call with room only copies; < 0 on error (e.g. the last call was not a
+ * successful fpl_process_fastq_host).  A split read appears twice, so the text can be longer than the chunk:
+ * 2 * n_bytes + 64 * n_records always suffices.
+ */
+int fpl_emit_fastq_host(fpl_ctx* ctx, int want_failed, uint8_t* out, int64_t out_cap, int64_t* out_bytes,
+                        uint8_t* failed, int64_t failed_cap, int64_t* failed_bytes);
 
 /* Output reads / masked regions of the last fpl_process_* call (--mask / --break only; *n = 0 otherwise). */
 int fpl_last_segments(fpl_ctx* ctx, fpl_segment* out, int64_t cap, int64_t* n);

@@ -19,6 +19,9 @@ GPU_BIN = os.path.join(ROOT, "build", "fastplong_gpu")
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+PARSE_ENV = {"device": None, "host": {"FPL_HOST_PARSE": "1"}, "device+emit": {"FPL_DEVICE_EMIT": "1"}}
+
+
 def md5(path):
     return hashlib.md5(open(path, "rb").read()).hexdigest()
 
@@ -57,12 +60,13 @@ def test_gpu_binary_matches_golden_reference_run(name, tmp_path):
 
 @needs_bin
 @pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/fastplong_ref not built")
-@pytest.mark.parametrize("parse", ["device", "host"])
+@pytest.mark.parametrize("parse", ["device", "host", "device+emit"])
 @pytest.mark.parametrize("name,threads", [("default_se", 1), ("cut_polyx_cplx", 4), ("fasta5", 3), ("literal_auto", 2),
                                           ("trims_limits", 3), ("end_only_wide_window", 8), ("fasta64_polyx", 5)])
 def test_gpu_binary_matches_reference_binary(name, threads, parse, tmp_path):
     """Fresh input, both binaries side by side (config-1 shape: ONT-like reads, known 30 bp adapters), with the FASTQ
-    parsed on the device (default for plain files) and by the reference's FastqReader (FPL_HOST_PARSE=1)."""
+    parsed on the device (default for plain files), by the reference's FastqReader (FPL_HOST_PARSE=1), and parsed on the
+    device with the output text assembled there too (FPL_DEVICE_EMIT=1, fpl_emit_fastq_host)."""
     opt = cases.OPTION_SETS[name]
     batch = synth.ont_like(700, 4000, 31 + threads, p_chimera=0.03, p_polya=0.03, q_mean=17.0)
     fq = str(tmp_path / "in.fq")
@@ -75,7 +79,7 @@ def test_gpu_binary_matches_reference_binary(name, threads, parse, tmp_path):
                 f.write(f">a{i:03d}\n{s}\n")
         extra = ["-a", fa]
     ref = run(REF_BIN, opt, fq, str(tmp_path), "ref", threads, extra)
-    got = run(GPU_BIN, opt, fq, str(tmp_path), "gpu", threads, extra, env={"FPL_HOST_PARSE": "1"} if parse == "host" else None)
+    got = run(GPU_BIN, opt, fq, str(tmp_path), "gpu", threads, extra, env=PARSE_ENV[parse])
     assert got["out_md5"] == ref["out_md5"]
     assert got["failed_md5"] == ref["failed_md5"]
     if got["json_text_md5"] != ref["json_text_md5"]:
@@ -103,7 +107,7 @@ def test_gpu_binary_mask_break_matches_golden_reference_run(name, tmp_path):
 
 @needs_bin
 @pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/fastplong_ref not built")
-@pytest.mark.parametrize("parse", ["device", "host"])
+@pytest.mark.parametrize("parse", ["device", "host", "device+emit"])
 @pytest.mark.parametrize("name,threads", [("break_default", 2), ("break_w20", 3), ("mask_default", 1), ("mask_cplx", 4),
                                           ("mask_and_break", 3), ("break_no_adapter", 2)])
 def test_gpu_binary_mask_break_matches_reference_binary(name, threads, parse, tmp_path):
@@ -113,7 +117,7 @@ def test_gpu_binary_mask_break_matches_reference_binary(name, threads, parse, tm
     fq = str(tmp_path / "in.fq")
     synth.to_fastq(batch, fq)
     ref = run(REF_BIN, opt, fq, str(tmp_path), "ref", threads)
-    got = run(GPU_BIN, opt, fq, str(tmp_path), "gpu", threads, env={"FPL_HOST_PARSE": "1"} if parse == "host" else None)
+    got = run(GPU_BIN, opt, fq, str(tmp_path), "gpu", threads, env=PARSE_ENV[parse])
     assert got["out_md5"] == ref["out_md5"]
     assert got["failed_md5"] == ref["failed_md5"]
     assert got["json_text_md5"] == ref["json_text_md5"]
@@ -188,6 +192,49 @@ def test_gpu_binary_non_strict_fastq_like_reference(kind, tmp_path):
     _mutate_fastq(plain, fq, kind)
     ref = run(REF_BIN, opt, fq, str(tmp_path), "ref", 3)
     got = run(GPU_BIN, opt, fq, str(tmp_path), "gpu", 3)
+    assert got["out_md5"] == ref["out_md5"]
+    assert got["failed_md5"] == ref["failed_md5"]
+    assert got["json_text_md5"] == ref["json_text_md5"]
+
+
+@needs_bin
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/fastplong_ref not built")
+@pytest.mark.parametrize("emit", ["host", "device"])
+@pytest.mark.parametrize("chunk_kb,threads", [(256, 4), (64, 7), (1, 2)])
+def test_gpu_binary_many_small_chunks(chunk_kb, threads, emit, tmp_path):
+    """The chunk plumbing of the raw-text path (reader -> T workers -> writer's round-robin walk, back-pressure keyed on
+    chunk order) with hundreds of chunks: FPL_CHUNK_KB cuts the text into small pieces; 1 KB is smaller than most records,
+    so the reader has to keep reading until a record boundary shows up."""
+    opt = cases.OPTION_SETS["cut_polyx_cplx"]
+    batch = synth.ont_like(2500 if chunk_kb > 1 else 300, 4000, 5 + chunk_kb, p_chimera=0.05, p_polya=0.03, q_mean=17.0)
+    fq = str(tmp_path / "in.fq")
+    synth.to_fastq(batch, fq)
+    env = {"FPL_CHUNK_KB": str(chunk_kb), "FPL_WRITER_BACKLOG": "1"}
+    if emit == "device":
+        env["FPL_DEVICE_EMIT"] = "1"
+    ref = run(REF_BIN, opt, fq, str(tmp_path), "ref", threads)
+    got = run(GPU_BIN, opt, fq, str(tmp_path), "gpu", threads, env=env)
+    assert got["out_md5"] == ref["out_md5"]
+    assert got["failed_md5"] == ref["failed_md5"]
+    assert got["json_text_md5"] == ref["json_text_md5"]
+
+
+@needs_bin
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/fastplong_ref not built")
+def test_gpu_binary_file_size_is_a_multiple_of_the_chunk(tmp_path):
+    """The last fread returns 0 bytes: the final chunk is whatever was left over (possibly nothing)."""
+    opt = cases.OPTION_SETS["default_se"]
+    batch = synth.ont_like(400, 3000, 12, q_mean=17.0)
+    fq = str(tmp_path / "in.fq")
+    synth.to_fastq(batch, fq)
+    size = os.path.getsize(fq)
+    unit = 64 << 10
+    pad = (-(size + 27)) % unit          # a last record "@p" + pad x's with 10 bases is pad + 27 bytes long
+    with open(fq, "ab") as f:
+        f.write(b"@p" + b"x" * pad + b"\nACGTACGTAC\n+\nIIIIIIIIII\n")
+    assert os.path.getsize(fq) % unit == 0
+    ref = run(REF_BIN, opt, fq, str(tmp_path), "ref", 3)
+    got = run(GPU_BIN, opt, fq, str(tmp_path), "gpu", 3, env={"FPL_CHUNK_KB": "64"})
     assert got["out_md5"] == ref["out_md5"]
     assert got["failed_md5"] == ref["failed_md5"]
     assert got["json_text_md5"] == ref["json_text_md5"]

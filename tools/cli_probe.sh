@@ -1,6 +1,7 @@
 #!/bin/bash
-# Development aid (run under gpurun): where the drop-in CLI's wall time goes on a 6.4 GB FASTQ, with different writer
-# backlogs.  usage: tools/cli_probe.sh
+# Development aid (run under gpurun): where the drop-in CLI's wall time goes on a 6.4 GB FASTQ (400 k reads of the
+# config-1 generator, files on tmpfs), host-side and device-side output assembly, against the reference binary.
+# usage: tools/cli_probe.sh [reference-too]
 cd "$(dirname "$0")/.."
 python - <<PY
 import sys; sys.path.insert(0, '.')
@@ -10,11 +11,20 @@ synth.to_fastq(b, '/dev/shm/c1_part.fq')
 PY
 rm -f /dev/shm/c1.fq; for i in $(seq 8); do cat /dev/shm/c1_part.fq >> /dev/shm/c1.fq; done; rm /dev/shm/c1_part.fq
 S=AATGTACTTCGTTCAGTTACGTATTGCTAA
-build/fastplong_gpu -i /dev/shm/c1.fq -o /dev/shm/gpu.fq -s $S -w 2 -j /dev/shm/g.json -h /dev/shm/g.html --reads_to_process 1000 >/dev/null 2>&1
-for bl in 2 8 1000; do
-  echo "== FPL_WRITER_BACKLOG=$bl"
-  FPL_WRITER_BACKLOG=$bl FPL_TIMING=1 build/fastplong_gpu -i /dev/shm/c1.fq -o /dev/shm/gpu.fq -s $S -w 4 -j /dev/shm/g.json -h /dev/shm/g.html 2>&1 | grep -E "fastplong_gpu\]"
+ARGS="-i /dev/shm/c1.fq -s $S -j /dev/shm/g.json -h /dev/shm/g.html"
+build/fastplong_gpu $ARGS -o /dev/shm/gpu.fq -w 2 --reads_to_process 1000 >/dev/null 2>&1      # page the binary and the driver in
+t() { local a=$(date +%s%N); "$@" >/dev/null 2>&1; local b=$(date +%s%N); echo "$(( (b - a) / 1000000 )) m"; }
+for rep in 1 2 3 4; do
+  rm -f /dev/shm/gpu.fq; echo "gpu -w 4, host assembly:   $(t build/fastplong_gpu $ARGS -o /dev/shm/gpu.fq -w 4) s"
+  rm -f /dev/shm/gpu2.fq; echo "gpu -w 4, device assembly: $(FPL_DEVICE_EMIT=1 t build/fastplong_gpu $ARGS -o /dev/shm/gpu2.fq -w 4) s"
 done
-echo "== FPL_JIT_V1=1"
-FPL_JIT_V1=1 FPL_TIMING=1 build/fastplong_gpu -i /dev/shm/c1.fq -o /dev/shm/gpu.fq -s $S -w 4 -j /dev/shm/g.json -h /dev/shm/g.html 2>&1 | grep -E "fastplong_gpu\]|specialisation"
-rm -f /dev/shm/c1.fq /dev/shm/gpu.fq
+cmp /dev/shm/gpu.fq /dev/shm/gpu2.fq && echo "host- and device-assembled outputs identical"
+echo "== stages, host assembly"
+FPL_TIMING=1 build/fastplong_gpu $ARGS -o /dev/shm/gpu.fq -w 4 2>&1 | grep -E "fastplong_gpu\]"
+echo "== stages, device assembly"
+FPL_DEVICE_EMIT=1 FPL_TIMING=1 build/fastplong_gpu $ARGS -o /dev/shm/gpu2.fq -w 4 2>&1 | grep -E "fastplong_gpu\]"
+if [ -n "$1" ]; then
+  rm -f /dev/shm/ref.fq; echo "ref -w 16: $(t oracle/_ref/fastplong_ref $ARGS -o /dev/shm/ref.fq -w 16) s"
+  cmp /dev/shm/ref.fq /dev/shm/gpu.fq && echo "reference and gpu outputs identical"
+fi
+rm -f /dev/shm/c1.fq /dev/shm/gpu.fq /dev/shm/gpu2.fq /dev/shm/ref.fq
