@@ -173,7 +173,9 @@ def h2d_peak_gbs(torch, dev):
     h = torch.empty(n, dtype=torch.uint8).pin_memory()
     d = torch.empty(n, dtype=torch.uint8, device=dev)
     best = 0.0
-    for _ in range(4):
+    d.copy_(h, non_blocking=True)          # first touch of both buffers
+    torch.cuda.synchronize()
+    for _ in range(8):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         d.copy_(h, non_blocking=True)
@@ -382,11 +384,14 @@ def run_ours(args):
                "how": "fpl_process_host on pinned host buffers, %d submissions/step (%d distinct chunks of this run's reads, "
                       "cycled); inside a call the upload runs in 16 MiB pieces on a copy stream and the kernels of a piece "
                       "start when it has arrived" % (E2E_SUBMISSIONS, len(chunks)),
-               "achieved_pcie_gbs": round((h2d + d2h) / e2e_s / 1e9, 2)}
+               "achieved_pcie_gbs": round(h2d / e2e_s / 1e9, 2)}       # host -> device direction (the records go the other way)
         if pcie:
-            e2e["roofline"] = {"bound": "pcie h2d", "peak": round(pcie, 2), "unit": "GB/s",
-                               "frac": round((h2d + d2h) / e2e_s / 1e9 / pcie, 4),
-                               "peak_source": "measured here: 1 GiB pinned host -> device copy, best of 4, CUDA events"}
+            ach = h2d / e2e_s / 1e9
+            e2e["roofline"] = {"bound": "pcie h2d", "peak": round(pcie, 2), "unit": "GB/s", "achieved": round(ach, 2),
+                               "frac": round(min(1.0, ach / pcie), 4),
+                               "peak_source": "measured here: 1 GiB pinned host -> device copy, best of 8, CUDA events"}
+            if ach > pcie:      # the copy measurement itself moves by a few % between runs of the same box
+                e2e["roofline"]["note"] = "this leg ran faster than the copy measurement: at the peak (frac capped at 1)"
 
     # ---- roofline of the dominant kernel (largest share of the step's device time) ----
     peak, peak_src = peaks()
