@@ -311,7 +311,12 @@ k_cycle_stats(const uint8_t* __restrict__ seqbuf, const uint8_t* __restrict__ qu
         int slot = 0, fill = DEPTH;
         for (int k = wid; k < n; k += (NT / 32)) {
             if (TMA) { mbar_wait(bar_warp + 8u * slot, (phase >> slot) & 1u); phase ^= 1u << slot; }
-            else cp_async_wait<DEPTH - 1>();
+            else {
+                cp_async_wait<DEPTH - 1>();
+                // the word in front of a lane's vector was copied by the lane below: a lane's wait covers its own copies
+                // only, and the slot refilled further down was read by the neighbours in the previous round
+                if (DO_KMER) __syncwarp();
+            }
             const uint32_t src = ring_lane + (uint32_t)slot * CS_SLOT;
             const uint4 ns = lds128(src), nq = lds128(src + 512);
             const uint32_t pw = DO_KMER ? lds32(src - 4) : 0u;     // the four bases in front of this lane's vector

@@ -21,7 +21,7 @@ python - <<PY
 import json
 d = json.load(open("$O/${TAG}_bench.json"))
 print(d["value"], d["ms_per_step"], d["parity_checked"], d["e2e"]["value"], d["e2e"]["roofline"]["frac"], d["cpu_baseline"]["value"],
-      d["roofline"]["kernel"], d["roofline"]["frac"], d["roofline"]["adapter_quality_kernel"])
+      d["roofline"]["kernel"], d["roofline"]["frac"], d["roofline"].get("adapter_quality_kernel"))
 print({k: round(v["ms_per_step"], 3) for k, v in d["kernels"].items()})
 print(open("$O/${TAG}_bench_reference.json").read()[:300])
 PY

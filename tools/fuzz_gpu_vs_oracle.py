@@ -1,7 +1,8 @@
 """Development aid (run under gpurun): random option sets x seeded batches (tests/cases.py:random_case), GPU library vs
 the oracle — every record, both Stats blocks, the counters and the --mask/--break lists.
-usage: python tools/fuzz_gpu_vs_oracle.py <seed> <seconds> [mixed|many|long]
-  mixed (default): cases.random_case; many: 6-40 FASTA adapters (k_trim's pre-filter); long: reads of 60-400 kb"""
+usage: python tools/fuzz_gpu_vs_oracle.py <seed> <seconds> [mixed|many|long|text]
+  mixed (default): cases.random_case; many: 6-40 FASTA adapters (k_trim's pre-filter); long: reads of 60-400 kb;
+  text: the mixed cases as FASTQ text through fpl_process_fastq_host + fpl_emit_fastq_host (records and both output texts)"""
 import os
 import random
 import sys
@@ -12,12 +13,27 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import cases  # noqa: E402
 from oracle_lib import OracleEngine, compare_lists, compare_results, compare_stats  # noqa: E402
+from fastplong_b200 import hostside  # noqa: E402
 from fastplong_b200.binding import Engine
 
 rng = random.Random(int(sys.argv[1]) if len(sys.argv) > 1 else 1)
 budget = float(sys.argv[2]) if len(sys.argv) > 2 else 120
+MODE = sys.argv[3] if len(sys.argv) > 3 else "mixed"
 FAMILY = {"mixed": cases.random_case, "many": cases.random_case_many_adapters,
-          "long": cases.random_case_long_reads}[sys.argv[3] if len(sys.argv) > 3 else "mixed"]
+          "long": cases.random_case_long_reads, "text": cases.random_case}[MODE]
+
+
+def fastq_of(batch, rng):
+    names, plus, parts = [], [], []
+    for i in range(batch.n_reads):
+        sq, q = batch.read(i)
+        nm = b"@r%d %s" % (i, b"d" * rng.randrange(0, 40))
+        pl = b"+" if rng.random() < 0.7 else b"+" + nm[1:]
+        names.append(nm); plus.append(pl)
+        parts.append(nm + b"\n" + sq + b"\n" + pl + b"\n" + q + b"\n")
+    return b"".join(parts), names, plus
+
+
 t0 = time.time()
 n = bad = 0
 while time.time() - t0 < budget:
@@ -25,7 +41,21 @@ while time.time() - t0 < budget:
     r = None
     try:
         o, r = OracleEngine(opt), Engine(opt)
-        compare_results(o.process(batch), r.process(batch), "records")
+        if MODE == "text":
+            text, names, plus = fastq_of(batch, rng)
+            ores = o.process(batch)
+            got = r.process_fastq(text)
+            assert got is not None and got[2] == len(text), "strict FASTQ refused"
+            compare_results(ores, got[1], "records")
+            if opt.mask or opt.break_reads:
+                exp = hostside.emit_fastq_ext(batch, names, ores, o.segments(), o.mask_regions(), strand=plus)
+            else:
+                exp = hostside.emit_fastq(batch, names, ores, strand=plus)
+            out = r.emit_fastq(True)
+            assert out[0] == exp[0], "--out text differs"
+            assert out[1] == exp[1], "--failed_out text differs"
+        else:
+            compare_results(o.process(batch), r.process(batch), "records")
         if opt.mask or opt.break_reads:
             compare_lists(o.segments(), r.segments(), "segments")
             compare_lists(o.mask_regions(), r.mask_regions(), "regions")
