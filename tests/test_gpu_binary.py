@@ -238,3 +238,25 @@ def test_gpu_binary_file_size_is_a_multiple_of_the_chunk(tmp_path):
     assert got["out_md5"] == ref["out_md5"]
     assert got["failed_md5"] == ref["failed_md5"]
     assert got["json_text_md5"] == ref["json_text_md5"]
+
+
+@needs_bin
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/fastplong_ref not built")
+@pytest.mark.parametrize("emit", ["host", "device"])
+def test_gpu_binary_plus_lines_kept_verbatim(emit, tmp_path):
+    """The third line of a record may repeat the name ('+name ...'): Read::appendToString writes it back as it was
+    (src/read.cpp:119-143), for passing reads, both halves of a split read and --failed_out alike."""
+    opt = cases.OPTION_SETS["cut_polyx_cplx"]
+    batch = synth.ont_like(600, 3000, 88, p_chimera=0.2, p_polya=0.05, q_mean=16.5)   # ~150 split reads, ~30 failed
+    fq = str(tmp_path / "in.fq")
+    with open(fq, "wb") as f:
+        for i in range(batch.n_reads):
+            s, q = batch.read(i)
+            name = b"@read%d len=%d" % (i, len(s))
+            plus = b"+" if i % 3 == 0 else (b"+" + name[1:] if i % 3 == 1 else b"+ free text %d" % i)
+            f.write(name + b"\n" + s + b"\n" + plus + b"\n" + q + b"\n")
+    ref = run(REF_BIN, opt, fq, str(tmp_path), "ref", 3)
+    got = run(GPU_BIN, opt, fq, str(tmp_path), "gpu", 3, env={"FPL_DEVICE_EMIT": "1"} if emit == "device" else None)
+    assert got["out_md5"] == ref["out_md5"]
+    assert got["failed_md5"] == ref["failed_md5"]
+    assert got["json_text_md5"] == ref["json_text_md5"]
