@@ -6,7 +6,9 @@
 Workload (BASELINE.json configs[1]): 1M DISTINCT ONT-like reads, mean 15 kb (32 GB of payload, generated on the
 device), adapters as the reference's evaluator auto-detects them on this generator's reads, --cut_front --cut_tail
 -W 10, default Q/length filters, pre+post Stats.  Before anything is timed the first reads of the input go through
-the GPU library and the CPU oracle and are compared word by word (`parity_checked`).
+the GPU library and the CPU oracle and are compared word by word (`parity_checked`); behind the timed legs the whole
+batch is checked once more at full size (`parity_full_scale`: records of read ranges spread over the 32 GB against the
+oracle, every word of both Stats blocks against an independent torch restatement — full_scale_check below).
 One step = one pass of processSingleEnd over the whole per-GPU batch (+ the Stats/FilterResult all-reduce when N>1).
 `value` = device-resident throughput; `e2e` = the same metric through fpl_process_host with pinned HOST buffers
 (H2D of every byte + D2H of the per-read records inside the timed region).
@@ -37,6 +39,9 @@ HBM_FALLBACK_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
 # do not dominate: 40k reads x 15 kb = 0.6 Gbases, a few seconds of reference CPU time per run with 16 workers
 REF_SAMPLE_READS = int(os.environ.get("FPL_BENCH_REF_READS", "40000"))   # the override exists for the CPU test of this arm
 PARITY_BASES = 60_000_000   # the slice compared with the oracle outside the timed region (a few seconds of CPU)
+FULL_CHECK_RANGES = 8       # read ranges spread over the whole batch whose records are compared with the oracle ...
+FULL_CHECK_BASES = 24_000_000   # ... this many bases in total
+FULL_CHECK_BUDGET_S = 150   # the torch restatement of the Stats blocks gives up beyond this (reported, not fatal)
 E2E_SUBMISSIONS = 64        # host submissions per step of the end-to-end leg
 E2E_HOST_CHUNKS = 4         # distinct pinned host chunks cycled through them
 
@@ -165,6 +170,75 @@ def parity_check(opt, host_slice):
     return {"reads": host_slice.n_reads, "bases": host_slice.n_bases,
             "compared": "records field by field, pre and post Stats blocks and FilterResult counters word by word, GPU library vs "
                         "the C oracle (oracle/fpl_oracle.c) on the first reads of this run's input, outside the timed region"}
+
+
+def full_scale_check(torch, eng, opt, tile, d_seq, d_qual, offsets, lens, tile_reads, mean_len, budget_s=FULL_CHECK_BUDGET_S):
+    """Parity at the size the number is quoted on, outside every timed region, on what the LAST device-resident pass over
+    the whole batch left in the context (the caller has just run one):
+    (1) the records of FULL_CHECK_RANGES read ranges spread over the batch — the last one ends with the last read, tens
+        of GB into the buffers — against the C oracle run on exactly those reads;
+    (2) every word of the pre- and post-filter Stats blocks, and every read's / passing segment's median quality, against
+        tests/stats_tables.py: an independent restatement of Stats::statRead as torch.bincount passes over the same
+        device buffers (pinned to the oracle on the CPU by tests/test_stats_tables.py);
+    (3) the FilterResult counters against the records (one filter result per segment, passing segments = post reads).
+    Raises AssertionError on the first difference; returns what was compared."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from fastplong_b200 import abi
+    from oracle_lib import OracleEngine, compare_results
+    from stats_tables import passing_segments, stats_block
+    t0 = time.time()
+    offsets = np.asarray(offsets, dtype=np.int64)
+    lens = np.asarray(lens)
+    n_reads = len(lens)
+    res = eng.fetch_results(n_reads)
+    out = {"reads": n_reads, "bases": int(lens.sum(dtype=np.int64))}
+    # (1) sampled records
+    m = int(min(tile_reads, max(4, FULL_CHECK_BASES // FULL_CHECK_RANGES // max(1, mean_len))))
+    n_cmp = b_cmp = 0
+    spans = []
+    for j in range(1, FULL_CHECK_RANGES + 1):
+        g1 = max(1, n_reads * j // FULL_CHECK_RANGES)
+        rep = (g1 - 1) // tile_reads                       # keep a range inside one replica of the tile
+        hi_t = g1 - rep * tile_reads
+        lo_t = max(0, hi_t - m)
+        g0 = rep * tile_reads + lo_t
+        hb = tile.to_host(lo_t, hi_t)
+        orc = OracleEngine(opt)
+        ref = orc.process(hb)
+        orc.close()
+        compare_results(res[g0:g1], ref, f"full-scale records, reads [{g0}, {g1}) at byte {int(offsets[g0])}")
+        n_cmp += g1 - g0
+        b_cmp += hb.n_bases
+        spans.append([int(g0), int(g1)])
+    out["records_vs_oracle"] = {"reads": n_cmp, "bases": b_cmp, "read_ranges": spans,
+                                "highest_byte_offset": int(offsets[n_reads - 1])}
+    # (3) counters against the records
+    cnt = eng.counters()
+    rd, k, starts, seg_lens = passing_segments(res, offsets)
+    assert int(cnt[abi.CNT_FILTER:abi.CNT_FILTER + 32].sum()) == int(res["n_segments"].sum()), "filter results != segments"
+    assert int(cnt[abi.CNT_FILTER + abi.PASS_FILTER]) == len(rd), "passed counter != passing segments"
+    # (2) Stats blocks
+    cap = eng.cycles
+    deadline = t0 + budget_s
+    for which, (st, ln, medians, nz) in enumerate(((offsets, lens.astype(np.int64), res["pre_median_qual"], lens > 0),
+                                                   (starts, seg_lens, res["seg_median_qual"][rd, k], seg_lens > 0))):
+        blk, med = stats_block(torch, d_seq, d_qual, st, ln, cap, deadline=deadline)
+        got = eng.stats(which)
+        if not np.array_equal(blk, got):
+            bad = np.nonzero(blk != got)[0]
+            raise AssertionError(f"full-scale Stats block {which}: {len(bad)} words differ, first at {int(bad[0])}: "
+                                 f"{int(got[bad[0]])} (library) vs {int(blk[bad[0]])} (torch restatement)")
+        if not np.array_equal(med[nz], medians[nz]):
+            raise AssertionError(f"full-scale medians of Stats block {which} differ on {int((med[nz] != medians[nz]).sum())} segments")
+    out["stats_vs_torch"] = {"blocks": ["pre", "post"], "words_each": int(abi.stats_words(cap)), "passing_segments": int(len(rd)),
+                             "medians": "every read (pre) and every passing segment (post)"}
+    out["ok"] = True
+    out["seconds"] = round(time.time() - t0, 1)
+    out["compared"] = ("after one more untimed device-resident pass over the whole batch: records of %d read ranges spread over the "
+                       "buffers vs the C oracle; every word of both Stats blocks and every median vs an independent torch.bincount "
+                       "restatement of Stats::statRead over the same device buffers (tests/stats_tables.py); FilterResult counters "
+                       "vs the records" % FULL_CHECK_RANGES)
+    return out
 
 
 def h2d_peak_gbs(torch, dev):
@@ -440,6 +514,23 @@ def run_ours(args):
             roofline["adapter_quality_kernel"] = {"kernel": "k_scan", "achieved": a, "frac": round(a / peak, 4),
                                                   "avg_launch_ms": kern["k_scan"]["ms_per_step"]}
 
+    # ---- parity at full size (single-GPU runs; after everything that is timed): one more device-resident pass of the whole
+    # batch, then its records / Stats blocks / counters are checked (full_scale_check).  Multi-GPU runs process the same
+    # kind of batch per rank with the same kernels and skip it (their ranks would idle at the barrier meanwhile). ----
+    full = None
+    if world == 1 and parity is not None and not args.no_full_check:
+        try:
+            eng.reset()
+            eng.process_device(d_seq.data_ptr(), d_qual.data_ptr(), offs.data_ptr(), lens.data_ptr(), n_reads, d_seq.numel())
+            eng.sync()
+            full = full_scale_check(torch, eng, opt, tile, d_seq, d_qual, offs.cpu().numpy(), lens.cpu().numpy(), tile_reads,
+                                    mean_len)
+        except AssertionError as e:
+            full = {"ok": False, "error": str(e)[:500]}
+        except Exception as e:      # the checker itself failed (time budget, memory): reported, never fatal for the line
+            full = {"ok": None, "error": "%s: %s" % (type(e).__name__, str(e)[:400])}
+        torch.cuda.empty_cache()
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_baseline = reference_cpu_run(sample_reads=REF_SAMPLE_READS, repeats=1)
@@ -468,7 +559,7 @@ def run_ours(args):
                    "variants": {"k_scan_jit": "v1 (round 1)" if os.environ.get("FPL_JIT_V1") else "v2",
                                 "k_cycle_stats_staging": "1-D TMA (cp.async.bulk + mbarrier)" if os.environ.get("FPL_CS_TMA", "0") not in ("", "0")
                                 else "cp.async (LDGSTS) ring"}},
-        "parity_checked": parity is not None, "parity": parity,
+        "parity_checked": parity is not None, "parity": parity, "parity_full_scale": full,
         "clocks": clocks,
         "e2e": e2e,
         "gpu_launches": int(launches),
@@ -610,6 +701,7 @@ def main():
     ap.add_argument("--replicas", type=int, default=0, help="... replicated this many times in HBM")
     ap.add_argument("--no-detect", action="store_true", help="profiling aid: skip the adapter auto-detection pre-pass (use the planted strings)")
     ap.add_argument("--no-parity", action="store_true", help="profiling aid: skip the oracle comparison of the first reads")
+    ap.add_argument("--no-full-check", action="store_true", help="profiling aid: skip the full-size parity check behind the timed legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling aid: skip the end-to-end leg (keeps an ncu launch list short)")
     args = ap.parse_args()
