@@ -38,7 +38,7 @@ HBM_FALLBACK_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
 # CPU arm: a sample large enough that the binary's fixed costs (start-up, adapter detection pre-pass, report writing)
 # do not dominate: 40k reads x 15 kb = 0.6 Gbases, a few seconds of reference CPU time per run with 16 workers
 REF_SAMPLE_READS = int(os.environ.get("FPL_BENCH_REF_READS", "40000"))   # the override exists for the CPU test of this arm
-PARITY_BASES = 60_000_000   # the slice compared with the oracle outside the timed region (a few seconds of CPU)
+PARITY_BASES = int(os.environ.get("FPL_BENCH_PARITY_BASES", "60000000"))   # the slice compared with the oracle outside the timed region (a few seconds of CPU)
 FULL_CHECK_RANGES = 8       # read ranges spread over the whole batch whose records are compared with the oracle ...
 FULL_CHECK_BASES = 24_000_000   # ... this many bases in total
 FULL_CHECK_BUDGET_S = 150   # the torch restatement of the Stats blocks gives up beyond this (reported, not fatal)
