@@ -38,3 +38,33 @@ def test_header_is_plain_c(compiler, flags, tmp_path):
     r = subprocess.run([compiler, *flags, "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src)],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+@pytest.mark.parametrize("name", ["r02_bench.json", "r02u_bench_full_check_65k_reads.json"])
+def test_committed_bench_lines_carry_the_contract_keys(name):
+    """The lines under profiles/ are what bench.py printed on a B200: the keys the driver and the judge read are all there
+    and consistent with each other (the roofline fraction follows from achieved / peak, the value from bases / time)."""
+    d = json.load(open(os.path.join(ROOT, "profiles", name)))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "clocks", "gpu_launches", "roofline", "kernels", "parity_checked"):
+        assert k in d, k
+    assert d["unit"] == "Gbases/s" and d["dtype"] == "u8" and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert "workload" in d["config"] and "model" not in d["config"]
+    r = d["roofline"]
+    for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in r, k
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-3
+    assert abs(r["achieved"] - r["alg_bytes_per_launch"] / (r["avg_launch_ms"] * 1e-3) / 1e9) / r["achieved"] < 1e-3
+    bases = d["config"]["bases_per_gpu"] * d["n_gpus"]
+    assert abs(d["value"] - bases / (d["ms_per_step"] * 1e-3) / 1e9) / d["value"] < 1e-3
+    assert d["gpu_launches"] > 0 and d["parity_checked"] is True
+    assert d["clocks"]["sm_mhz"] and not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    if d.get("e2e"):
+        for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+            assert k in d["e2e"], k
+        assert d["e2e"]["h2d_bytes_per_step"] >= 2 * d["config"]["bases_per_gpu"] and d["e2e"]["value"] < d["value"]
+    if d.get("cpu_baseline"):
+        for k in ("value", "unit", "cores", "kind", "sample"):
+            assert k in d["cpu_baseline"], k
+    if d.get("parity_full_scale"):
+        assert d["parity_full_scale"]["ok"] is True
