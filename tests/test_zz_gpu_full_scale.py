@@ -1,0 +1,36 @@
+"""bench.py's full-size parity check (full_scale_check) on the GPU at a size the whole oracle would need minutes for: a
+device-generated batch goes through fpl_process_device exactly as in the bench; the records of read ranges spread over
+the batch are held to the oracle, every word of both Stats blocks and every median to the torch restatement
+(tests/stats_tables.py, pinned to the oracle by tests/test_stats_tables.py), the filter counters to the records.
+(Named to run last: it drives bench.py's own code.)"""
+import numpy as np
+import pytest
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("optset,n,mean", [("cut_polyx_cplx", 20000, 6000), ("default_se", 3000, 40000)])
+def test_full_scale_check_on_a_device_resident_batch(optset, n, mean, monkeypatch):
+    import torch
+    import bench
+    import cases
+    from fastplong_b200 import synth_fast
+    from fastplong_b200.binding import Engine
+    monkeypatch.setattr(bench, "FULL_CHECK_BASES", 6_000_000)
+    dev = torch.device("cuda:0")
+    opt = cases.OPTION_SETS[optset]
+    tile = synth_fast.ont_like_device(n, mean, 4242, dev, p_chimera=0.02)
+    offs = torch.from_numpy(tile.offsets).to(dev)
+    lens = torch.from_numpy(tile.lens).to(dev)
+    torch.cuda.synchronize()
+    eng = Engine(opt)
+    eng.process_device(tile.seq.data_ptr(), tile.qual.data_ptr(), offs.data_ptr(), lens.data_ptr(), tile.n_reads, tile.seq.numel())
+    eng.sync()
+    out = bench.full_scale_check(torch, eng, opt, tile, tile.seq, tile.qual, tile.offsets, tile.lens, tile.n_reads, mean)
+    assert out["ok"] is True and out["reads"] == n
+    assert out["records_vs_oracle"]["read_ranges"][-1][1] == n and out["stats_vs_torch"]["passing_segments"] > 0
+    # the checker does see a difference: one more pass doubles the accumulators but not the restatement
+    eng.process_device(tile.seq.data_ptr(), tile.qual.data_ptr(), offs.data_ptr(), lens.data_ptr(), tile.n_reads, tile.seq.numel())
+    eng.sync()
+    with pytest.raises(AssertionError):
+        bench.full_scale_check(torch, eng, opt, tile, tile.seq, tile.qual, tile.offsets, tile.lens, tile.n_reads, mean)
+    eng.close()
