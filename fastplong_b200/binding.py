@@ -60,6 +60,7 @@ def load_library():
     lib.fpl_allreduce_stats.argtypes = [C.c_void_p, C.c_int64]
     lib.fpl_eval_adapter_kmers.argtypes = [C.c_int, C.POINTER(FplBatch), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                            C.POINTER(C.c_int64)]
+    lib.fpl_eval_pick_adapter.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_char_p, C.c_int32]
     lib.fpl_reset.argtypes = [C.c_void_p]
     lib.fpl_last_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_float),
                                           C.POINTER(C.c_int64), C.c_int]
@@ -76,7 +77,7 @@ EXPORTS = ["fpl_last_error", "fpl_abi_version", "fpl_create", "fpl_destroy", "fp
            "fpl_sync", "fpl_stream", "fpl_last_segments", "fpl_last_mask_regions", "fpl_fetch_results", "fpl_stats_cycles", "fpl_stats_reserve", "fpl_stats_download",
            "fpl_stats_device_ptr", "fpl_counter_words", "fpl_counters_download", "fpl_counters_device_ptr",
            "fpl_comm_unique_id", "fpl_comm_init", "fpl_comm_destroy", "fpl_comm_size", "fpl_comm_agree_cycles", "fpl_allreduce_stats",
-           "fpl_eval_adapter_kmers", "fpl_reset", "fpl_last_kernel_times", "fpl_launch_count", "fpl_set_timing"]
+           "fpl_eval_adapter_kmers", "fpl_eval_pick_adapter", "fpl_reset", "fpl_last_kernel_times", "fpl_launch_count", "fpl_set_timing"]
 
 
 class _DeviceArray:
@@ -279,6 +280,21 @@ def eval_adapter_kmers(batch, side, shift_tail=1, device=0):
     if rc != 0:
         raise FplError(f"fpl_eval_adapter_kmers failed ({rc})")
     return counts, acc, int(total.value)
+
+
+def eval_pick_adapter(counts, position_acc, total, is_rna=False):
+    """Table half of Evaluator::evalAdapterAndReadNum for one side (host only, fpl_eval_pick_adapter): the adapter string,
+    or None when nothing is detected."""
+    lib = load_library()
+    counts = np.ascontiguousarray(counts, dtype=np.uint32)
+    acc = np.ascontiguousarray(position_acc, dtype=np.uint64)
+    if counts.shape != (1 << 20,) or acc.shape != (1 << 20,):
+        raise FplError("eval_pick_adapter: the tables have 1 << 20 entries")
+    buf = C.create_string_buffer(80)
+    n = lib.fpl_eval_pick_adapter(counts.ctypes.data, acc.ctypes.data, int(total), int(bool(is_rna)), buf, 80)
+    if n < 0:
+        raise FplError(f"fpl_eval_pick_adapter failed ({n})")
+    return buf.value.decode() if n > 0 else None
 
 
 def relayout_stats(raw, cap, cycles):

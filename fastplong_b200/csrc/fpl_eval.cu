@@ -83,3 +83,95 @@ extern "C" int fpl_eval_adapter_kmers(int device, const fpl_batch* b, int32_t sh
     cudaFree(d_seq); cudaFree(d_off); cudaFree(d_len); cudaFree(d_cnt); cudaFree(d_acc); cudaFree(d_tot);
     return rc;
 }
+
+// ---- the table half (host only): Evaluator::getTopKey + the acceptance rule + Evaluator::extendKeyToAdapter ----
+namespace {
+constexpr int EV_SIZE = 1 << (2 * KEYLEN);
+constexpr int EV_MAX_LEN = 64;
+
+// src/evaluator.cpp:266-322.  `val` is the COUNT: the reference's "neighbouring bases differ" loop shifts it, not the key.
+int ev_top_key(const uint32_t* counts) {
+    int top = -1;
+    uint32_t topCount = 0;
+    for (int k = 1; k < EV_SIZE; k++) {                   // k == 0 (AAAAAAAAAA) is never a top key (:310, and its count is ignored)
+        const uint32_t val = counts[k];
+        if (val <= topCount) continue;                    // only a strictly larger count can replace the top key
+        int n[4] = {0, 0, 0, 0};
+        for (int i = 0; i < KEYLEN; i++) n[(k >> (2 * i)) & 3]++;
+        int zero = 0;
+        bool low = false;
+        for (int b = 0; b < 4; b++) { low = low || n[b] >= KEYLEN - 4; zero += n[b] == 0; }
+        low = low || zero >= 2 || (k >> KEYLEN) == (k & ((1 << KEYLEN) - 1));
+        int diff = 0;
+        for (int s = 0; s < KEYLEN - 1; s++)
+            diff += ((val >> ((KEYLEN - s) * 2)) & 3u) != ((val >> ((KEYLEN - s - 1) * 2)) & 3u);
+        if (diff < 3 || low) continue;
+        if (n[2] + n[3] >= KEYLEN - 2) continue;          // too many C/G
+        if ((k >> 12) == 0xff) continue;                  // starts with GGGG
+        topCount = val;
+        top = k;
+    }
+    return top;
+}
+
+// src/evaluator.cpp:324-407; returns the length written into out (<= EV_MAX_LEN).
+int ev_extend(int key, const uint32_t* counts, const uint64_t* acc, bool rna, char* out) {
+    const char bases[4] = {'A', rna ? 'U' : 'T', 'C', 'G'};
+    const int mask = EV_SIZE - 1;
+    char buf[2 * EV_MAX_LEN + KEYLEN];                    // grows to both sides of the middle
+    int lo = EV_MAX_LEN, hi = EV_MAX_LEN;
+    for (int i = 0; i < KEYLEN; i++) buf[hi++] = bases[(key >> (2 * (KEYLEN - 1 - i))) & 3];
+    bool leftDone = false, rightDone = false, left = true;
+    while (true) {
+        int cur = key;
+        while (hi - lo < EV_MAX_LEN) {
+            int nk[4];
+            long long totalCount = 0;
+            uint32_t cnk[4];                                  // the reference zeroes counts[AAAAAAAAAA] before all of this (:195)
+            for (int b = 0; b < 4; b++) {
+                nk[b] = left ? ((b << ((KEYLEN - 1) * 2)) | (cur >> 2)) : (b | (mask & (cur << 2)));
+                cnk[b] = nk[b] == 0 ? 0u : counts[nk[b]];
+                totalCount += cnk[b];
+            }
+            bool extended = false;
+            for (int b = 0; b < 4 && !extended; b++) {
+                const uint32_t cn = cnk[b];
+                if (cn == 0) continue;
+                const double offset = (double)acc[nk[b]] / cn - (double)acc[cur] / counts[cur];
+                if ((double)cn / (double)totalCount < 0.7) continue;
+                if ((double)cn / (double)counts[key] < 0.5) continue;
+                if (offset > 2 || offset < -4) continue;
+                cur = nk[b];
+                extended = true;
+                if (left) buf[--lo] = bases[b]; else buf[hi++] = bases[b];
+            }
+            if (!extended) { (left ? leftDone : rightDone) = true; break; }
+            if (hi - lo == EV_MAX_LEN) { leftDone = rightDone = true; break; }
+        }
+        left = !left;
+        if (leftDone && rightDone) break;
+    }
+    const int n = hi - lo;
+    for (int i = 0; i < n; i++) out[i] = buf[lo + i];
+    return n;
+}
+}  // namespace
+
+extern "C" int fpl_eval_pick_adapter(const uint32_t* counts, const uint64_t* position_acc, int64_t total, int32_t is_rna,
+                                     char* adapter, int32_t cap) {
+    if (!counts || !position_acc || !adapter || cap < EV_MAX_LEN + 1 || total < 0) return -1;
+    adapter[0] = 0;
+    long long keys = 0;                                   // src/evaluator.cpp:190-193 (before AAAAAAAAAA is zeroed)
+    for (int k = 0; k < EV_SIZE; k++) keys += counts[k] > 0;
+    const int key = ev_top_key(counts);
+    if (key < 0) return 0;
+    const long long count = counts[key];
+    if (!(count > 10 && (double)(count * keys) > (double)total * 100.0)) return 0;
+    char buf[EV_MAX_LEN + 1];
+    const int n = ev_extend(key, counts, position_acc, is_rna != 0, buf);
+    if (n <= 16) return 0;                                // "too short" (:203): the option stays "auto"
+    for (int i = 0; i < n; i++) adapter[i] = buf[i];
+    adapter[n] = 0;
+    return n;
+}
+

@@ -120,11 +120,13 @@ def detect_one(counts, position_acc, total, is_rna=False):
     return None
 
 
-def detect_adapters(batch, trim_tail=0, is_rna=False, device=0, kmers=None):
+def detect_adapters(batch, trim_tail=0, is_rna=False, device=0, kmers=None, pick="abi"):
     """(start, end) as Evaluator::evalAdapterAndReadNum would set opt.adapter.sequenceStart / sequenceEnd when both are
     "auto" ("auto" is kept where nothing is detected).  `batch`: a host PackedBatch holding the head of
-    the input; `kmers(batch, side, shift_tail)` supplies the tables (default: the device kernel)."""
-    from .binding import eval_adapter_kmers
+    the input; `kmers(batch, side, shift_tail)` supplies the tables (default: the device kernel); pick = "abi": the table
+    half is the C ABI's fpl_eval_pick_adapter (C++, host only), "python": detect_one above — the same rules twice, held to
+    each other and to the reference binary by tests/test_evaluator.py and tools/fuzz_evaluator_vs_binary.py."""
+    from .binding import eval_adapter_kmers, eval_pick_adapter
     n = evaluated_prefix(batch.lens)
     head = batch.slice(0, n)
     if n < 100:
@@ -134,6 +136,7 @@ def detect_adapters(batch, trim_tail=0, is_rna=False, device=0, kmers=None):
     out = []
     for side in (0, 1):
         counts, acc, total = fn(head, side, shift_tail)
-        a = detect_one(counts, acc, total, is_rna if side == 1 else False)
+        rna = is_rna if side == 1 else False
+        a = eval_pick_adapter(counts, acc, total, rna) if pick == "abi" else detect_one(counts, acc, total, rna)
         out.append(a if a else "auto")
     return out[0], out[1]

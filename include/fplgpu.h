@@ -356,6 +356,22 @@ int fpl_allreduce_stats(fpl_ctx* ctx, int64_t cycles);
 int fpl_eval_adapter_kmers(int device, const fpl_batch* host_batch, int32_t shift_tail, int32_t side, uint32_t* counts,
                            uint64_t* position_acc, int64_t* total);
 
+/*
+ * SURVEY §8f row 4 — the table half of Evaluator::evalAdapterAndReadNum for one side, host only (no CUDA call; works
+ * without a device): from the two ten-mer tables fpl_eval_adapter_kmers filled to the adapter string, by the
+ * reference's rules — the number of non-empty keys is taken, counts[AAAAAAAAAA] is ignored, Evaluator::getTopKey
+ * (src/evaluator.cpp:266-322) picks the most frequent ten-mer that is not low-complexity (including its quirk of reading
+ * the "different neighbours" test off the COUNT's bits), the key is accepted when count > 10 and count * keys > total * 100
+ * (:199-201, :241-243), and Evaluator::extendKeyToAdapter (:324-407) grows it base by base, left first, up to 64 bases;
+ * a result of <= 16 bases counts as not detected (:203, :245).  is_rna writes U for T (the reference passes isRNA for the
+ * read-end adapter only).  counts / position_acc: 1 << 20 entries, not modified.  Writes the NUL-terminated adapter into
+ * `adapter` (cap >= 65) and returns its length; 0 = nothing detected (the option stays "auto"); < 0 = bad argument.
+ * The same rules as fastplong_b200/evaluator.py:detect_one (tests/test_evaluator.py holds the two to each other and to the
+ * reference binary's own detection).
+ */
+int fpl_eval_pick_adapter(const uint32_t* counts, const uint64_t* position_acc, int64_t total, int32_t is_rna, char* adapter,
+                          int32_t cap);
+
 /* Zero all accumulators (a fresh ThreadConfig); stream-ordered, asynchronous. */
 int fpl_reset(fpl_ctx* ctx);
 

@@ -1,5 +1,6 @@
 """Development aid (CPU): adapter auto-detection — fastplong_b200/evaluator.py (the host half of
-Evaluator::evalAdapterAndReadNum, src/evaluator.cpp:105-265) on the numpy ten-mer tables against what the unmodified
+Evaluator::evalAdapterAndReadNum, src/evaluator.cpp:105-265) on the numpy ten-mer tables, with the table half taken once from the C ABI (fpl_eval_pick_adapter) and once from its
+Python twin, against what the unmodified
 reference BINARY detects on the same FASTQ (its JSON's adapter_cutting.read_start_adapter / read_end_adapter).
 Random adapters (plain, low-complexity, repetitive, G-rich, short), random presence rates, read counts around the
 100-read rule, read lengths around the 128-base evaluation window, --trim_tail values.
@@ -66,14 +67,15 @@ def main():
                 continue
             ac = json.load(open(d + "/j.json")).get("adapter_cutting", {})
         ref = (ac.get("read_start_adapter"), ac.get("read_end_adapter"))
-        got = evaluator.detect_adapters(batch, trim_tail=trim_tail, kmers=kmer10_tables)
-        got = tuple("unspecified" if s == "auto" else s for s in got)     # src/options.cpp:247-259
         found += sum(s != "unspecified" for s in ref)
-        if got != ref:
-            bad += 1
-            print("MISMATCH case", n, "reads", n_reads, "mean", mean, "trim_tail", trim_tail, kw, "\n  ours", got, "\n  ref ", ref)
-            if bad > 5:
-                break
+        for pick in ("abi", "python"):      # the C ABI's fpl_eval_pick_adapter and evaluator.detect_one
+            got = evaluator.detect_adapters(batch, trim_tail=trim_tail, kmers=kmer10_tables, pick=pick)
+            got = tuple("unspecified" if s == "auto" else s for s in got)     # src/options.cpp:247-259
+            if got != ref:
+                bad += 1
+                print("MISMATCH case", n, pick, "reads", n_reads, "mean", mean, "trim_tail", trim_tail, kw, "\n  ours", got, "\n  ref ", ref)
+        if bad > 5:
+            break
         n += 1
     print("cases", n, "mismatches", bad, "(adapters the reference detected:", found, ")")
 
