@@ -318,7 +318,7 @@ def run_ours(args):
 
     # ---- config 2 says "auto-detected adapters": detect them on this input as the CLI's pre-pass would — the ten-mer tables
     # of Evaluator::evalAdapterAndReadNum on the device (fpl_eval_adapter_kmers), top key + extension on the host
-    # (fastplong_b200/evaluator.py), over the first <= 64 Ki reads / 512 Mbases; outside the timed path ----
+    # (fpl_eval_pick_adapter, through fastplong_b200/evaluator.py), over the first <= 64 Ki reads / 512 Mbases; outside the timed path ----
     detected = None
     if args.workload == "c2" and not args.no_detect:
         from fastplong_b200 import evaluator, synth
@@ -332,8 +332,9 @@ def run_ours(args):
         planted = (synth.ADAPTER_START, synth.ADAPTER_END)
         detected = {"start": box[0][0], "end": box[0][1], "equals_planted": tuple(box[0]) == planted,
                     "reads_evaluated": int(evaluator.evaluated_prefix(tile.lens)), "seconds": round(time.time() - t0, 2),
-                    "how": "fpl_eval_adapter_kmers (device ten-mer tables) + fastplong_b200/evaluator.py (getTopKey / extendKeyToAdapter "
-                           "restated), the reference's rules: first <= 64 Ki reads / 512 Mbases of the input"}
+                    "how": "fpl_eval_adapter_kmers (device ten-mer tables) + fpl_eval_pick_adapter (getTopKey / extendKeyToAdapter "
+                           "restated as host C++ in the C ABI), driven by fastplong_b200/evaluator.py with the reference's rules: "
+                           "first <= 64 Ki reads / 512 Mbases of the input"}
         if box[0][0] != "auto":
             opt.start_adapter = box[0][0]
         if box[0][1] != "auto":
