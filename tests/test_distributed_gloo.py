@@ -68,3 +68,34 @@ def test_shard_bounds_edge_cases():
     assert shard_reads_by_bases([5], 2)[-1] == 1
     b = shard_reads_by_bases([10] * 8, 8)
     assert b == list(range(9))
+
+
+def test_shard_and_slice_properties():
+    """Seeded random length vectors x world sizes: the shards are contiguous, cover every read once, are balanced by bases
+    to within one read, and PackedBatch.slice hands back exactly the reads of its range with offsets rebased to 0 (a rank
+    uploads its own bytes only) — including zero-length reads and empty shards."""
+    import numpy as np
+    from fastplong_b200 import pack_reads
+    from fastplong_b200.pack import SLOT_ALIGN, shard_reads_by_bases
+    rng = np.random.default_rng(17)
+    for case in range(40):
+        n = int(rng.integers(0, 60))
+        lens = np.where(rng.random(n) < 0.15, 0, rng.integers(1, 700, size=n)).astype(np.int64)
+        if case % 7 == 0 and n:
+            lens[int(rng.integers(n))] = 20000          # one read that outweighs a whole shard
+        reads = [(bytes(rng.integers(65, 91, size=int(L), dtype=np.uint8)), bytes(rng.integers(34, 80, size=int(L), dtype=np.uint8))) for L in lens]
+        batch = pack_reads(reads) if n else pack_reads([(b"", b"")]).slice(0, 0)
+        for world in (1, 2, 3, 8):
+            b = shard_reads_by_bases(lens, world)
+            assert len(b) == world + 1 and b[0] == 0 and b[-1] == n and all(x <= y for x, y in zip(b, b[1:]))
+            total, biggest = int(lens.sum()), int(lens.max()) if n else 0
+            for r in range(world):
+                # a boundary sits at the first read whose prefix sum reaches r/world of the bases
+                assert abs(int(lens[:b[r]].sum()) - total * r // world) <= biggest
+                sh = batch.slice(b[r], b[r + 1])
+                assert sh.n_reads == b[r + 1] - b[r]
+                if sh.n_reads:
+                    assert int(sh.offsets[0]) == 0 and (sh.offsets % SLOT_ALIGN == 0).all()
+                    assert int(sh.offsets[-1]) + int(sh.lens[-1]) <= sh.n_bytes
+                for i in range(sh.n_reads):
+                    assert sh.read(i) == reads[b[r] + i]
