@@ -128,3 +128,16 @@ def test_device_tables_match_numpy(side):
 def test_device_detection_finds_the_planted_adapters():
     batch = synth.ont_like(800, 2000, 21)
     assert evaluator.detect_adapters(batch) == (synth.ADAPTER_START, synth.ADAPTER_END)
+
+
+def test_reference_known_answer_int2seq_roundtrip():
+    """The reference's own evaluator test (test/evaluator_test.cpp:4-8): int2seq(seq2int("ATCGATCGAT")) is the string —
+    here with the ten-mer table as seq2int (the only key counted for that read is the string's) and both int2seq forms."""
+    from fastplong_b200 import pack_reads
+    s = b"ATCGATCGAT"
+    batch = pack_reads([(s + b"A", b"I" * 11)])           # shift_tail 1: exactly one ten-mer position
+    counts, acc, total = kmer10_tables(batch, 0, 1)
+    keys = np.nonzero(counts)[0]
+    assert total == 1 and len(keys) == 1
+    assert evaluator.int2seq(int(keys[0])) == s.decode()
+    assert evaluator.int2seq(int(keys[0]), is_rna=True) == s.decode().replace("T", "U")
