@@ -102,6 +102,38 @@ def ont_batch(seed, n=300, mean=2000, **kw):
     return synth.ont_like(n, mean, seed, **kw)
 
 
+# ---- RNA reads (direct-RNA ONT: U instead of T).  The reference handles them on the same path: Stats::base2val maps U to
+# T's code (src/stats.cpp:411-425), 'U' & 7 is its own content bin (5), adapters are compared byte-wise (so a DNA adapter
+# never matches an RNA read), polyX counts A/T/C/G only (src/polyx.cpp:28-45), and the evaluator prints the detected end
+# adapter with U (src/evaluator.cpp:245).  No other batch here holds a U inside a valid 5-mer. ----
+def to_rna(text):
+    return text.replace("T", "U")
+
+
+RNA_SETS = {
+    "rna_adapters": Options(start_adapter=to_rna(S), end_adapter=to_rna(E), cut_front=True, cut_tail=True, cut_window_size=10,
+                            trim_poly_x=True, low_complexity_filter=True),
+    "rna_reads_dna_adapters": Options(start_adapter=S, end_adapter=E, trim_poly_x=True, poly_x_min_len=8),
+    "rna_mixed_adapter_fasta": Options(start_adapter=to_rna(S), end_adapter=E, adapter_fasta=[to_rna(FASTA5[0]), FASTA5[3], to_rna(FASTA5[4])],
+                                       cut_tail=True),
+}
+
+
+def rna_batch(seed, n=200, mean=1500, mixed=False):
+    """ont_like reads with every T turned into U (planted adapters, poly-T tails and slot padding included); mixed=True
+    keeps T in every third read — a file the reference BINARY refuses ("contains both U and T") but its operators take."""
+    from fastplong_b200 import PackedBatch
+    b = synth.ont_like(n, mean, seed, p_chimera=0.1, p_polya=0.2, planted=[FASTA5[0], FASTA5[4]], p_planted=0.3)
+    seq = b.seq.copy()
+    for i in range(b.n_reads):
+        if mixed and i % 3 == 0:
+            continue
+        o, L = int(b.offsets[i]), int(b.lens[i])
+        v = seq[o:o + L]
+        v[v == ord("T")] = ord("U")
+    return PackedBatch(seq, b.qual, b.offsets, b.lens)
+
+
 # ---- --mask / --break (SURVEY §8f row 3) ----
 MASK_BREAK_SETS = {
     "break_default": Options(start_adapter=S, break_reads=True),

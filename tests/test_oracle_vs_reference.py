@@ -51,6 +51,16 @@ def test_edit_distance_random_pairs():
         assert o.edit_distance(a, b) == r.edit_distance(a, b)
 
 
+@pytest.mark.parametrize("name", sorted(cases.RNA_SETS))
+@pytest.mark.parametrize("mixed", [False, True])
+def test_rna_reads(name, mixed):
+    """U instead of T: 5-mers through base2val's U case, content bin 5, byte-wise adapter comparison, polyX that does not
+    count U."""
+    batch = cases.rna_batch(41, mixed=mixed)
+    assert (batch.seq == ord("U")).sum() > 10000
+    check(cases.RNA_SETS[name], batch, f"{name}/rna{int(mixed)}")
+
+
 def test_empty_batch():
     check(cases.OPTION_SETS["default_se"], pack_reads([]), "empty")
 

@@ -34,3 +34,15 @@ def test_full_scale_check_on_a_device_resident_batch(optset, n, mean, monkeypatc
     with pytest.raises(AssertionError):
         bench.full_scale_check(torch, eng, opt, tile, tile.seq, tile.qual, tile.offsets, tile.lens, tile.n_reads, mean)
     eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["rna_adapters", "rna_reads_dna_adapters", "rna_mixed_adapter_fasta"])
+@pytest.mark.parametrize("mixed", [False, True])
+def test_rna_reads_vs_oracle(name, mixed):
+    """Direct-RNA input (U instead of T; cases.RNA_SETS, pinned oracle-vs-reference on the CPU): U inside valid 5-mers
+    (k_cycle_stats' exact ACGTU test, k_kmer_fix), content bin 5, U bytes on the bit-plane path of the whole-read scan
+    (never an adapter letter, never an N), adapters that contain U (byte-wise paths), polyX that does not count U."""
+    import cases
+    from test_gpu_parity import check_against_oracle
+    check_against_oracle(cases.RNA_SETS[name], cases.rna_batch(41, mixed=mixed), f"{name}/rna{int(mixed)}")
