@@ -134,6 +134,127 @@ def rna_batch(seed, n=200, mean=1500, mixed=False):
     return PackedBatch(seq, b.qual, b.offsets, b.lens)
 
 
+# ---- crafted boundary cases: every one of them is a single-token mutant of the oracle that the batches above did not
+# tell apart from the reference (mutation run over oracle/fpl_oracle.c) ----
+def _q(n, q):
+    return bytes([33 + q]) * n
+
+
+def _rb(rng, n):
+    return synth.BASES[rng.integers(0, 4, size=n)].tobytes()
+
+
+def edge_cases():
+    """name -> (Options, PackedBatch)"""
+    rng = np.random.default_rng(2718)
+    out = {}
+    # (a) more adapter events on one read than the record's four inline slots (FPL_INLINE_EVENTS): three FASTA entries
+    # stacked at each end plus -s / -e; the event table and n_events keep counting
+    fa = sorted(_rand_adapter(n, 300 + n) for n in (22, 26, 30, 34))
+    s_ad, e_ad = _rand_adapter(28, 401), _rand_adapter(28, 402)
+    reads = []
+    for k in range(12):
+        head = s_ad + "".join(fa[(k + j) % 4] for j in range(3))
+        tail = "".join(fa[(k + j + 1) % 4] for j in range(3)) + e_ad
+        body = _rb(rng, 300 + 17 * k)
+        reads.append((head.encode() + body + tail.encode(), _q(len(head) + len(body) + len(tail), 25)))
+    out["many_events"] = (Options(start_adapter=s_ad, end_adapter=e_ad, adapter_fasta=fa, trimming_extension=0), pack_reads(reads))
+    # (b) global trims that eat the whole read exactly (Filter::trimAndCut, src/filter.cpp:137-157), with and without cuts
+    lens = [10, 11, 12, 13, 14, 16, 17, 18, 30]
+    reads = [(_rb(rng, n), _q(n, 30)) for n in lens for _ in range(2)]
+    for name, kw in (("trims_eat_read", {}), ("trims_eat_read_cut_front", dict(cut_front=True, cut_window_size=4)),
+                     ("trims_eat_read_cut_tail", dict(cut_tail=True, cut_window_size=1))):
+        out[name] = (Options(disable_adapter_trimming=True, trim_front=5, trim_tail=7, length_required=0, **kw), pack_reads(reads))
+    # (c) cut_front alone with a tail trim: no window qualifies / only the last one does (the scan stops one window short
+    # of the end, src/filter.cpp:170-180); the same from the other side
+    reads = []
+    for n in (40, 41, 57, 80):
+        reads.append((_rb(rng, n), _q(n, 3)))                                        # nothing qualifies
+        reads.append((_rb(rng, n), _q(n - 12, 3) + _q(12, 35)))                      # good bases only at the very end
+        reads.append((_rb(rng, n), _q(12, 35) + _q(n - 12, 3)))                      # ... only at the very start
+        reads.append((_rb(rng, n), _q(n - 9, 3) + _q(6, 35) + _q(3, 3)))             # the last full window before the tail trim
+    out["cut_front_tail_trim"] = (Options(disable_adapter_trimming=True, cut_front=True, cut_window_size=6, cut_mean_quality=20,
+                                          trim_tail=3, length_required=0), pack_reads(reads))
+    out["cut_tail_front_trim"] = (Options(disable_adapter_trimming=True, cut_tail=True, cut_window_size=6, cut_mean_quality=20,
+                                          trim_front=3, length_required=0), pack_reads(reads))
+    # (d) polyX: N inside the run counts for every base (src/polyx.cpp:40-45), for each of A/T/C/G; the stop rule at
+    # pos == 8 with a long minimum length (:54)
+    reads = []
+    for base in b"ATCG":
+        for k in (12, 20, 33):
+            run = bytearray([base]) * k
+            for p in rng.integers(1, k - 1, size=3):
+                run[int(p)] = ord("N")
+            body = _rb(rng, 120)
+            reads.append((body + bytes(run), _q(120 + k, 30)))
+            reads.append((body + bytes(run[:8]) + b"ACGT"[:1] + bytes(run[8:]), _q(121 + k, 30)))
+        reads.append((_rb(rng, 100) + bytes([base]) * 8 + b"CAGT" + bytes([base]) * 9, _q(121, 30)))
+    for ml in (5, 10, 20):
+        out[f"polyx_with_n_min{ml}"] = (Options(disable_adapter_trimming=True, trim_poly_x=True, poly_x_min_len=ml), pack_reads(reads))
+    # polyX stop rule around pos == 8 (:54): two mismatches among the last nine bases stop the walk (9 - 7 > 9 / 8) although
+    # the run behind them would have been long enough to trim (`pos >= 8` vs `pos > 8` turns out to be an equivalent mutant:
+    # the mismatch count cannot fall, so the walk stops one base later at the latest and neither stop reaches the minimum)
+    reads = []
+    for base, other in ((b"T", b"CG"), (b"A", b"CT"), (b"G", b"AT"), (b"C", b"GA")):
+        tail = base * 26 + other[1:2] + base * 3 + other[0:1] + base * 3                 # reading from the end: 3, x, 3, y, 26
+        reads.append((_rb(rng, 150) + tail, _q(150 + len(tail), 30)))
+        tail = base * 26 + other[1:2] + base * 4 + other[0:1] + base * 3                 # the second mismatch one position later
+        reads.append((_rb(rng, 150) + tail, _q(150 + len(tail), 30)))
+    for ml in (9, 12):
+        out[f"polyx_stop_at_8_min{ml}"] = (Options(disable_adapter_trimming=True, trim_poly_x=True, poly_x_min_len=ml), pack_reads(reads))
+    # findMiddleAdapters with the end adapter at position 0 of the trimmed read (src/adaptertrimmer.cpp:19: `>= 0`): the
+    # start trim removes a leading start adapter and leaves the read beginning with an end adapter; a second start adapter
+    # sits further in
+    reads = []
+    for k in range(6):
+        body1, body2 = _rb(rng, 320 + 11 * k), _rb(rng, 400)
+        reads.append((S.encode() + E.encode() + body1 + S.encode() + body2, _q(30 + 30 + len(body1) + 30 + 400, 30)))
+        reads.append((S.encode() + E.encode() + body1 + body2, _q(30 + 30 + len(body1) + 400, 30)))
+    out["middle_end_adapter_at_0"] = (Options(start_adapter=S, end_adapter=E, trimming_extension=0), pack_reads(reads))
+    out["middle_end_adapter_at_0_ext"] = (Options(start_adapter=S, end_adapter=E), pack_reads(reads))
+    # (e) quality filter without the length filter (-L) and the other way round: the counts are taken when EITHER is on
+    # (src/filter.cpp:23), the thresholds of each only when it is on; reads that fail on low-quality share, mean, N share, N count
+    reads = []
+    for k in range(6):
+        n = 200 + 10 * k
+        reads.append((_rb(rng, n), _q(n // 2, 5) + _q(n - n // 2, 30)))              # 50 % unqualified
+        reads.append((_rb(rng, n), _q(n, 9)))                                        # low mean
+        s = bytearray(_rb(rng, n))
+        s[10:10 + n // 8] = b"N" * (n // 8)
+        reads.append((bytes(s), _q(n, 30)))                                          # 12 % N
+        reads.append((_rb(rng, 12), _q(12, 30)))                                     # short
+    for name, kw in (("qual_filter_without_length_filter", dict(disable_length_filtering=True)),
+                     ("length_filter_without_qual_filter", dict(disable_quality_filtering=True)),
+                     ("neither_filter_but_complexity", dict(disable_length_filtering=True, disable_quality_filtering=True,
+                                                            low_complexity_filter=True))):
+        out[name] = (Options(disable_adapter_trimming=True, mean_qual=12, n_base_limit=20, **kw), pack_reads(reads))
+    # (f) ties of the integer-valued comparisons: mean quality == requirement (integer division, src/filter.cpp:33),
+    # complexity == threshold and one transition either side (:75-78), unqualified share and N share == limit (:31, :35)
+    reads = []
+    for n in (20, 21, 50):
+        for q in (9, 10, 11):
+            reads.append((_rb(rng, n), _q(n, q)))
+        reads.append((_rb(rng, n), _q(n // 2, 10) + _q(n - n // 2, 11)))             # floor(mean) == 10
+        reads.append((_rb(rng, n), _q(n // 2, 9) + _q(n - n // 2, 10)))              # floor(mean) == 9
+    for L, d in ((11, 3), (11, 2), (11, 4), (21, 6), (21, 5), (21, 7), (101, 30), (101, 29), (101, 31), (41, 12), (41, 11)):
+        s = bytearray(b"A" * L)                                                      # exactly d positions with seq[i] != seq[i+1]
+        cur, flips = ord("A"), set(int(x) for x in rng.choice(L - 1, size=d, replace=False))
+        for i in range(L):
+            s[i] = cur
+            if i in flips:
+                cur = ord("C") if cur == ord("A") else ord("A")
+        reads.append((bytes(s), _q(L, 30)))
+    for n, low, nn in ((20, 8, 2), (20, 9, 3), (50, 20, 5), (50, 21, 6), (100, 40, 10), (100, 41, 11)):
+        s = bytearray(_rb(rng, n))
+        s[:nn] = b"N" * nn
+        reads.append((bytes(s), _q(low, 5) + _q(n - low, 30)))                       # low == 40 % / nn == 10 % and one more
+    for n in (9, 10, 11, 199, 200, 201):                                             # length_required / length_limit and one either side
+        reads.append((_rb(rng, n), _q(n, 30)))
+    out["filter_ties"] = (Options(disable_adapter_trimming=True, mean_qual=10, qualified_quality_phred=8, low_complexity_filter=True,
+                                  complexity_threshold=30, length_required=10, length_limit=200), pack_reads(reads))
+    return out
+
+
 # ---- --mask / --break (SURVEY §8f row 3) ----
 MASK_BREAK_SETS = {
     "break_default": Options(start_adapter=S, break_reads=True),

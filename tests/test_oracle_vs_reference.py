@@ -61,6 +61,15 @@ def test_rna_reads(name, mixed):
     check(cases.RNA_SETS[name], batch, f"{name}/rna{int(mixed)}")
 
 
+@pytest.mark.parametrize("name", sorted(cases.edge_cases()))
+def test_crafted_boundary_cases(name):
+    """cases.edge_cases(): the boundaries a mutation run over the oracle found unpinned (more events than inline slots, global
+    trims that eat the read exactly, a cut from one side with a trim on the other, N inside polyX runs, one filter without
+    the other, ties of the filter thresholds)."""
+    opt, batch = cases.edge_cases()[name]
+    check(opt, batch, name)
+
+
 def test_empty_batch():
     check(cases.OPTION_SETS["default_se"], pack_reads([]), "empty")
 

@@ -46,3 +46,18 @@ def test_rna_reads_vs_oracle(name, mixed):
     import cases
     from test_gpu_parity import check_against_oracle
     check_against_oracle(cases.RNA_SETS[name], cases.rna_batch(41, mixed=mixed), f"{name}/rna{int(mixed)}")
+
+
+def _edge_names():
+    import cases
+    return sorted(cases.edge_cases())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", _edge_names())
+def test_crafted_boundary_cases_vs_oracle(name):
+    """cases.edge_cases() (each pinned oracle-vs-reference on the CPU): boundaries no other batch reaches."""
+    import cases
+    from test_gpu_parity import check_against_oracle
+    opt, batch = cases.edge_cases()[name]
+    check_against_oracle(opt, batch, name)
