@@ -1,0 +1,104 @@
+// TEST INFRASTRUCTURE: the scheduler of tests/simt/emu_cuda.h (include once per harness translation unit).
+#pragma once
+#include "emu_cuda.h"
+
+uint3 emu_threadIdx, emu_blockIdx;
+dim3 emu_blockDim, emu_gridDim;
+
+namespace emu {
+long long collectives = 0;
+namespace {
+constexpr size_t STACK = 512 * 1024;
+struct Fiber { ucontext_t ctx; bool done; };
+ucontext_t sched_ctx;
+std::vector<Fiber> fibers;
+std::vector<char*> stacks;          // pooled, never shrunk
+std::vector<Group> warps;
+Group blk;
+const std::function<void()>* body_ = nullptr;
+int cur = -1;
+bool progress = false;
+
+void complete(Group& g, int n) {
+    memcpy(g.res, g.slot, sizeof(uint64_t) * (size_t)n);
+    memset(g.slot, 0, sizeof(uint64_t) * (size_t)n);
+    g.res_mask = (unsigned)g.in_lo;
+    g.in_lo = 0;
+    g.arrived = 0;
+    g.gen++;
+    progress = true;
+}
+void fiber_main() {
+    (*body_)();
+    Fiber& f = fibers[cur];
+    f.done = true;
+    progress = true;
+    Group& w = warps[cur >> 5];
+    w.alive--; blk.alive--;
+    if (w.arrived > 0 && w.arrived == w.alive) complete(w, 32);
+    if (blk.arrived > 0 && blk.arrived == blk.alive) complete(blk, (int)emu_blockDim.x);
+    // returning switches to sched_ctx (uc_link)
+}
+}  // namespace
+
+void yield() { swapcontext(&fibers[cur].ctx, &sched_ctx); }
+Group& warp() { return warps[cur >> 5]; }
+Group& block() { return blk; }
+int lane() { return cur & 31; }
+int tid_in_block() { return cur; }
+
+Group& collect(Group& g, int index, uint64_t v) {
+    collectives++;
+    g.slot[index] = v;
+    if (index < 64) g.in_lo |= 1ull << index;
+    g.arrived++;
+    const unsigned my = g.gen;
+    if (g.arrived == g.alive) complete(g, &g == &blk ? (int)emu_blockDim.x : 32);
+    else while (g.gen == my) yield();
+    return g;
+}
+
+void launch(dim3 grid, dim3 block, const std::function<void()>& body) {
+    if (block.y != 1 || block.z != 1 || grid.y != 1 || grid.z != 1 || block.x > 1024) { fprintf(stderr, "emu: 1-D launches only\n"); abort(); }
+    const int n = (int)block.x;
+    emu_blockDim = block; emu_gridDim = grid;
+    body_ = &body;
+    while ((int)stacks.size() < n) stacks.push_back((char*)malloc(STACK));
+    for (unsigned b = 0; b < grid.x; b++) {
+        emu_blockIdx = {b, 0, 0};
+        fibers.assign((size_t)n, Fiber());
+        warps.assign((size_t)((n + 31) / 32), Group());
+        for (int w = 0; w < (int)warps.size(); w++) warps[w].alive = (w * 32 + 32 <= n) ? 32 : n - w * 32;
+        blk = Group();
+        blk.alive = n;
+        for (int i = 0; i < n; i++) {
+            fibers[i].done = false;
+            getcontext(&fibers[i].ctx);
+            fibers[i].ctx.uc_stack.ss_sp = stacks[i];
+            fibers[i].ctx.uc_stack.ss_size = STACK;
+            fibers[i].ctx.uc_link = &sched_ctx;
+            makecontext(&fibers[i].ctx, (void (*)())fiber_main, 0);
+        }
+        int left = n;
+        bool first = true;
+        while (left > 0) {
+            progress = first;
+            first = false;
+            left = 0;
+            for (int i = 0; i < n; i++) {
+                if (fibers[i].done) continue;
+                cur = i;
+                emu_threadIdx = {(unsigned)i, 0, 0};
+                swapcontext(&sched_ctx, &fibers[i].ctx);
+                if (!fibers[i].done) left++;
+            }
+            if (left > 0 && !progress) {
+                fprintf(stderr, "emu: deadlock in block %u: %d threads wait at a collective the others never reach "
+                                "(divergent __syncthreads / *_sync)\n", b, left);
+                abort();
+            }
+        }
+    }
+    cur = -1;
+}
+}  // namespace emu

@@ -1,0 +1,85 @@
+"""The record path of libfplgpu — k_trim, k_trim_fasta, the generic k_scan, k_final, k_count: their source text, executed on
+the CPU under the SIMT emulator (tests/simt_emu.py, tests/simt/emu_cuda.h) — against the oracle, on the whole option
+matrix, the crafted boundary cases, RNA reads and seeded random cases.  Every record field except the two medians (k_read_qual
+is a Stats kernel and not emulated) and every counter word."""
+import random
+
+import numpy as np
+import pytest
+
+import cases
+import simt_emu
+from fastplong_b200 import Options, pack_reads, synth
+from fastplong_b200.abi import RESULT_DTYPE
+from oracle_lib import OracleEngine, compare_stats
+
+NOT_EMULATED = ("seg_median_qual", "pre_median_qual")
+
+
+def check(opt, batch, what):
+    e, o = simt_emu.EmuEngine(opt), OracleEngine(opt)
+    res, ref = e.process(batch), o.process(batch)
+    for name in RESULT_DTYPE.names:
+        if name in NOT_EMULATED:
+            continue
+        if not np.array_equal(res[name], ref[name]):
+            bad = np.nonzero((res[name] != ref[name]).reshape(len(res), -1).any(axis=1))[0]
+            i = int(bad[0])
+            raise AssertionError(f"{what}: field {name} differs on {len(bad)} reads, first read {i}: {res[i]} vs {ref[i]}")
+    compare_stats(e.counters(), o.counters(), what + "/counters")
+    o.close()
+
+
+PLAIN_SETS = sorted(n for n in cases.OPTION_SETS if not n.startswith("long_adapter_"))
+
+
+@pytest.mark.parametrize("name", PLAIN_SETS)
+def test_option_matrix_on_adversarial_reads(name):
+    check(cases.OPTION_SETS[name], cases.adversarial_batch(1), name + "/adv")
+
+
+@pytest.mark.parametrize("name", PLAIN_SETS)
+def test_option_matrix_on_ont_like_reads(name):
+    check(cases.OPTION_SETS[name], cases.ont_batch(77, n=60, mean=2500, p_chimera=0.1, p_polya=0.05), name + "/ont")
+
+
+@pytest.mark.parametrize("n", sorted(cases.LONG_ADAPTERS))
+def test_long_adapters_every_size_class(n):
+    """-s / -e of 31..1024 bp: k_trim<0/1/2>, k_final<0/2>, the 64- / 128-bit and multi-word Myers forms"""
+    check(cases.OPTION_SETS[f"long_adapter_{n}"], cases.long_adapter_batch(n, 900 + n, n=24), f"long{n}")
+
+
+def test_config3_shape_64_entry_fasta():
+    check(cases.OPTION_SETS["fasta64_polyx"], cases.hifi_fasta64_batch(3, n=60), "fasta64")
+
+
+@pytest.mark.parametrize("name", sorted(cases.edge_cases()))
+def test_crafted_boundary_cases(name):
+    opt, batch = cases.edge_cases()[name]
+    check(opt, batch, name)
+
+
+@pytest.mark.parametrize("name", sorted(cases.RNA_SETS))
+@pytest.mark.parametrize("mixed", [False, True])
+def test_rna_reads(name, mixed):
+    check(cases.RNA_SETS[name], cases.rna_batch(41, n=60, mean=1200, mixed=mixed), f"{name}/{int(mixed)}")
+
+
+def test_empty_tiny_and_very_long_reads():
+    check(cases.OPTION_SETS["cut_polyx_cplx"], pack_reads([]), "empty")
+    reads = [(b"ACGTACGTACGTACGTACGT"[:n], bytes([33 + 30]) * n) for n in (0, 1, 2, 3, 4, 5, 6, 9, 15, 16, 17)] * 2
+    check(Options(disable_adapter_trimming=True, length_required=0), pack_reads(reads), "tiny")
+    check(cases.OPTION_SETS["cut_polyx_cplx"], pack_reads(reads), "tiny/adapters")
+    check(cases.OPTION_SETS["cut_polyx_cplx"], synth.ont_like(3, 60000, 5, p_chimera=1.0), "long reads")
+
+
+@pytest.mark.parametrize("family,count", [("random_case", 30), ("random_case_many_adapters", 15), ("random_case_long_reads", 6)])
+def test_random_option_sets(family, count):
+    rng = random.Random(20260924)
+    done = 0
+    while done < count:
+        opt, batch, what = getattr(cases, family)(rng)
+        if opt.mask or opt.break_reads:            # fpl_ext.cu is not emulated
+            continue
+        check(opt, batch, f"{family}[{done}] {what}")
+        done += 1
