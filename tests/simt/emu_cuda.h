@@ -61,8 +61,12 @@ int lane();
 int tid_in_block();
 // deposit v, wait for the group, return the group's generation result (res[], res_mask valid until the next collective)
 Group& collect(Group& g, int index, uint64_t v);
-void launch(dim3 grid, dim3 block, const std::function<void()>& body);
+void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()>& body);
 extern long long collectives;
+extern uint8_t* dynamic_smem;          // `extern __shared__` of the running kernel
+// 32-bit "shared window" addresses (what cvta.to.shared yields on the device): a 16 MB window per region of host memory
+uint32_t to_shared(const void* p);
+void* from_shared(uint32_t a);
 }  // namespace emu
 
 // ---- warp collectives (full masks only: the kernels never pass anything else) ----
@@ -158,5 +162,5 @@ template <class T, class U> static inline T atomicMax(T* p, U v) { T o = *p; if 
 template <class T, class U> static inline T atomicExch(T* p, U v) { T o = *p; *p = (T)v; return o; }
 template <class T, class U, class V> static inline T atomicCAS(T* p, U cmp, V v) { T o = *p; if (o == (T)cmp) *p = (T)v; return o; }
 
-// KERNEL<<<grid, block, smem, stream>>>(args) is rewritten by tests/simt_emu.py into EMU_LAUNCH(grid, block, KERNEL(args))
-#define EMU_LAUNCH(grid, block, call) emu::launch(dim3(grid), dim3(block), [&]() { call; })
+// KERNEL<<<grid, block, smem, stream>>>(args) is rewritten by tests/simt_emu.py into EMU_LAUNCH(grid, block, smem, KERNEL(args))
+#define EMU_LAUNCH(grid, block, smem, ...) emu::launch(dim3(grid), dim3(block), (size_t)(smem), [&]() { __VA_ARGS__; })

@@ -7,7 +7,10 @@ dim3 emu_blockDim, emu_gridDim;
 
 namespace emu {
 long long collectives = 0;
+uint8_t* dynamic_smem = nullptr;
 namespace {
+std::vector<char*> windows;          // base of each 16 MB shared window
+std::vector<uint8_t> dyn;
 constexpr size_t STACK = 512 * 1024;
 struct Fiber { ucontext_t ctx; bool done; };
 ucontext_t sched_ctx;
@@ -41,6 +44,19 @@ void fiber_main() {
 }
 }  // namespace
 
+uint32_t to_shared(const void* p) {
+    const char* c = (const char*)p;
+    for (size_t i = 0; i < windows.size(); i++)
+        if (c >= windows[i] && c < windows[i] + (1 << 24)) return (uint32_t)(((i + 1) << 24) | (size_t)(c - windows[i]));
+    windows.push_back((char*)((uintptr_t)c & ~(uintptr_t)0xFFFF));          // windows start on 64 KB boundaries
+    if (windows.size() > 200) { fprintf(stderr, "emu: too many shared windows\n"); abort(); }
+    return to_shared(p);
+}
+void* from_shared(uint32_t a) {
+    const size_t i = (a >> 24);
+    if (i == 0 || i > windows.size()) { fprintf(stderr, "emu: bad shared address %08x\n", a); abort(); }
+    return windows[i - 1] + (a & 0xFFFFFFu);
+}
 void yield() { swapcontext(&fibers[cur].ctx, &sched_ctx); }
 Group& warp() { return warps[cur >> 5]; }
 Group& block() { return blk; }
@@ -58,14 +74,18 @@ Group& collect(Group& g, int index, uint64_t v) {
     return g;
 }
 
-void launch(dim3 grid, dim3 block, const std::function<void()>& body) {
-    if (block.y != 1 || block.z != 1 || grid.y != 1 || grid.z != 1 || block.x > 1024) { fprintf(stderr, "emu: 1-D launches only\n"); abort(); }
+void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()>& body) {
+    if (block.y != 1 || block.z != 1 || grid.z != 1 || block.x > 1024) { fprintf(stderr, "emu: 1-D blocks, 2-D grids only\n"); abort(); }
+    if (dyn.size() < smem_bytes + 64) dyn.resize(smem_bytes + 64);
+    dynamic_smem = (uint8_t*)(((uintptr_t)dyn.data() + 63) & ~(uintptr_t)63);
     const int n = (int)block.x;
     emu_blockDim = block; emu_gridDim = grid;
     body_ = &body;
     while ((int)stacks.size() < n) stacks.push_back((char*)malloc(STACK));
-    for (unsigned b = 0; b < grid.x; b++) {
-        emu_blockIdx = {b, 0, 0};
+    for (unsigned long long bb = 0; bb < (unsigned long long)grid.x * grid.y; bb++) {
+        const unsigned b = (unsigned)(bb % grid.x);
+        emu_blockIdx = {b, (unsigned)(bb / grid.x), 0};
+        memset(dynamic_smem, 0xCD, smem_bytes);           // shared memory is not zero at block start
         fibers.assign((size_t)n, Fiber());
         warps.assign((size_t)((n + 31) / 32), Group());
         for (int w = 0; w < (int)warps.size(); w++) warps[w].alive = (w * 32 + 32 <= n) ? 32 : n - w * 32;

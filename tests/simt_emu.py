@@ -1,16 +1,18 @@
-"""TEST INFRASTRUCTURE: the record path of libfplgpu executed on the CPU.
+"""TEST INFRASTRUCTURE: the default path of libfplgpu executed on the CPU.
 
-The source text of fpl_device.cuh, fpl_trim.cu (k_trim, k_trim_fasta) and fpl_scan.cu (the generic k_scan, k_final, k_count)
-is preprocessed — CUDA includes dropped, `mad.lo.u32` inline PTX rewritten as C, `kernel<<<grid, block, smem, stream>>>(args)`
+The source text of fpl_device.cuh, fpl_trim.cu (k_trim, k_trim_fasta), fpl_scan.cu (the generic k_scan, k_final, k_count) and
+fpl_stats.cu (k_make_preseg, k_cs_keys / k_cs_gather, k_cycle_stats, k_kmer_fix, k_read_qual) is preprocessed — CUDA includes
+dropped, `mad.lo.u32` inline PTX rewritten as C, the small PTX wrappers (cp.async, ld.shared, red.shared, prmt, mbarrier / bulk
+copy) replaced by host forms, `extern __shared__` bound to the emulator's buffer, `kernel<<<grid, block, smem, stream>>>(args)`
 turned into a call of the SIMT emulator (tests/simt/emu_cuda.h: one fiber per CUDA thread, warp / block collectives with their
-real semantics) — and compiled with g++ together with the table builder cut out of fpl_create (fpl_api.cu), so that adapters,
-thresholds and match masks are prepared by the product's own code.  `process(options, batch)` then runs
-launch_trim -> launch_scan -> launch_final -> launch_count in run_batch's order and returns the per-read records and the
-counter vector, to be compared with the oracle like a GPU result.
+real semantics) — and compiled with g++ together with the launch functions of those files and the table builder cut out of
+fpl_create (fpl_api.cu), so that adapters, thresholds, match masks, grids and kernel variants are chosen by the product's own
+code.  `EmuEngine.process()` runs the kernels in run_batch's order on host memory and returns records, both Stats blocks and
+the counter vector, to be compared with the oracle like a GPU result.
 
-What this covers: everything the records and counters depend on except the NVRTC-specialised scan (the generic k_scan
-computes the same ReadState by contract; the GPU tests hold the variants to each other).  Not covered: the Stats kernels
-(cp.async rings, shared-memory reductions in PTX, cub sorts), FASTQ ingest / emit, --mask/--break, timing, races.
+Not covered: the NVRTC-specialised scan and k_scan_fast (the generic k_scan computes the same ReadState by contract; the GPU
+tests hold the variants to each other; their helpers are host-tested in tests/test_device_helpers_host.py), FASTQ ingest / emit,
+--mask/--break, the NCCL merge; and what no functional emulation shows: timing, bank conflicts, memory ordering, races.
 Nothing here is shipped or reachable from the product path.
 """
 import ctypes as C
@@ -29,7 +31,7 @@ SIMT = os.path.join(ROOT, "tests", "simt")
 
 
 def _drop_function(text, name):
-    m = re.search(r"^[A-Za-z_][^\n;{}()]*\b" + name + r"\s*\([^;{}]*\)\s*\{", text, re.M)
+    m = re.search(r"^(?:template\s*<[^>\n]*>\s*\n)?[A-Za-z_][^\n;{}()]*\b" + name + r"\s*\([^;{}]*\)\s*\{", text, re.M)
     if not m:
         raise KeyError(name)
     end = _match_brace(text, m.end() - 1)
@@ -71,14 +73,17 @@ def _rewrite_launches(text):
             if depth == 0:
                 break
             q += 1
-        out += text[i:m.start()] + f"EMU_LAUNCH(({cfg[0]}), ({cfg[1]}), {m.group(1)}{text[p:q + 1]})"
+        smem = cfg[2] if len(cfg) > 2 else "0"
+        out += text[i:m.start()] + f"EMU_LAUNCH(({cfg[0]}), ({cfg[1]}), ({smem}), {m.group(1)}{text[p:q + 1]})"
         i = q + 1
 
 
 def device_text(fn, drop=()):
     text = open(os.path.join(CSRC, fn)).read()
-    text = re.sub(r'^\s*#include\s+[<"](cuda_runtime\.h|fpl_device\.cuh|cuda\.h)[>"].*$', "", text, flags=re.M)
+    text = re.sub(r'^\s*#include\s+[<"](cuda_runtime\.h|fpl_device\.cuh|cuda\.h|cub/cub\.cuh)[>"].*$', "", text, flags=re.M)
     text = text.replace("#pragma once", "")
+    text = re.sub(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?(\w+)\s+(\w+)\[\];", r"\1* \2 = (\1*)emu::dynamic_smem;", text)
+    text = re.sub(r'asm\s+volatile\s*\(\s*"fence[^"]*"[^;]*;', ";", text)
     for name in drop:
         text = _drop_function(text, name)
     return f"// ======== {fn} (preprocessed) ========\n" + _rewrite_launches(_asm_to_c(text))
@@ -95,20 +100,74 @@ def table_builder():
 HARNESS = r"""
 #include <math.h>
 #include <stdarg.h>
+#include <algorithm>
 #include <string>
 #include "emu_cuda_impl.h"
 #include "fplgpu.h"
 #include "fpl_scanplan.h"
-@@DEVICE@@
 
-// a host-memory stand-in for the few runtime calls inside the table builder
+// ---- a host-memory stand-in for the runtime calls inside the table builder and the launch functions ----
 enum cudaError_t { cudaSuccess = 0 };
-enum { cudaMemcpyHostToDevice = 1, cudaStreamNonBlocking = 1 };
+enum { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3, cudaStreamNonBlocking = 1,
+       cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 static const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
 template <class T> static cudaError_t cudaMalloc(T** p, size_t n) { *p = (T*)calloc(n ? n : 1, 1); return cudaSuccess; }
+static cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
 static cudaError_t cudaMemcpy(void* d, const void* s, size_t n, int) { memcpy(d, s, n); return cudaSuccess; }
+static cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, int, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
 static cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
+static cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { memset(d, v, n); return cudaSuccess; }
 static cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, int) { *s = nullptr; return cudaSuccess; }
+static cudaError_t cudaGetLastError() { return cudaSuccess; }
+static cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+static cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+static cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+static cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+template <class F> static cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
+namespace cub {
+struct DeviceRadixSort {      // a stable LSD radix sort on key bits [begin_bit, end_bit), like the library's
+    template <class K, class V>
+    static cudaError_t SortPairsDescending(void* tmp, size_t& bytes, const K* kin, K* kout, const V* vin, V* vout, int n, int begin_bit,
+                                           int end_bit, cudaStream_t) {
+        if (!tmp) { bytes = 64; return cudaSuccess; }
+        std::vector<int> idx((size_t)n);
+        for (int i = 0; i < n; i++) idx[i] = i;
+        const K mask = end_bit - begin_bit >= (int)(8 * sizeof(K)) ? ~(K)0 : (K)((((K)1 << (end_bit - begin_bit)) - 1) << begin_bit);
+        std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return (kin[a] & mask) > (kin[b] & mask); });
+        for (int i = 0; i < n; i++) { kout[i] = kin[idx[i]]; vout[i] = vin[idx[i]]; }
+        return cudaSuccess;
+    }
+};
+}  // namespace cub
+
+// ---- host forms of the PTX wrappers of fpl_device.cuh / fpl_stats.cu (their definitions are cut out of the text) ----
+static inline uint32_t shared_addr(const void* p) { return emu::to_shared(p); }
+static inline void red_shared_add(uint32_t a, uint32_t v) { *(uint32_t*)emu::from_shared(a) += v; }
+template <int IMM> static inline void red_shared_add_imm(uint32_t a, uint32_t v) { *(uint32_t*)emu::from_shared(a + (uint32_t)IMM) += v; }
+static inline uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {       // prmt.b32, default mode
+    const uint64_t src = ((uint64_t)b << 32) | a;
+    uint32_t d = 0;
+    for (int i = 0; i < 4; i++) {
+        const uint32_t c = (sel >> (4 * i)) & 0xF;
+        uint32_t byte = (uint32_t)(src >> (8 * (c & 7))) & 0xFF;
+        if (c & 8) byte = (byte & 0x80) ? 0xFF : 0x00;
+        d |= byte << (8 * i);
+    }
+    return d;
+}
+// cp.async completes at an unspecified time before the matching wait; completing it at once is one legal order
+static inline void cp_async16(uint32_t dst, const void* src, int n) { uint8_t* d = (uint8_t*)emu::from_shared(dst); if (n > 0) memcpy(d, src, n); memset(d + n, 0, 16 - n); }
+static inline void cp_async4(uint32_t dst, const void* src, int n) { uint8_t* d = (uint8_t*)emu::from_shared(dst); if (n > 0) memcpy(d, src, n); memset(d + n, 0, 4 - n); }
+static inline void cp_async_commit() {}
+template <int N> static inline void cp_async_wait() {}
+static inline uint4 lds128(uint32_t a) { uint4 v; memcpy(&v, emu::from_shared(a), 16); return v; }
+static inline uint32_t lds32(uint32_t a) { uint32_t v; memcpy(&v, emu::from_shared(a), 4); return v; }
+static inline void mbar_init(uint32_t, uint32_t) {}
+static inline void mbar_expect_tx(uint32_t, uint32_t) {}
+static inline void mbar_wait(uint32_t, uint32_t) {}
+static inline void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t) { memcpy(emu::from_shared(dst), src, bytes); }
+
+@@DEVICE@@
 
 struct EmuCtx {
     DevParams P; ScanPlan plan; int n_adapters = 0; cudaStream_t stream = nullptr;
@@ -125,9 +184,12 @@ static void fpl_destroy(EmuCtx* c) {
 extern "C" const char* emu_last_error() { return g_err; }
 extern "C" long long emu_collectives() { return emu::collectives; }
 
-// processSingleEnd's record path in run_batch's order (fpl_api.cu), on host memory
+// processSingleEnd over a packed batch in run_batch's order (fpl_api.cu), on host memory.  stats0 / stats1: FPL_STATS_WORDS(C)
+// words each (zeroed by the caller; may be null: records and counters only, the Stats kernels are skipped and the two
+// median fields stay 0).  tma: the FPL_CS_TMA staging variant of k_cycle_stats.
 extern "C" int emu_process(const fpl_options* opt, const fpl_adapters* ad, const fpl_batch* hb, fpl_read_result* results,
-                           unsigned long long* counters, int64_t n_counter_words) {
+                           unsigned long long* counters, int64_t n_counter_words, unsigned long long* stats0,
+                           unsigned long long* stats1, int64_t C) {
     g_err[0] = 0;
     const int n = 2 + (ad->n_fasta > 0 ? ad->n_fasta : 0);
     EmuCtx* c = new EmuCtx();
@@ -138,22 +200,41 @@ extern "C" int emu_process(const fpl_options* opt, const fpl_adapters* ad, const
     const int64_t nr = hb->n_reads;
     DevBatch b = {hb->seq, hb->qual, hb->offsets, hb->lens, nr};
     std::vector<ReadState> st((size_t)nr + 1);
-    std::vector<StatSeg> post(2 * (size_t)nr + 2);
+    std::vector<StatSeg> pre((size_t)nr + 1), post(2 * (size_t)nr + 2);
+    int64_t tmax = 0;
+    bool slots16 = true;
+    for (int64_t i = 0; i < nr; i++) { if (hb->lens[i] > tmax) tmax = hb->lens[i]; if (hb->offsets[i] & 15) slots16 = false; }
+    if (stats0 && tmax > C) { fpl_destroy(c); return fail("C too small"); }
     memset(results, 0xAB, sizeof(fpl_read_result) * (size_t)nr);          // k_trim must write every record
-    launch_trim(c->P, b, st.data(), results, c->d_counters, nullptr);
-    launch_scan(c->P, b, st.data(), nullptr);
-    launch_final(c->P, b, st.data(), results, post.data(), nullptr);
-    launch_count(results, nr, c->d_counters, true, nullptr);
+    CycleWs ws;
+    cudaStream_t s = nullptr;
+    if (stats0) launch_make_preseg(b, pre.data(), s);
+    launch_trim(c->P, b, st.data(), results, c->d_counters, s);
+    if (stats0 && launch_cycle_stats(&ws, hb->seq, hb->qual, pre.data(), nr, tmax, stats0, C, true, stats1 + 16 * C + FPL_STATS_KMER, slots16, s))
+        return fail("launch_cycle_stats(pre) failed");
+    launch_scan(c->P, b, st.data(), s);
+    launch_final(c->P, b, st.data(), results, post.data(), s);
+    launch_count(results, nr, c->d_counters, true, s);
+    if (stats0) {
+        if (launch_cycle_stats(&ws, hb->seq, hb->qual, post.data(), 2 * nr, tmax, stats1, C, false, nullptr, false, s))
+            return fail("launch_cycle_stats(post) failed");
+        launch_kmer_fix(b, results, stats1 + 16 * C + FPL_STATS_KMER, s);
+        launch_read_qual(b, stats0, stats1, C, results, false, s);
+        fpl_cycle_ws_free(&ws);
+    }
     memcpy(counters, c->d_counters, sizeof(unsigned long long) * (size_t)c->counter_words);
     fpl_destroy(c);
     return 0;
 }
 """
 
+PTX_WRAPPERS = ("prmt", "cp_async16", "cp_async4", "cp_async_commit", "cp_async_wait", "lds128", "lds32", "mbar_init", "mbar_expect_tx",
+                "mbar_wait", "bulk_g2s", "red_shared_add_imm")
+
 
 def source():
     dev = "\n".join([device_text("fpl_device.cuh", drop=("red_shared_add", "shared_addr")), device_text("fpl_trim.cu"),
-                     device_text("fpl_scan.cu")])
+                     device_text("fpl_scan.cu"), '#include "fpl_stats.h"', device_text("fpl_stats.cu", drop=PTX_WRAPPERS)])
     return HARNESS.replace("@@DEVICE@@", dev).replace("@@BUILDER@@", table_builder())
 
 
@@ -177,31 +258,57 @@ def load():
     lib = C.CDLL(so)
     lib.emu_last_error.restype = C.c_char_p
     lib.emu_collectives.restype = C.c_longlong
-    lib.emu_process.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(FplBatch), C.c_void_p, C.c_void_p, C.c_int64]
+    lib.emu_process.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(FplBatch), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                C.c_int64]
     _lib = lib
     return lib
 
 
 class EmuEngine:
-    """binding.Engine's process() / counters() for the emulated record path."""
+    """binding.Engine's process() / stats() / counters() for the emulated kernels.  with_stats=False: records and counters only
+    (the Stats kernels are skipped; the two median fields of the records stay 0)."""
 
-    def __init__(self, options):
+    def __init__(self, options, with_stats=True):
         self.lib = load()
         self.options = options
         self._abi = options.to_abi()
         self.n_adapters = 2 + len(options.adapter_fasta)
         self._counters = np.zeros(abi.counter_words(self.n_adapters), dtype=np.int64)
+        self.with_stats = with_stats
+        self._blocks = None        # [pre, post] at self._C cycles
 
     def process(self, batch):
         o, ad, keep = self._abi
         res = np.zeros(batch.n_reads, dtype=RESULT_DTYPE)
         cnt = np.zeros_like(self._counters)
         b = batch.to_abi()
-        rc = self.lib.emu_process(C.byref(o), C.byref(ad), C.byref(b), res.ctypes.data, cnt.ctypes.data, cnt.shape[0])
+        s0 = s1 = None
+        cyc = 0
+        if self.with_stats:
+            need = max(64, int(batch.lens.max()) if batch.n_reads else 1)
+            cyc = 1 << int(np.ceil(np.log2(need)))
+            s0 = np.zeros(abi.stats_words(cyc), dtype=np.int64)
+            s1 = np.zeros(abi.stats_words(cyc), dtype=np.int64)
+        rc = self.lib.emu_process(C.byref(o), C.byref(ad), C.byref(b), res.ctypes.data, cnt.ctypes.data, cnt.shape[0],
+                                  s0.ctypes.data if s0 is not None else None, s1.ctypes.data if s1 is not None else None, cyc)
         if rc != 0:
             raise RuntimeError(self.lib.emu_last_error().decode())
         self._counters += cnt
+        if self.with_stats:
+            from fastplong_b200.binding import relayout_stats
+            if self._blocks is None:
+                self._blocks, self._C = [s0, s1], cyc
+            else:
+                c2 = max(cyc, self._C)
+                self._blocks = [relayout_stats(x, self._C, c2) + relayout_stats(y, cyc, c2) for x, y in zip(self._blocks, (s0, s1))]
+                self._C = c2
         return res
+
+    def stats(self, which, cycles):
+        from fastplong_b200.binding import relayout_stats
+        if self._blocks is None:
+            return np.zeros(abi.stats_words(cycles), dtype=np.int64)
+        return relayout_stats(self._blocks[which], self._C, int(cycles))
 
     def counters(self):
         return self._counters.copy()

@@ -1,7 +1,8 @@
-"""The record path of libfplgpu — k_trim, k_trim_fasta, the generic k_scan, k_final, k_count: their source text, executed on
-the CPU under the SIMT emulator (tests/simt_emu.py, tests/simt/emu_cuda.h) — against the oracle, on the whole option
-matrix, the crafted boundary cases, RNA reads and seeded random cases.  Every record field except the two medians (k_read_qual
-is a Stats kernel and not emulated) and every counter word."""
+"""The kernels of libfplgpu's default path — k_make_preseg, k_trim, k_trim_fasta, k_cs_keys / k_cs_gather, k_cycle_stats (both
+variants; cp.async ring, packed shared-memory counters, lane-private 5-mer tables), the generic k_scan, k_final, k_count,
+k_kmer_fix, k_read_qual: their own source text, executed on the CPU under the SIMT emulator (tests/simt_emu.py,
+tests/simt/emu_cuda.h) in run_batch's order — against the oracle, on the whole option matrix, the crafted boundary cases,
+RNA reads and seeded random cases: every field of every record, every word of both Stats blocks, every counter."""
 import random
 
 import numpy as np
@@ -10,22 +11,15 @@ import pytest
 import cases
 import simt_emu
 from fastplong_b200 import Options, pack_reads, synth
-from fastplong_b200.abi import RESULT_DTYPE
-from oracle_lib import OracleEngine, compare_stats
-
-NOT_EMULATED = ("seg_median_qual", "pre_median_qual")
+from oracle_lib import OracleEngine, compare_results, compare_stats
 
 
 def check(opt, batch, what):
     e, o = simt_emu.EmuEngine(opt), OracleEngine(opt)
-    res, ref = e.process(batch), o.process(batch)
-    for name in RESULT_DTYPE.names:
-        if name in NOT_EMULATED:
-            continue
-        if not np.array_equal(res[name], ref[name]):
-            bad = np.nonzero((res[name] != ref[name]).reshape(len(res), -1).any(axis=1))[0]
-            i = int(bad[0])
-            raise AssertionError(f"{what}: field {name} differs on {len(bad)} reads, first read {i}: {res[i]} vs {ref[i]}")
+    compare_results(e.process(batch), o.process(batch), what)
+    cyc = max(1, int(batch.lens.max()) if batch.n_reads else 1)
+    for w in (0, 1):
+        compare_stats(e.stats(w, cyc), o.stats(w, cyc), f"{what}/stats{w}")
     compare_stats(e.counters(), o.counters(), what + "/counters")
     o.close()
 
