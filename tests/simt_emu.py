@@ -187,15 +187,18 @@ extern "C" long long emu_collectives() { return emu::collectives; }
 // processSingleEnd over a packed batch in run_batch's order (fpl_api.cu), on host memory.  stats0 / stats1: FPL_STATS_WORDS(C)
 // words each (zeroed by the caller; may be null: records and counters only, the Stats kernels are skipped and the two
 // median fields stay 0).  tma: the FPL_CS_TMA staging variant of k_cycle_stats.
+typedef void (*scan_fn)(const uint8_t*, const uint8_t*, const int64_t*, void*, int64_t);
 extern "C" int emu_process(const fpl_options* opt, const fpl_adapters* ad, const fpl_batch* hb, fpl_read_result* results,
                            unsigned long long* counters, int64_t n_counter_words, unsigned long long* stats0,
-                           unsigned long long* stats1, int64_t C) {
+                           unsigned long long* stats1, int64_t C, scan_fn scan_override, int* plan_fast) {
     g_err[0] = 0;
     const int n = 2 + (ad->n_fasta > 0 ? ad->n_fasta : 0);
     EmuCtx* c = new EmuCtx();
     c->n_adapters = n;
     auto stamp = [](const char*) {};
 @@BUILDER@@
+    if (plan_fast) *plan_fast = c->plan.fast;
+    if (!hb) { fpl_destroy(c); return 0; }                              // only the tables were wanted
     if (n_counter_words != c->counter_words) { fpl_destroy(c); return fail("counter words %lld != %lld", (long long)n_counter_words, (long long)c->counter_words); }
     const int64_t nr = hb->n_reads;
     DevBatch b = {hb->seq, hb->qual, hb->offsets, hb->lens, nr};
@@ -212,7 +215,8 @@ extern "C" int emu_process(const fpl_options* opt, const fpl_adapters* ad, const
     launch_trim(c->P, b, st.data(), results, c->d_counters, s);
     if (stats0 && launch_cycle_stats(&ws, hb->seq, hb->qual, pre.data(), nr, tmax, stats0, C, true, stats1 + 16 * C + FPL_STATS_KMER, slots16, s))
         return fail("launch_cycle_stats(pre) failed");
-    launch_scan(c->P, b, st.data(), s);
+    if (scan_override) { if (nr) scan_override(hb->seq, hb->qual, hb->offsets, st.data(), nr); }     // k_scan_jit (tests/simt_emu.py:JitScan)
+    else launch_scan(c->P, b, st.data(), s);
     launch_final(c->P, b, st.data(), results, post.data(), s);
     launch_count(results, nr, c->d_counters, true, s);
     if (stats0) {
@@ -258,18 +262,73 @@ def load():
     lib = C.CDLL(so)
     lib.emu_last_error.restype = C.c_char_p
     lib.emu_collectives.restype = C.c_longlong
-    lib.emu_process.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(FplBatch), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
-                                C.c_int64]
+    lib.emu_process.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                C.c_int64, C.c_void_p, C.POINTER(C.c_int)]
     _lib = lib
     return lib
+
+
+JIT_HARNESS = r"""
+#include "emu_cuda_impl.h"
+namespace jit {
+@@DEFS@@
+@@SOURCE@@
+}  // namespace jit
+extern "C" void jit_scan(const uint8_t* seq, const uint8_t* qual, const int64_t* offsets, void* st, int64_t n) {
+    EMU_LAUNCH(((unsigned)n), (128), (0), jit::k_scan_jit(seq, qual, (const jit::int64_t*)offsets, (jit::ReadState*)st, (jit::int64_t)n, 1u));
+}
+"""
+
+_jit_cache = {}
+
+
+def jit_scan(options):
+    """k_scan_jit v2 for these options, as fpl_create would have NVRTC build it (fpl_jit.cu: fpl_jit_build_scan's #defines +
+    the generated source of fpl_jit_debug_source), compiled for the host under the emulator.  Returns the ctypes function to hand
+    to emu_process, or None where the library would not specialise (an adapter that is empty, not ACGT-only or > 128 bp)."""
+    from fastplong_b200.binding import load_library
+    o, ad, keep = options.to_abi()
+    a0, a1 = (ad.start or b"").decode(), (ad.end or b"").decode()
+    do_adapters = bool(o.adapter_enabled)
+    if do_adapters and not all(1 <= len(a) <= 128 and set(a) <= set("ACGT") for a in (a0, a1)):
+        return None
+    if not do_adapters:
+        a0 = a1 = ""
+    do_counts = bool(o.qual_filter_enabled or o.length_filter_enabled)
+    key = (a0, a1, do_adapters, do_counts, bool(o.complexity_enabled), o.qualified_qual & 0x7F)
+    if key in _jit_cache:
+        return _jit_cache[key]
+    lib = load_library()
+    lib.fpl_jit_debug_source.restype = C.c_char_p
+    lib.fpl_jit_debug_source.argtypes = [C.c_char_p, C.c_char_p]
+    body = lib.fpl_jit_debug_source(a0.encode(), a1.encode()).decode()
+    t = lambda x: "true" if x else "false"
+    defs = (f'#define FPL_A0 "{a0}"\n#define FPL_A1 "{a1}"\n#define FPL_ALEN0 {len(a0)}\n#define FPL_ALEN1 {len(a1)}\n#define FPL_JIT_VERSION 2\n'
+            f'#define FPL_DO_ADAPTERS {t(do_adapters)}\n#define FPL_DO_COUNTS {t(do_counts)}\n#define FPL_DO_CPLX {t(o.complexity_enabled)}\n'
+            f'#define FPL_QQ {o.qualified_qual & 0x7F}\n#define FPL_MINBLOCKS 8\n')
+    src = JIT_HARNESS.replace("@@DEFS@@", defs).replace("@@SOURCE@@", _asm_to_c(body))
+    for h in ("emu_cuda.h", "emu_cuda_impl.h"):
+        src += "\n// " + hashlib.md5(open(os.path.join(SIMT, h)).read().encode()).hexdigest()
+    so = f"/tmp/fpl_simt_jit_{hashlib.md5(src.encode()).hexdigest()[:12]}.so"
+    if not os.path.exists(so):
+        cpp = so[:-3] + ".cpp"
+        open(cpp, "w").write(src)
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-w", "-I", SIMT, "-o", so, cpp])
+    fn = C.CDLL(so).jit_scan
+    _jit_cache[key] = fn
+    return fn
 
 
 class EmuEngine:
     """binding.Engine's process() / stats() / counters() for the emulated kernels.  with_stats=False: records and counters only
     (the Stats kernels are skipped; the two median fields of the records stay 0)."""
 
-    def __init__(self, options, with_stats=True):
+    def __init__(self, options, with_stats=True, scan="generic"):
+        """scan = "generic": launch_scan (k_scan); "jit": k_scan_jit v2 specialised on the options where the library would
+        specialise (self.jit tells), the generic kernel elsewhere."""
         self.lib = load()
+        self.scan_fn = jit_scan(options) if scan == "jit" else None
+        self.jit = self.scan_fn is not None
         self.options = options
         self._abi = options.to_abi()
         self.n_adapters = 2 + len(options.adapter_fasta)
@@ -289,8 +348,9 @@ class EmuEngine:
             cyc = 1 << int(np.ceil(np.log2(need)))
             s0 = np.zeros(abi.stats_words(cyc), dtype=np.int64)
             s1 = np.zeros(abi.stats_words(cyc), dtype=np.int64)
-        rc = self.lib.emu_process(C.byref(o), C.byref(ad), C.byref(b), res.ctypes.data, cnt.ctypes.data, cnt.shape[0],
-                                  s0.ctypes.data if s0 is not None else None, s1.ctypes.data if s1 is not None else None, cyc)
+        rc = self.lib.emu_process(C.addressof(o), C.addressof(ad), C.addressof(b), res.ctypes.data, cnt.ctypes.data, cnt.shape[0],
+                                  s0.ctypes.data if s0 is not None else None, s1.ctypes.data if s1 is not None else None, cyc,
+                                  C.cast(self.scan_fn, C.c_void_p) if self.scan_fn is not None else None, None)
         if rc != 0:
             raise RuntimeError(self.lib.emu_last_error().decode())
         self._counters += cnt
@@ -303,6 +363,14 @@ class EmuEngine:
                 self._blocks = [relayout_stats(x, self._C, c2) + relayout_stats(y, cyc, c2) for x, y in zip(self._blocks, (s0, s1))]
                 self._C = c2
         return res
+
+    def plan_fast(self):
+        """fpl_create's own verdict (ScanPlan.fast): may the bit-sliced scan kernels be used for these adapters"""
+        o, ad, keep = self._abi
+        v = C.c_int(-1)
+        rc = self.lib.emu_process(C.addressof(o), C.addressof(ad), None, None, None, 0, None, None, 0, None, C.byref(v))
+        assert rc == 0
+        return bool(v.value)
 
     def stats(self, which, cycles):
         from fastplong_b200.binding import relayout_stats

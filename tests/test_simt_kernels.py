@@ -1,7 +1,8 @@
 """The kernels of libfplgpu's default path — k_make_preseg, k_trim, k_trim_fasta, k_cs_keys / k_cs_gather, k_cycle_stats (both
 variants; cp.async ring, packed shared-memory counters, lane-private 5-mer tables), the generic k_scan, k_final, k_count,
-k_kmer_fix, k_read_qual: their own source text, executed on the CPU under the SIMT emulator (tests/simt_emu.py,
-tests/simt/emu_cuda.h) in run_batch's order — against the oracle, on the whole option matrix, the crafted boundary cases,
+k_kmer_fix, k_read_qual — and k_scan_jit v2, the source fpl_jit.cu generates for the options' adapters (what NVRTC compiles on
+the GPU): their own source text, executed on the CPU under the SIMT emulator (tests/simt_emu.py, tests/simt/emu_cuda.h) in
+run_batch's order — against the oracle, on the whole option matrix, the crafted boundary cases,
 RNA reads and seeded random cases: every field of every record, every word of both Stats blocks, every counter."""
 import random
 
@@ -14,8 +15,12 @@ from fastplong_b200 import Options, pack_reads, synth
 from oracle_lib import OracleEngine, compare_results, compare_stats
 
 
-def check(opt, batch, what):
-    e, o = simt_emu.EmuEngine(opt), OracleEngine(opt)
+def check(opt, batch, what, scan="jit"):
+    """scan = "jit": the whole-read scan is k_scan_jit v2, specialised on the options exactly where fpl_create would have NVRTC
+    specialise it (the emulator harness reports ScanPlan.fast, the product's own verdict); the generic k_scan elsewhere."""
+    e, o = simt_emu.EmuEngine(opt, scan=scan), OracleEngine(opt)
+    if scan == "jit":
+        assert e.jit == e.plan_fast(), what
     compare_results(e.process(batch), o.process(batch), what)
     cyc = max(1, int(batch.lens.max()) if batch.n_reads else 1)
     for w in (0, 1):
@@ -27,9 +32,10 @@ def check(opt, batch, what):
 PLAIN_SETS = sorted(n for n in cases.OPTION_SETS if not n.startswith("long_adapter_"))
 
 
+@pytest.mark.parametrize("scan", ["jit", "generic"])
 @pytest.mark.parametrize("name", PLAIN_SETS)
-def test_option_matrix_on_adversarial_reads(name):
-    check(cases.OPTION_SETS[name], cases.adversarial_batch(1), name + "/adv")
+def test_option_matrix_on_adversarial_reads(name, scan):
+    check(cases.OPTION_SETS[name], cases.adversarial_batch(1), name + "/adv", scan)
 
 
 @pytest.mark.parametrize("name", PLAIN_SETS)
@@ -39,7 +45,8 @@ def test_option_matrix_on_ont_like_reads(name):
 
 @pytest.mark.parametrize("n", sorted(cases.LONG_ADAPTERS))
 def test_long_adapters_every_size_class(n):
-    """-s / -e of 31..1024 bp: k_trim<0/1/2>, k_final<0/2>, the 64- / 128-bit and multi-word Myers forms"""
+    """-s / -e of 31..1024 bp: k_trim<0/1/2>, k_final<0/2>, the 64- / 128-bit and multi-word Myers forms; k_scan_jit with 5..8
+    count planes and 1..4 halo words up to 128 bp, the generic k_scan beyond"""
     check(cases.OPTION_SETS[f"long_adapter_{n}"], cases.long_adapter_batch(n, 900 + n, n=24), f"long{n}")
 
 
@@ -61,10 +68,11 @@ def test_rna_reads(name, mixed):
 
 def test_empty_tiny_and_very_long_reads():
     check(cases.OPTION_SETS["cut_polyx_cplx"], pack_reads([]), "empty")
-    reads = [(b"ACGTACGTACGTACGTACGT"[:n], bytes([33 + 30]) * n) for n in (0, 1, 2, 3, 4, 5, 6, 9, 15, 16, 17)] * 2
+    reads = [((b"ACGTTGCAAC" * 8)[:n], bytes([33 + 30]) * n) for n in (0, 1, 2, 3, 4, 5, 6, 9, 15, 16, 17, 31, 32, 33, 63, 64, 65)] * 2
     check(Options(disable_adapter_trimming=True, length_required=0), pack_reads(reads), "tiny")
     check(cases.OPTION_SETS["cut_polyx_cplx"], pack_reads(reads), "tiny/adapters")
     check(cases.OPTION_SETS["cut_polyx_cplx"], synth.ont_like(3, 60000, 5, p_chimera=1.0), "long reads")
+    check(cases.OPTION_SETS["cut_polyx_cplx"], synth.ont_like(3, 60000, 5, p_chimera=1.0), "long reads/generic", "generic")
 
 
 @pytest.mark.parametrize("family,count", [("random_case", 30), ("random_case_many_adapters", 15), ("random_case_long_reads", 6)])
