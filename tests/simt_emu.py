@@ -215,7 +215,9 @@ extern "C" int emu_process(const fpl_options* opt, const fpl_adapters* ad, const
     launch_trim(c->P, b, st.data(), results, c->d_counters, s);
     if (stats0 && launch_cycle_stats(&ws, hb->seq, hb->qual, pre.data(), nr, tmax, stats0, C, true, stats1 + 16 * C + FPL_STATS_KMER, slots16, s))
         return fail("launch_cycle_stats(pre) failed");
-    if (scan_override) { if (nr) scan_override(hb->seq, hb->qual, hb->offsets, st.data(), nr); }     // k_scan_jit (tests/simt_emu.py:JitScan)
+    if (scan_override == (scan_fn)1) {          // the precompiled bit-sliced kernel (FPL_NO_JIT), where fpl_create would use it
+        if (c->plan.fast) scanfast::launch_scan_fast(c->P, c->plan, b, st.data(), s); else launch_scan(c->P, b, st.data(), s);
+    } else if (scan_override) { if (nr) scan_override(hb->seq, hb->qual, hb->offsets, st.data(), nr); }     // k_scan_jit (jit_scan below)
     else launch_scan(c->P, b, st.data(), s);
     launch_final(c->P, b, st.data(), results, post.data(), s);
     launch_count(results, nr, c->d_counters, true, s);
@@ -238,7 +240,8 @@ PTX_WRAPPERS = ("prmt", "cp_async16", "cp_async4", "cp_async_commit", "cp_async_
 
 def source():
     dev = "\n".join([device_text("fpl_device.cuh", drop=("red_shared_add", "shared_addr")), device_text("fpl_trim.cu"),
-                     device_text("fpl_scan.cu"), '#include "fpl_stats.h"', device_text("fpl_stats.cu", drop=PTX_WRAPPERS)])
+                     device_text("fpl_scan.cu"), "namespace scanfast {", device_text("fpl_scan_fast.cu"), "}  // namespace scanfast",
+                     '#include "fpl_stats.h"', device_text("fpl_stats.cu", drop=PTX_WRAPPERS)])
     return HARNESS.replace("@@DEVICE@@", dev).replace("@@BUILDER@@", table_builder())
 
 
@@ -324,11 +327,12 @@ class EmuEngine:
     (the Stats kernels are skipped; the two median fields of the records stay 0)."""
 
     def __init__(self, options, with_stats=True, scan="generic"):
-        """scan = "generic": launch_scan (k_scan); "jit": k_scan_jit v2 specialised on the options where the library would
+        """scan = "generic": launch_scan (k_scan); "fast": launch_scan_fast (the precompiled k_scan_fast that FPL_NO_JIT selects) where
+        ScanPlan.fast allows it; "jit": k_scan_jit v2 specialised on the options where the library would
         specialise (self.jit tells), the generic kernel elsewhere."""
         self.lib = load()
-        self.scan_fn = jit_scan(options) if scan == "jit" else None
-        self.jit = self.scan_fn is not None
+        self.scan_fn = jit_scan(options) if scan == "jit" else C.cast(1, C.c_void_p) if scan == "fast" else None
+        self.jit = scan == "jit" and self.scan_fn is not None
         self.options = options
         self._abi = options.to_abi()
         self.n_adapters = 2 + len(options.adapter_fasta)

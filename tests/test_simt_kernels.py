@@ -17,7 +17,8 @@ from oracle_lib import OracleEngine, compare_results, compare_stats
 
 def check(opt, batch, what, scan="jit"):
     """scan = "jit": the whole-read scan is k_scan_jit v2, specialised on the options exactly where fpl_create would have NVRTC
-    specialise it (the emulator harness reports ScanPlan.fast, the product's own verdict); the generic k_scan elsewhere."""
+    specialise it (the emulator harness reports ScanPlan.fast, the product's own verdict); "fast": the precompiled k_scan_fast
+    (what FPL_NO_JIT or a missing NVRTC leaves) in the same places; the generic k_scan elsewhere and with "generic"."""
     e, o = simt_emu.EmuEngine(opt, scan=scan), OracleEngine(opt)
     if scan == "jit":
         assert e.jit == e.plan_fast(), what
@@ -32,7 +33,7 @@ def check(opt, batch, what, scan="jit"):
 PLAIN_SETS = sorted(n for n in cases.OPTION_SETS if not n.startswith("long_adapter_"))
 
 
-@pytest.mark.parametrize("scan", ["jit", "generic"])
+@pytest.mark.parametrize("scan", ["jit", "fast", "generic"])
 @pytest.mark.parametrize("name", PLAIN_SETS)
 def test_option_matrix_on_adversarial_reads(name, scan):
     check(cases.OPTION_SETS[name], cases.adversarial_batch(1), name + "/adv", scan)
@@ -48,6 +49,8 @@ def test_long_adapters_every_size_class(n):
     """-s / -e of 31..1024 bp: k_trim<0/1/2>, k_final<0/2>, the 64- / 128-bit and multi-word Myers forms; k_scan_jit with 5..8
     count planes and 1..4 halo words up to 128 bp, the generic k_scan beyond"""
     check(cases.OPTION_SETS[f"long_adapter_{n}"], cases.long_adapter_batch(n, 900 + n, n=24), f"long{n}")
+    if n <= 128:
+        check(cases.OPTION_SETS[f"long_adapter_{n}"], cases.long_adapter_batch(n, 900 + n, n=24), f"long{n}/fast", "fast")
 
 
 def test_config3_shape_64_entry_fasta():
@@ -85,3 +88,18 @@ def test_random_option_sets(family, count):
             continue
         check(opt, batch, f"{family}[{done}] {what}")
         done += 1
+
+
+def test_cycle_stats_bulk_copy_variant_in_a_subprocess():
+    """FPL_CS_TMA=1 (read once per process): k_cycle_stats<..., TMA = true>, whose rows arrive by one lane's bulk copies; the
+    emulator completes a bulk copy at issue, so this checks the variant's addressing and bookkeeping, not its mbarrier waits."""
+    import os
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import cases, test_simt_kernels as t\n"
+            "t.check(cases.OPTION_SETS['cut_polyx_cplx'], cases.adversarial_batch(1), 'tma/adv')\n"
+            "t.check(cases.OPTION_SETS['default_se'], cases.ont_batch(9, n=40, mean=3000, p_chimera=0.2), 'tma/ont')\n"
+            "print('TMA_VARIANT_OK')\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, env=dict(os.environ, FPL_CS_TMA="1"))
+    assert r.returncode == 0 and "TMA_VARIANT_OK" in r.stdout, r.stdout[-800:] + r.stderr[-1500:]
