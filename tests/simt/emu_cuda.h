@@ -55,6 +55,7 @@ struct Group {             // a warp or a block: the live threads that must all 
     unsigned gen = 0;
 };
 void yield();
+void note_progress();      // a waiting fiber's condition may have changed without a collective completing (mbarrier emulation)
 Group& warp();
 Group& block();
 int lane();

@@ -58,6 +58,7 @@ void* from_shared(uint32_t a) {
     return windows[i - 1] + (a & 0xFFFFFFu);
 }
 void yield() { swapcontext(&fibers[cur].ctx, &sched_ctx); }
+void note_progress() { progress = true; }
 Group& warp() { return warps[cur >> 5]; }
 Group& block() { return blk; }
 int lane() { return cur & 31; }
@@ -85,7 +86,7 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
     for (unsigned long long bb = 0; bb < (unsigned long long)grid.x * grid.y; bb++) {
         const unsigned b = (unsigned)(bb % grid.x);
         emu_blockIdx = {b, (unsigned)(bb / grid.x), 0};
-        memset(dynamic_smem, 0xCD, smem_bytes);           // shared memory is not zero at block start
+        { static const char* f = getenv("EMU_SMEM_FILL"); memset(dynamic_smem, f ? (int)strtol(f, nullptr, 0) : 0xCD, smem_bytes); }   // shared memory is not zero at block start
         fibers.assign((size_t)n, Fiber());
         warps.assign((size_t)((n + 31) / 32), Group());
         for (int w = 0; w < (int)warps.size(); w++) warps[w].alive = (w * 32 + 32 <= n) ? 32 : n - w * 32;

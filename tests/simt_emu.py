@@ -162,10 +162,17 @@ static inline void cp_async_commit() {}
 template <int N> static inline void cp_async_wait() {}
 static inline uint4 lds128(uint32_t a) { uint4 v; memcpy(&v, emu::from_shared(a), 16); return v; }
 static inline uint32_t lds32(uint32_t a) { uint32_t v; memcpy(&v, emu::from_shared(a), 4); return v; }
-static inline void mbar_init(uint32_t, uint32_t) {}
-static inline void mbar_expect_tx(uint32_t, uint32_t) {}
-static inline void mbar_wait(uint32_t, uint32_t) {}
-static inline void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t) { memcpy(emu::from_shared(dst), src, bytes); }
+// mbarrier with one expected arrival + a transaction count, in its 8 bytes of shared memory: {completed phases, pending}.
+// A bulk copy completes at issue (one legal order); the phase completes when the arrival has happened and no bytes are pending.
+struct EmuMbar { uint32_t phase; int32_t pending; };       // pending: bytes still to arrive, +2^30 while the arrival is outstanding
+static inline void mbar_init(uint32_t bar, uint32_t) { EmuMbar* m = (EmuMbar*)emu::from_shared(bar); m->phase = 0; m->pending = 1 << 30; }
+static inline void mbar_settle(EmuMbar* m) { if (m->pending == 0) { m->phase++; m->pending = 1 << 30; emu::note_progress(); } }
+static inline void mbar_expect_tx(uint32_t bar, uint32_t bytes) { EmuMbar* m = (EmuMbar*)emu::from_shared(bar); m->pending += (int32_t)bytes - (1 << 30); mbar_settle(m); }
+static inline void mbar_wait(uint32_t bar, uint32_t parity) { EmuMbar* m = (EmuMbar*)emu::from_shared(bar); while ((m->phase & 1u) == parity) emu::yield(); }
+static inline void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    memcpy(emu::from_shared(dst), src, bytes);
+    EmuMbar* m = (EmuMbar*)emu::from_shared(bar); m->pending -= (int32_t)bytes; mbar_settle(m);
+}
 
 @@DEVICE@@
 
