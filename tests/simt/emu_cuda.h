@@ -64,6 +64,7 @@ int tid_in_block();
 Group& collect(Group& g, int index, uint64_t v);
 void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()>& body);
 extern long long collectives;
+extern unsigned long long block_serial;      // counts the blocks run so far (per-thread emulation state resets on a new block)
 extern uint8_t* dynamic_smem;          // `extern __shared__` of the running kernel
 // 32-bit "shared window" addresses (what cvta.to.shared yields on the device): a 16 MB window per region of host memory
 uint32_t to_shared(const void* p);

@@ -7,6 +7,7 @@ dim3 emu_blockDim, emu_gridDim;
 
 namespace emu {
 long long collectives = 0;
+unsigned long long block_serial = 0;
 uint8_t* dynamic_smem = nullptr;
 namespace {
 std::vector<char*> windows;          // base of each 16 MB shared window
@@ -86,6 +87,7 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
     for (unsigned long long bb = 0; bb < (unsigned long long)grid.x * grid.y; bb++) {
         const unsigned b = (unsigned)(bb % grid.x);
         emu_blockIdx = {b, (unsigned)(bb / grid.x), 0};
+        block_serial++;
         { static const char* f = getenv("EMU_SMEM_FILL"); memset(dynamic_smem, f ? (int)strtol(f, nullptr, 0) : 0xCD, smem_bytes); }   // shared memory is not zero at block start
         fibers.assign((size_t)n, Fiber());
         warps.assign((size_t)((n + 31) / 32), Group());

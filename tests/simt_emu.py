@@ -155,11 +155,28 @@ static inline uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {       // prm
     }
     return d;
 }
-// cp.async completes at an unspecified time before the matching wait; completing it at once is one legal order
-static inline void cp_async16(uint32_t dst, const void* src, int n) { uint8_t* d = (uint8_t*)emu::from_shared(dst); if (n > 0) memcpy(d, src, n); memset(d + n, 0, 16 - n); }
-static inline void cp_async4(uint32_t dst, const void* src, int n) { uint8_t* d = (uint8_t*)emu::from_shared(dst); if (n > 0) memcpy(d, src, n); memset(d + n, 0, 4 - n); }
-static inline void cp_async_commit() {}
-template <int N> static inline void cp_async_wait() {}
+// cp.async completes at an unspecified time between its issue and the wait that covers its group.  Both extremes are
+// emulated: eager (at issue) and lazy (at that wait, the default) — under the lazy order a thread that reads bytes another
+// thread copied, without a barrier behind that thread's wait, sees the stale slot (the hazard racecheck reports on the GPU).
+static int g_cp_lazy = 1;
+extern "C" void emu_set_cp_async_lazy(int on) { g_cp_lazy = on; }
+struct EmuCopy { uint8_t* dst; const uint8_t* src; int n, size; };
+struct EmuCopyQueue { unsigned long long serial = 0; std::vector<EmuCopy> open; std::vector<std::vector<EmuCopy>> groups; };
+static EmuCopyQueue g_cpq[1024];
+static inline EmuCopyQueue& cpq() { EmuCopyQueue& q = g_cpq[emu::tid_in_block()]; if (q.serial != emu::block_serial) { q.serial = emu::block_serial; q.open.clear(); q.groups.clear(); } return q; }
+static inline void emu_copy_now(const EmuCopy& c) { if (c.n > 0) memcpy(c.dst, c.src, c.n); memset(c.dst + c.n, 0, c.size - c.n); }
+static inline void cp_async_any(uint32_t dst, const void* src, int n, int size) {
+    EmuCopy c = {(uint8_t*)emu::from_shared(dst), (const uint8_t*)src, n, size};
+    if (g_cp_lazy) cpq().open.push_back(c); else emu_copy_now(c);
+}
+static inline void cp_async16(uint32_t dst, const void* src, int n) { cp_async_any(dst, src, n, 16); }
+static inline void cp_async4(uint32_t dst, const void* src, int n) { cp_async_any(dst, src, n, 4); }
+static inline void cp_async_commit() { if (g_cp_lazy) { EmuCopyQueue& q = cpq(); q.groups.push_back(q.open); q.open.clear(); } }
+template <int N> static inline void cp_async_wait() {      // all but the N most recent groups of this thread are complete
+    if (!g_cp_lazy) return;
+    EmuCopyQueue& q = cpq();
+    while ((int)q.groups.size() > N) { for (const EmuCopy& c : q.groups.front()) emu_copy_now(c); q.groups.erase(q.groups.begin()); }
+}
 static inline uint4 lds128(uint32_t a) { uint4 v; memcpy(&v, emu::from_shared(a), 16); return v; }
 static inline uint32_t lds32(uint32_t a) { uint32_t v; memcpy(&v, emu::from_shared(a), 4); return v; }
 // mbarrier with one expected arrival + a transaction count, in its 8 bytes of shared memory: {completed phases, pending}.
@@ -271,6 +288,7 @@ def load():
                                "-I", CSRC, "-o", so, cpp])
     lib = C.CDLL(so)
     lib.emu_last_error.restype = C.c_char_p
+    lib.emu_set_cp_async_lazy.argtypes = [C.c_int]
     lib.emu_collectives.restype = C.c_longlong
     lib.emu_process.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                 C.c_int64, C.c_void_p, C.POINTER(C.c_int)]

@@ -103,3 +103,16 @@ def test_cycle_stats_bulk_copy_variant_in_a_subprocess():
             "print('TMA_VARIANT_OK')\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, env=dict(os.environ, FPL_CS_TMA="1"))
     assert r.returncode == 0 and "TMA_VARIANT_OK" in r.stdout, r.stdout[-800:] + r.stderr[-1500:]
+
+
+def test_cp_async_completion_order_does_not_matter():
+    """cp.async may complete anywhere between its issue and the wait covering its group: the emulator's default is the latest
+    legal moment, this repeats two batches with the earliest one (a kernel correct under both extremes does not lean on when
+    the copies land; removing the warp barrier behind k_cycle_stats' wait fails under both, as racecheck reported on the GPU)."""
+    lib = simt_emu.load()
+    try:
+        lib.emu_set_cp_async_lazy(0)
+        check(cases.OPTION_SETS["cut_polyx_cplx"], cases.adversarial_batch(2), "eager/adv")
+        check(cases.OPTION_SETS["default_se"], cases.ont_batch(9, n=40, mean=3000, p_chimera=0.2), "eager/ont")
+    finally:
+        lib.emu_set_cp_async_lazy(1)
