@@ -80,7 +80,7 @@ def _rewrite_launches(text):
 
 def device_text(fn, drop=()):
     text = open(os.path.join(CSRC, fn)).read()
-    text = re.sub(r'^\s*#include\s+[<"](cuda_runtime\.h|fpl_device\.cuh|cuda\.h|cub/cub\.cuh)[>"].*$', "", text, flags=re.M)
+    text = re.sub(r'^\s*#include\s+[<"](cuda_runtime\.h|fpl_device\.cuh|cuda\.h|cub/[\w/.]+|fpl_ext\.h|fpl_ingest\.h|fpl_emit\.h)[>"].*$', "", text, flags=re.M)
     text = text.replace("#pragma once", "")
     text = re.sub(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?(\w+)\s+(\w+)\[\];", r"\1* \2 = (\1*)emu::dynamic_smem;", text)
     text = re.sub(r'asm\s+volatile\s*\(\s*"fence[^"]*"[^;]*;', ";", text)
@@ -135,6 +135,15 @@ struct DeviceRadixSort {      // a stable LSD radix sort on key bits [begin_bit,
         const K mask = end_bit - begin_bit >= (int)(8 * sizeof(K)) ? ~(K)0 : (K)((((K)1 << (end_bit - begin_bit)) - 1) << begin_bit);
         std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return (kin[a] & mask) > (kin[b] & mask); });
         for (int i = 0; i < n; i++) { kout[i] = kin[idx[i]]; vout[i] = vin[idx[i]]; }
+        return cudaSuccess;
+    }
+};
+struct DeviceScan {
+    template <class I, class O>
+    static cudaError_t ExclusiveSum(void* tmp, size_t& bytes, I in, O out, int64_t n, cudaStream_t = nullptr) {
+        if (!tmp) { bytes = 64; return cudaSuccess; }
+        typename std::remove_reference<decltype(out[0])>::type acc = 0;
+        for (int64_t i = 0; i < n; i++) { auto v = in[i]; out[i] = acc; acc += v; }       // in may alias out
         return cudaSuccess;
     }
 };
@@ -214,7 +223,8 @@ extern "C" long long emu_collectives() { return emu::collectives; }
 typedef void (*scan_fn)(const uint8_t*, const uint8_t*, const int64_t*, void*, int64_t);
 extern "C" int emu_process(const fpl_options* opt, const fpl_adapters* ad, const fpl_batch* hb, fpl_read_result* results,
                            unsigned long long* counters, int64_t n_counter_words, unsigned long long* stats0,
-                           unsigned long long* stats1, int64_t C, scan_fn scan_override, int* plan_fast) {
+                           unsigned long long* stats1, int64_t C, scan_fn scan_override, int* plan_fast, fpl_segment* segs_out,
+                           int64_t segs_cap, int64_t* n_segs, fpl_region* regs_out, int64_t regs_cap, int64_t* n_regs) {
     g_err[0] = 0;
     const int n = 2 + (ad->n_fasta > 0 ? ad->n_fasta : 0);
     EmuCtx* c = new EmuCtx();
@@ -237,13 +247,35 @@ extern "C" int emu_process(const fpl_options* opt, const fpl_adapters* ad, const
     cudaStream_t s = nullptr;
     if (stats0) launch_make_preseg(b, pre.data(), s);
     launch_trim(c->P, b, st.data(), results, c->d_counters, s);
-    if (stats0 && launch_cycle_stats(&ws, hb->seq, hb->qual, pre.data(), nr, tmax, stats0, C, true, stats1 + 16 * C + FPL_STATS_KMER, slots16, s))
+    const bool ext = c->P.opt.mask_enabled || c->P.opt.break_enabled;   // variable number of output reads: run_batch's other branch
+    if (stats0 && launch_cycle_stats(&ws, hb->seq, hb->qual, pre.data(), nr, tmax, stats0, C, true,
+                                     ext ? nullptr : stats1 + 16 * C + FPL_STATS_KMER, slots16, s))
         return fail("launch_cycle_stats(pre) failed");
     if (scan_override == (scan_fn)1) {          // the precompiled bit-sliced kernel (FPL_NO_JIT), where fpl_create would use it
         if (c->plan.fast) scanfast::launch_scan_fast(c->P, c->plan, b, st.data(), s); else launch_scan(c->P, b, st.data(), s);
     } else if (scan_override) { if (nr) scan_override(hb->seq, hb->qual, hb->offsets, st.data(), nr); }     // k_scan_jit (jit_scan below)
     else launch_scan(c->P, b, st.data(), s);
     launch_final(c->P, b, st.data(), results, post.data(), s);
+    if (ext) {          // --mask / --break (needs the Stats blocks)
+        if (!stats0) { fpl_destroy(c); return fail("--mask/--break needs the Stats blocks"); }
+        extns::FplExt x;
+        char xerr[256] = "";
+        const uint8_t* fseq = hb->seq;
+        launch_read_qual(b, stats0, stats1, C, results, true, s);
+        launch_count(results, nr, c->d_counters, false, s);
+        if (extns::fpl_ext_run(&x, c->P, b, hb->n_bytes, results, c->d_counters, stats1, C, &fseq, s, xerr, sizeof(xerr))) return fail("ext: %s", xerr);
+        if (launch_cycle_stats(&ws, fseq, hb->qual, x.d_stat, x.n_segs, tmax, stats1, C, true, nullptr, false, s)) return fail("launch_cycle_stats(ext) failed");
+        if (n_segs) *n_segs = x.n_segs;
+        if (n_regs) *n_regs = x.n_regs;
+        if (x.n_segs > segs_cap || x.n_regs > regs_cap) return fail("segment / region capacity");
+        if (x.n_segs) memcpy(segs_out, x.d_segs, sizeof(fpl_segment) * (size_t)x.n_segs);
+        if (x.n_regs) memcpy(regs_out, x.d_regs, sizeof(fpl_region) * (size_t)x.n_regs);
+        extns::fpl_ext_free(&x);
+        fpl_cycle_ws_free(&ws);
+        memcpy(counters, c->d_counters, sizeof(unsigned long long) * (size_t)c->counter_words);
+        fpl_destroy(c);
+        return 0;
+    }
     launch_count(results, nr, c->d_counters, true, s);
     if (stats0) {
         if (launch_cycle_stats(&ws, hb->seq, hb->qual, post.data(), 2 * nr, tmax, stats1, C, false, nullptr, false, s))
@@ -265,7 +297,8 @@ PTX_WRAPPERS = ("prmt", "cp_async16", "cp_async4", "cp_async_commit", "cp_async_
 def source():
     dev = "\n".join([device_text("fpl_device.cuh", drop=("red_shared_add", "shared_addr")), device_text("fpl_trim.cu"),
                      device_text("fpl_scan.cu"), "namespace scanfast {", device_text("fpl_scan_fast.cu"), "}  // namespace scanfast",
-                     '#include "fpl_stats.h"', device_text("fpl_stats.cu", drop=PTX_WRAPPERS)])
+                     '#include "fpl_stats.h"', device_text("fpl_stats.cu", drop=PTX_WRAPPERS), "namespace extns {",
+                     device_text("fpl_ext.h"), device_text("fpl_ext.cu"), "}  // namespace extns"])
     return HARNESS.replace("@@DEVICE@@", dev).replace("@@BUILDER@@", table_builder())
 
 
@@ -291,7 +324,8 @@ def load():
     lib.emu_set_cp_async_lazy.argtypes = [C.c_int]
     lib.emu_collectives.restype = C.c_longlong
     lib.emu_process.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
-                                C.c_int64, C.c_void_p, C.POINTER(C.c_int)]
+                                C.c_int64, C.c_void_p, C.POINTER(C.c_int), C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p, C.c_int64,
+                                C.POINTER(C.c_int64)]
     _lib = lib
     return lib
 
@@ -377,9 +411,14 @@ class EmuEngine:
             cyc = 1 << int(np.ceil(np.log2(need)))
             s0 = np.zeros(abi.stats_words(cyc), dtype=np.int64)
             s1 = np.zeros(abi.stats_words(cyc), dtype=np.int64)
+        segs = np.zeros(64 * batch.n_reads + 4096 if (self.options.mask or self.options.break_reads) else 1, dtype=abi.SEGMENT_DTYPE)
+        regs = np.zeros(len(segs), dtype=abi.REGION_DTYPE)
+        n_segs, n_regs = C.c_int64(0), C.c_int64(0)
         rc = self.lib.emu_process(C.addressof(o), C.addressof(ad), C.addressof(b), res.ctypes.data, cnt.ctypes.data, cnt.shape[0],
                                   s0.ctypes.data if s0 is not None else None, s1.ctypes.data if s1 is not None else None, cyc,
-                                  C.cast(self.scan_fn, C.c_void_p) if self.scan_fn is not None else None, None)
+                                  C.cast(self.scan_fn, C.c_void_p) if self.scan_fn is not None else None, None,
+                                  segs.ctypes.data, segs.shape[0], C.byref(n_segs), regs.ctypes.data, regs.shape[0], C.byref(n_regs))
+        self._segs, self._regs = segs[:n_segs.value].copy(), regs[:n_regs.value].copy()
         if rc != 0:
             raise RuntimeError(self.lib.emu_last_error().decode())
         self._counters += cnt
@@ -393,11 +432,19 @@ class EmuEngine:
                 self._C = c2
         return res
 
+    def segments(self):
+        """--mask/--break: every output read of the last process() call (fpl_last_segments)"""
+        return self._segs
+
+    def mask_regions(self):
+        return self._regs
+
     def plan_fast(self):
         """fpl_create's own verdict (ScanPlan.fast): may the bit-sliced scan kernels be used for these adapters"""
         o, ad, keep = self._abi
         v = C.c_int(-1)
-        rc = self.lib.emu_process(C.addressof(o), C.addressof(ad), None, None, None, 0, None, None, 0, None, C.byref(v))
+        rc = self.lib.emu_process(C.addressof(o), C.addressof(ad), None, None, None, 0, None, None, 0, None, C.byref(v), None, 0, None,
+                                  None, 0, None)
         assert rc == 0
         return bool(v.value)
 

@@ -1,6 +1,6 @@
 """The kernels of libfplgpu's default path — k_make_preseg, k_trim, k_trim_fasta, k_cs_keys / k_cs_gather, k_cycle_stats (both
 variants; cp.async ring, packed shared-memory counters, lane-private 5-mer tables), the generic k_scan, k_final, k_count,
-k_kmer_fix, k_read_qual — and k_scan_jit v2, the source fpl_jit.cu generates for the options' adapters (what NVRTC compiles on
+k_kmer_fix, k_read_qual, the --mask/--break kernels of fpl_ext.cu — and k_scan_jit v2, the source fpl_jit.cu generates for the options' adapters (what NVRTC compiles on
 the GPU): their own source text, executed on the CPU under the SIMT emulator (tests/simt_emu.py, tests/simt/emu_cuda.h) in
 run_batch's order — against the oracle, on the whole option matrix, the crafted boundary cases,
 RNA reads and seeded random cases: every field of every record, every word of both Stats blocks, every counter."""
@@ -12,7 +12,7 @@ import pytest
 import cases
 import simt_emu
 from fastplong_b200 import Options, pack_reads, synth
-from oracle_lib import OracleEngine, compare_results, compare_stats
+from oracle_lib import OracleEngine, compare_lists, compare_results, compare_stats
 
 
 def check(opt, batch, what, scan="jit"):
@@ -23,6 +23,9 @@ def check(opt, batch, what, scan="jit"):
     if scan == "jit":
         assert e.jit == e.plan_fast(), what
     compare_results(e.process(batch), o.process(batch), what)
+    if opt.mask or opt.break_reads:
+        compare_lists(e.segments(), o.segments(), what + "/segments")
+        compare_lists(e.mask_regions(), o.mask_regions(), what + "/regions")
     cyc = max(1, int(batch.lens.max()) if batch.n_reads else 1)
     for w in (0, 1):
         compare_stats(e.stats(w, cyc), o.stats(w, cyc), f"{what}/stats{w}")
@@ -69,6 +72,15 @@ def test_rna_reads(name, mixed):
     check(cases.RNA_SETS[name], cases.rna_batch(41, n=60, mean=1200, mixed=mixed), f"{name}/{int(mixed)}")
 
 
+@pytest.mark.parametrize("name", sorted(cases.MASK_BREAK_SETS))
+@pytest.mark.parametrize("kind", ["blocky", "adversarial"])
+def test_mask_and_break(name, kind):
+    """--mask / --break (fpl_ext.cu: k_ext_count / emit / mask_count / mask_emit / filter / seg_qual / fill_records around two
+    exclusive scans): records, the output-read list, the masked regions, the post-filter Stats over the masked bases"""
+    batch = cases.blocky_quality_batch(5, n=60) if kind == "blocky" else cases.adversarial_batch(3)
+    check(cases.MASK_BREAK_SETS[name], batch, f"{name}/{kind}")
+
+
 def test_empty_tiny_and_very_long_reads():
     check(cases.OPTION_SETS["cut_polyx_cplx"], pack_reads([]), "empty")
     reads = [((b"ACGTTGCAAC" * 8)[:n], bytes([33 + 30]) * n) for n in (0, 1, 2, 3, 4, 5, 6, 9, 15, 16, 17, 31, 32, 33, 63, 64, 65)] * 2
@@ -84,8 +96,6 @@ def test_random_option_sets(family, count):
     done = 0
     while done < count:
         opt, batch, what = getattr(cases, family)(rng)
-        if opt.mask or opt.break_reads:            # fpl_ext.cu is not emulated
-            continue
         check(opt, batch, f"{family}[{done}] {what}")
         done += 1
 
