@@ -138,6 +138,21 @@ struct DeviceRadixSort {      // a stable LSD radix sort on key bits [begin_bit,
         return cudaSuccess;
     }
 };
+template <class T> struct CountingInputIterator {
+    T base;
+    explicit CountingInputIterator(T b) : base(b) {}
+    T operator[](int64_t i) const { return base + (T)i; }
+};
+struct DeviceSelect {
+    template <class In, class Out, class Num, class Pred>
+    static cudaError_t If(void* tmp, size_t& bytes, In in, Out out, Num num_out, int64_t n, Pred pred, cudaStream_t = nullptr) {
+        if (!tmp) { bytes = 64; return cudaSuccess; }
+        int64_t k = 0;
+        for (int64_t i = 0; i < n; i++) { const auto v = in[i]; if (pred(v)) out[k++] = v; }
+        *num_out = k;
+        return cudaSuccess;
+    }
+};
 struct DeviceScan {
     template <class I, class O>
     static cudaError_t ExclusiveSum(void* tmp, size_t& bytes, I in, O out, int64_t n, cudaStream_t = nullptr) {
@@ -217,76 +232,149 @@ static void fpl_destroy(EmuCtx* c) {
 extern "C" const char* emu_last_error() { return g_err; }
 extern "C" long long emu_collectives() { return emu::collectives; }
 
-// processSingleEnd over a packed batch in run_batch's order (fpl_api.cu), on host memory.  stats0 / stats1: FPL_STATS_WORDS(C)
-// words each (zeroed by the caller; may be null: records and counters only, the Stats kernels are skipped and the two
-// median fields stay 0).  tma: the FPL_CS_TMA staging variant of k_cycle_stats.
 typedef void (*scan_fn)(const uint8_t*, const uint8_t*, const int64_t*, void*, int64_t);
-extern "C" int emu_process(const fpl_options* opt, const fpl_adapters* ad, const fpl_batch* hb, fpl_read_result* results,
-                           unsigned long long* counters, int64_t n_counter_words, unsigned long long* stats0,
-                           unsigned long long* stats1, int64_t C, scan_fn scan_override, int* plan_fast, fpl_segment* segs_out,
-                           int64_t segs_cap, int64_t* n_segs, fpl_region* regs_out, int64_t regs_cap, int64_t* n_regs) {
+
+static EmuCtx* emu_create(const fpl_options* opt, const fpl_adapters* ad) {
     g_err[0] = 0;
     const int n = 2 + (ad->n_fasta > 0 ? ad->n_fasta : 0);
     EmuCtx* c = new EmuCtx();
     c->n_adapters = n;
     auto stamp = [](const char*) {};
+    auto body = [&]() -> int {
 @@BUILDER@@
-    if (plan_fast) *plan_fast = c->plan.fast;
-    if (!hb) { fpl_destroy(c); return 0; }                              // only the tables were wanted
-    if (n_counter_words != c->counter_words) { fpl_destroy(c); return fail("counter words %lld != %lld", (long long)n_counter_words, (long long)c->counter_words); }
-    const int64_t nr = hb->n_reads;
-    DevBatch b = {hb->seq, hb->qual, hb->offsets, hb->lens, nr};
+        return 0;
+    };
+    if (body()) return nullptr;         // (the builder's error paths have destroyed c)
+    return c;
+}
+
+// run_batch's kernel order (fpl_api.cu) over a batch in host memory.  stats0 / stats1: FPL_STATS_WORDS(C) words each, zeroed by the
+// caller; null: records and counters only (the Stats kernels are skipped, the two median fields stay 0).  keep: where the --mask/--break
+// lists stay alive for the caller (freed by the caller).
+static int emu_run(EmuCtx* c, const DevBatch& b, int64_t n_bytes, fpl_read_result* results, unsigned long long* stats0,
+                   unsigned long long* stats1, int64_t C, scan_fn scan_override, extns::FplExt* keep) {
+    const int64_t nr = b.n_reads;
     std::vector<ReadState> st((size_t)nr + 1);
     std::vector<StatSeg> pre((size_t)nr + 1), post(2 * (size_t)nr + 2);
     int64_t tmax = 0;
     bool slots16 = true;
-    for (int64_t i = 0; i < nr; i++) { if (hb->lens[i] > tmax) tmax = hb->lens[i]; if (hb->offsets[i] & 15) slots16 = false; }
-    if (stats0 && tmax > C) { fpl_destroy(c); return fail("C too small"); }
+    for (int64_t i = 0; i < nr; i++) { if (b.lens[i] > tmax) tmax = b.lens[i]; if (b.offsets[i] & 15) slots16 = false; }
+    if (stats0 && tmax > C) return fail("C too small");
     memset(results, 0xAB, sizeof(fpl_read_result) * (size_t)nr);          // k_trim must write every record
     CycleWs ws;
     cudaStream_t s = nullptr;
+    const bool ext = c->P.opt.mask_enabled || c->P.opt.break_enabled;   // variable number of output reads: run_batch's other branch
     if (stats0) launch_make_preseg(b, pre.data(), s);
     launch_trim(c->P, b, st.data(), results, c->d_counters, s);
-    const bool ext = c->P.opt.mask_enabled || c->P.opt.break_enabled;   // variable number of output reads: run_batch's other branch
-    if (stats0 && launch_cycle_stats(&ws, hb->seq, hb->qual, pre.data(), nr, tmax, stats0, C, true,
+    if (stats0 && launch_cycle_stats(&ws, b.seq, b.qual, pre.data(), nr, tmax, stats0, C, true,
                                      ext ? nullptr : stats1 + 16 * C + FPL_STATS_KMER, slots16, s))
         return fail("launch_cycle_stats(pre) failed");
     if (scan_override == (scan_fn)1) {          // the precompiled bit-sliced kernel (FPL_NO_JIT), where fpl_create would use it
         if (c->plan.fast) scanfast::launch_scan_fast(c->P, c->plan, b, st.data(), s); else launch_scan(c->P, b, st.data(), s);
-    } else if (scan_override) { if (nr) scan_override(hb->seq, hb->qual, hb->offsets, st.data(), nr); }     // k_scan_jit (jit_scan below)
+    } else if (scan_override) { if (nr) scan_override(b.seq, b.qual, b.offsets, st.data(), nr); }     // k_scan_jit (jit_scan below)
     else launch_scan(c->P, b, st.data(), s);
     launch_final(c->P, b, st.data(), results, post.data(), s);
     if (ext) {          // --mask / --break (needs the Stats blocks)
-        if (!stats0) { fpl_destroy(c); return fail("--mask/--break needs the Stats blocks"); }
-        extns::FplExt x;
+        if (!stats0) return fail("--mask/--break needs the Stats blocks");
+        extns::FplExt local;
+        extns::FplExt& x = keep ? *keep : local;
         char xerr[256] = "";
-        const uint8_t* fseq = hb->seq;
+        const uint8_t* fseq = b.seq;
         launch_read_qual(b, stats0, stats1, C, results, true, s);
         launch_count(results, nr, c->d_counters, false, s);
-        if (extns::fpl_ext_run(&x, c->P, b, hb->n_bytes, results, c->d_counters, stats1, C, &fseq, s, xerr, sizeof(xerr))) return fail("ext: %s", xerr);
-        if (launch_cycle_stats(&ws, fseq, hb->qual, x.d_stat, x.n_segs, tmax, stats1, C, true, nullptr, false, s)) return fail("launch_cycle_stats(ext) failed");
-        if (n_segs) *n_segs = x.n_segs;
-        if (n_regs) *n_regs = x.n_regs;
-        if (x.n_segs > segs_cap || x.n_regs > regs_cap) return fail("segment / region capacity");
-        if (x.n_segs) memcpy(segs_out, x.d_segs, sizeof(fpl_segment) * (size_t)x.n_segs);
-        if (x.n_regs) memcpy(regs_out, x.d_regs, sizeof(fpl_region) * (size_t)x.n_regs);
-        extns::fpl_ext_free(&x);
+        if (extns::fpl_ext_run(&x, c->P, b, n_bytes, results, c->d_counters, stats1, C, &fseq, s, xerr, sizeof(xerr))) return fail("ext: %s", xerr);
+        if (launch_cycle_stats(&ws, fseq, b.qual, x.d_stat, x.n_segs, tmax, stats1, C, true, nullptr, false, s)) return fail("launch_cycle_stats(ext) failed");
+        if (!keep) extns::fpl_ext_free(&x);
         fpl_cycle_ws_free(&ws);
-        memcpy(counters, c->d_counters, sizeof(unsigned long long) * (size_t)c->counter_words);
-        fpl_destroy(c);
         return 0;
     }
     launch_count(results, nr, c->d_counters, true, s);
     if (stats0) {
-        if (launch_cycle_stats(&ws, hb->seq, hb->qual, post.data(), 2 * nr, tmax, stats1, C, false, nullptr, false, s))
+        if (launch_cycle_stats(&ws, b.seq, b.qual, post.data(), 2 * nr, tmax, stats1, C, false, nullptr, false, s))
             return fail("launch_cycle_stats(post) failed");
         launch_kmer_fix(b, results, stats1 + 16 * C + FPL_STATS_KMER, s);
         launch_read_qual(b, stats0, stats1, C, results, false, s);
         fpl_cycle_ws_free(&ws);
     }
-    memcpy(counters, c->d_counters, sizeof(unsigned long long) * (size_t)c->counter_words);
-    fpl_destroy(c);
     return 0;
+}
+
+// fpl_process_host's work (minus the copies): a packed batch -> records, counters, Stats, -N/-b lists
+extern "C" int emu_process(const fpl_options* opt, const fpl_adapters* ad, const fpl_batch* hb, fpl_read_result* results,
+                           unsigned long long* counters, int64_t n_counter_words, unsigned long long* stats0,
+                           unsigned long long* stats1, int64_t C, scan_fn scan_override, int* plan_fast, fpl_segment* segs_out,
+                           int64_t segs_cap, int64_t* n_segs, fpl_region* regs_out, int64_t regs_cap, int64_t* n_regs) {
+    EmuCtx* c = emu_create(opt, ad);
+    if (!c) return -1;
+    if (plan_fast) *plan_fast = c->plan.fast;
+    if (!hb) { fpl_destroy(c); return 0; }                              // only the tables were wanted
+    if (n_counter_words != c->counter_words) { fpl_destroy(c); return fail("counter words %lld != %lld", (long long)n_counter_words, (long long)c->counter_words); }
+    DevBatch b = {hb->seq, hb->qual, hb->offsets, hb->lens, hb->n_reads};
+    extns::FplExt x;
+    int rc = emu_run(c, b, hb->n_bytes, results, stats0, stats1, C, scan_override, &x);
+    if (!rc) {
+        if (n_segs) *n_segs = x.n_segs;
+        if (n_regs) *n_regs = x.n_regs;
+        if (x.n_segs > segs_cap || x.n_regs > regs_cap) rc = fail("segment / region capacity");
+        else {
+            if (x.n_segs) memcpy(segs_out, x.d_segs, sizeof(fpl_segment) * (size_t)x.n_segs);
+            if (x.n_regs) memcpy(regs_out, x.d_regs, sizeof(fpl_region) * (size_t)x.n_regs);
+        }
+        memcpy(counters, c->d_counters, sizeof(unsigned long long) * (size_t)c->counter_words);
+    }
+    extns::fpl_ext_free(&x);
+    fpl_destroy(c);
+    return rc;
+}
+
+// fpl_process_fastq_host + fpl_emit_fastq_host (fpl_api.cu) on host memory: a chunk of FASTQ text -> record table, records,
+// counters, Stats and the --out / --failed_out text.  Returns 1 where the device parser refuses the layout.
+extern "C" int emu_process_fastq(const fpl_options* opt, const fpl_adapters* ad, const uint8_t* text, int64_t n_bytes, int is_last,
+                                 fpl_fastq_record* records, fpl_read_result* results, int64_t max_records, int64_t* n_records,
+                                 int64_t* consumed, unsigned long long* counters, unsigned long long* stats0, unsigned long long* stats1,
+                                 int64_t C, scan_fn scan_override, int want_failed, uint8_t* out, int64_t out_cap, int64_t* out_bytes,
+                                 uint8_t* failed, int64_t failed_cap, int64_t* failed_bytes) {
+    EmuCtx* c = emu_create(opt, ad);
+    if (!c) return -1;
+    ingestns::FplIngest g;
+    char err[256] = "";
+    int64_t nrec = 0;
+    *out_bytes = *failed_bytes = 0;
+    int rc = ingestns::fpl_ingest_index(&g, text, n_bytes, is_last, nullptr, &nrec, consumed, err, sizeof(err));
+    if (rc < 0) { fpl_destroy(c); return fail("ingest: %s", err); }
+    if (rc > 0 || nrec > max_records) { ingestns::fpl_ingest_free(&g); fpl_destroy(c); return 1; }
+    *n_records = nrec;
+    std::vector<uint8_t> d_seq((size_t)g.packed_bytes + 64, 0), d_qual((size_t)g.packed_bytes + 64, 0);
+    extns::FplExt x;
+    emitns::FplEmit e;
+    if (nrec) {
+        if (ingestns::fpl_ingest_pack(&g, nrec, d_seq.data(), d_qual.data(), nullptr, err, sizeof(err))) rc = fail("pack: %s", err);
+        memcpy(records, g.d_rec, sizeof(fpl_fastq_record) * (size_t)nrec);
+        DevBatch b = {d_seq.data(), d_qual.data(), g.d_offsets, g.d_lens, nrec};
+        if (!rc) rc = emu_run(c, b, g.packed_bytes, results, stats0, stats1, C, scan_override, &x);
+        if (!rc) {
+            const bool ext = c->P.opt.mask_enabled || c->P.opt.break_enabled;
+            emitns::EmitSource src;
+            src.text = g.d_text; src.rec = g.d_rec; src.res = results; src.n_reads = nrec;
+            src.segs = ext ? x.d_segs : nullptr;
+            src.seg_off = ext ? x.d_off : nullptr;
+            src.mseq = (c->P.opt.mask_enabled && x.n_segs > 0) ? x.d_mseq : nullptr;
+            src.offsets = g.d_offsets;
+            if (emitns::fpl_emit_build(&e, src, want_failed != 0, nullptr, err, sizeof(err))) rc = fail("emit: %s", err);
+            else if (e.out_bytes > out_cap || e.failed_bytes > failed_cap) rc = fail("text capacity");
+            else {
+                *out_bytes = e.out_bytes; *failed_bytes = e.failed_bytes;
+                if (e.out_bytes) memcpy(out, e.d_out, (size_t)e.out_bytes);
+                if (e.failed_bytes) memcpy(failed, e.d_failed, (size_t)e.failed_bytes);
+            }
+        }
+    }
+    memcpy(counters, c->d_counters, sizeof(unsigned long long) * (size_t)c->counter_words);
+    emitns::fpl_emit_free(&e);
+    extns::fpl_ext_free(&x);
+    ingestns::fpl_ingest_free(&g);
+    fpl_destroy(c);
+    return rc;
 }
 """
 
@@ -298,7 +386,9 @@ def source():
     dev = "\n".join([device_text("fpl_device.cuh", drop=("red_shared_add", "shared_addr")), device_text("fpl_trim.cu"),
                      device_text("fpl_scan.cu"), "namespace scanfast {", device_text("fpl_scan_fast.cu"), "}  // namespace scanfast",
                      '#include "fpl_stats.h"', device_text("fpl_stats.cu", drop=PTX_WRAPPERS), "namespace extns {",
-                     device_text("fpl_ext.h"), device_text("fpl_ext.cu"), "}  // namespace extns"])
+                     device_text("fpl_ext.h"), device_text("fpl_ext.cu"), "}  // namespace extns", "namespace ingestns {",
+                     device_text("fpl_ingest.h"), device_text("fpl_ingest.cu"), "}  // namespace ingestns", "namespace emitns {",
+                     device_text("fpl_emit.h"), device_text("fpl_emit.cu"), "}  // namespace emitns"])
     return HARNESS.replace("@@DEVICE@@", dev).replace("@@BUILDER@@", table_builder())
 
 
@@ -320,6 +410,9 @@ def load():
         subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-w", "-I", SIMT, "-I", os.path.join(ROOT, "include"),
                                "-I", CSRC, "-o", so, cpp])
     lib = C.CDLL(so)
+    lib.emu_process_fastq.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
+                                      C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                      C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
     lib.emu_last_error.restype = C.c_char_p
     lib.emu_set_cp_async_lazy.argtypes = [C.c_int]
     lib.emu_collectives.restype = C.c_longlong
@@ -431,6 +524,36 @@ class EmuEngine:
                 self._blocks = [relayout_stats(x, self._C, c2) + relayout_stats(y, cyc, c2) for x, y in zip(self._blocks, (s0, s1))]
                 self._C = c2
         return res
+
+    def process_fastq(self, text, is_last=True, want_failed=True):
+        """binding.Engine.process_fastq + emit_fastq in one call: a chunk of plain FASTQ text through k_count_lines / the newline
+        select / k_fastq_records / k_fastq_pack, the kernels of process(), k_emit_sizes / k_emit_copy.  Returns None where the
+        device parser refuses the layout, else (record table, records, bytes consumed, --out text, --failed_out text)."""
+        from fastplong_b200.abi import FASTQ_RECORD_DTYPE
+        from fastplong_b200.binding import relayout_stats
+        o, ad, keep = self._abi
+        buf = np.frombuffer(bytes(text) + b"\0" * 64, dtype=np.uint8)[:len(text)]
+        cap = max(16, len(text) // 8)
+        recs = np.zeros(cap, dtype=FASTQ_RECORD_DTYPE)
+        res = np.zeros(cap, dtype=RESULT_DTYPE)
+        cnt = np.zeros_like(self._counters)
+        longest = max((len(ln) for ln in bytes(text).split(b"\n")), default=1)
+        cyc = 1 << int(np.ceil(np.log2(max(64, longest))))
+        s0, s1 = np.zeros(abi.stats_words(cyc), dtype=np.int64), np.zeros(abi.stats_words(cyc), dtype=np.int64)
+        out, failed = np.zeros(2 * len(text) + 4096, dtype=np.uint8), np.zeros(2 * len(text) + 4096, dtype=np.uint8)
+        n, used, nout, nfail = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        rc = self.lib.emu_process_fastq(C.addressof(o), C.addressof(ad), buf.ctypes.data if len(text) else None, len(text), int(is_last),
+                                        recs.ctypes.data, res.ctypes.data, cap, C.byref(n), C.byref(used), cnt.ctypes.data, s0.ctypes.data,
+                                        s1.ctypes.data, cyc, C.cast(self.scan_fn, C.c_void_p) if self.scan_fn is not None else None,
+                                        int(want_failed), out.ctypes.data, out.shape[0], C.byref(nout), failed.ctypes.data, failed.shape[0],
+                                        C.byref(nfail))
+        if rc == 1:
+            return None
+        if rc != 0:
+            raise RuntimeError(self.lib.emu_last_error().decode())
+        self._counters += cnt
+        self._blocks, self._C = [s0, s1], cyc
+        return recs[:n.value], res[:n.value], used.value, out[:nout.value].tobytes(), failed[:nfail.value].tobytes()
 
     def segments(self):
         """--mask/--break: every output read of the last process() call (fpl_last_segments)"""

@@ -126,3 +126,72 @@ def test_cp_async_completion_order_does_not_matter():
         check(cases.OPTION_SETS["default_se"], cases.ont_batch(9, n=40, mean=3000, p_chimera=0.2), "eager/ont")
     finally:
         lib.emu_set_cp_async_lazy(1)
+
+
+# ---- FASTQ text in, FASTQ text out: k_count_lines, the newline select, k_fastq_records, k_fastq_pack,
+# the kernels above, k_emit_sizes, k_emit_copy — the harness mirrors fpl_process_fastq_host + fpl_emit_fastq_host ----
+def _fastq_of(batch):
+    """names of varying length, '+' lines that sometimes repeat the name (as tests/test_gpu_emit.py)"""
+    names, plus, parts = [], [], []
+    for i in range(batch.n_reads):
+        s, q = batch.read(i)
+        nm = b"@read%d %s" % (i, b"x" * (i % 41))
+        pl = b"+" if i % 3 else b"+read%d" % i
+        names.append(nm)
+        plus.append(pl)
+        parts.append(nm + b"\n" + s + b"\n" + pl + b"\n" + q + b"\n")
+    return b"".join(parts), names, plus
+
+
+def check_text(opt, batch, what, want_failed=True, last_newline=True):
+    from fastplong_b200 import hostside
+    text, names, plus = _fastq_of(batch)
+    if not last_newline:
+        text = text[:-1]
+    e, o = simt_emu.EmuEngine(opt, scan="jit"), OracleEngine(opt)
+    got = e.process_fastq(text, want_failed=want_failed)
+    assert got is not None, what
+    recs, res, used, out, failed = got
+    assert used == len(text) and len(recs) == batch.n_reads
+    ores = o.process(batch)
+    compare_results(res, ores, what)
+    if opt.mask or opt.break_reads:
+        exp_out, exp_failed = hostside.emit_fastq_ext(batch, names, ores, o.segments(), o.mask_regions(), strand=plus)
+    else:
+        exp_out, exp_failed = hostside.emit_fastq(batch, names, ores, strand=plus)
+    assert out == exp_out, f"{what}: --out text differs ({len(out)} bytes, expected {len(exp_out)})"
+    assert failed == (exp_failed if want_failed else b""), f"{what}: --failed_out text differs"
+    cyc = max(1, int(batch.lens.max()))
+    for w in (0, 1):
+        compare_stats(e.stats(w, cyc), o.stats(w, cyc), f"{what}/stats{w}")
+    compare_stats(e.counters(), o.counters(), what + "/counters")
+    o.close()
+
+
+@pytest.mark.parametrize("name", ["default_se", "cut_polyx_cplx", "trims_limits", "fasta5", "no_adapter_no_filters"])
+def test_fastq_text_path(name):
+    check_text(cases.OPTION_SETS[name], cases.adversarial_batch(3), name + "/text/adv")
+    check_text(cases.OPTION_SETS[name], cases.ont_batch(91, n=50, mean=2000, p_chimera=0.2), name + "/text/ont", last_newline=False)
+
+
+@pytest.mark.parametrize("name", sorted(cases.MASK_BREAK_SETS))
+def test_fastq_text_path_mask_break(name):
+    check_text(cases.MASK_BREAK_SETS[name], cases.blocky_quality_batch(5, n=50), name + "/text")
+
+
+def test_fastq_text_path_without_failed_writer_and_empty_reads():
+    check_text(cases.OPTION_SETS["default_se"], cases.adversarial_batch(4), "nofailed", want_failed=False)
+    reads = [(b"", b""), (b"A", b"I"), ((b"ACGTTGCAAC" * 9)[:90], b"I" * 90), (b"", b"")]
+    check_text(Options(disable_adapter_trimming=True, length_required=0), pack_reads(reads), "empty reads in the text")
+
+
+@pytest.mark.parametrize("kind", ["crlf", "blank_line", "no_at", "no_plus", "len_mismatch", "three_lines"])
+def test_fastq_parser_refuses_non_strict_layouts(kind):
+    """what FastqReader would treat by its own rules goes back to the caller (return value 1 of fpl_process_fastq_host)"""
+    text = b"@r0\nACGTACGTAC\n+\nIIIIIIIIII\n@r1\nGGGTTTAAAC\n+\nIIIIIIIIII\n"
+    text = {"crlf": lambda t: t.replace(b"\n", b"\r\n"), "blank_line": lambda t: t.replace(b"IIIIIIIIII\n@r1", b"IIIIIIIIII\n\n@r1"),
+            "no_at": lambda t: t.replace(b"@r1", b"r1x"), "no_plus": lambda t: t.replace(b"\n+\n", b"\n-\n"),
+            "len_mismatch": lambda t: t.replace(b"GGGTTTAAAC", b"GGGTTTAAA"),
+            "three_lines": lambda t: t[: t.rfind(b"\n", 0, len(t) - 1) + 1]}[kind](text)
+    e = simt_emu.EmuEngine(cases.OPTION_SETS["default_se"])
+    assert e.process_fastq(text) is None
