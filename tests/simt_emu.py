@@ -10,9 +10,10 @@ fpl_create (fpl_api.cu), so that adapters, thresholds, match masks, grids and ke
 code.  `EmuEngine.process()` runs the kernels in run_batch's order on host memory and returns records, both Stats blocks and
 the counter vector, to be compared with the oracle like a GPU result.
 
-Not covered: the NVRTC-specialised scan and k_scan_fast (the generic k_scan computes the same ReadState by contract; the GPU
-tests hold the variants to each other; their helpers are host-tested in tests/test_device_helpers_host.py), FASTQ ingest / emit,
---mask/--break, the NCCL merge; and what no functional emulation shows: timing, bank conflicts, memory ordering, races.
+Also under the emulator: k_scan_jit v2 as fpl_jit.cu generates it for the options' adapters (jit_scan), k_scan_fast, the
+--mask/--break kernels (fpl_ext.cu) and the FASTQ text path (fpl_ingest.cu, fpl_emit.cu).  Not covered: the NCCL merge, the
+upload overlap of fpl_process_host, k_eval_kmers, cub's own kernels (host stand-ins); and what no functional emulation shows:
+timing, bank conflicts, memory ordering between warps.
 Nothing here is shipped or reachable from the product path.
 """
 import ctypes as C
