@@ -389,7 +389,7 @@ def source():
                      '#include "fpl_stats.h"', device_text("fpl_stats.cu", drop=PTX_WRAPPERS), "namespace extns {",
                      device_text("fpl_ext.h"), device_text("fpl_ext.cu"), "}  // namespace extns", "namespace ingestns {",
                      device_text("fpl_ingest.h"), device_text("fpl_ingest.cu"), "}  // namespace ingestns", "namespace emitns {",
-                     device_text("fpl_emit.h"), device_text("fpl_emit.cu"), "}  // namespace emitns"])
+                     device_text("fpl_emit.h"), device_text("fpl_emit.cu"), "}  // namespace emitns", device_text("fpl_eval.cu")])
     return HARNESS.replace("@@DEVICE@@", dev).replace("@@BUILDER@@", table_builder())
 
 
@@ -414,6 +414,7 @@ def load():
     lib.emu_process_fastq.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
                                       C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                       C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+    lib.fpl_eval_adapter_kmers.argtypes = [C.c_int, C.POINTER(FplBatch), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
     lib.emu_last_error.restype = C.c_char_p
     lib.emu_set_cp_async_lazy.argtypes = [C.c_int]
     lib.emu_collectives.restype = C.c_longlong
@@ -580,3 +581,16 @@ class EmuEngine:
 
     def counters(self):
         return self._counters.copy()
+
+
+def eval_adapter_kmers(batch, side, shift_tail=1):
+    """binding.eval_adapter_kmers through the emulated k_eval_kmers (fpl_eval.cu with its own host function)"""
+    lib = load()
+    counts = np.zeros(1 << 20, dtype=np.uint32)
+    acc = np.zeros(1 << 20, dtype=np.uint64)
+    total = C.c_int64()
+    b = batch.to_abi()
+    rc = lib.fpl_eval_adapter_kmers(0, C.byref(b), int(shift_tail), int(side), counts.ctypes.data, acc.ctypes.data, C.byref(total))
+    if rc != 0:
+        raise RuntimeError(f"fpl_eval_adapter_kmers failed ({rc})")
+    return counts, acc, int(total.value)

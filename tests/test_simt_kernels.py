@@ -195,3 +195,20 @@ def test_fastq_parser_refuses_non_strict_layouts(kind):
             "three_lines": lambda t: t[: t.rfind(b"\n", 0, len(t) - 1) + 1]}[kind](text)
     e = simt_emu.EmuEngine(cases.OPTION_SETS["default_se"])
     assert e.process_fastq(text) is None
+
+
+@pytest.mark.parametrize("side", [0, 1])
+def test_adapter_detection_tables(side):
+    """k_eval_kmers (fpl_eval.cu, the counting half of Evaluator::evalAdapterAndReadNum) against the numpy restatement, and the
+    whole detection — emulated tables + the C ABI's fpl_eval_pick_adapter — finding the planted adapters"""
+    from fastplong_b200 import evaluator
+    from oracle_lib import kmer10_tables
+    reads = synth.adversarial_reads(9) + [synth.ont_like(120, 900, 4).read(i) for i in range(120)]
+    batch = pack_reads(reads)
+    for shift in (1, 3):
+        c, a, t = simt_emu.eval_adapter_kmers(batch, side, shift)
+        rc, ra, rt = kmer10_tables(batch, side, shift)
+        assert t == rt and np.array_equal(c, rc) and np.array_equal(a, ra)
+    if side == 0:
+        b = synth.ont_like(400, 1500, 21)
+        assert evaluator.detect_adapters(b, kmers=simt_emu.eval_adapter_kmers) == (synth.ADAPTER_START, synth.ADAPTER_END)
