@@ -68,12 +68,12 @@ def _planted_tables(rng):
 
 
 def test_abi_pick_equals_python_twin_on_planted_tables():
-    """fpl_eval_pick_adapter (C++, include/fplgpu.h) against evaluator.detect_one on 100 synthetic table pairs, DNA and RNA;
+    """fpl_eval_pick_adapter (C++, include/fplgpu.h) against evaluator.detect_one on 40 synthetic table pairs, DNA and RNA;
     neither modifies its input."""
     from fastplong_b200.binding import eval_pick_adapter
     rng = np.random.default_rng(2026)
     found = 0
-    for case in range(100):
+    for case in range(40):
         counts, acc, total = _planted_tables(rng)
         c0, a0 = counts.copy(), acc.copy()
         for rna in (False, True):
@@ -82,7 +82,7 @@ def test_abi_pick_equals_python_twin_on_planted_tables():
             assert got == exp, (case, rna, got, exp)
             found += got is not None
         assert np.array_equal(counts, c0) and np.array_equal(acc, a0)
-    assert found > 30
+    assert found > 10
 
 
 def test_abi_pick_rejects_bad_arguments():

@@ -36,8 +36,10 @@ def check(opt, batch, what, scan="jit"):
 PLAIN_SETS = sorted(n for n in cases.OPTION_SETS if not n.startswith("long_adapter_"))
 
 
-@pytest.mark.parametrize("scan", ["jit", "fast", "generic"])
-@pytest.mark.parametrize("name", PLAIN_SETS)
+OTHER_SCANS = [(n, sc) for n in ("default_se", "cut_polyx_cplx", "fasta5", "literal_auto", "empty_adapters", "loose_ed") for sc in ("fast", "generic")]
+
+
+@pytest.mark.parametrize("name,scan", [(n, "jit") for n in PLAIN_SETS] + OTHER_SCANS)
 def test_option_matrix_on_adversarial_reads(name, scan):
     check(cases.OPTION_SETS[name], cases.adversarial_batch(1), name + "/adv", scan)
 
@@ -90,7 +92,7 @@ def test_empty_tiny_and_very_long_reads():
     check(cases.OPTION_SETS["cut_polyx_cplx"], synth.ont_like(3, 60000, 5, p_chimera=1.0), "long reads/generic", "generic")
 
 
-@pytest.mark.parametrize("family,count", [("random_case", 30), ("random_case_many_adapters", 15), ("random_case_long_reads", 6)])
+@pytest.mark.parametrize("family,count", [("random_case", 20), ("random_case_many_adapters", 8), ("random_case_long_reads", 3)])
 def test_random_option_sets(family, count):
     rng = random.Random(20260924)
     done = 0
