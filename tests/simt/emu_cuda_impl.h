@@ -1,6 +1,7 @@
 // TEST INFRASTRUCTURE: the scheduler of tests/simt/emu_cuda.h (include once per harness translation unit).
 #pragma once
 #include "emu_cuda.h"
+#include <mutex>
 
 uint3 emu_threadIdx, emu_blockIdx;
 dim3 emu_blockDim, emu_gridDim;
@@ -76,7 +77,9 @@ Group& collect(Group& g, int index, uint64_t v) {
     return g;
 }
 
+static std::mutex launch_mu;      // one kernel at a time: callers on several host threads (one context each) take turns
 void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()>& body) {
+    std::lock_guard<std::mutex> lock(launch_mu);
     if (block.y != 1 || block.z != 1 || grid.z != 1 || block.x > 1024) { fprintf(stderr, "emu: 1-D blocks, 2-D grids only\n"); abort(); }
     if (dyn.size() < smem_bytes + 64) dyn.resize(smem_bytes + 64);
     dynamic_smem = (uint8_t*)(((uintptr_t)dyn.data() + 63) & ~(uintptr_t)63);

@@ -594,3 +594,66 @@ def eval_adapter_kmers(batch, side, shift_tail=1):
     if rc != 0:
         raise RuntimeError(f"fpl_eval_adapter_kmers failed ({rc})")
     return counts, acc, int(total.value)
+
+
+# =====================================================================================================================
+# The whole library on the CPU: every .cu of fastplong_b200/csrc — fpl_api.cu's C ABI and host logic included — built for
+# the host against tests/simt/fake/ (a host-memory <cuda_runtime.h>, cub stand-ins, NVRTC that compiles with g++) and the
+# SIMT emulator.  The result exports include/fplgpu.h like libfplgpu.so does, so binding.Engine, the C tests and the
+# drop-in binary run on it unchanged.
+# =====================================================================================================================
+LIB_SOURCES = ("fpl_api.cu", "fpl_trim.cu", "fpl_scan.cu", "fpl_scan_fast.cu", "fpl_stats.cu", "fpl_jit.cu", "fpl_ingest.cu", "fpl_ext.cu",
+               "fpl_eval.cu", "fpl_emit.cu")
+
+
+def _lib_text(fn):
+    text = open(os.path.join(CSRC, fn)).read()
+    drops = {"fpl_device.cuh": ("red_shared_add", "shared_addr"), "fpl_stats.cu": PTX_WRAPPERS}.get(fn, ())
+    for name in drops:
+        text = _drop_function(text, name)
+    text = re.sub(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?(\w+)\s+(\w+)\[\];", r"\1* \2 = (\1*)emu::dynamic_smem;", text)
+    text = re.sub(r'asm\s+volatile\s*\(\s*"fence[^"]*"[^;]*;', ";", text)
+    text = text.replace('dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL)', "dlopen(EMU_LIB_PATH, RTLD_NOW)")
+    return _rewrite_launches(_asm_to_c(text))
+
+
+_emu_lib_path = None
+
+
+def build_library():
+    """-> path of libfplgpu_emu.so (built once per source state into /tmp)"""
+    global _emu_lib_path
+    if _emu_lib_path:
+        return _emu_lib_path
+    files = {}
+    for fn in sorted(os.listdir(CSRC)):
+        if fn.endswith((".cu", ".cuh", ".h")):
+            files[fn] = _lib_text(fn)
+    extra = ""
+    for root, _, names in os.walk(SIMT):
+        for nm in sorted(names):
+            extra += open(os.path.join(root, nm)).read()
+    tag = hashlib.md5(("".join(files[k] for k in sorted(files)) + extra).encode()).hexdigest()[:12]
+    out = f"/tmp/fpl_emu_lib_{tag}"
+    so = os.path.join(out, "libfplgpu_emu.so")
+    if not os.path.exists(so):
+        os.makedirs(out, exist_ok=True)
+        for fn, text in files.items():
+            open(os.path.join(out, fn[:-3] + ".cpp" if fn.endswith(".cu") else fn), "w").write(text)
+        defs = [f'-DEMU_LIB_PATH="{so}"', f'-DEMU_LIB_DIR="{out}"', f'-DEMU_SIMT_DIR="{SIMT}"', f'-DEMU_BUILD_TAG="{tag}"']
+        inc = ["-I", out, "-I", os.path.join(SIMT, "fake"), "-I", SIMT, "-I", os.path.join(ROOT, "include")]
+        objs = []
+        jobs = []
+        for src in [os.path.join(out, fn[:-3] + ".cpp") for fn in LIB_SOURCES] + [os.path.join(SIMT, "emu_core.cpp")]:
+            obj = os.path.join(out, os.path.basename(src)[:-4] + ".o")
+            objs.append(obj)
+            jobs.append(subprocess.Popen(["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-w", "-c", *defs, *inc, "-o", obj, src],
+                                         stderr=subprocess.PIPE, text=True))
+        for j in jobs:
+            err = j.communicate()[1]
+            if j.returncode != 0:
+                raise RuntimeError("emulated build failed:\n" + err[:6000])
+        subprocess.check_call(["g++", "-shared", "-o", so + ".tmp", *objs, "-ldl", "-lpthread"])
+        os.replace(so + ".tmp", so)
+    _emu_lib_path = so
+    return so
