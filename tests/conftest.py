@@ -17,7 +17,7 @@ def pytest_configure(config):
 # `-m gpu` tests run on it, except the ones that need CUDA memory from torch, a second GPU, or sizes the emulator takes minutes for.
 EMULATE = os.environ.get("FPL_EMULATE", "") not in ("", "0")
 NOT_UNDER_EMULATION = ("test_device_resident_entry_point", "test_size_independent_properties_large", "test_gpu_multigpu", "test_full_scale_check",
-                       "test_gpu_binary", "test_config1_shape_vs_oracle")
+                       "test_config1_full_size_bit_exact", "test_config1_shape_vs_oracle")
 
 
 def pytest_sessionstart(session):
@@ -27,6 +27,7 @@ def pytest_sessionstart(session):
         from fastplong_b200 import binding
         binding.LIB_PATH = simt_emu.build_library()
         binding._lib = None
+        os.environ["FPL_GPU_BIN"] = simt_emu.build_binary()      # tests/test_gpu_binary.py: the drop-in CLI on the emulated library
 
 
 def pytest_collection_modifyitems(config, items):

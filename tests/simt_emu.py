@@ -657,3 +657,32 @@ def build_library():
         os.replace(so + ".tmp", so)
     _emu_lib_path = so
     return so
+
+
+_emu_bin_path = None
+
+
+def build_binary():
+    """-> path of fastplong_gpu_emu: host/seprocessor_gpu.cpp (unchanged) + the reference's unmodified objects (oracle/_ref/obj, as
+    fastplong_b200/host/Makefile links them) + the emulated library.  The drop-in CLI without a GPU."""
+    global _emu_bin_path
+    if _emu_bin_path:
+        return _emu_bin_path
+    lib = build_library()
+    out = os.path.dirname(lib)
+    exe = os.path.join(out, "fastplong_gpu_emu")
+    host = os.path.join(ROOT, "fastplong_b200", "host", "seprocessor_gpu.cpp")
+    objdir = os.path.join(ROOT, "oracle", "_ref", "obj")
+    stamp = os.path.join(out, "host.md5")
+    tag = hashlib.md5(open(host, "rb").read()).hexdigest()
+    if not os.path.exists(exe) or not os.path.exists(stamp) or open(stamp).read() != tag:
+        if not os.path.exists(os.path.join(objdir, "main.o")):
+            raise RuntimeError("oracle/_ref/obj is not built (make -C oracle)")
+        obj = os.path.join(out, "seprocessor_gpu.o")
+        subprocess.check_call(["g++", "-std=c++14", "-pthread", "-O2", "-w", "-I", os.path.join(SIMT, "fake"), "-I", os.path.join(ROOT, "oracle", "shim"),
+                               "-I", "/root/reference/src", "-I", os.path.join(ROOT, "include"), "-c", host, "-o", obj])
+        refobj = sorted(os.path.join(objdir, f) for f in os.listdir(objdir) if f.endswith(".o") and f != "seprocessor.o")
+        subprocess.check_call(["g++", "-pthread", "-o", exe, obj, *refobj, lib, "-lz", "-ldl", f"-Wl,-rpath,{out}"])
+        open(stamp, "w").write(tag)
+    _emu_bin_path = exe
+    return exe

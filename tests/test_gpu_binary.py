@@ -15,7 +15,7 @@ from oracle_lib import REF_BIN
 pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-GPU_BIN = os.path.join(ROOT, "build", "fastplong_gpu")
+GPU_BIN = os.environ.get("FPL_GPU_BIN") or os.path.join(ROOT, "build", "fastplong_gpu")      # FPL_EMULATE=1 (conftest.py) points this at the emulated build
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
