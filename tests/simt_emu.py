@@ -633,7 +633,8 @@ def build_library():
     for root, _, names in os.walk(SIMT):
         for nm in sorted(names):
             extra += open(os.path.join(root, nm)).read()
-    tag = hashlib.md5(("".join(files[k] for k in sorted(files)) + extra).encode()).hexdigest()[:12]
+    san = os.environ.get("FPL_EMU_SANITIZE", "")          # e.g. "undefined": the kernels and fpl_api.cu's host code under UBSan
+    tag = hashlib.md5(("".join(files[k] for k in sorted(files)) + extra + san).encode()).hexdigest()[:12]
     out = f"/tmp/fpl_emu_lib_{tag}"
     so = os.path.join(out, "libfplgpu_emu.so")
     if not os.path.exists(so):
@@ -647,13 +648,14 @@ def build_library():
         for src in [os.path.join(out, fn[:-3] + ".cpp") for fn in LIB_SOURCES] + [os.path.join(SIMT, "emu_core.cpp")]:
             obj = os.path.join(out, os.path.basename(src)[:-4] + ".o")
             objs.append(obj)
-            jobs.append(subprocess.Popen(["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-w", "-c", *defs, *inc, "-o", obj, src],
+            sflags = [f"-fsanitize={san}", "-fno-sanitize-recover=all", "-fno-omit-frame-pointer"] if san else []
+            jobs.append(subprocess.Popen(["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-w", "-c", *sflags, *defs, *inc, "-o", obj, src],
                                          stderr=subprocess.PIPE, text=True))
         for j in jobs:
             err = j.communicate()[1]
             if j.returncode != 0:
                 raise RuntimeError("emulated build failed:\n" + err[:6000])
-        subprocess.check_call(["g++", "-shared", "-o", so + ".tmp", *objs, "-ldl", "-lpthread"])
+        subprocess.check_call(["g++", "-shared", *([f"-fsanitize={san}"] if san else []), "-o", so + ".tmp", *objs, "-ldl", "-lpthread"])
         os.replace(so + ".tmp", so)
     _emu_lib_path = so
     return so
