@@ -449,11 +449,13 @@ __device__ void prefilter_round(const DevParams& P, const uint8_t* head, const u
     W eA = 0, eC = 0, eG = 0, eT = 0;
     if (filterable) { eA = eq_of('A'); eC = eq_of('C'); eG = eq_of('G'); eT = eq_of('T'); }
     // the probe pattern: the adapter's LAST plen chars on the start side, its FIRST plen chars on the end side
-    const int sh16 = side == 0 ? alen - plen : 0;
+    // (an adapter wider than W is not filtered — both verdicts are "maybe" — so its columns run on a 1-bit dummy pattern:
+    //  shifting by alen - 1 or alen - plen >= the word width would be undefined; found by UBSan on the emulated build)
+    const int sh16 = (filterable && side == 0) ? alen - plen : 0;
     const uint32_t m16 = plen >= 32 ? 0xFFFFFFFFu : ((1u << plen) - 1u);
     SearchMyers<W> F;
     SearchMyers<uint32_t> Q;
-    F.init(max(alen, 1)); Q.init(max(plen, 1));
+    F.init(filterable ? alen : 1); Q.init(max(plen, 1));
     const uint8_t* text = side == 0 ? head : tail;
     for (int j = 0; j < hw; j++) {
         const uint32_t b = text[j];

@@ -648,7 +648,7 @@ def build_library():
         for src in [os.path.join(out, fn[:-3] + ".cpp") for fn in LIB_SOURCES] + [os.path.join(SIMT, "emu_core.cpp")]:
             obj = os.path.join(out, os.path.basename(src)[:-4] + ".o")
             objs.append(obj)
-            sflags = [f"-fsanitize={san}", "-fno-sanitize-recover=all", "-fno-omit-frame-pointer"] if san else []
+            sflags = [f"-fsanitize={san}", "-fno-omit-frame-pointer"] if san else []        # reports go to stderr, the run goes on
             jobs.append(subprocess.Popen(["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-w", "-c", *sflags, *defs, *inc, "-o", obj, src],
                                          stderr=subprocess.PIPE, text=True))
         for j in jobs:
