@@ -14,10 +14,11 @@ def pytest_configure(config):
 
 # FPL_EMULATE=1: no GPU needed — binding.Engine loads the EMULATED build of the library (tests/simt_emu.py:build_library: every
 # .cu of fastplong_b200/csrc compiled for the host behind the SIMT emulator, the C ABI and fpl_api.cu's host code included) and the
-# `-m gpu` tests run on it, except the ones that need CUDA memory from torch, a second GPU, or sizes the emulator takes minutes for.
+# `-m gpu` tests run on it, except the ones that need a second GPU or sizes the emulator takes minutes for (tests that hand the library
+# device pointers use torch CPU tensors then: the emulated library's device memory is host memory).
 EMULATE = os.environ.get("FPL_EMULATE", "") not in ("", "0")
-NOT_UNDER_EMULATION = ("test_device_resident_entry_point", "test_size_independent_properties_large", "test_gpu_multigpu", "test_full_scale_check",
-                       "test_config1_full_size_bit_exact", "test_config1_shape_vs_oracle")
+NOT_UNDER_EMULATION = ("test_size_independent_properties_large", "test_gpu_multigpu", "test_config1_full_size_bit_exact",
+                       "test_config1_shape_vs_oracle")
 
 
 def pytest_sessionstart(session):

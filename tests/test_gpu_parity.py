@@ -157,7 +157,8 @@ def test_size_independent_properties_large():
 
 def _device_batch(batch):
     import torch
-    dev = torch.device("cuda:0")
+    # FPL_EMULATE=1 (conftest.py): the emulated library's device memory is host memory
+    dev = torch.device("cpu" if os.environ.get("FPL_EMULATE", "") not in ("", "0") else "cuda:0")
     pad = 256
     seq = torch.zeros(batch.seq.size + pad, dtype=torch.uint8, device=dev)
     qual = torch.zeros(batch.qual.size + pad, dtype=torch.uint8, device=dev)
@@ -165,7 +166,8 @@ def _device_batch(batch):
     qual[:batch.qual.size] = torch.from_numpy(batch.qual).to(dev)
     offs = torch.from_numpy(batch.offsets.astype(np.int64)).to(dev)
     lens = torch.from_numpy(batch.lens.astype(np.int32)).to(dev)
-    torch.cuda.synchronize()
+    if dev.type == "cuda":
+        torch.cuda.synchronize()
     return seq, qual, offs, lens
 
 

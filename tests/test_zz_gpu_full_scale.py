@@ -3,6 +3,8 @@ device-generated batch goes through fpl_process_device exactly as in the bench; 
 the batch are held to the oracle, every word of both Stats blocks and every median to the torch restatement
 (tests/stats_tables.py, pinned to the oracle by tests/test_stats_tables.py), the filter counters to the records.
 (Named to run last: it drives bench.py's own code.)"""
+import os
+
 import numpy as np
 import pytest
 
@@ -16,12 +18,16 @@ def test_full_scale_check_on_a_device_resident_batch(optset, n, mean, monkeypatc
     from fastplong_b200 import synth_fast
     from fastplong_b200.binding import Engine
     monkeypatch.setattr(bench, "FULL_CHECK_BASES", 6_000_000)
-    dev = torch.device("cuda:0")
+    emulated = os.environ.get("FPL_EMULATE", "") not in ("", "0")      # conftest.py: device memory of the emulated library is host memory
+    dev = torch.device("cpu" if emulated else "cuda:0")
+    if emulated:
+        n, mean = max(200, n // 20), min(mean, 6000)
     opt = cases.OPTION_SETS[optset]
     tile = synth_fast.ont_like_device(n, mean, 4242, dev, p_chimera=0.02)
     offs = torch.from_numpy(tile.offsets).to(dev)
     lens = torch.from_numpy(tile.lens).to(dev)
-    torch.cuda.synchronize()
+    if not emulated:
+        torch.cuda.synchronize()
     eng = Engine(opt)
     eng.process_device(tile.seq.data_ptr(), tile.qual.data_ptr(), offs.data_ptr(), lens.data_ptr(), tile.n_reads, tile.seq.numel())
     eng.sync()
