@@ -21,10 +21,8 @@ from test_abi_exports import header_functions
 @pytest.fixture()
 def emulated_binding():
     """binding.Engine on the emulated library for the duration of one test"""
-    old = binding.LIB_PATH, binding._lib
-    binding.LIB_PATH, binding._lib = simt_emu.build_library(), None
-    yield binding
-    binding.LIB_PATH, binding._lib = old
+    with simt_emu._Bound() as b:
+        yield b
 
 
 def test_emulated_library_exports_the_c_abi():

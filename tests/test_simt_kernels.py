@@ -1,9 +1,11 @@
-"""The kernels of libfplgpu's default path — k_make_preseg, k_trim, k_trim_fasta, k_cs_keys / k_cs_gather, k_cycle_stats (both
-variants; cp.async ring, packed shared-memory counters, lane-private 5-mer tables), the generic k_scan, k_final, k_count,
-k_kmer_fix, k_read_qual, the --mask/--break kernels of fpl_ext.cu — and k_scan_jit v2, the source fpl_jit.cu generates for the options' adapters (what NVRTC compiles on
-the GPU): their own source text, executed on the CPU under the SIMT emulator (tests/simt_emu.py, tests/simt/emu_cuda.h) in
-run_batch's order — against the oracle, on the whole option matrix, the crafted boundary cases,
-RNA reads and seeded random cases: every field of every record, every word of both Stats blocks, every counter."""
+"""Every kernel of libfplgpu executed on the CPU: binding.Engine on the EMULATED library (tests/simt_emu.py: every .cu of
+fastplong_b200/csrc, fpl_api.cu and fpl_jit.cu included, built for the host behind the SIMT emulator of tests/simt/) against the
+oracle — k_make_preseg, k_trim / k_trim_fasta in their size classes, k_cs_keys / k_cs_gather, k_cycle_stats (5-mer and plain,
+cp.async ring and bulk-copy variant), k_scan_jit v2 as fpl_jit.cu generates and "compiles" it per context, k_scan_fast, the
+generic k_scan, k_final, k_count, k_kmer_fix, k_read_qual, the --mask/--break kernels, FASTQ text in / text out (k_count_lines,
+k_fastq_records, k_fastq_pack, k_emit_sizes, k_emit_copy), k_eval_kmers: every field of every record, every word of both Stats
+blocks, every counter, the -N/-b lists, the output text — on the option matrix, adapters up to 1024 bp, the 64-entry FASTA, the
+crafted boundaries, RNA reads and seeded random option sets."""
 import random
 
 import numpy as np
@@ -16,12 +18,9 @@ from oracle_lib import OracleEngine, compare_lists, compare_results, compare_sta
 
 
 def check(opt, batch, what, scan="jit"):
-    """scan = "jit": the whole-read scan is k_scan_jit v2, specialised on the options exactly where fpl_create would have NVRTC
-    specialise it (the emulator harness reports ScanPlan.fast, the product's own verdict); "fast": the precompiled k_scan_fast
-    (what FPL_NO_JIT or a missing NVRTC leaves) in the same places; the generic k_scan elsewhere and with "generic"."""
+    """scan: which whole-read scan fpl_create sets up on the emulated library — "jit": k_scan_jit v2 specialised through the NVRTC
+    stand-in wherever the library specialises, "fast": the precompiled k_scan_fast (FPL_NO_JIT), "generic": k_scan."""
     e, o = simt_emu.EmuEngine(opt, scan=scan), OracleEngine(opt)
-    if scan == "jit":
-        assert e.jit == e.plan_fast(), what
     compare_results(e.process(batch), o.process(batch), what)
     if opt.mask or opt.break_reads:
         compare_lists(e.segments(), o.segments(), what + "/segments")
@@ -30,6 +29,7 @@ def check(opt, batch, what, scan="jit"):
     for w in (0, 1):
         compare_stats(e.stats(w, cyc), o.stats(w, cyc), f"{what}/stats{w}")
     compare_stats(e.counters(), o.counters(), what + "/counters")
+    e.close()
     o.close()
 
 
@@ -121,7 +121,7 @@ def test_cp_async_completion_order_does_not_matter():
     """cp.async may complete anywhere between its issue and the wait covering its group: the emulator's default is the latest
     legal moment, this repeats two batches with the earliest one (a kernel correct under both extremes does not lean on when
     the copies land; removing the warp barrier behind k_cycle_stats' wait fails under both, as racecheck reported on the GPU)."""
-    lib = simt_emu.load()
+    lib = simt_emu.emulated_library()
     try:
         lib.emu_set_cp_async_lazy(0)
         check(cases.OPTION_SETS["cut_polyx_cplx"], cases.adversarial_batch(2), "eager/adv")
@@ -150,10 +150,11 @@ def check_text(opt, batch, what, want_failed=True, last_newline=True):
     text, names, plus = _fastq_of(batch)
     if not last_newline:
         text = text[:-1]
-    e, o = simt_emu.EmuEngine(opt, scan="jit"), OracleEngine(opt)
-    got = e.process_fastq(text, want_failed=want_failed)
+    e, o = simt_emu.EmuEngine(opt), OracleEngine(opt)
+    got = e.process_fastq(text)
     assert got is not None, what
-    recs, res, used, out, failed = got
+    recs, res, used = got
+    out, failed = e.emit_fastq(want_failed)
     assert used == len(text) and len(recs) == batch.n_reads
     ores = o.process(batch)
     compare_results(res, ores, what)
@@ -167,6 +168,7 @@ def check_text(opt, batch, what, want_failed=True, last_newline=True):
     for w in (0, 1):
         compare_stats(e.stats(w, cyc), o.stats(w, cyc), f"{what}/stats{w}")
     compare_stats(e.counters(), o.counters(), what + "/counters")
+    e.close()
     o.close()
 
 
