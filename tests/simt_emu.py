@@ -158,10 +158,12 @@ def build_binary():
         if not os.path.exists(os.path.join(objdir, "main.o")):
             raise RuntimeError("oracle/_ref/obj is not built (make -C oracle)")
         obj = os.path.join(out, "seprocessor_gpu.o")
-        subprocess.check_call(["g++", "-std=c++14", "-pthread", "-O2", "-w", "-I", os.path.join(SIMT, "fake"), "-I", os.path.join(ROOT, "oracle", "shim"),
+        san = os.environ.get("FPL_EMU_SANITIZE", "")
+        sflags = [f"-fsanitize={san}", "-fno-omit-frame-pointer", "-g"] if san else []
+        subprocess.check_call(["g++", "-std=c++14", "-pthread", "-O2", "-w", *sflags, "-I", os.path.join(SIMT, "fake"), "-I", os.path.join(ROOT, "oracle", "shim"),
                                "-I", "/root/reference/src", "-I", os.path.join(ROOT, "include"), "-c", host, "-o", obj])
         refobj = sorted(os.path.join(objdir, f) for f in os.listdir(objdir) if f.endswith(".o") and f != "seprocessor.o")
-        subprocess.check_call(["g++", "-pthread", "-o", exe, obj, *refobj, lib, "-lz", "-ldl", f"-Wl,-rpath,{out}"])
+        subprocess.check_call(["g++", "-pthread", *sflags[:1], "-o", exe, obj, *refobj, lib, "-lz", "-ldl", f"-Wl,-rpath,{out}"])
         open(stamp, "w").write(tag)
     _emu_bin_path = exe
     return exe
