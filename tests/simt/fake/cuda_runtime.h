@@ -15,8 +15,16 @@ static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSucces
 static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 static inline cudaError_t cudaSetDevice(int d) { return d == 0 ? cudaSuccess : cudaErrorInvalidValue; }
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
-template <class T> static inline cudaError_t cudaMalloc(T** p, size_t n) { *p = (T*)calloc(n ? n : 1, 1); return *p ? cudaSuccess : cudaErrorInvalidValue; }
-template <class T> static inline cudaError_t cudaMallocHost(T** p, size_t n) { *p = (T*)calloc(n ? n : 1, 1); return *p ? cudaSuccess : cudaErrorInvalidValue; }
+// cudaMalloc does not zero memory: EMU_MALLOC_FILL=<byte> fills every allocation with that byte (default 0), so that a kernel or
+// host path leaning on fresh allocations being zero shows up
+static inline void* emu_alloc(size_t n) {
+    static const char* f = getenv("EMU_MALLOC_FILL");
+    void* p = malloc(n ? n : 1);
+    if (p) memset(p, f ? (int)strtol(f, nullptr, 0) : 0, n ? n : 1);
+    return p;
+}
+template <class T> static inline cudaError_t cudaMalloc(T** p, size_t n) { *p = (T*)emu_alloc(n); return *p ? cudaSuccess : cudaErrorInvalidValue; }
+template <class T> static inline cudaError_t cudaMallocHost(T** p, size_t n) { *p = (T*)emu_alloc(n); return *p ? cudaSuccess : cudaErrorInvalidValue; }
 static inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
 static inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
 static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { if (n) memmove(d, s, n); return cudaSuccess; }
