@@ -77,6 +77,21 @@ Group& collect(Group& g, int index, uint64_t v) {
     return g;
 }
 
+static int sched_mode = [] {
+    const char* m = getenv("EMU_SCHED");
+    return !m ? 0 : !strncmp(m, "reverse", 7) ? 1 : !strncmp(m, "random", 6) ? 2 : 0;
+}();
+static unsigned long long sched_rng = [] { const char* m = getenv("EMU_SCHED"); const char* c = m ? strchr(m, ':') : nullptr; return c ? strtoull(c + 1, nullptr, 0) * 2654435761ull + 1 : 88172645463325252ull; }();
+static std::vector<int> perm;
+static void shuffle(int n) {
+    perm.resize((size_t)n);
+    for (int i = 0; i < n; i++) perm[i] = i;
+    for (int i = n - 1; i > 0; i--) {
+        sched_rng ^= sched_rng << 13; sched_rng ^= sched_rng >> 7; sched_rng ^= sched_rng << 17;
+        const int j = (int)(sched_rng % (unsigned long long)(i + 1));
+        const int t = perm[i]; perm[i] = perm[j]; perm[j] = t;
+    }
+}
 static std::mutex launch_mu;      // one kernel at a time: callers on several host threads (one context each) take turns
 void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()>& body) {
     std::lock_guard<std::mutex> lock(launch_mu);
@@ -111,7 +126,12 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
             progress = first;
             first = false;
             left = 0;
-            for (int i = 0; i < n; i++) {
+            for (int k = 0; k < n; k++) {
+                // which live thread runs next is the scheduler's business: EMU_SCHED=reverse / random[:seed] change the order in which
+                // the threads of a block get their turns (results must not depend on it: an ordering assumption without a barrier shows)
+                int i = k;
+                if (sched_mode == 1) i = n - 1 - k;
+                else if (sched_mode == 2) { if (k == 0) shuffle(n); i = perm[k]; }
                 if (fibers[i].done) continue;
                 cur = i;
                 emu_threadIdx = {(unsigned)i, 0, 0};
