@@ -255,6 +255,32 @@ def edge_cases():
     return out
 
 
+# ---- option values at the ends of what the reference's CLI accepts (src/options.cpp:validate): the longest windows, a distance
+# threshold of 1, extensions and trims larger than most reads, 4-bp adapters, 200 FASTA entries, filters at 0 and 100 % ----
+def _extreme_sets():
+    rng = np.random.default_rng(5)
+    fa = sorted("".join("ACGT"[i] for i in rng.integers(0, 4, size=int(rng.integers(6, 60)))) for _ in range(200))
+    return {
+        "window1000": Options(start_adapter=S, end_adapter=E, cut_front=True, cut_tail=True, cut_window_size=1000, cut_mean_quality=18),
+        "window999_q36": Options(disable_adapter_trimming=True, cut_front=True, cut_tail=True, cut_window_size=999, cut_mean_quality=36),
+        "ext100": Options(start_adapter=S, end_adapter=E, trimming_extension=100),
+        "ed1": Options(start_adapter=S, end_adapter=E, distance_threshold=1.0),
+        "polyx_min50": Options(start_adapter=S, trim_poly_x=True, poly_x_min_len=50),
+        "polyx_min1": Options(start_adapter=S, trim_poly_x=True, poly_x_min_len=1),
+        "front_tail_big": Options(start_adapter=S, trim_front=300, trim_tail=400, length_required=0),
+        "adapters_4bp": Options(start_adapter="ACGT", end_adapter="TTGCA"),
+        "fasta_200_entries": Options(start_adapter=S, end_adapter=E, adapter_fasta=fa),
+        "complexity100": Options(start_adapter=S, low_complexity_filter=True, complexity_threshold=100),
+        "complexity0": Options(start_adapter=S, low_complexity_filter=True, complexity_threshold=0),
+        "qual_phred0_limits0": Options(start_adapter=S, qualified_quality_phred=0, unqualified_percent_limit=0, n_base_limit=0, n_percent_limit=0),
+        "mask_break_w5_q30": Options(start_adapter=S, mask=True, mask_window_size=5, mask_mean_quality=30, break_reads=True,
+                                     break_window_size=5, break_mean_quality=30),
+    }
+
+
+EXTREME_SETS = _extreme_sets()
+
+
 # ---- --mask / --break ----
 MASK_BREAK_SETS = {
     "break_default": Options(start_adapter=S, break_reads=True),

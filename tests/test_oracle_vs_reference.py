@@ -70,6 +70,21 @@ def test_crafted_boundary_cases(name):
     check(opt, batch, name)
 
 
+@pytest.mark.parametrize("name", sorted(cases.EXTREME_SETS))
+def test_extreme_option_values(name):
+    opt = cases.EXTREME_SETS[name]
+    batch = cases.ont_batch(8, n=40, mean=2500, p_chimera=0.2, p_polya=0.2) if name == "fasta_200_entries" else cases.adversarial_batch(12)
+    o, r = OracleEngine(opt), RefEngine(opt)
+    compare_results(o.process(batch), r.process(batch), name)
+    if opt.mask or opt.break_reads:
+        compare_lists(o.segments(), r.segments(), name + "/segments")
+        compare_lists(o.mask_regions(), r.mask_regions(), name + "/regions")
+    cyc = int(batch.lens.max())
+    for w in (0, 1):
+        compare_stats(o.stats(w, cyc), r.stats(w, cyc), f"{name}/stats{w}")
+    compare_stats(o.counters(), r.counters(), name + "/counters")
+
+
 def test_empty_batch():
     check(cases.OPTION_SETS["default_se"], pack_reads([]), "empty")
 

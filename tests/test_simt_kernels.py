@@ -68,6 +68,12 @@ def test_crafted_boundary_cases(name):
     check(opt, batch, name)
 
 
+@pytest.mark.parametrize("name", sorted(cases.EXTREME_SETS))
+def test_extreme_option_values(name):
+    batch = cases.ont_batch(8, n=40, mean=2500, p_chimera=0.2, p_polya=0.2) if name == "fasta_200_entries" else cases.adversarial_batch(12)
+    check(cases.EXTREME_SETS[name], batch, name)
+
+
 @pytest.mark.parametrize("name", sorted(cases.RNA_SETS))
 @pytest.mark.parametrize("mixed", [False, True])
 def test_rna_reads(name, mixed):

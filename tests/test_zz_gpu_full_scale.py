@@ -67,3 +67,18 @@ def test_crafted_boundary_cases_vs_oracle(name):
     from test_gpu_parity import check_against_oracle
     opt, batch = cases.edge_cases()[name]
     check_against_oracle(opt, batch, name)
+
+
+def _extreme_names():
+    import cases
+    return sorted(cases.EXTREME_SETS)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", _extreme_names())
+def test_extreme_option_values_vs_oracle(name):
+    """cases.EXTREME_SETS: option values at the ends of what the CLI accepts (pinned oracle-vs-reference on the CPU)"""
+    import cases
+    from test_gpu_parity import check_against_oracle
+    batch = cases.ont_batch(8, n=40, mean=2500, p_chimera=0.2, p_polya=0.2) if name == "fasta_200_entries" else cases.adversarial_batch(12)
+    check_against_oracle(cases.EXTREME_SETS[name], batch, name)
