@@ -80,3 +80,18 @@ def test_emulated_drop_in_binary_writes_the_reference_binary_s_files(flags, thre
         md5[name] = [hashlib.md5(x).hexdigest() for x in (open(d + "/o.fq", "rb").read(), open(d + "/f.fq", "rb").read(), js)]
         assert os.path.getsize(d + "/o.fq") > 50000
     assert md5["emu"] == md5["ref"]
+
+
+def test_limits_of_the_c_abi_on_the_emulated_library():
+    """FPL_MAX_ADAPTERS and FPL_MAX_ADAPTER_LEN: the largest accepted adapter set works (1022 FASTA entries + -s / -e, bit-exact),
+    one more entry or one more base is a loud error of fpl_create"""
+    from fastplong_b200 import Options
+    from test_simt_kernels import check
+    rng = np.random.default_rng(1)
+    ad = lambda n: "".join("ACGT"[i] for i in rng.integers(0, 4, size=n))
+    fa = sorted(ad(int(rng.integers(8, 30))) for _ in range(1022))
+    check(Options(start_adapter=synth.ADAPTER_START, end_adapter=synth.ADAPTER_END, adapter_fasta=fa), cases.ont_batch(3, n=6, mean=800), "1022 adapters")
+    with pytest.raises(binding.FplError, match="FPL_MAX_ADAPTERS"):
+        simt_emu.EmuEngine(Options(adapter_fasta=fa + [ad(10)]))
+    with pytest.raises(binding.FplError, match="FPL_MAX_ADAPTER_LEN"):
+        simt_emu.EmuEngine(Options(start_adapter=ad(1025)))
