@@ -83,8 +83,8 @@ LIB_SOURCES = ("fpl_api.cu", "fpl_trim.cu", "fpl_scan.cu", "fpl_scan_fast.cu", "
                "fpl_eval.cu", "fpl_emit.cu")
 
 
-def _lib_text(fn):
-    text = open(os.path.join(CSRC, fn)).read()
+def _lib_text(fn, text=None):
+    text = open(os.path.join(CSRC, fn)).read() if text is None else text
     drops = {"fpl_device.cuh": ("red_shared_add", "shared_addr"), "fpl_stats.cu": PTX_WRAPPERS}.get(fn, ())
     for name in drops:
         text = _drop_function(text, name)
@@ -97,15 +97,16 @@ def _lib_text(fn):
 _emu_lib_path = None
 
 
-def build_library():
-    """-> path of libfplgpu_emu.so (built once per source state into /tmp)"""
+def build_library(override=None):
+    """-> path of libfplgpu_emu.so (built once per source state into /tmp).  override: {file name: source text} replacing files of
+    fastplong_b200/csrc (tools/mutate_kernels.py builds mutants this way; such builds are not remembered as THE library)."""
     global _emu_lib_path
-    if _emu_lib_path:
+    if _emu_lib_path and not override:
         return _emu_lib_path
     files = {}
     for fn in sorted(os.listdir(CSRC)):
         if fn.endswith((".cu", ".cuh", ".h")):
-            files[fn] = _lib_text(fn)
+            files[fn] = _lib_text(fn, (override or {}).get(fn))
     extra = ""
     for root, _, names in os.walk(SIMT):
         for nm in sorted(names):
@@ -134,7 +135,8 @@ def build_library():
                 raise RuntimeError("emulated build failed:\n" + err[:6000])
         subprocess.check_call(["g++", "-shared", *([f"-fsanitize={san}"] if san else []), "-o", so + ".tmp", *objs, "-ldl", "-lpthread"])
         os.replace(so + ".tmp", so)
-    _emu_lib_path = so
+    if not override:
+        _emu_lib_path = so
     return so
 
 
