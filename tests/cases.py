@@ -228,6 +228,13 @@ def edge_cases():
                      ("neither_filter_but_complexity", dict(disable_length_filtering=True, disable_quality_filtering=True,
                                                             low_complexity_filter=True))):
         out[name] = (Options(disable_adapter_trimming=True, mean_qual=12, n_base_limit=20, **kw), pack_reads(reads))
+    # reads of one and two bases under the complexity filter without the length filter: `rlen <= 1` fails complexity in the
+    # reference (src/filter.cpp:70); the kernels' integer form would pass such a read without its own guard (0 >= pct * 0) — a
+    # mutant of k_final's pass_filter that the emulated battery did not catch (tools/mutate_kernels.py)
+    reads = [(b"A", _q(1, 30)), (b"AC", _q(2, 30)), (b"AA", _q(2, 30)), (b"ACG", _q(3, 30)), (b"G", _q(1, 30))]
+    for pct in (0, 30, 100):
+        out[f"complexity_on_tiny_reads_{pct}"] = (Options(disable_adapter_trimming=True, disable_length_filtering=True, low_complexity_filter=True,
+                                                         complexity_threshold=pct), pack_reads(reads))
     # (f) ties of the integer-valued comparisons: mean quality == requirement (integer division, src/filter.cpp:33),
     # complexity == threshold and one transition either side (:75-78), unqualified share and N share == limit (:31, :35)
     reads = []

@@ -38,6 +38,8 @@ def battery(lib):
         for n in (33, 65, 129):
             T.check(cases.OPTION_SETS[f"long_adapter_{n}"], cases.long_adapter_batch(n, 900 + n, n=16), f"long{n}")
         T.check(cases.OPTION_SETS["fasta64_polyx"], cases.hifi_fasta64_batch(3, n=40), "fasta64")
+        from fastplong_b200 import synth
+        T.check(cases.OPTION_SETS["cut_polyx_cplx"], synth.ont_like(2, 110000, 5, p_chimera=1.0), "reads beyond 96 kb")      # block-wide paths
         T.check_text(cases.OPTION_SETS["cut_polyx_cplx"], cases.adversarial_batch(3), "text")
         T.check_text(cases.MASK_BREAK_SETS["mask_and_break"], cases.blocky_quality_batch(5, n=30), "text/ext")
         print("SURVIVED")
