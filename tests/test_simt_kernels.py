@@ -68,6 +68,20 @@ def test_crafted_boundary_cases(name):
     check(opt, batch, name)
 
 
+FILTER_CASES = sorted(n for n in cases.edge_cases() if n.startswith(("filter_ties", "complexity_on_tiny", "qual_filter_without", "length_filter_without",
+                                                                     "neither_filter")))
+
+
+@pytest.mark.parametrize("scan", ["fast", "generic"])
+@pytest.mark.parametrize("name", FILTER_CASES)
+def test_filter_counts_of_the_other_scan_kernels(name, scan):
+    """passFilter's counts (low-quality bases, N, quality sum, unequal neighbours) are taken by whichever scan kernel runs: the
+    threshold ties and the tiny reads also through k_scan_fast and the generic k_scan (a mutant of the generic kernel's
+    neighbour-byte pick survived the battery: tools/mutate_kernels.py)"""
+    opt, batch = cases.edge_cases()[name]
+    check(opt, batch, f"{name}/{scan}", scan)
+
+
 @pytest.mark.parametrize("name", sorted(cases.EXTREME_SETS))
 def test_extreme_option_values(name):
     batch = cases.ont_batch(8, n=40, mean=2500, p_chimera=0.2, p_polya=0.2) if name == "fasta_200_entries" else cases.adversarial_batch(12)

@@ -82,3 +82,15 @@ def test_extreme_option_values_vs_oracle(name):
     from test_gpu_parity import check_against_oracle
     batch = cases.ont_batch(8, n=40, mean=2500, p_chimera=0.2, p_polya=0.2) if name == "fasta_200_entries" else cases.adversarial_batch(12)
     check_against_oracle(cases.EXTREME_SETS[name], batch, name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("switch", ["FPL_NO_JIT", "FPL_FORCE_GENERIC_SCAN"])
+@pytest.mark.parametrize("name", ["filter_ties", "complexity_on_tiny_reads_30", "qual_filter_without_length_filter"])
+def test_filter_counts_of_the_other_scan_kernels(name, switch, monkeypatch):
+    """the threshold ties and the tiny reads with passFilter's counts taken by k_scan_fast / the generic k_scan instead of k_scan_jit"""
+    import cases
+    from test_gpu_parity import check_against_oracle
+    monkeypatch.setenv(switch, "1")
+    opt, batch = cases.edge_cases()[name]
+    check_against_oracle(opt, batch, f"{name}/{switch}")
