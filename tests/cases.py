@@ -235,6 +235,28 @@ def edge_cases():
     for pct in (0, 30, 100):
         out[f"complexity_on_tiny_reads_{pct}"] = (Options(disable_adapter_trimming=True, disable_length_filtering=True, low_complexity_filter=True,
                                                          complexity_threshold=pct), pack_reads(reads))
+    # the same ties on the two sides of a SPLIT read (a start adapter in the middle, beyond the 200-base end windows): k_final
+    # recounts the smaller parts of [A | gap | B] byte-wise at their ragged ends and takes the largest by subtraction; a mutant of
+    # that recount's neighbour-byte pick survived the battery (tools/mutate_kernels.py).  Low-complexity two-letter sides with
+    # exactly (len - 1) * 30 % unequal neighbours, one fewer, one more; side lengths that move the ragged ends through a word
+    def two_letter(L, d, a=b"A", c=b"C"):        # (every flip moves on through a cycle of letters that starts with a, c)
+        cycle = [a, c] + [x for x in (b"G", b"T", b"A", b"C") if x not in (a, c)]
+        flips = set(int(x) for x in rng.choice(L - 1, size=d, replace=False))
+        out_, k = bytearray(), 0
+        for i in range(L):
+            out_ += cycle[k % 4]
+            if i in flips:
+                k += 1
+        return bytes(out_)
+    reads = []
+    for la in (241, 251, 261, 271):
+        for lb in (321, 331):
+            for da, db in ((0, 0), (-1, 0), (0, -1), (1, 1)):
+                sA = two_letter(la, (la - 1) * 3 // 10 + da)
+                sB = two_letter(lb, (lb - 1) * 3 // 10 + db, b"G", b"T")
+                reads.append((sA + S.encode() + sB, _q(la + 30 + lb, 30)))
+    out["split_read_complexity_ties"] = (Options(start_adapter=S, end_adapter=E, trimming_extension=0, low_complexity_filter=True,
+                                                 complexity_threshold=30, length_required=10), pack_reads(reads))
     # (f) ties of the integer-valued comparisons: mean quality == requirement (integer division, src/filter.cpp:33),
     # complexity == threshold and one transition either side (:75-78), unqualified share and N share == limit (:31, :35)
     reads = []

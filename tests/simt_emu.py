@@ -186,15 +186,16 @@ class _Bound:
     def __enter__(self):
         from fastplong_b200 import binding
         self.binding, self.saved = binding, (binding.LIB_PATH, binding._lib)
-        binding.LIB_PATH, binding._lib = build_library(), _Bound.lib
-        _Bound.lib = binding.load_library()
+        path = build_library()
+        binding.LIB_PATH, binding._lib = path, _Bound.libs.get(path)
+        _Bound.libs[path] = binding.load_library()
         return binding
 
     def __exit__(self, *exc):
         self.binding.LIB_PATH, self.binding._lib = self.saved
 
 
-_Bound.lib = None
+_Bound.libs = {}      # path -> loaded handle (a mutant build is another path)
 
 
 def EmuEngine(options, scan="jit"):
